@@ -1,0 +1,30 @@
+# Builds the CUDA library for sm_100a in-tree (the .so travels to the GPU box with the snapshot).
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Wno-deprecated-gpu-targets
+CSRC := ectrans_b200/csrc
+OBJ := $(CSRC)/_build
+LIB := ectrans_b200/lib/libectrans_b200.so
+SRCS := api.cu legendre.cu fourier.cu fft_plan.cu host_plan.cu
+OBJS := $(patsubst %.cu,$(OBJ)/%.o,$(SRCS))
+HDRS := $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
+
+all: $(LIB)
+
+$(OBJ)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) $(EXTRA_$*) -Xptxas -v -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; exit 1)
+
+# the table kernel is kept free of FMA contraction so that it reproduces the reference recurrence bit for bit
+EXTRA_legendre :=
+
+$(LIB): $(OBJS)
+	@mkdir -p ectrans_b200/lib
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -lnccl
+
+emu:
+	@mkdir -p tests/hostemu/_build
+	$(NVCC) -std=c++17 -O2 -shared -Xcompiler -fPIC -Wno-deprecated-gpu-targets -o tests/hostemu/_build/libemu.so tests/hostemu/emu.cu $(CSRC)/fft_plan.cu
+
+clean:
+	rm -rf $(OBJ) $(LIB) tests/hostemu/_build

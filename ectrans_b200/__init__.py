@@ -1,0 +1,348 @@
+"""ectrans_b200 -- B200-native global spectral transform (SETUP_TRANS / INV_TRANS / DIR_TRANS).
+
+Host-side Python face over the C ABI in ``include/ectrans_b200.h`` (ctypes).  The
+compute path is the CUDA library ``ectrans_b200/lib/libectrans_b200.so`` built for
+sm_100a; there is no CPU fallback -- if the library is missing or no GPU is present
+the calls fail loudly.
+
+Array conventions are the reference's Fortran layouts seen from C:
+  spectral  : ``(nspec2, nfld)``  C-contiguous  == Fortran ``PSPEC(nfld, nspec2)``
+  gridpoint : ``(ngpblks, nfld, nproma)``       == Fortran ``PGP(nproma, nfld, ngpblks)``
+(reference: src/trans/include/ectrans/inv_trans.h:38-76, dir_trans.h:36-61;
+transi ``rspscalar[nspec2][nscalar]``, ``rgp[ngpblks][nfld][nproma]`` src/transi/transi.h:986-1010).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "lib", "libectrans_b200.so")
+_lib = None
+
+ECT_MEM_HOST, ECT_MEM_DEVICE = 0, 1
+ECT_SETUP_HOST_ONLY = 1
+ECT_NCCL_UID_BYTES = 128
+(ARR_NLOEN, ARR_NMEN, ARR_NDGLU, ARR_MYMS, ARR_NASM0, ARR_NPROCM, ARR_RMU, ARR_RGW, ARR_LATFIRST,
+ ARR_LATCOUNT, ARR_SENDCNT, ARR_RECVCNT, ARR_RACTHE) = range(1, 14)
+
+
+class EctError(RuntimeError):
+    pass
+
+
+class _SetupOpts(C.Structure):
+    _fields_ = [("nsmax", C.c_int), ("ndgl", C.c_int), ("nloen", C.POINTER(C.c_int)), ("nranks", C.c_int),
+                ("rank", C.c_int), ("flags", C.c_int), ("device", C.c_int), ("stream", C.c_void_p),
+                ("nccl_uid", C.c_void_p)]
+
+
+class Info(C.Structure):
+    _fields_ = [("nsmax", C.c_int), ("ndgl", C.c_int), ("ndgnh", C.c_int), ("nranks", C.c_int), ("rank", C.c_int),
+                ("nspec2", C.c_int), ("nspec2g", C.c_int), ("ngptot", C.c_int), ("ngptotg", C.c_int),
+                ("nump", C.c_int), ("lat0", C.c_int), ("nlat", C.c_int), ("table_bytes", C.c_longlong)]
+
+
+class _InvArgs(C.Structure):
+    _fields_ = [("memspace", C.c_int), ("nproma", C.c_int), ("scders", C.c_int), ("vorgp", C.c_int),
+                ("divgp", C.c_int), ("uvder", C.c_int),
+                ("spvor", C.c_void_p), ("spdiv", C.c_void_p), ("nuv", C.c_int),
+                ("spscalar", C.c_void_p), ("nscalar", C.c_int),
+                ("spsc2", C.c_void_p), ("nsc2", C.c_int),
+                ("spsc3a", C.c_void_p), ("nsc3a_lev", C.c_int), ("nsc3a_fld", C.c_int),
+                ("spsc3b", C.c_void_p), ("nsc3b_lev", C.c_int), ("nsc3b_fld", C.c_int),
+                ("gp", C.c_void_p), ("gpuv", C.c_void_p), ("gp2", C.c_void_p), ("gp3a", C.c_void_p),
+                ("gp3b", C.c_void_p)]
+
+
+class _DirArgs(C.Structure):
+    _fields_ = [("memspace", C.c_int), ("nproma", C.c_int), ("nuv", C.c_int), ("nscalar", C.c_int),
+                ("gp", C.c_void_p), ("gpuv", C.c_void_p),
+                ("gp2", C.c_void_p), ("nsc2", C.c_int),
+                ("gp3a", C.c_void_p), ("nsc3a_lev", C.c_int), ("nsc3a_fld", C.c_int),
+                ("gp3b", C.c_void_p), ("nsc3b_lev", C.c_int), ("nsc3b_fld", C.c_int),
+                ("spvor", C.c_void_p), ("spdiv", C.c_void_p), ("spscalar", C.c_void_p),
+                ("spsc2", C.c_void_p), ("spsc3a", C.c_void_p), ("spsc3b", C.c_void_p)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("h2d", C.c_float), ("prologue", C.c_float), ("legendre", C.c_float), ("transpose", C.c_float),
+                ("fourier", C.c_float), ("epilogue", C.c_float), ("d2h", C.c_float), ("total", C.c_float),
+                ("launches", C.c_longlong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTED_SYMBOLS = [
+    "ect_setup", "ect_inquire", "ect_inquire_array", "ect_inv_trans", "ect_dir_trans", "ect_specnorm",
+    "ect_get_timings", "ect_synchronize", "ect_release", "ect_finalize", "ect_strerror", "ect_last_error",
+    "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
+]
+
+
+def lib():
+    """Load the CUDA library (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            raise EctError(f"{_LIBPATH} not found: build it with `make` (or __graft_entry__.build()); "
+                           "there is no CPU fallback")
+        L = C.CDLL(_LIBPATH, mode=C.RTLD_GLOBAL)
+        L.ect_strerror.restype = C.c_char_p
+        L.ect_last_error.restype = C.c_char_p
+        L.ect_setup.argtypes = [C.POINTER(_SetupOpts), C.POINTER(C.c_int)]
+        L.ect_inquire.argtypes = [C.c_int, C.POINTER(Info)]
+        L.ect_inquire_array.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong]
+        L.ect_inv_trans.argtypes = [C.c_int, C.POINTER(_InvArgs)]
+        L.ect_dir_trans.argtypes = [C.c_int, C.POINTER(_DirArgs)]
+        L.ect_specnorm.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ect_get_timings.argtypes = [C.c_int, C.POINTER(Timings)]
+        L.ect_debug_get_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
+        L.ect_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.ect_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_longlong]
+        L.ect_host_free.argtypes = [C.c_void_p]
+        L.ect_nccl_unique_id.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        L = lib()
+        raise EctError(f"{what} failed: {L.ect_strerror(rc).decode()} ({rc}): {L.ect_last_error().decode()}")
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(ECT_NCCL_UID_BYTES)
+    _check(lib().ect_nccl_unique_id(buf), "ect_nccl_unique_id")
+    return buf.raw
+
+
+def measure_fp64_peak(which: int) -> float:
+    v = C.c_double(0.0)
+    _check(lib().ect_measure_fp64_peak(which, C.byref(v)), "ect_measure_fp64_peak")
+    return v.value
+
+
+def octahedral_nloen(n: int) -> np.ndarray:
+    """O<N> grid (src/programs/ectrans-benchmark.F90:1043-1047)."""
+    half = 20 + 4 * np.arange(n, dtype=np.int32)
+    return np.concatenate([half, half[::-1]]).astype(np.int32)
+
+
+def _is_torch(x):
+    return x is not None and type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(x.ctypes.data)
+
+
+class PinnedArray:
+    """float64 host array in page-locked memory from ect_host_alloc (the reference benchmark's
+    pinned allocation, src/programs/util/ectrans_memory.c)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in shape)
+        n = int(np.prod(self.shape)) if self.shape else 1
+        self._p = C.c_void_p()
+        _check(lib().ect_host_alloc(C.byref(self._p), n * 8), "ect_host_alloc")
+        buf = (C.c_double * max(n, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(self.shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().ect_host_free(self._p)
+            self._p = None
+
+
+class Transform:
+    """One resolution handle (SETUP_TRANS) on one GPU / rank.
+
+    Mirrors the reference's SETUP_TRANS / TRANS_INQ / INV_TRANS / DIR_TRANS / SPECNORM /
+    TRANS_RELEASE (src/trans/include/ectrans/*.h).  Inputs may be NumPy arrays (host; the call
+    copies H2D/D2H inside, like the reference GPU backend) or torch CUDA tensors (device resident,
+    asynchronous on the handle's stream; call ``synchronize()``).
+    """
+
+    def __init__(self, nsmax, nloen, nranks=1, rank=0, device=-1, stream=None, nccl_uid=None, host_only=False):
+        L = lib()
+        nl = np.ascontiguousarray(nloen, dtype=np.int32)
+        self._uid = C.create_string_buffer(nccl_uid, ECT_NCCL_UID_BYTES) if nccl_uid else None
+        o = _SetupOpts(int(nsmax), int(nl.size), nl.ctypes.data_as(C.POINTER(C.c_int)), int(nranks), int(rank),
+                       ECT_SETUP_HOST_ONLY if host_only else 0, int(device),
+                       C.c_void_p(stream) if stream else None,
+                       C.cast(self._uid, C.c_void_p) if self._uid else None)
+        h = C.c_int(0)
+        _check(L.ect_setup(C.byref(o), C.byref(h)), "ect_setup")
+        self.handle = h.value
+        self.info = Info()
+        _check(L.ect_inquire(self.handle, C.byref(self.info)), "ect_inquire")
+        i = self.info
+        self.nsmax, self.ndgl, self.nspec2, self.ngptot = i.nsmax, i.ndgl, i.nspec2, i.ngptot
+        self.nspec2g, self.ngptotg, self.nump = i.nspec2g, i.ngptotg, i.nump
+        self.nranks, self.rank = i.nranks, i.rank
+        self.nloen = self._arr(ARR_NLOEN, np.int32, i.ndgl)
+        self.nmen = self._arr(ARR_NMEN, np.int32, i.ndgl)
+        self.ndglu = self._arr(ARR_NDGLU, np.int32, i.nsmax + 1)
+        self.myms = self._arr(ARR_MYMS, np.int32, i.nump)
+        self.nasm0 = self._arr(ARR_NASM0, np.int32, i.nsmax + 1)
+        self.nprocm = self._arr(ARR_NPROCM, np.int32, i.nsmax + 1)
+        self.rmu = self._arr(ARR_RMU, np.float64, i.ndgl)
+        self.rgw = self._arr(ARR_RGW, np.float64, i.ndgl)
+        self.racthe = self._arr(ARR_RACTHE, np.float64, i.ndgl)
+        self.lat_first = self._arr(ARR_LATFIRST, np.int32, i.nranks)
+        self.lat_count = self._arr(ARR_LATCOUNT, np.int32, i.nranks)
+        self.send_cnt = self._arr(ARR_SENDCNT, np.int64, i.nranks)
+        self.recv_cnt = self._arr(ARR_RECVCNT, np.int64, i.nranks)
+
+    def _arr(self, which, dtype, n):
+        out = np.zeros(max(int(n), 1), dtype=dtype)
+        _check(lib().ect_inquire_array(self.handle, which, out.ctypes.data, int(n)), "ect_inquire_array")
+        return out[:int(n)]
+
+    # ------------------------------------------------------------------
+    def gp_fields(self, nuv, nscalar, scders=False, vorgp=False, divgp=False, uvder=False):
+        """Number of grid-point output fields of INV_TRANS (inv_trans.F90:356-367)."""
+        n = 2 * nuv + nscalar
+        if vorgp:
+            n += nuv
+        if divgp:
+            n += nuv
+        if scders:
+            n += 2 * nscalar
+        if uvder:
+            n += 2 * nuv
+        return n
+
+    def _blocks(self, nproma):
+        nproma = self.ngptot if (nproma <= 0 or nproma >= self.ngptot) else nproma
+        return nproma, (self.ngptot + nproma - 1) // max(nproma, 1)
+
+    def inv_trans(self, spvor=None, spdiv=None, spscalar=None, scders=False, vorgp=False, divgp=False,
+                  uvder=False, nproma=0, out=None):
+        """INV_TRANS, call mode 1.  Returns gp ``(ngpblks, nfld, nproma)``."""
+        dev = _is_torch(spvor) or _is_torch(spscalar)
+        nuv = 0 if spvor is None else int(spvor.shape[1])
+        nsc = 0 if spscalar is None else int(spscalar.shape[1])
+        for a in (spvor, spdiv, spscalar):
+            if a is not None:
+                assert a.shape[0] == self.nspec2, "spectral arrays are (nspec2, nfld)"
+        nfld = self.gp_fields(nuv, nsc, scders, vorgp, divgp, uvder)
+        nproma, nblk = self._blocks(nproma)
+        if out is None:
+            if dev:
+                import torch
+                ref = spvor if spvor is not None else spscalar
+                out = torch.empty((nblk, nfld, nproma), dtype=torch.float64, device=ref.device)
+            else:
+                out = np.empty((nblk, nfld, nproma), dtype=np.float64)
+        if not dev:
+            spvor, spdiv, spscalar = (None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+                                      for a in (spvor, spdiv, spscalar))
+        a = _InvArgs()
+        a.memspace = ECT_MEM_DEVICE if dev else ECT_MEM_HOST
+        a.nproma = nproma
+        a.scders, a.vorgp, a.divgp, a.uvder = int(scders), int(vorgp), int(divgp), int(uvder)
+        a.spvor, a.spdiv, a.nuv = _ptr(spvor), _ptr(spdiv), nuv
+        a.spscalar, a.nscalar = _ptr(spscalar), nsc
+        a.gp = _ptr(out)
+        self._keep = (spvor, spdiv, spscalar, out)
+        _check(lib().ect_inv_trans(self.handle, C.byref(a)), "ect_inv_trans")
+        return out
+
+    def dir_trans(self, gp, nuv=0, nscalar=0, nproma=0, out=None):
+        """DIR_TRANS, call mode 1.  gp ``(ngpblks, 2*nuv+nscalar, nproma)`` ordered u, v, scalars.
+        Returns (spvor, spdiv, spscalar) each ``(nspec2, nfld)`` or None."""
+        dev = _is_torch(gp)
+        nproma, nblk = self._blocks(nproma)
+        assert tuple(gp.shape) == (nblk, 2 * nuv + nscalar, nproma), (tuple(gp.shape), (nblk, 2 * nuv + nscalar, nproma))
+        if dev:
+            import torch
+            mk = lambda n: torch.empty((self.nspec2, n), dtype=torch.float64, device=gp.device) if n else None
+        else:
+            gp = np.ascontiguousarray(gp, dtype=np.float64)
+            mk = lambda n: np.empty((self.nspec2, n), dtype=np.float64) if n else None
+        if out is None:
+            out = (mk(nuv), mk(nuv), mk(nscalar))
+        spvor, spdiv, spsc = out
+        a = _DirArgs()
+        a.memspace = ECT_MEM_DEVICE if dev else ECT_MEM_HOST
+        a.nproma, a.nuv, a.nscalar = nproma, nuv, nscalar
+        a.gp = _ptr(gp)
+        a.spvor, a.spdiv, a.spscalar = _ptr(spvor), _ptr(spdiv), _ptr(spsc)
+        self._keep = (gp, out)
+        _check(lib().ect_dir_trans(self.handle, C.byref(a)), "ect_dir_trans")
+        return spvor, spdiv, spsc
+
+    def inv_trans_raw(self, **kw):
+        """Direct access to every ect_inv_args member (call mode 2 arrays etc.)."""
+        a = _InvArgs()
+        keep = []
+        for k, v in kw.items():
+            if hasattr(v, "shape"):
+                keep.append(v)
+                setattr(a, k, _ptr(v))
+            else:
+                setattr(a, k, v)
+        self._keep = keep
+        _check(lib().ect_inv_trans(self.handle, C.byref(a)), "ect_inv_trans")
+
+    def dir_trans_raw(self, **kw):
+        a = _DirArgs()
+        keep = []
+        for k, v in kw.items():
+            if hasattr(v, "shape"):
+                keep.append(v)
+                setattr(a, k, _ptr(v))
+            else:
+                setattr(a, k, v)
+        self._keep = keep
+        _check(lib().ect_dir_trans(self.handle, C.byref(a)), "ect_dir_trans")
+
+    def specnorm(self, spec):
+        """SPECNORM: spectral L2 norm per field (global over ranks)."""
+        dev = _is_torch(spec)
+        nf = int(spec.shape[1])
+        if not dev:
+            spec = np.ascontiguousarray(spec, dtype=np.float64)
+        out = np.zeros(nf)
+        _check(lib().ect_specnorm(self.handle, _ptr(spec), nf, ECT_MEM_DEVICE if dev else ECT_MEM_HOST,
+                                  out.ctypes.data), "ect_specnorm")
+        return out
+
+    def legendre_table(self, ml, parity):
+        """Test access: P[k, i] for local wavenumber index ml; parity 0: n-m even, 1: odd."""
+        m = int(self.myms[ml])
+        k = (self.nsmax - m + 3) // 2 if parity == 0 else (self.nsmax - m + 2) // 2
+        nl = int(self.ndglu[m])
+        out = np.zeros((k, nl))
+        _check(lib().ect_debug_get_table(self.handle, ml, parity, out.ctypes.data, out.size), "ect_debug_get_table")
+        return out
+
+    def timings(self):
+        t = Timings()
+        _check(lib().ect_get_timings(self.handle, C.byref(t)), "ect_get_timings")
+        return t.as_dict()
+
+    def synchronize(self):
+        _check(lib().ect_synchronize(self.handle), "ect_synchronize")
+
+    def release(self):
+        if getattr(self, "handle", 0):
+            lib().ect_release(self.handle)
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

@@ -1,0 +1,741 @@
+// C ABI of the B200 spectral transform: handle registry, field bookkeeping and stage sequencing.
+// Sequencing follows the reference control routines
+//   INV_TRANS  cpu/external/inv_trans.F90:182-609 -> inv_trans_ctl_mod.F90:282-291
+//              (LTINV -> TRMTOL -> FOURIER_IN/FSC/FTINV -> TRLTOG)
+//   DIR_TRANS  cpu/external/dir_trans.F90 -> dir_trans_ctl_mod.F90
+//              (TRGTOL -> FTDIR/FOURIER_OUT -> TRLTOM -> LTDIR)
+#include "ect_internal.h"
+#include "fourier_phases.h"
+#include <nccl.h>
+#include <mutex>
+#include <map>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+
+struct EctSpecFieldH { const double* base; long long stride; };
+
+static std::mutex g_mu;
+static std::map<int, EctHandle*> g_handles;
+static int g_next = 1;
+
+static EctHandle* get_handle(int id) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_handles.find(id);
+    return it == g_handles.end() ? nullptr : it->second;
+}
+
+extern "C" const char* ect_strerror(int code) {
+    switch (code) {
+        case ECT_SUCCESS: return "success";
+        case ECT_ERR_GENERIC: return "error";
+        case ECT_ERR_NOTIMPL: return "not implemented";
+        case ECT_ERR_MISSING: return "missing argument";
+        case ECT_ERR_BADARG: return "unrecognised or inconsistent argument";
+        case ECT_ERR_STALE: return "stale argument";
+        case ECT_ERR_CUDA: return "CUDA error";
+        case ECT_ERR_NCCL: return "NCCL error";
+        case ECT_ERR_HANDLE: return "invalid handle";
+        default: return "unknown error code";
+    }
+}
+
+#define ECT_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) { \
+    ect_set_error("%s:%d: NCCL: %s", __FILE__, __LINE__, ncclGetErrorString(r__)); return ECT_ERR_NCCL; } } while (0)
+
+extern "C" int ect_nccl_unique_id(void* out_bytes) {
+    if (!out_bytes) return ECT_ERR_MISSING;
+    static_assert(sizeof(ncclUniqueId) <= ECT_NCCL_UID_BYTES, "uid size");
+    ncclUniqueId id;
+    ECT_NCCL(ncclGetUniqueId(&id));
+    memset(out_bytes, 0, ECT_NCCL_UID_BYTES);
+    memcpy(out_bytes, &id, sizeof(id));
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_host_alloc(void** ptr, long long bytes) {
+    if (!ptr || bytes < 0) return ECT_ERR_BADARG;
+    ECT_CUDA(cudaHostAlloc(ptr, (size_t)std::max<long long>(bytes, 1), cudaHostAllocDefault));
+    return ECT_SUCCESS;
+}
+extern "C" int ect_host_free(void* ptr) {
+    if (ptr) ECT_CUDA(cudaFreeHost(ptr));
+    return ECT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------
+// setup / release
+// ---------------------------------------------------------------------------------------
+int ect_device_setup(EctHandle* h, cudaStream_t stream, int device, const void* uid) {
+    EctHostPlan& P = h->hp;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        ect_set_error("ect_setup: no CUDA device available (%s); this library has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return ECT_ERR_CUDA;
+    }
+    EctDevice* d = new EctDevice();
+    h->d = d;
+    if (device >= 0) ECT_CUDA(cudaSetDevice(device));
+    ECT_CUDA(cudaGetDevice(&d->dev));
+    if (stream) { d->stream = stream; d->own_stream = false; }
+    else { ECT_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking)); d->own_stream = true; }
+    for (auto& ev : d->ev) ECT_CUDA(cudaEventCreate(&ev));
+    ECT_CUDA(cudaMalloc(&d->rw, P.ndgl * sizeof(double)));
+    ECT_CUDA(cudaMalloc(&d->racthe, P.ndgl * sizeof(double)));
+    ECT_CUDA(cudaMemcpy(d->rw, P.rw.data(), P.ndgl * sizeof(double), cudaMemcpyHostToDevice));
+    ECT_CUDA(cudaMemcpy(d->racthe, P.racthe.data(), P.ndgl * sizeof(double), cudaMemcpyHostToDevice));
+    int rc;
+    if ((rc = ect_legendre_setup(h))) return rc;
+    if ((rc = ect_fourier_setup(h))) return rc;
+    if (P.nranks > 1) {
+        if (!uid) { ect_set_error("ect_setup: nranks > 1 needs nccl_uid"); return ECT_ERR_MISSING; }
+        ncclUniqueId id;
+        memcpy(&id, uid, sizeof(id));
+        ncclComm_t comm;
+        ECT_NCCL(ncclCommInitRank(&comm, P.nranks, id, P.rank));
+        d->comm = comm;
+    }
+    return ECT_SUCCESS;
+}
+
+void ect_device_free(EctHandle* h) {
+    EctDevice* d = h->d;
+    if (!d) return;
+    cudaStreamSynchronize(d->stream);
+    if (d->comm) ncclCommDestroy((ncclComm_t)d->comm);
+    void* ptrs[] = {d->rw, d->racthe, d->racthe_loc, d->nloen, d->gpoff, d->ptab, d->legm, d->leg_rec_n, d->leg_rec_s,
+                    d->nasm0, d->inv_tiles, d->dir_tiles, d->plans, d->latplans, d->perm_pool, d->tw_pool,
+                    d->cz_pool, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->xwork, d->fbuf_leg,
+                    d->stage_sp, d->stage_gp, d->callbuf, d->normbuf};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (d->fbuf_fft && d->fbuf_fft != d->fbuf_leg) cudaFree(d->fbuf_fft);
+    for (auto& b : d->buckets) if (b.d_lats) cudaFree(b.d_lats);
+    if (d->h_callbuf) cudaFreeHost(d->h_callbuf);
+    for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
+    if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+    h->d = nullptr;
+}
+
+extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
+    if (!o || !handle) { ect_set_error("ect_setup: null argument"); return ECT_ERR_MISSING; }
+    EctHandle* h = new EctHandle();
+    int rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, o->nranks < 1 ? 1 : o->nranks, o->rank);
+    if (rc) { delete h; return rc; }
+    if (!(o->flags & ECT_SETUP_HOST_ONLY)) {
+        rc = ect_device_setup(h, (cudaStream_t)o->stream, o->device, o->nccl_uid);
+        if (rc) { ect_device_free(h); delete h; return rc; }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    *handle = g_next++;
+    g_handles[*handle] = h;
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_release(int handle) {
+    EctHandle* h;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_handles.find(handle);
+        if (it == g_handles.end()) { ect_set_error("ect_release: invalid handle %d", handle); return ECT_ERR_HANDLE; }
+        h = it->second;
+        g_handles.erase(it);
+    }
+    ect_device_free(h);
+    delete h;
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_finalize(void) {
+    std::vector<int> ids;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (auto& kv : g_handles) ids.push_back(kv.first);
+    }
+    for (int id : ids) ect_release(id);
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_inquire(int handle, ect_info* info) {
+    EctHandle* h = get_handle(handle);
+    if (!h) { ect_set_error("ect_inquire: invalid handle %d", handle); return ECT_ERR_HANDLE; }
+    if (!info) return ECT_ERR_MISSING;
+    const EctHostPlan& P = h->hp;
+    info->nsmax = P.nsmax; info->ndgl = P.ndgl; info->ndgnh = P.ndgnh;
+    info->nranks = P.nranks; info->rank = P.rank;
+    info->nspec2 = P.nspec2; info->nspec2g = P.nspec2_g;
+    info->ngptot = P.ngptot; info->ngptotg = P.ngptotg;
+    info->nump = P.nump; info->lat0 = P.lat0; info->nlat = P.nlat;
+    info->table_bytes = h->d ? h->d->ptab_elems * (long long)sizeof(double) : 0;
+    return ECT_SUCCESS;
+}
+
+template <typename T, typename S>
+static int copy_out(void* out, long long cap, const std::vector<S>& v) {
+    if ((long long)v.size() > cap) { ect_set_error("ect_inquire_array: capacity %lld < %zu", cap, v.size()); return ECT_ERR_BADARG; }
+    T* o = (T*)out;
+    for (size_t i = 0; i < v.size(); ++i) o[i] = (T)v[i];
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_inquire_array(int handle, int which, void* out, long long cap) {
+    EctHandle* h = get_handle(handle);
+    if (!h) { ect_set_error("ect_inquire_array: invalid handle %d", handle); return ECT_ERR_HANDLE; }
+    if (!out) return ECT_ERR_MISSING;
+    const EctHostPlan& P = h->hp;
+    switch (which) {
+        case ECT_ARR_NLOEN: return copy_out<int>(out, cap, P.nloen);
+        case ECT_ARR_NMEN: return copy_out<int>(out, cap, P.nmen);
+        case ECT_ARR_NDGLU: return copy_out<int>(out, cap, P.ndglu);
+        case ECT_ARR_MYMS: return copy_out<int>(out, cap, P.myms);
+        case ECT_ARR_NASM0: return copy_out<int>(out, cap, P.nasm0);
+        case ECT_ARR_NPROCM: return copy_out<int>(out, cap, P.nprocm);
+        case ECT_ARR_RMU: return copy_out<double>(out, cap, P.rmu);
+        case ECT_ARR_RGW: return copy_out<double>(out, cap, P.rw);
+        case ECT_ARR_RACTHE: return copy_out<double>(out, cap, P.racthe);
+        case ECT_ARR_LATFIRST: return copy_out<int>(out, cap, P.lat_first);
+        case ECT_ARR_LATCOUNT: return copy_out<int>(out, cap, P.lat_count);
+        case ECT_ARR_SENDCNT: return copy_out<long long>(out, cap, P.send_cnt);
+        case ECT_ARR_RECVCNT: return copy_out<long long>(out, cap, P.recv_cnt);
+        default: ect_set_error("ect_inquire_array: unknown array id %d", which); return ECT_ERR_BADARG;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// workspaces
+// ---------------------------------------------------------------------------------------
+static int ensure(double*& p, i64& have, i64 need, cudaStream_t s, bool zero) {
+    if (need <= have && p) return ECT_SUCCESS;
+    if (p) { ECT_CUDA(cudaStreamSynchronize(s)); ECT_CUDA(cudaFree(p)); p = nullptr; have = 0; }
+    need = std::max<i64>(need, 16);
+    ECT_CUDA(cudaMalloc(&p, (size_t)need * sizeof(double)));
+    if (zero) ECT_CUDA(cudaMemsetAsync(p, 0, (size_t)need * sizeof(double), s));
+    have = need;
+    return ECT_SUCCESS;
+}
+
+static int ensure_work(EctHandle* h, const EctFieldCfg& f) {
+    EctDevice* d = h->d;
+    const EctHostPlan& P = h->hp;
+    int rc;
+    if ((rc = ensure(d->xwork, d->xwork_elems, (d->xrows + 2) * (i64)f.cp, d->stream, true))) return rc;
+    if ((rc = ensure(d->fbuf_leg, d->fbuf_leg_elems, (P.nrec_leg + 1) * (i64)f.cp, d->stream, true))) return rc;
+    if (P.nranks > 1) {
+        if ((rc = ensure(d->fbuf_fft, d->fbuf_fft_elems, (P.nrec_fft + 1) * (i64)f.cp, d->stream, true))) return rc;
+    } else {
+        d->fbuf_fft = d->fbuf_leg;
+        d->fbuf_fft_elems = d->fbuf_leg_elems;
+    }
+    return ECT_SUCCESS;
+}
+
+static int ensure_callbuf(EctDevice* d, size_t bytes) {
+    if (bytes <= d->callbuf_bytes) return ECT_SUCCESS;
+    if (d->callbuf) { ECT_CUDA(cudaStreamSynchronize(d->stream)); ECT_CUDA(cudaFree(d->callbuf)); ECT_CUDA(cudaFreeHost(d->h_callbuf)); }
+    bytes = (bytes + 4095) / 4096 * 4096;
+    ECT_CUDA(cudaMalloc(&d->callbuf, bytes));
+    ECT_CUDA(cudaHostAlloc(&d->h_callbuf, bytes, cudaHostAllocDefault));
+    d->callbuf_bytes = bytes;
+    return ECT_SUCCESS;
+}
+
+// TRMTOL (to_fft = 1) / TRLTOM (to_fft = 0): all-to-all-v of (lat, m) records over the W-set.
+// Reference cpu/internal/trmtol_mod.F90:101-141, trltom_mod.F90; single task = same buffer.
+int ect_transpose(EctHandle* h, const EctFieldCfg& f, int to_fft) {
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    if (P.nranks == 1) return ECT_SUCCESS;
+    ncclComm_t comm = (ncclComm_t)d->comm;
+    const i64 cp = f.cp;
+    ECT_NCCL(ncclGroupStart());
+    for (int p = 0; p < P.nranks; ++p) {
+        double* lb = d->fbuf_leg + P.send_off[p] * cp;
+        double* fb = d->fbuf_fft + P.recv_off[p] * cp;
+        const size_t nl = (size_t)(P.send_cnt[p] * cp), nf = (size_t)(P.recv_cnt[p] * cp);
+        if (to_fft) {
+            if (nl) ECT_NCCL(ncclSend(lb, nl, ncclDouble, p, comm, d->stream));
+            if (nf) ECT_NCCL(ncclRecv(fb, nf, ncclDouble, p, comm, d->stream));
+        } else {
+            if (nf) ECT_NCCL(ncclSend(fb, nf, ncclDouble, p, comm, d->stream));
+            if (nl) ECT_NCCL(ncclRecv(lb, nl, ncclDouble, p, comm, d->stream));
+        }
+    }
+    ECT_NCCL(ncclGroupEnd());
+    return ECT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------
+// field bookkeeping shared by both directions
+// ---------------------------------------------------------------------------------------
+struct ScalarSeg { const double* host; long long nfld_in_array; int lev, fld; int kind; };  // kind 0: (nf,nspec2) 1: 3-D
+
+struct CallLayout {
+    int kf_uv = 0, kf_sc = 0, nsc2 = 0, n3a_lev = 0, n3a_fld = 0, n3b_lev = 0, n3b_fld = 0;
+    bool mode2_sp = false;
+};
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
+    EctHandle* h = get_handle(handle);
+    if (!h) { ect_set_error("ect_inv_trans: invalid handle %d", handle); return ECT_ERR_HANDLE; }
+    if (!a) return ECT_ERR_MISSING;
+    if (!h->d) { ect_set_error("ect_inv_trans: handle was set up host-only (no device state)"); return ECT_ERR_CUDA; }
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    ECT_CUDA(cudaSetDevice(d->dev));
+    // ---- field counting (inv_trans.F90:212-387) ----
+    const int kf_uv = a->nuv;
+    if (kf_uv < 0 || a->nscalar < 0) { ect_set_error("ect_inv_trans: negative field count"); return ECT_ERR_BADARG; }
+    if (kf_uv > 0 && (!a->spvor || !a->spdiv)) { ect_set_error("ect_inv_trans: nuv > 0 needs spvor and spdiv"); return ECT_ERR_MISSING; }
+    const bool mode2_sp = (a->spscalar == nullptr) && (a->spsc2 || a->spsc3a || a->spsc3b);
+    int nsc2 = 0, n3a = 0, n3b = 0, kf_sc = 0;
+    if (mode2_sp) {
+        nsc2 = a->spsc2 ? a->nsc2 : 0;
+        n3a = a->spsc3a ? a->nsc3a_lev * a->nsc3a_fld : 0;
+        n3b = a->spsc3b ? a->nsc3b_lev * a->nsc3b_fld : 0;
+        kf_sc = nsc2 + n3a + n3b;
+    } else {
+        kf_sc = a->spscalar ? a->nscalar : 0;
+    }
+    const bool mode2_gp = (a->gp == nullptr);
+    if (mode2_gp) {
+        if (kf_uv > 0 && !a->gpuv) { ect_set_error("ect_inv_trans: gp == NULL and gpuv == NULL"); return ECT_ERR_MISSING; }
+        if (!mode2_sp && kf_sc > 0) { ect_set_error("ect_inv_trans: PSPSCALAR requires PGP (inv_trans.F90:418-424)"); return ECT_ERR_BADARG; }
+        if (nsc2 > 0 && !a->gp2) { ect_set_error("ect_inv_trans: spsc2 given without gp2"); return ECT_ERR_MISSING; }
+        if (n3a > 0 && !a->gp3a) { ect_set_error("ect_inv_trans: spsc3a given without gp3a"); return ECT_ERR_MISSING; }
+        if (n3b > 0 && !a->gp3b) { ect_set_error("ect_inv_trans: spsc3b given without gp3b"); return ECT_ERR_MISSING; }
+    }
+    EctFieldCfg f;
+    f.kf_uv = kf_uv; f.kf_sc = kf_sc;
+    f.scders = a->scders && kf_sc > 0; f.vorgp = a->vorgp && kf_uv > 0; f.divgp = a->divgp && kf_uv > 0;
+    f.uvder = a->uvder && kf_uv > 0;
+    const int n_vor = f.vorgp ? kf_uv : 0, n_div = f.divgp ? kf_uv : 0, n_nsd = f.scders ? kf_sc : 0;
+    f.nleg = n_vor + n_div + 2 * kf_uv + kf_sc + n_nsd;
+    f.nfs = f.nleg + (f.uvder ? 2 * kf_uv : 0) + n_nsd;
+    if (f.nfs == 0) return ECT_SUCCESS;
+    f.cp = round_up(2 * f.nleg, ECT_CPAD);
+    const int nproma = (a->nproma > 0 && a->nproma < P.ngptot) ? a->nproma : std::max(P.ngptot, 1);
+    const int ngpblks = (P.ngptot + nproma - 1) / nproma;
+    int rc;
+    if ((rc = ensure_work(h, f))) return rc;
+    d->launches = 0;
+    const bool host = (a->memspace == ECT_MEM_HOST);
+    ECT_CUDA(cudaEventRecord(d->ev[0], d->stream));
+    // ---- spectral inputs on the device ----
+    const i64 nsp = P.nspec2;
+    const double *dvor = a->spvor, *ddiv = a->spdiv, *dsc = a->spscalar, *dsc2 = a->spsc2, *dsc3a = a->spsc3a, *dsc3b = a->spsc3b;
+    if (host) {
+        const i64 tot = (2 * (i64)kf_uv + kf_sc) * nsp;
+        if ((rc = ensure(d->stage_sp, d->stage_sp_elems, tot, d->stream, false))) return rc;
+        double* p = d->stage_sp;
+        auto stage = [&](const double*& ptr, i64 n) -> int {
+            if (!ptr || n == 0) return ECT_SUCCESS;
+            ECT_CUDA(cudaMemcpyAsync(p, ptr, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+            ptr = p; p += n;
+            return ECT_SUCCESS;
+        };
+        if (kf_uv) { if ((rc = stage(dvor, kf_uv * nsp))) return rc; if ((rc = stage(ddiv, kf_uv * nsp))) return rc; }
+        if (!mode2_sp) { if ((rc = stage(dsc, kf_sc * nsp))) return rc; }
+        else {
+            if ((rc = stage(dsc2, nsc2 * nsp))) return rc;
+            if ((rc = stage(dsc3a, n3a * nsp))) return rc;
+            if ((rc = stage(dsc3b, n3b * nsp))) return rc;
+        }
+    }
+    ECT_CUDA(cudaEventRecord(d->ev[1], d->stream));
+    // ---- grid-point outputs on the device ----
+    double *dgp = a->gp, *dgpuv = a->gpuv, *dgp2 = a->gp2, *dgp3a = a->gp3a, *dgp3b = a->gp3b;
+    const int nvar_uv = (f.vorgp ? 1 : 0) + (f.divgp ? 1 : 0) + 2 + (f.uvder ? 2 : 0);
+    const int dfac = f.scders ? 3 : 1;
+    const i64 blk = (i64)nproma * ngpblks;
+    const i64 sz_gp = (i64)f.nfs * blk, sz_uv = (i64)kf_uv * nvar_uv * blk, sz_2 = (i64)nsc2 * dfac * blk,
+              sz_3a = (i64)n3a * dfac * blk, sz_3b = (i64)n3b * dfac * blk;
+    if (host) {
+        const i64 tot = mode2_gp ? (sz_uv + sz_2 + sz_3a + sz_3b) : sz_gp;
+        if ((rc = ensure(d->stage_gp, d->stage_gp_elems, tot, d->stream, false))) return rc;
+        double* p = d->stage_gp;
+        if (!mode2_gp) dgp = p;
+        else { dgpuv = p; p += sz_uv; dgp2 = p; p += sz_2; dgp3a = p; p += sz_3a; dgp3b = p; }
+    }
+    // ---- per-call tables ----
+    const size_t n_spec = (size_t)(2 * kf_uv + kf_sc);
+    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (sizeof(double*) + sizeof(i64) + sizeof(EctFsField)) + 64;
+    if ((rc = ensure_callbuf(d, bytes))) return rc;
+    char* hb = (char*)d->h_callbuf;
+    EctSpecFieldH* t_vor = (EctSpecFieldH*)hb;
+    EctSpecFieldH* t_div = t_vor + kf_uv;
+    EctSpecFieldH* t_sc = t_div + kf_uv;
+    double** t_gpb = (double**)(t_sc + kf_sc);
+    i64* t_gps = (i64*)(t_gpb + f.nfs);
+    EctFsField* t_fs = (EctFsField*)(t_gps + f.nfs);
+    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {dvor + j, kf_uv}; t_div[j] = {ddiv + j, kf_uv}; }
+    if (!mode2_sp) for (int s = 0; s < kf_sc; ++s) t_sc[s] = {dsc + s, kf_sc};
+    else {
+        int s = 0;
+        for (int j = 0; j < nsc2; ++j) t_sc[s++] = {dsc2 + j, nsc2};
+        for (int j3 = 0; j3 < (a->spsc3a ? a->nsc3a_fld : 0); ++j3)
+            for (int l = 0; l < a->nsc3a_lev; ++l) t_sc[s++] = {dsc3a + (i64)j3 * a->nsc3a_lev * nsp + l, a->nsc3a_lev};
+        for (int j3 = 0; j3 < (a->spsc3b ? a->nsc3b_fld : 0); ++j3)
+            for (int l = 0; l < a->nsc3b_lev; ++l) t_sc[s++] = {dsc3b + (i64)j3 * a->nsc3b_lev * nsp + l, a->nsc3b_lev};
+    }
+    // Fourier-space field list: [vor][div] u v scalars [nsd] [du dv] [ewd]   (ftinv_ctl_mod.F90:144-166)
+    {
+        int fi = 0, lf = 0;    // Fourier index, Legendre index
+        const int l_u = n_vor + n_div, l_sc = l_u + 2 * kf_uv;
+        for (int j = 0; j < n_vor + n_div; ++j, ++fi, ++lf) t_fs[fi] = {2 * lf, 0, 0};
+        for (int j = 0; j < 2 * kf_uv; ++j, ++fi, ++lf) t_fs[fi] = {2 * lf, 1, 0};
+        for (int j = 0; j < kf_sc; ++j, ++fi, ++lf) t_fs[fi] = {2 * lf, 0, 0};
+        for (int j = 0; j < n_nsd; ++j, ++fi, ++lf) t_fs[fi] = {2 * lf, 1, 0};
+        if (f.uvder) for (int j = 0; j < 2 * kf_uv; ++j, ++fi) t_fs[fi] = {2 * (l_u + j), 1, 1};
+        for (int j = 0; j < n_nsd; ++j, ++fi) t_fs[fi] = {2 * (l_sc + j), 0, 1};
+    }
+    // grid-point destinations (trltog_mod.F90:579-731)
+    if (!mode2_gp) {
+        for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = dgp + (i64)i * nproma; t_gps[i] = (i64)f.nfs * nproma; }
+    } else {
+        int fi = 0, var = 0;
+        auto uvgroup = [&](int v) { for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = dgpuv + ((i64)v * kf_uv + l) * nproma; t_gps[fi] = (i64)nproma * kf_uv * nvar_uv; } };
+        if (f.vorgp) uvgroup(var++);
+        if (f.divgp) uvgroup(var++);
+        if (kf_uv) { uvgroup(var++); uvgroup(var++); }
+        auto scgroup = [&](int part) {   // part 0: fields, 1: N-S derivatives, 2: E-W derivatives
+            for (int j = 0; j < nsc2; ++j, ++fi) { t_gpb[fi] = dgp2 + ((i64)part * nsc2 + j) * nproma; t_gps[fi] = (i64)nproma * nsc2 * dfac; }
+            for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3)
+                for (int l = 0; l < a->nsc3a_lev; ++l, ++fi) {
+                    t_gpb[fi] = dgp3a + (((i64)part * a->nsc3a_fld + j3) * a->nsc3a_lev + l) * nproma;
+                    t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld * dfac;
+                }
+            for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3)
+                for (int l = 0; l < a->nsc3b_lev; ++l, ++fi) {
+                    t_gpb[fi] = dgp3b + (((i64)part * a->nsc3b_fld + j3) * a->nsc3b_lev + l) * nproma;
+                    t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld * dfac;
+                }
+        };
+        scgroup(0);
+        if (f.scders) scgroup(1);
+        if (f.uvder) { uvgroup(var++); uvgroup(var++); }
+        if (f.scders) scgroup(2);
+    }
+    ECT_CUDA(cudaMemcpyAsync(d->callbuf, d->h_callbuf, bytes, cudaMemcpyHostToDevice, d->stream));
+    char* db = (char*)d->callbuf;
+    const void* d_vor = db;
+    const void* d_div = db + ((char*)t_div - hb);
+    const void* d_sc = db + ((char*)t_sc - hb);
+    double* const* d_gpb = (double* const*)(db + ((char*)t_gpb - hb));
+    const i64* d_gps = (const i64*)(db + ((char*)t_gps - hb));
+    const void* d_fs = db + ((char*)t_fs - hb);
+    // ---- stages ----
+    ect_launch_ltinv_prologue(h, f, d_vor, d_div, d_sc);
+    ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
+    ect_launch_leinv(h, f);
+    ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
+    if ((rc = ect_transpose(h, f, 1))) return rc;
+    ECT_CUDA(cudaEventRecord(d->ev[4], d->stream));
+    ect_launch_ftinv(h, f, d_gpb, d_gps, d_fs, nproma);
+    ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
+    ECT_CUDA(cudaGetLastError());
+    if (host) {
+        if (!mode2_gp) ECT_CUDA(cudaMemcpyAsync(a->gp, dgp, (size_t)sz_gp * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+        else {
+            if (sz_uv) ECT_CUDA(cudaMemcpyAsync(a->gpuv, dgpuv, (size_t)sz_uv * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+            if (sz_2) ECT_CUDA(cudaMemcpyAsync(a->gp2, dgp2, (size_t)sz_2 * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+            if (sz_3a) ECT_CUDA(cudaMemcpyAsync(a->gp3a, dgp3a, (size_t)sz_3a * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+            if (sz_3b) ECT_CUDA(cudaMemcpyAsync(a->gp3b, dgp3b, (size_t)sz_3b * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+        }
+    }
+    ECT_CUDA(cudaEventRecord(d->ev[6], d->stream));
+    d->last_dir = 0;
+    d->timed = true;
+    if (host) ECT_CUDA(cudaStreamSynchronize(d->stream));
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
+    EctHandle* h = get_handle(handle);
+    if (!h) { ect_set_error("ect_dir_trans: invalid handle %d", handle); return ECT_ERR_HANDLE; }
+    if (!a) return ECT_ERR_MISSING;
+    if (!h->d) { ect_set_error("ect_dir_trans: handle was set up host-only (no device state)"); return ECT_ERR_CUDA; }
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    ECT_CUDA(cudaSetDevice(d->dev));
+    const bool mode2 = (a->gp == nullptr);
+    const int kf_uv = a->nuv;
+    int nsc2 = 0, n3a = 0, n3b = 0, kf_sc = 0;
+    if (kf_uv < 0 || a->nscalar < 0) { ect_set_error("ect_dir_trans: negative field count"); return ECT_ERR_BADARG; }
+    if (mode2) {
+        nsc2 = a->gp2 ? a->nsc2 : 0;
+        n3a = a->gp3a ? a->nsc3a_lev * a->nsc3a_fld : 0;
+        n3b = a->gp3b ? a->nsc3b_lev * a->nsc3b_fld : 0;
+        kf_sc = nsc2 + n3a + n3b;
+        if (kf_uv > 0 && !a->gpuv) { ect_set_error("ect_dir_trans: nuv > 0 but neither gp nor gpuv given"); return ECT_ERR_MISSING; }
+        if ((nsc2 && !a->spsc2) || (n3a && !a->spsc3a) || (n3b && !a->spsc3b)) { ect_set_error("ect_dir_trans: missing spectral output for call mode 2"); return ECT_ERR_MISSING; }
+    } else {
+        kf_sc = a->nscalar;
+        if (kf_sc > 0 && !a->spscalar) { ect_set_error("ect_dir_trans: nscalar > 0 needs spscalar"); return ECT_ERR_MISSING; }
+    }
+    if (kf_uv > 0 && (!a->spvor || !a->spdiv)) { ect_set_error("ect_dir_trans: nuv > 0 needs spvor and spdiv"); return ECT_ERR_MISSING; }
+    EctFieldCfg f;
+    f.kf_uv = kf_uv; f.kf_sc = kf_sc;
+    f.nleg = f.nfs = 2 * kf_uv + kf_sc;
+    if (f.nfs == 0) return ECT_SUCCESS;
+    f.cp = round_up(2 * f.nleg, ECT_CPAD);
+    const int nproma = (a->nproma > 0 && a->nproma < P.ngptot) ? a->nproma : std::max(P.ngptot, 1);
+    const int ngpblks = (P.ngptot + nproma - 1) / nproma;
+    int rc;
+    if ((rc = ensure_work(h, f))) return rc;
+    d->launches = 0;
+    const bool host = (a->memspace == ECT_MEM_HOST);
+    const i64 nsp = P.nspec2, blk = (i64)nproma * ngpblks;
+    const i64 sz_gp = (i64)f.nfs * blk, sz_uv = (i64)kf_uv * 2 * blk, sz_2 = (i64)nsc2 * blk, sz_3a = (i64)n3a * blk, sz_3b = (i64)n3b * blk;
+    ECT_CUDA(cudaEventRecord(d->ev[0], d->stream));
+    const double *dgp = a->gp, *dgpuv = a->gpuv, *dgp2 = a->gp2, *dgp3a = a->gp3a, *dgp3b = a->gp3b;
+    if (host) {
+        const i64 tot = mode2 ? (sz_uv + sz_2 + sz_3a + sz_3b) : sz_gp;
+        if ((rc = ensure(d->stage_gp, d->stage_gp_elems, tot, d->stream, false))) return rc;
+        double* p = d->stage_gp;
+        auto stage = [&](const double*& ptr, i64 n) -> int {
+            if (!ptr || n == 0) return ECT_SUCCESS;
+            ECT_CUDA(cudaMemcpyAsync(p, ptr, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+            ptr = p; p += n;
+            return ECT_SUCCESS;
+        };
+        if (!mode2) { if ((rc = stage(dgp, sz_gp))) return rc; }
+        else {
+            if ((rc = stage(dgpuv, sz_uv))) return rc;
+            if ((rc = stage(dgp2, sz_2))) return rc;
+            if ((rc = stage(dgp3a, sz_3a))) return rc;
+            if ((rc = stage(dgp3b, sz_3b))) return rc;
+        }
+    }
+    ECT_CUDA(cudaEventRecord(d->ev[1], d->stream));
+    double *dvor = a->spvor, *ddiv = a->spdiv, *dsc = a->spscalar, *dsc2 = a->spsc2, *dsc3a = a->spsc3a, *dsc3b = a->spsc3b;
+    if (host) {
+        const i64 tot = (2 * (i64)kf_uv + kf_sc) * nsp;
+        if ((rc = ensure(d->stage_sp, d->stage_sp_elems, tot, d->stream, false))) return rc;
+        double* p = d->stage_sp;
+        dvor = p; p += kf_uv * nsp; ddiv = p; p += kf_uv * nsp;
+        if (!mode2) { dsc = p; }
+        else { dsc2 = p; p += nsc2 * nsp; dsc3a = p; p += n3a * nsp; dsc3b = p; }
+    }
+    const size_t n_spec = (size_t)(2 * kf_uv + kf_sc);
+    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (sizeof(double*) + sizeof(i64)) + 64;
+    if ((rc = ensure_callbuf(d, bytes))) return rc;
+    char* hb = (char*)d->h_callbuf;
+    EctSpecFieldH* t_vor = (EctSpecFieldH*)hb;
+    EctSpecFieldH* t_div = t_vor + kf_uv;
+    EctSpecFieldH* t_sc = t_div + kf_uv;
+    double** t_gpb = (double**)(t_sc + kf_sc);
+    i64* t_gps = (i64*)(t_gpb + f.nfs);
+    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {dvor + j, kf_uv}; t_div[j] = {ddiv + j, kf_uv}; }
+    if (!mode2) {
+        for (int s = 0; s < kf_sc; ++s) t_sc[s] = {dsc + s, kf_sc};
+        for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = (double*)dgp + (i64)i * nproma; t_gps[i] = (i64)f.nfs * nproma; }
+    } else {
+        int s = 0, fi = 0;
+        for (int v = 0; v < (kf_uv ? 2 : 0); ++v)
+            for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = (double*)dgpuv + ((i64)v * kf_uv + l) * nproma; t_gps[fi] = (i64)nproma * kf_uv * 2; }
+        for (int j = 0; j < nsc2; ++j, ++fi) {
+            t_sc[s++] = {dsc2 + j, nsc2};
+            t_gpb[fi] = (double*)dgp2 + (i64)j * nproma; t_gps[fi] = (i64)nproma * nsc2;
+        }
+        for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3)
+            for (int l = 0; l < a->nsc3a_lev; ++l, ++fi) {
+                t_sc[s++] = {dsc3a + (i64)j3 * a->nsc3a_lev * nsp + l, a->nsc3a_lev};
+                t_gpb[fi] = (double*)dgp3a + ((i64)j3 * a->nsc3a_lev + l) * nproma; t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld;
+            }
+        for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3)
+            for (int l = 0; l < a->nsc3b_lev; ++l, ++fi) {
+                t_sc[s++] = {dsc3b + (i64)j3 * a->nsc3b_lev * nsp + l, a->nsc3b_lev};
+                t_gpb[fi] = (double*)dgp3b + ((i64)j3 * a->nsc3b_lev + l) * nproma; t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld;
+            }
+    }
+    ECT_CUDA(cudaMemcpyAsync(d->callbuf, d->h_callbuf, bytes, cudaMemcpyHostToDevice, d->stream));
+    char* db = (char*)d->callbuf;
+    void* d_vor = db;
+    void* d_div = db + ((char*)t_div - hb);
+    void* d_sc = db + ((char*)t_sc - hb);
+    double* const* d_gpb = (double* const*)(db + ((char*)t_gpb - hb));
+    const i64* d_gps = (const i64*)(db + ((char*)t_gps - hb));
+    ect_launch_ftdir(h, f, d_gpb, d_gps, nproma);
+    ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
+    if ((rc = ect_transpose(h, f, 0))) return rc;
+    ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
+    ect_launch_ledir(h, f);
+    ECT_CUDA(cudaEventRecord(d->ev[4], d->stream));
+    ect_launch_ltdir_epilogue(h, f, d_vor, d_div, d_sc);
+    ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
+    ECT_CUDA(cudaGetLastError());
+    if (host) {
+        auto back = [&](double* dst, const double* src, i64 n) -> int {
+            if (!dst || n == 0) return ECT_SUCCESS;
+            ECT_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+            return ECT_SUCCESS;
+        };
+        if ((rc = back(a->spvor, dvor, kf_uv * nsp))) return rc;
+        if ((rc = back(a->spdiv, ddiv, kf_uv * nsp))) return rc;
+        if (!mode2) { if ((rc = back(a->spscalar, dsc, kf_sc * nsp))) return rc; }
+        else {
+            if ((rc = back(a->spsc2, dsc2, nsc2 * nsp))) return rc;
+            if ((rc = back(a->spsc3a, dsc3a, n3a * nsp))) return rc;
+            if ((rc = back(a->spsc3b, dsc3b, n3b * nsp))) return rc;
+        }
+    }
+    ECT_CUDA(cudaEventRecord(d->ev[6], d->stream));
+    d->last_dir = 1;
+    d->timed = true;
+    if (host) ECT_CUDA(cudaStreamSynchronize(d->stream));
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_synchronize(int handle) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) return ECT_ERR_HANDLE;
+    ECT_CUDA(cudaStreamSynchronize(h->d->stream));
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_get_timings(int handle, ect_timings* t) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) return ECT_ERR_HANDLE;
+    if (!t) return ECT_ERR_MISSING;
+    EctDevice* d = h->d;
+    memset(t, 0, sizeof(*t));
+    if (!d->timed) return ECT_SUCCESS;
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    float ms[6];
+    for (int i = 0; i < 6; ++i) ECT_CUDA(cudaEventElapsedTime(&ms[i], d->ev[i], d->ev[i + 1]));
+    ECT_CUDA(cudaEventElapsedTime(&t->total, d->ev[0], d->ev[6]));
+    if (d->last_dir == 0) {
+        t->h2d = ms[0]; t->prologue = ms[1]; t->legendre = ms[2]; t->transpose = ms[3]; t->fourier = ms[4]; t->d2h = ms[5];
+    } else {
+        t->h2d = ms[0]; t->fourier = ms[1]; t->transpose = ms[2]; t->legendre = ms[3]; t->epilogue = ms[4]; t->d2h = ms[5];
+    }
+    t->launches = d->launches;
+    return ECT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------
+// SPECNORM: cpu/internal/spnormd_mod.F90:36-51, spnorm_ctl_mod.F90:56-57
+// ---------------------------------------------------------------------------------------
+__global__ void k_specnorm(const double* __restrict__ sp, int nfld, int nspec2, int z0, int z1, int chunk,
+                           double* __restrict__ acc) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfld) return;
+    const int i0 = blockIdx.y * chunk, i1 = min(i0 + chunk, nspec2);
+    double s = 0.0;
+    for (int i = i0; i < i1; ++i) {
+        const double v = sp[(long long)i * nfld + f];
+        const bool zonal = (i >= z0 && i < z1);
+        if (zonal) { if (((i - z0) & 1) == 0) s += v * v; }
+        else s += 2.0 * v * v;
+    }
+    atomicAdd(acc + f, s);
+}
+
+extern "C" int ect_specnorm(int handle, const double* spec, int nfld, int memspace, double* norms) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) { ect_set_error("ect_specnorm: invalid handle"); return ECT_ERR_HANDLE; }
+    if (!spec || !norms || nfld <= 0) return ECT_ERR_MISSING;
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    ECT_CUDA(cudaSetDevice(d->dev));
+    const double* dsp = spec;
+    int rc;
+    if (memspace == ECT_MEM_HOST) {
+        if ((rc = ensure(d->stage_sp, d->stage_sp_elems, (i64)nfld * P.nspec2, d->stream, false))) return rc;
+        ECT_CUDA(cudaMemcpyAsync(d->stage_sp, spec, (size_t)nfld * P.nspec2 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        dsp = d->stage_sp;
+    }
+    if (d->normbuf_n < nfld) {
+        if (d->normbuf) cudaFree(d->normbuf);
+        ECT_CUDA(cudaMalloc(&d->normbuf, nfld * sizeof(double)));
+        d->normbuf_n = nfld;
+    }
+    ECT_CUDA(cudaMemsetAsync(d->normbuf, 0, nfld * sizeof(double), d->stream));
+    const int z0 = P.nasm0[0] >= 0 ? P.nasm0[0] : -1, z1 = z0 >= 0 ? z0 + 2 * (P.nsmax + 1) : -1;
+    if (P.nspec2 > 0) {
+        const int chunk = 2048;
+        dim3 grid((nfld + 127) / 128, (P.nspec2 + chunk - 1) / chunk);
+        k_specnorm<<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nspec2, z0, z1, chunk, d->normbuf);
+    }
+    if (P.nranks > 1) ECT_NCCL(ncclAllReduce(d->normbuf, d->normbuf, nfld, ncclDouble, ncclSum, (ncclComm_t)d->comm, d->stream));
+    ECT_CUDA(cudaMemcpyAsync(norms, d->normbuf, nfld * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    for (int i = 0; i < nfld; ++i) norms[i] = sqrt(norms[i]);
+    return ECT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------
+// test / debug access (not part of the reference API)
+// ---------------------------------------------------------------------------------------
+extern "C" int ect_debug_get_table(int handle, int ml, int par, double* out, long long cap) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) return ECT_ERR_HANDLE;
+    return ect_legendre_get_table(h, ml, par, out, cap);
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 peak microbenchmarks (roofline denominators for the Legendre stage)
+// ---------------------------------------------------------------------------------------
+__global__ void k_peak_dmma(double* out, int iters) {
+    double c[8][2];
+    for (int i = 0; i < 8; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_peak_dfma(double* out, int iters) {
+    double c[16];
+    for (int i = 0; i < 16; ++i) c[i] = i * 1e-3;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int ect_measure_fp64_peak(int which, double* tflops) {
+    if (!tflops) return ECT_ERR_MISSING;
+    int dev = 0, sms = 0;
+    ECT_CUDA(cudaGetDevice(&dev));
+    ECT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    ECT_CUDA(cudaMalloc(&out, (size_t)sms * 8 * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    ECT_CUDA(cudaEventCreate(&e0));
+    ECT_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 4, threads = 256, iters = 20000;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        ECT_CUDA(cudaEventRecord(e0));
+        if (which == 0) k_peak_dmma<<<blocks, threads>>>(out, iters);
+        else k_peak_dfma<<<blocks, threads>>>(out, iters);
+        ECT_CUDA(cudaEventRecord(e1));
+        ECT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        ECT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double flops;
+        if (which == 0) flops = (double)blocks * (threads / 32) * (double)iters * 8.0 * (2.0 * 8 * 8 * 4);
+        else flops = (double)blocks * threads * (double)iters * 16.0 * 2.0;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    ECT_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return ECT_SUCCESS;
+}

@@ -1,0 +1,153 @@
+// Internal handle and plan structures of the B200 spectral-transform library.
+#pragma once
+#include <vector>
+#include <string>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "fft_plan.h"
+#include "../../include/ectrans_b200.h"
+
+#define ECT_RA 6371229.0          // common/external/setup_trans0.F90:129
+#define ECT_LAT_PAD 64            // latitude pitch of the Legendre tables (multiple of the GEMM tile)
+#define ECT_CPAD 16               // record pitch granularity (doubles)
+
+typedef long long i64;
+
+// ---------------------------------------------------------------------------------------
+// Host plan: geometry + decomposition (no CUDA).  Mirrors what SETUP_TRANS leaves in the
+// reference's R/G/D/F module globals (common/internal/tpm_dim.F90, tpm_geometry.F90,
+// tpm_distr.F90, tpm_fields.F90).
+// ---------------------------------------------------------------------------------------
+struct EctHostPlan {
+    int nsmax = 0, ndgl = 0, ndgnh = 0;
+    int nranks = 1, rank = 0;
+    std::vector<int> nloen, nmen, ndglu;
+    std::vector<double> rmu, rw, r1mu2, racthe;
+    // spectral space: zonal wavenumbers (SUWAVEDI)
+    std::vector<int> nprocm;                 // m -> owning rank
+    std::vector<std::vector<int>> ms_of;     // rank -> its m's in local order (MYMS)
+    std::vector<int> myms;
+    std::vector<int> nasm0;                  // m -> 0-based offset in the local spectral array, -1 if not mine
+    int nump = 0, nspec2 = 0, nspec2_g = 0;
+    // Fourier / grid-point space: latitude bands (SUMPLATF)
+    std::vector<int> lat_first, lat_count;   // per rank
+    int lat0 = 0, nlat = 0;
+    std::vector<int> gpoff;                  // local latitude -> first local grid point
+    int ngptot = 0, ngptotg = 0;
+    // Fourier-buffer records.  A record = one (latitude, m) pair, m <= NMEN(lat).
+    //   leg side (this rank's m, all latitudes): [dest rank][lat of dest][local m]
+    //   fft side (this rank's latitudes, all m): [src rank][local lat][m of src]
+    std::vector<i64> mrow0;                  // local m -> start in leg_rec_n/s (length ndglu(m))
+    std::vector<int> leg_rec_n, leg_rec_s;   // record of (m, northern lat i) / its southern mirror
+    std::vector<i64> latrow0;                // local lat -> start in fft_rec (length nmen+1)
+    std::vector<int> fft_rec;
+    std::vector<i64> send_cnt, send_off, recv_cnt, recv_off;   // records, per peer (leg -> fft direction)
+    i64 nrec_leg = 0, nrec_fft = 0;
+    std::string err;
+};
+
+int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank);
+void ect_gauss_latitudes(int ndgl, std::vector<double>& mu, std::vector<double>& w);
+
+// ---------------------------------------------------------------------------------------
+// Device state
+// ---------------------------------------------------------------------------------------
+struct EctLegM {           // per local m, device-resident descriptor
+    int m;
+    int ndglu;             // latitudes carrying m (northern hemisphere)
+    int ldp;               // latitude pitch of the table rows (multiple of ECT_LAT_PAD)
+    int ils, ila;          // rows: n-m even (symmetric), odd (antisymmetric)
+    i64 ps_off, pa_off;    // offsets (doubles) into the polynomial table: P[k][lat]
+    i64 xrow0;             // first row of this m in the spectral work array X / POA (rows n = m .. T+1)
+    i64 rec0;              // = mrow0: start in leg_rec_n / leg_rec_s
+    int isl;               // 0-based global index of the first northern latitude (ndgnh - ndglu)
+    int pad;
+};
+
+struct EctFieldCfg {       // field bookkeeping of one call (INV_TRANS inv_trans.F90:212-387)
+    int kf_uv = 0, kf_sc = 0;
+    int scders = 0, vorgp = 0, divgp = 0, uvder = 0;
+    int nleg = 0;          // Legendre fields (inverse: KF_OUT_LT, direct: KF_FS)
+    int nfs = 0;           // Fourier / grid-point fields
+    int cp = 0;            // record pitch in doubles = roundup(2*nleg, ECT_CPAD)
+};
+
+struct EctDevice {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // geometry
+    double *rw = nullptr, *racthe = nullptr;      // indexed by global latitude
+    double* racthe_loc = nullptr;                 // indexed by local latitude
+    int *nloen = nullptr, *nmen = nullptr, *gpoff = nullptr;
+    // Legendre
+    double* ptab = nullptr;  i64 ptab_elems = 0;
+    EctLegM* legm = nullptr;
+    std::vector<EctLegM> h_legm;
+    int *leg_rec_n = nullptr, *leg_rec_s = nullptr;
+    int* nasm0 = nullptr;                 // per local m index
+    i64 xrows = 0;                        // total rows of the spectral work array
+    // tile schedules
+    int2* inv_tiles = nullptr; int n_inv_tiles = 0;     // (local m, latitude tile)
+    int2* dir_tiles = nullptr; int n_dir_tiles = 0;     // (local m, n tile)
+    // Fourier
+    EctFftTables fft;
+    EctFftPlan* plans = nullptr;
+    EctLatPlan* latplans = nullptr;
+    uint16_t* perm_pool = nullptr;
+    double2 *tw_pool = nullptr, *cz_pool = nullptr, *roots = nullptr;
+    int* lat_plan = nullptr;              // local lat -> latplan id
+    i64* latrow0 = nullptr;
+    int* fft_rec = nullptr;
+    std::vector<int> h_lat_plan;
+    // per smem-class work lists (latitudes sorted by cost)
+    struct Bucket { int smem; int threads; int maxr; std::vector<int> lats; int* d_lats = nullptr; };
+    std::vector<Bucket> buckets;
+    // workspaces (grow only)
+    double* xwork = nullptr; i64 xwork_elems = 0;       // X (inverse input) / POA (direct output)
+    double* fbuf_leg = nullptr; i64 fbuf_leg_elems = 0; // Fourier buffer, Legendre side
+    double* fbuf_fft = nullptr; i64 fbuf_fft_elems = 0; // Fourier buffer, FFT side (== leg side when 1 rank)
+    // staging for host-pointer calls
+    double* stage_sp = nullptr; i64 stage_sp_elems = 0;
+    double* stage_gp = nullptr; i64 stage_gp_elems = 0;
+    // per-call small tables
+    void* callbuf = nullptr; void* h_callbuf = nullptr; size_t callbuf_bytes = 0;
+    double* normbuf = nullptr; int normbuf_n = 0;
+    // NCCL
+    void* comm = nullptr;
+    // timing
+    cudaEvent_t ev[16] = {};
+    int last_dir = 0; bool timed = false;
+    i64 launches = 0;
+};
+
+struct EctHandle {
+    EctHostPlan hp;
+    EctDevice* d = nullptr;
+    int precision = 0;
+};
+
+// setup (device)
+int ect_device_setup(EctHandle* h, cudaStream_t stream, int device, const void* nccl_uid);
+void ect_device_free(EctHandle* h);
+
+// stage launchers (all asynchronous on d->stream)
+// d_vor/d_div/d_sc: device arrays of EctSpecField {base, stride} per field
+void ect_launch_ltinv_prologue(EctHandle* h, const EctFieldCfg& f, const void* d_vor, const void* d_div,
+                               const void* d_sc);
+void ect_launch_leinv(EctHandle* h, const EctFieldCfg& f);
+void ect_launch_ftinv(EctHandle* h, const EctFieldCfg& f, double* const* d_gp_base, const i64* d_gp_blkstride,
+                      const void* d_fsfields, int nproma);
+void ect_launch_ftdir(EctHandle* h, const EctFieldCfg& f, double* const* d_gp_base, const i64* d_gp_blkstride,
+                      int nproma);
+void ect_launch_ledir(EctHandle* h, const EctFieldCfg& f);
+void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, void* d_div, void* d_sc);
+int ect_legendre_setup(EctHandle* h);
+int ect_fourier_setup(EctHandle* h);
+int ect_legendre_get_table(EctHandle* h, int ml, int par, double* out, long long cap);
+int ect_transpose(EctHandle* h, const EctFieldCfg& f, int to_fft);   // TRMTOL (1) / TRLTOM (0)
+
+const char* ect_cuda_err(cudaError_t e);
+#define ECT_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+    ect_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); return ECT_ERR_CUDA; } } while (0)
+void ect_set_error(const char* fmt, ...);

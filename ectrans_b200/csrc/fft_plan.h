@@ -1,0 +1,37 @@
+// Host-side FFT plan construction for the Fourier stage: factorisation, digit-reversal
+// permutation, quarter-wave twiddle tables and Bluestein (chirp-z) tables for lengths
+// with a prime factor > ECT_MAX_RADIX.  Replaces the reference's FFTW plan cache
+// (cpu/internal/tpm_fftw.F90:84-213) and cuFFT plan cache (gpu/algor/hicfft.cuda.cu:136-163).
+#pragma once
+#include <vector>
+#include <map>
+#include "fft_core.h"
+
+struct EctLatPlan {        // one per distinct (nlon, nmen)
+    int nlon, km;
+    int plan;              // index into plans[]: the length-nlon plan (direct) or the length-M plan (Bluestein)
+    int bluestein;         // 0 / 1
+    int m;                 // Bluestein convolution length (0 if direct)
+    int chirp_off;         // double2 pool: c[j] = exp(+i pi j^2 / nlon), j = 0 .. nlon/2
+    int bhat_inv_off;      // double2 pool: permuted spectrum of the inverse-direction kernel (includes 1/M)
+    int bhat_dir_off;      // same for the direct direction
+    int smem_bytes;        // dynamic shared memory for one field pair + twiddle table
+};
+
+struct EctFftTables {
+    std::vector<EctFftPlan> plans;
+    std::vector<uint16_t> perm_pool;
+    std::vector<double2> tw_pool;
+    std::vector<double2> cz_pool;       // chirps and Bluestein kernels
+    std::vector<double2> roots;         // [ECT_ROOTS_SIZE]: odd radix R at ECT_ROOTS_OFF(R)
+    std::vector<EctLatPlan> latplans;
+    std::map<int, int> plan_of_len;
+    std::map<std::pair<int, int>, int> latplan_of;
+    int get_plan(int n);                          // smooth n (multiple of 4)
+    int get_latplan(int nlon, int km);
+};
+
+bool ect_fft_factorize(int n, std::vector<int>& radices);   // false if a prime factor > ECT_MAX_RADIX
+int ect_fft_smooth_size(int need);                           // smallest 7-smooth multiple of 4 >= need
+// reference host FFT (uses the same core single-threaded); sign +, unnormalised, natural order in/out
+void ect_fft_host(const EctFftTables& T, int plan, std::vector<double2>& data);

@@ -1,0 +1,173 @@
+/*
+ * ectrans_b200.h -- C ABI of the B200-native global spectral transform.
+ *
+ * This is the drop-in boundary underneath the three faces of the reference
+ * (SURVEY.md 8(b)).  Every entry point cites the reference interface it replaces
+ * (paths relative to /root/reference):
+ *
+ *   ect_setup      <- SETUP_TRANS0 + SETUP_TRANS   src/trans/include/ectrans/setup_trans0.h:12-89,
+ *                                                  setup_trans.h:12-115; transi trans_setup() src/transi/transi.h
+ *   ect_inquire*   <- TRANS_INQ                    src/trans/include/ectrans/trans_inq.h:12-21; transi trans_inquire()
+ *   ect_inv_trans  <- INV_TRANS                    src/trans/include/ectrans/inv_trans.h:12-161; transi trans_invtrans()
+ *   ect_dir_trans  <- DIR_TRANS                    src/trans/include/ectrans/dir_trans.h:12-140; transi trans_dirtrans()
+ *   ect_specnorm   <- SPECNORM                     src/trans/include/ectrans/specnorm.h
+ *   ect_release    <- TRANS_RELEASE / trans_delete src/trans/include/ectrans/trans_release.h
+ *   ect_finalize   <- TRANS_END / trans_finalize   src/trans/include/ectrans/trans_end.h
+ *
+ * Conventions
+ *   - plain C types only; all arrays are raw pointers with explicit extents.
+ *   - memory layouts are the reference's Fortran layouts (column major), i.e. for the C
+ *     reader: spectral arrays are [nspec2][nfld] (field fastest), grid-point arrays are
+ *     [ngpblks][nfld][nproma] (point-in-block fastest).  These equal transi's
+ *     rspscalar[nspec2][nscalar] and rgp[ngpblks][nfld][nproma] (transi.h:986-1010).
+ *   - memspace ECT_MEM_HOST: the call copies inputs host->device and results
+ *     device->host inside the call, like the reference GPU backend
+ *     (gpu/internal/ltinv_mod.F90:333-339, trltog_mod.F90:950-990).
+ *     ECT_MEM_DEVICE: pointers are device pointers, no copies.
+ *   - every function returns ECT_SUCCESS (0) or a negative code; nothing aborts.
+ *     The codes -1..-5 equal transi's (transi.c:33-58).
+ *   - one handle = one resolution on one GPU/rank; calls on a handle are serialised by
+ *     the caller (same contract as the reference: SET_RESOL global state, not re-entrant).
+ *   - there is no CPU fallback: without a CUDA device ect_setup() fails with
+ *     ECT_ERR_CUDA unless ECT_SETUP_HOST_ONLY is given (plan/inquire only).
+ */
+#ifndef ECTRANS_B200_H
+#define ECTRANS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECT_SUCCESS        0
+#define ECT_ERR_GENERIC   -1
+#define ECT_ERR_NOTIMPL   -2
+#define ECT_ERR_MISSING   -3
+#define ECT_ERR_BADARG    -4
+#define ECT_ERR_STALE     -5
+#define ECT_ERR_CUDA      -6
+#define ECT_ERR_NCCL      -7
+#define ECT_ERR_HANDLE    -8
+
+#define ECT_MEM_HOST   0
+#define ECT_MEM_DEVICE 1
+
+#define ECT_SETUP_HOST_ONLY 1   /* build geometry + decomposition only, no CUDA (inquire works) */
+
+#define ECT_NCCL_UID_BYTES 128
+
+typedef struct ect_setup_opts {
+    int nsmax;            /* KSMAX: spectral truncation                                  */
+    int ndgl;             /* KDGL : number of Gaussian latitudes (even)                  */
+    const int* nloen;     /* KLOEN(ndgl): points per latitude, north -> south            */
+    int nranks;           /* number of tasks = NPRTRW (NPRTRV = 1); 1 = LDMPOFF          */
+    int rank;             /* 0-based task id (MYSETW-1)                                  */
+    int flags;            /* ECT_SETUP_*                                                 */
+    int device;           /* CUDA device ordinal, -1 = current                           */
+    void* stream;         /* cudaStream_t to run on, NULL = library-owned stream         */
+    const void* nccl_uid; /* ECT_NCCL_UID_BYTES from ect_nccl_unique_id() of rank 0; NULL if nranks == 1 */
+} ect_setup_opts;
+
+typedef struct ect_info {
+    int nsmax, ndgl, ndgnh;
+    int nranks, rank;
+    int nspec2, nspec2g;     /* local / global number of real spectral coefficients (2 per (m,n)) */
+    int ngptot, ngptotg;     /* local / global number of grid points                              */
+    int nump;                /* number of local zonal wavenumbers                                 */
+    int lat0, nlat;          /* local latitude band (0-based first, count) in Fourier/grid space  */
+    long long table_bytes;   /* Legendre table bytes resident in HBM                              */
+} ect_info;
+
+/* arrays for ect_inquire_array() */
+#define ECT_ARR_NLOEN   1   /* int[ndgl]                                                    */
+#define ECT_ARR_NMEN    2   /* int[ndgl]     G%NMEN                                          */
+#define ECT_ARR_NDGLU   3   /* int[nsmax+1]  G%NDGLU                                         */
+#define ECT_ARR_MYMS    4   /* int[nump]     D%MYMS                                          */
+#define ECT_ARR_NASM0   5   /* int[nsmax+1]  D%NASM0, 0-based offsets, -1 = not local        */
+#define ECT_ARR_NPROCM  6   /* int[nsmax+1]  D%NPROCM, 0-based rank                          */
+#define ECT_ARR_RMU     7   /* double[ndgl]  F%RMU                                           */
+#define ECT_ARR_RGW     8   /* double[ndgl]  F%RW                                            */
+#define ECT_ARR_LATFIRST 9  /* int[nranks]   first latitude of each rank's band              */
+#define ECT_ARR_LATCOUNT 10 /* int[nranks]                                                   */
+#define ECT_ARR_SENDCNT 11  /* long long[nranks] TRMTOL send counts in (lat,m) records       */
+#define ECT_ARR_RECVCNT 12  /* long long[nranks]                                             */
+#define ECT_ARR_RACTHE  13  /* double[ndgl]  F%RACTHE                                        */
+
+typedef struct ect_inv_args {
+    int memspace;                 /* ECT_MEM_HOST / ECT_MEM_DEVICE                          */
+    int nproma;                   /* KPROMA, <= 0 means ngptot (one block)                  */
+    int scders, vorgp, divgp, uvder;   /* LDSCDERS, LDVORGP, LDDIVGP, LDUVDER               */
+    /* spectral input, call mode 1 */
+    const double* spvor;          /* PSPVOR(nuv, nspec2)                                    */
+    const double* spdiv;          /* PSPDIV(nuv, nspec2)                                    */
+    int nuv;
+    const double* spscalar;       /* PSPSCALAR(nscalar, nspec2)                             */
+    int nscalar;
+    /* spectral input, call mode 2 (used when spscalar == NULL) */
+    const double* spsc2;  int nsc2;                         /* PSPSC2(nsc2, nspec2)          */
+    const double* spsc3a; int nsc3a_lev, nsc3a_fld;         /* PSPSC3A(lev, nspec2, fld)     */
+    const double* spsc3b; int nsc3b_lev, nsc3b_fld;         /* PSPSC3B(lev, nspec2, fld)     */
+    /* grid-point output, call mode 1: PGP(nproma, nfld_gp, ngpblks), field order
+       [vor][div] u v scalars [N-S ders] [E-W du dv] [E-W ders]  (inv_trans.h:66-76)        */
+    double* gp;
+    /* grid-point output, call mode 2 (used when gp == NULL) */
+    double* gpuv;                 /* PGPUV(nproma, nuv, nvar, ngpblks), var: [vor][div] u v [du dv] */
+    double* gp2;                  /* PGP2 (nproma, nsc2*(1|3), ngpblks)                      */
+    double* gp3a;                 /* PGP3A(nproma, lev, fld*(1|3), ngpblks)                  */
+    double* gp3b;
+} ect_inv_args;
+
+typedef struct ect_dir_args {
+    int memspace;
+    int nproma;
+    int nuv, nscalar;             /* counts for call mode 1                                  */
+    /* grid-point input, call mode 1: PGP(nproma, 2*nuv+nscalar, ngpblks), order u v scalars (dir_trans.h:59-61) */
+    const double* gp;
+    /* call mode 2 */
+    const double* gpuv;           /* PGPUV(nproma, nuv, 2, ngpblks): u, v                    */
+    const double* gp2;  int nsc2;
+    const double* gp3a; int nsc3a_lev, nsc3a_fld;
+    const double* gp3b; int nsc3b_lev, nsc3b_fld;
+    /* spectral output */
+    double* spvor; double* spdiv; double* spscalar;
+    double* spsc2; double* spsc3a; double* spsc3b;
+} ect_dir_args;
+
+/* timings of the last call on this handle, milliseconds, CUDA events on the handle's stream */
+typedef struct ect_timings {
+    float h2d, prologue, legendre, transpose, fourier, epilogue, d2h, total;
+    long long launches;     /* kernels launched by the last call */
+} ect_timings;
+
+int ect_setup(const ect_setup_opts* opts, int* handle);
+int ect_inquire(int handle, ect_info* info);
+int ect_inquire_array(int handle, int which, void* out, long long capacity_elems);
+int ect_inv_trans(int handle, const ect_inv_args* args);
+int ect_dir_trans(int handle, const ect_dir_args* args);
+int ect_specnorm(int handle, const double* spec, int nfld, int memspace, double* norms /* host, nfld */);
+int ect_get_timings(int handle, ect_timings* t);
+int ect_synchronize(int handle);   /* wait for asynchronous ECT_MEM_DEVICE calls on this handle */
+int ect_release(int handle);
+int ect_finalize(void);
+const char* ect_strerror(int code);
+const char* ect_last_error(void);
+
+/* multi-GPU plumbing: rank 0 creates the id, the caller broadcasts it (MPI_Bcast in a
+   Fortran/MPI host, torch.distributed in the Python harness) and passes it to ect_setup. */
+int ect_nccl_unique_id(void* out_bytes /* ECT_NCCL_UID_BYTES */);
+
+/* pinned host allocation for callers that want fast H2D/D2H (the reference benchmark's
+   ectrans_memory.c / --no-pinning switch, src/programs/util/ectrans_memory.c) */
+int ect_host_alloc(void** ptr, long long bytes);
+int ect_host_free(void* ptr);
+
+/* test access: copies the Legendre table of local wavenumber index ml (par 0: n-m even, 1: odd),
+   laid out [k][ndglu], to host memory */
+int ect_debug_get_table(int handle, int ml, int par, double* out, long long capacity_elems);
+
+/* FP64 peak microbenchmarks used for the roofline denominators (not part of the reference API) */
+int ect_measure_fp64_peak(int which /*0 DMMA m8n8k4, 1 DFMA*/, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,93 @@
+// Test-only CPU harness: runs the __host__ __device__ Fourier-stage phases of
+// ectrans_b200/csrc single-threaded so that index logic is checked without a GPU.
+// Built by tests/conftest.py into tests/hostemu/_build/; never loaded by the product.
+#include "../../ectrans_b200/csrc/fourier_phases.h"
+#include <vector>
+#include <cstring>
+extern int g_ect_force_bluestein;
+
+static void run_stages(double2* data, const EctPairCtx& c, bool dif, int nthr) {
+    const EctFftPlan& p = c.plan;
+    if (dif) {
+        for (int s = p.nst - 1; s >= 0; --s)
+            for (int t = 0; t < nthr; ++t) fft_stage<true>(data, p.n, p.radix[s], p.sublen[s], c.qt, c.roots, t, nthr);
+    } else {
+        for (int s = 0; s < p.nst; ++s)
+            for (int t = 0; t < nthr; ++t) fft_stage<false>(data, p.n, p.radix[s], p.sublen[s], c.qt, c.roots, t, nthr);
+    }
+}
+
+static void make_ctx(EctFftTables& T, EctPairCtx& c, int nlon, int km, int dir, std::vector<int>& rec) {
+    int id = T.get_latplan(nlon, km);
+    const EctLatPlan& lp = T.latplans[id];
+    c.nlon = nlon; c.km = km; c.racthe = 1.0;
+    c.plan = T.plans[lp.plan];
+    c.perm = T.perm_pool.data() + c.plan.perm_off;
+    c.qt = T.tw_pool.data() + c.plan.tw_off;
+    c.roots = T.roots.data();
+    c.bluestein = lp.bluestein; c.m = lp.m;
+    c.chirp = lp.bluestein ? T.cz_pool.data() + lp.chirp_off : nullptr;
+    c.bhat = lp.bluestein ? T.cz_pool.data() + (dir == 0 ? lp.bhat_inv_off : lp.bhat_dir_off) : nullptr;
+    rec.resize(km + 1);
+    for (int k = 0; k <= km; ++k) rec[k] = k;
+    c.rec = rec.data(); c.cp = 4;
+}
+
+extern "C" {
+int emu_smooth(int n) { std::vector<int> r; return ect_fft_factorize(n, r) ? 1 : 0; }
+
+// complex sign-+ FFT of smooth length n
+int emu_fft(int n, const double* in, double* out) {
+    EctFftTables T;
+    int id = T.get_plan(n);
+    if (id < 0) return -1;
+    std::vector<double2> d(n);
+    for (int i = 0; i < n; ++i) d[i] = make_double2(in[2 * i], in[2 * i + 1]);
+    ect_fft_host(T, id, d);
+    for (int i = 0; i < n; ++i) { out[2 * i] = d[i].x; out[2 * i + 1] = d[i].y; }
+    return 0;
+}
+
+// inverse pair: spec [km+1][4] = (reA, imA, reB, imB) records; out rows [nlon] each
+int emu_ftinv_pair(int nlon, int km, const double* spec, double* outa, double* outb, int nthr, int force_blue) {
+    g_ect_force_bluestein = force_blue;
+    EctFftTables T; EctPairCtx c; std::vector<int> rec;
+    make_ctx(T, c, nlon, km, 0, rec);
+    std::vector<double2> data(c.bluestein ? c.m : nlon);
+    EctFsField fa{0, 0, 0}, fb{2, 0, 0};
+    for (int t = 0; t < nthr; ++t) ftinv_load(data.data(), spec, c, fa, fb, t, nthr);
+    if (c.bluestein) {
+        run_stages(data.data(), c, true, nthr);
+        for (int t = 0; t < nthr; ++t) blue_pointwise(data.data(), c, t, nthr);
+    }
+    run_stages(data.data(), c, false, nthr);
+    for (int j = 0; j < nlon; ++j) { double2 x = ftinv_out(data.data(), c, j); outa[j] = x.x; outb[j] = x.y; }
+    g_ect_force_bluestein = 0;
+    return c.bluestein;
+}
+
+// direct pair: rows -> spec records [km+1][4]
+int emu_ftdir_pair(int nlon, int km, const double* rowa, const double* rowb, double* spec, int nthr, int force_blue) {
+    g_ect_force_bluestein = force_blue;
+    EctFftTables T; EctPairCtx c; std::vector<int> rec;
+    make_ctx(T, c, nlon, km, 1, rec);
+    std::vector<double2> data(c.bluestein ? c.m : nlon);
+    for (int j = 0; j < nlon; ++j) ftdir_put(data.data(), c, j, rowa[j], rowb[j]);
+    for (int t = 0; t < nthr; ++t) ftdir_zero_tail(data.data(), c, t, nthr);
+    if (c.bluestein) {
+        run_stages(data.data(), c, true, nthr);
+        for (int t = 0; t < nthr; ++t) blue_pointwise(data.data(), c, t, nthr);
+    }
+    run_stages(data.data(), c, false, nthr);
+    for (int t = 0; t < nthr; ++t) ftdir_store(data.data(), spec, c, 0, 2, t, nthr);
+    g_ect_force_bluestein = 0;
+    return c.bluestein;
+}
+}
+
+#include "../../ectrans_b200/csrc/supolf.h"
+extern "C" void emu_supolf(int km, int par, int kcount, int knsmax, int nlat, const double* mu, double* out) {
+    EctSupolfM cm;
+    ect_supolf_consts(km, cm);
+    for (int i = 0; i < nlat; ++i) ect_supolf_column(km, par, kcount, knsmax, mu[i], cm, out + i, nlat);
+}
