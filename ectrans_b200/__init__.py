@@ -24,9 +24,11 @@ _lib = None
 
 ECT_MEM_HOST, ECT_MEM_DEVICE = 0, 1
 ECT_SETUP_HOST_ONLY = 1
+ECT_SETUP_STREAM_GIVEN = 2
 ECT_NCCL_UID_BYTES = 128
 (ARR_NLOEN, ARR_NMEN, ARR_NDGLU, ARR_MYMS, ARR_NASM0, ARR_NPROCM, ARR_RMU, ARR_RGW, ARR_LATFIRST,
- ARR_LATCOUNT, ARR_SENDCNT, ARR_RECVCNT, ARR_RACTHE) = range(1, 14)
+ ARR_LATCOUNT, ARR_SENDCNT, ARR_RECVCNT, ARR_RACTHE, ARR_MROW0, ARR_LEGRECN, ARR_LEGRECS, ARR_LATROW0,
+ ARR_FFTREC, ARR_SENDOFF, ARR_RECVOFF) = range(1, 21)
 
 
 class EctError(RuntimeError):
@@ -178,8 +180,8 @@ class Transform:
         nl = np.ascontiguousarray(nloen, dtype=np.int32)
         self._uid = C.create_string_buffer(nccl_uid, ECT_NCCL_UID_BYTES) if nccl_uid else None
         o = _SetupOpts(int(nsmax), int(nl.size), nl.ctypes.data_as(C.POINTER(C.c_int)), int(nranks), int(rank),
-                       ECT_SETUP_HOST_ONLY if host_only else 0, int(device),
-                       C.c_void_p(stream) if stream else None,
+                       (ECT_SETUP_HOST_ONLY if host_only else 0) | (ECT_SETUP_STREAM_GIVEN if stream is not None else 0),
+                       int(device), C.c_void_p(stream) if stream else None,
                        C.cast(self._uid, C.c_void_p) if self._uid else None)
         h = C.c_int(0)
         _check(L.ect_setup(C.byref(o), C.byref(h)), "ect_setup")
@@ -203,6 +205,18 @@ class Transform:
         self.lat_count = self._arr(ARR_LATCOUNT, np.int32, i.nranks)
         self.send_cnt = self._arr(ARR_SENDCNT, np.int64, i.nranks)
         self.recv_cnt = self._arr(ARR_RECVCNT, np.int64, i.nranks)
+        self.send_off = self._arr(ARR_SENDOFF, np.int64, i.nranks)
+        self.recv_off = self._arr(ARR_RECVOFF, np.int64, i.nranks)
+
+    def record_tables(self):
+        """Fourier-buffer record tables of this rank (test / diagnostic access)."""
+        i = self.info
+        mrow0 = self._arr(ARR_MROW0, np.int64, i.nump + 1)
+        latrow0 = self._arr(ARR_LATROW0, np.int64, i.nlat + 1)
+        return {"mrow0": mrow0, "latrow0": latrow0,
+                "leg_rec_n": self._arr(ARR_LEGRECN, np.int32, int(mrow0[-1])),
+                "leg_rec_s": self._arr(ARR_LEGRECS, np.int32, int(mrow0[-1])),
+                "fft_rec": self._arr(ARR_FFTREC, np.int32, int(latrow0[-1]))}
 
     def _arr(self, which, dtype, n):
         out = np.zeros(max(int(n), 1), dtype=dtype)

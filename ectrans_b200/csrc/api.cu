@@ -66,7 +66,7 @@ extern "C" int ect_host_free(void* ptr) {
 // ---------------------------------------------------------------------------------------
 // setup / release
 // ---------------------------------------------------------------------------------------
-int ect_device_setup(EctHandle* h, cudaStream_t stream, int device, const void* uid) {
+int ect_device_setup(EctHandle* h, cudaStream_t stream, bool use_given_stream, int device, const void* uid) {
     EctHostPlan& P = h->hp;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -79,7 +79,7 @@ int ect_device_setup(EctHandle* h, cudaStream_t stream, int device, const void* 
     h->d = d;
     if (device >= 0) ECT_CUDA(cudaSetDevice(device));
     ECT_CUDA(cudaGetDevice(&d->dev));
-    if (stream) { d->stream = stream; d->own_stream = false; }
+    if (stream || use_given_stream) { d->stream = stream; d->own_stream = false; }
     else { ECT_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking)); d->own_stream = true; }
     for (auto& ev : d->ev) ECT_CUDA(cudaEventCreate(&ev));
     ECT_CUDA(cudaMalloc(&d->rw, P.ndgl * sizeof(double)));
@@ -108,11 +108,15 @@ void ect_device_free(EctHandle* h) {
     void* ptrs[] = {d->rw, d->racthe, d->racthe_loc, d->nloen, d->gpoff, d->ptab, d->legm, d->leg_rec_n, d->leg_rec_s,
                     d->nasm0, d->inv_tiles, d->dir_tiles, d->plans, d->latplans, d->perm_pool, d->tw_pool,
                     d->cz_pool, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->xwork, d->fbuf_leg,
-                    d->stage_sp, d->stage_gp, d->callbuf, d->normbuf};
+                    d->stage_sp, d->stage_gp, d->normbuf};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < EctDevice::kSlots; ++i) {
+        if (d->ring_d[i]) cudaFree(d->ring_d[i]);
+        if (d->ring_h[i]) cudaFreeHost(d->ring_h[i]);
+        if (d->ring_ev[i]) cudaEventDestroy(d->ring_ev[i]);
+    }
     if (d->fbuf_fft && d->fbuf_fft != d->fbuf_leg) cudaFree(d->fbuf_fft);
     for (auto& b : d->buckets) if (b.d_lats) cudaFree(b.d_lats);
-    if (d->h_callbuf) cudaFreeHost(d->h_callbuf);
     for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
     if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
     delete d;
@@ -125,7 +129,7 @@ extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
     int rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, o->nranks < 1 ? 1 : o->nranks, o->rank);
     if (rc) { delete h; return rc; }
     if (!(o->flags & ECT_SETUP_HOST_ONLY)) {
-        rc = ect_device_setup(h, (cudaStream_t)o->stream, o->device, o->nccl_uid);
+        rc = ect_device_setup(h, (cudaStream_t)o->stream, (o->flags & ECT_SETUP_STREAM_GIVEN) != 0, o->device, o->nccl_uid);
         if (rc) { ect_device_free(h); delete h; return rc; }
     }
     std::lock_guard<std::mutex> lk(g_mu);
@@ -199,6 +203,13 @@ extern "C" int ect_inquire_array(int handle, int which, void* out, long long cap
         case ECT_ARR_LATCOUNT: return copy_out<int>(out, cap, P.lat_count);
         case ECT_ARR_SENDCNT: return copy_out<long long>(out, cap, P.send_cnt);
         case ECT_ARR_RECVCNT: return copy_out<long long>(out, cap, P.recv_cnt);
+        case ECT_ARR_SENDOFF: return copy_out<long long>(out, cap, P.send_off);
+        case ECT_ARR_RECVOFF: return copy_out<long long>(out, cap, P.recv_off);
+        case ECT_ARR_MROW0: return copy_out<long long>(out, cap, P.mrow0);
+        case ECT_ARR_LEGRECN: return copy_out<int>(out, cap, P.leg_rec_n);
+        case ECT_ARR_LEGRECS: return copy_out<int>(out, cap, P.leg_rec_s);
+        case ECT_ARR_LATROW0: return copy_out<long long>(out, cap, P.latrow0);
+        case ECT_ARR_FFTREC: return copy_out<int>(out, cap, P.fft_rec);
         default: ect_set_error("ect_inquire_array: unknown array id %d", which); return ECT_ERR_BADARG;
     }
 }
@@ -232,12 +243,25 @@ static int ensure_work(EctHandle* h, const EctFieldCfg& f) {
 }
 
 static int ensure_callbuf(EctDevice* d, size_t bytes) {
-    if (bytes <= d->callbuf_bytes) return ECT_SUCCESS;
-    if (d->callbuf) { ECT_CUDA(cudaStreamSynchronize(d->stream)); ECT_CUDA(cudaFree(d->callbuf)); ECT_CUDA(cudaFreeHost(d->h_callbuf)); }
-    bytes = (bytes + 4095) / 4096 * 4096;
-    ECT_CUDA(cudaMalloc(&d->callbuf, bytes));
-    ECT_CUDA(cudaHostAlloc(&d->h_callbuf, bytes, cudaHostAllocDefault));
-    d->callbuf_bytes = bytes;
+    const int i = d->ring_next;
+    d->ring_next = (i + 1) % EctDevice::kSlots;
+    d->ring_cur = i;
+    if (!d->ring_ev[i]) ECT_CUDA(cudaEventCreateWithFlags(&d->ring_ev[i], cudaEventDisableTiming));
+    if (d->ring_used[i]) ECT_CUDA(cudaEventSynchronize(d->ring_ev[i]));     // previous user of this slot is done
+    if (bytes > d->ring_bytes[i]) {
+        if (d->ring_d[i]) { ECT_CUDA(cudaFree(d->ring_d[i])); ECT_CUDA(cudaFreeHost(d->ring_h[i])); }
+        bytes = (bytes + 4095) / 4096 * 4096;
+        ECT_CUDA(cudaMalloc(&d->ring_d[i], bytes));
+        ECT_CUDA(cudaHostAlloc(&d->ring_h[i], bytes, cudaHostAllocDefault));
+        d->ring_bytes[i] = bytes;
+    }
+    d->callbuf = d->ring_d[i];
+    d->h_callbuf = d->ring_h[i];
+    return ECT_SUCCESS;
+}
+static int release_callbuf(EctDevice* d) {
+    ECT_CUDA(cudaEventRecord(d->ring_ev[d->ring_cur], d->stream));
+    d->ring_used[d->ring_cur] = true;
     return ECT_SUCCESS;
 }
 
@@ -277,6 +301,16 @@ struct CallLayout {
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static std::vector<int2> make_pairs(const std::vector<int>& groups) {
+    std::vector<int2> pairs;
+    int f0 = 0;
+    for (int g : groups) {
+        for (int j = 0; j < g; j += 2) pairs.push_back(make_int2(f0 + j, j + 1 < g ? f0 + j + 1 : -1));
+        f0 += g;
+    }
+    return pairs;
+}
 
 extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     EctHandle* h = get_handle(handle);
@@ -362,7 +396,28 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     }
     // ---- per-call tables ----
     const size_t n_spec = (size_t)(2 * kf_uv + kf_sc);
-    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (sizeof(double*) + sizeof(i64) + sizeof(EctFsField)) + 64;
+    // field groups: only fields of the same kind / array share a complex transform (keeps their
+    // rounding errors decoupled: magnitudes within a group are comparable)
+    std::vector<int> groups;   // sizes in Fourier order
+    {
+        auto scal = [&]() {
+            if (!mode2_sp) { if (kf_sc) groups.push_back(kf_sc); return; }
+            if (nsc2) groups.push_back(nsc2);
+            for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3) groups.push_back(a->nsc3a_lev);
+            for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3) groups.push_back(a->nsc3b_lev);
+        };
+        if (f.vorgp) groups.push_back(kf_uv);
+        if (f.divgp) groups.push_back(kf_uv);
+        if (kf_uv) { groups.push_back(kf_uv); groups.push_back(kf_uv); }
+        scal();
+        if (f.scders) scal();
+        if (f.uvder) { groups.push_back(kf_uv); groups.push_back(kf_uv); }
+        if (f.scders) scal();
+    }
+    std::vector<int2> pairs = make_pairs(groups);
+    f.npairs = (int)pairs.size();
+    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (sizeof(double*) + sizeof(i64) + sizeof(EctFsField)) +
+                         pairs.size() * sizeof(int2) + 64;
     if ((rc = ensure_callbuf(d, bytes))) return rc;
     char* hb = (char*)d->h_callbuf;
     EctSpecFieldH* t_vor = (EctSpecFieldH*)hb;
@@ -370,7 +425,9 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     EctSpecFieldH* t_sc = t_div + kf_uv;
     double** t_gpb = (double**)(t_sc + kf_sc);
     i64* t_gps = (i64*)(t_gpb + f.nfs);
-    EctFsField* t_fs = (EctFsField*)(t_gps + f.nfs);
+    int2* t_pairs = (int2*)(t_gps + f.nfs);
+    EctFsField* t_fs = (EctFsField*)(t_pairs + pairs.size());
+    memcpy(t_pairs, pairs.data(), pairs.size() * sizeof(int2));
     for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {dvor + j, kf_uv}; t_div[j] = {ddiv + j, kf_uv}; }
     if (!mode2_sp) for (int s = 0; s < kf_sc; ++s) t_sc[s] = {dsc + s, kf_sc};
     else {
@@ -427,6 +484,7 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     double* const* d_gpb = (double* const*)(db + ((char*)t_gpb - hb));
     const i64* d_gps = (const i64*)(db + ((char*)t_gps - hb));
     const void* d_fs = db + ((char*)t_fs - hb);
+    const void* d_pairs = db + ((char*)t_pairs - hb);
     // ---- stages ----
     ect_launch_ltinv_prologue(h, f, d_vor, d_div, d_sc);
     ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
@@ -434,9 +492,10 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
     if ((rc = ect_transpose(h, f, 1))) return rc;
     ECT_CUDA(cudaEventRecord(d->ev[4], d->stream));
-    ect_launch_ftinv(h, f, d_gpb, d_gps, d_fs, nproma);
+    ect_launch_ftinv(h, f, d_gpb, d_gps, d_fs, d_pairs, nproma);
     ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
     ECT_CUDA(cudaGetLastError());
+    if ((rc = release_callbuf(d))) return rc;
     if (host) {
         if (!mode2_gp) ECT_CUDA(cudaMemcpyAsync(a->gp, dgp, (size_t)sz_gp * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
         else {
@@ -471,6 +530,7 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
         n3b = a->gp3b ? a->nsc3b_lev * a->nsc3b_fld : 0;
         kf_sc = nsc2 + n3a + n3b;
         if (kf_uv > 0 && !a->gpuv) { ect_set_error("ect_dir_trans: nuv > 0 but neither gp nor gpuv given"); return ECT_ERR_MISSING; }
+        if (a->nscalar > 0 && kf_sc == 0) { ect_set_error("ect_dir_trans: nscalar > 0 but no grid-point input array given"); return ECT_ERR_MISSING; }
         if ((nsc2 && !a->spsc2) || (n3a && !a->spsc3a) || (n3b && !a->spsc3b)) { ect_set_error("ect_dir_trans: missing spectral output for call mode 2"); return ECT_ERR_MISSING; }
     } else {
         kf_sc = a->nscalar;
@@ -521,7 +581,18 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
         else { dsc2 = p; p += nsc2 * nsp; dsc3a = p; p += n3a * nsp; dsc3b = p; }
     }
     const size_t n_spec = (size_t)(2 * kf_uv + kf_sc);
-    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (sizeof(double*) + sizeof(i64)) + 64;
+    std::vector<int> groups;
+    if (kf_uv) { groups.push_back(kf_uv); groups.push_back(kf_uv); }
+    if (!mode2) { if (kf_sc) groups.push_back(kf_sc); }
+    else {
+        if (nsc2) groups.push_back(nsc2);
+        for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3) groups.push_back(a->nsc3a_lev);
+        for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3) groups.push_back(a->nsc3b_lev);
+    }
+    std::vector<int2> pairs = make_pairs(groups);
+    f.npairs = (int)pairs.size();
+    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (sizeof(double*) + sizeof(i64)) +
+                         pairs.size() * sizeof(int2) + 64;
     if ((rc = ensure_callbuf(d, bytes))) return rc;
     char* hb = (char*)d->h_callbuf;
     EctSpecFieldH* t_vor = (EctSpecFieldH*)hb;
@@ -529,6 +600,8 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
     EctSpecFieldH* t_sc = t_div + kf_uv;
     double** t_gpb = (double**)(t_sc + kf_sc);
     i64* t_gps = (i64*)(t_gpb + f.nfs);
+    int2* t_pairs = (int2*)(t_gps + f.nfs);
+    memcpy(t_pairs, pairs.data(), pairs.size() * sizeof(int2));
     for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {dvor + j, kf_uv}; t_div[j] = {ddiv + j, kf_uv}; }
     if (!mode2) {
         for (int s = 0; s < kf_sc; ++s) t_sc[s] = {dsc + s, kf_sc};
@@ -559,7 +632,8 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
     void* d_sc = db + ((char*)t_sc - hb);
     double* const* d_gpb = (double* const*)(db + ((char*)t_gpb - hb));
     const i64* d_gps = (const i64*)(db + ((char*)t_gps - hb));
-    ect_launch_ftdir(h, f, d_gpb, d_gps, nproma);
+    const void* d_pairs = db + ((char*)t_pairs - hb);
+    ect_launch_ftdir(h, f, d_gpb, d_gps, d_pairs, nproma);
     ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
     if ((rc = ect_transpose(h, f, 0))) return rc;
     ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
@@ -568,6 +642,7 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
     ect_launch_ltdir_epilogue(h, f, d_vor, d_div, d_sc);
     ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
     ECT_CUDA(cudaGetLastError());
+    if ((rc = release_callbuf(d))) return rc;
     if (host) {
         auto back = [&](double* dst, const double* src, i64 n) -> int {
             if (!dst || n == 0) return ECT_SUCCESS;

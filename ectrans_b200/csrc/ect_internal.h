@@ -70,6 +70,7 @@ struct EctFieldCfg {       // field bookkeeping of one call (INV_TRANS inv_trans
     int nleg = 0;          // Legendre fields (inverse: KF_OUT_LT, direct: KF_FS)
     int nfs = 0;           // Fourier / grid-point fields
     int cp = 0;            // record pitch in doubles = roundup(2*nleg, ECT_CPAD)
+    int npairs = 0;        // field pairs of the Fourier stage
 };
 
 struct EctDevice {
@@ -111,7 +112,12 @@ struct EctDevice {
     double* stage_sp = nullptr; i64 stage_sp_elems = 0;
     double* stage_gp = nullptr; i64 stage_gp_elems = 0;
     // per-call small tables
+    // per-call small tables: ring of slots, each (pinned host, device) pair guarded by an event recorded
+    // after the last kernel of the call that used it (calls are asynchronous in ECT_MEM_DEVICE mode)
+    static const int kSlots = 4;
     void* callbuf = nullptr; void* h_callbuf = nullptr; size_t callbuf_bytes = 0;
+    void* ring_d[kSlots] = {}; void* ring_h[kSlots] = {}; size_t ring_bytes[kSlots] = {};
+    cudaEvent_t ring_ev[kSlots] = {}; bool ring_used[kSlots] = {}; int ring_next = 0; int ring_cur = 0;
     double* normbuf = nullptr; int normbuf_n = 0;
     // NCCL
     void* comm = nullptr;
@@ -128,7 +134,7 @@ struct EctHandle {
 };
 
 // setup (device)
-int ect_device_setup(EctHandle* h, cudaStream_t stream, int device, const void* nccl_uid);
+int ect_device_setup(EctHandle* h, cudaStream_t stream, bool use_given_stream, int device, const void* nccl_uid);
 void ect_device_free(EctHandle* h);
 
 // stage launchers (all asynchronous on d->stream)
@@ -137,9 +143,9 @@ void ect_launch_ltinv_prologue(EctHandle* h, const EctFieldCfg& f, const void* d
                                const void* d_sc);
 void ect_launch_leinv(EctHandle* h, const EctFieldCfg& f);
 void ect_launch_ftinv(EctHandle* h, const EctFieldCfg& f, double* const* d_gp_base, const i64* d_gp_blkstride,
-                      const void* d_fsfields, int nproma);
+                      const void* d_fsfields, const void* d_pairs, int nproma);
 void ect_launch_ftdir(EctHandle* h, const EctFieldCfg& f, double* const* d_gp_base, const i64* d_gp_blkstride,
-                      int nproma);
+                      const void* d_pairs, int nproma);
 void ect_launch_ledir(EctHandle* h, const EctFieldCfg& f);
 void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, void* d_div, void* d_sc);
 int ect_legendre_setup(EctHandle* h);

@@ -23,6 +23,7 @@ struct FtArgs {
     int nfs; int npairs; int nchunks;    // pair chunks per latitude
     double* const* gp_base; const i64* gp_blk;   // per Fourier field
     const EctFsField* fsf;        // inverse only
+    const int2* pairs;            // (field a, field b or -1): only fields of one group share a transform
     int nproma; int ngptot;
 };
 
@@ -60,8 +61,9 @@ __global__ void k_fourier(FtArgs a) {
     __syncthreads();
     const int p0 = chunk * FT_PAIRS_PER_CTA, p1 = min(p0 + FT_PAIRS_PER_CTA, a.npairs);
     for (int p = p0; p < p1; ++p) {
-        const int fa = 2 * p, fb2 = 2 * p + 1;
-        const bool hasb = fb2 < a.nfs;
+        const int2 pr = a.pairs[p];
+        const int fa = pr.x, fb2 = pr.y;
+        const bool hasb = fb2 >= 0;
         if (INVERSE) {
             EctFsField sfa = a.fsf[fa], sfb;
             if (hasb) sfb = a.fsf[fb2]; else { sfb.src_c = -1; sfb.pw = 0; sfb.deriv = 0; }
@@ -113,7 +115,7 @@ static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     a.lat_plan = d->lat_plan; a.latrow0 = d->latrow0; a.fft_rec = d->fft_rec;
     a.gpoff = d->gpoff; a.nloen_loc = d->nloen; a.racthe_loc = d->racthe_loc;
     a.fb = d->fbuf_fft; a.cp = f.cp;
-    a.nfs = f.nfs; a.npairs = (f.nfs + 1) / 2;
+    a.nfs = f.nfs; a.npairs = f.npairs;
     a.nchunks = (a.npairs + FT_PAIRS_PER_CTA - 1) / FT_PAIRS_PER_CTA;
     a.ngptot = h->hp.ngptot;
 }
@@ -132,20 +134,20 @@ static void launch_fourier(EctHandle* h, FtArgs& a) {
 }
 
 void ect_launch_ftinv(EctHandle* h, const EctFieldCfg& f, double* const* d_gp_base, const i64* d_gp_blkstride,
-                      const void* d_fsfields, int nproma) {
+                      const void* d_fsfields, const void* d_pairs, int nproma) {
     if (h->hp.nlat == 0 || f.nfs == 0) return;
     FtArgs a;
     fill_args(h, f, a);
-    a.gp_base = d_gp_base; a.gp_blk = d_gp_blkstride; a.fsf = (const EctFsField*)d_fsfields; a.nproma = nproma;
+    a.gp_base = d_gp_base; a.gp_blk = d_gp_blkstride; a.fsf = (const EctFsField*)d_fsfields; a.pairs = (const int2*)d_pairs; a.nproma = nproma;
     launch_fourier<true>(h, a);
 }
 
 void ect_launch_ftdir(EctHandle* h, const EctFieldCfg& f, double* const* d_gp_base, const i64* d_gp_blkstride,
-                      int nproma) {
+                      const void* d_pairs, int nproma) {
     if (h->hp.nlat == 0 || f.nfs == 0) return;
     FtArgs a;
     fill_args(h, f, a);
-    a.gp_base = d_gp_base; a.gp_blk = d_gp_blkstride; a.fsf = nullptr; a.nproma = nproma;
+    a.gp_base = d_gp_base; a.gp_blk = d_gp_blkstride; a.fsf = nullptr; a.pairs = (const int2*)d_pairs; a.nproma = nproma;
     launch_fourier<false>(h, a);
 }
 

@@ -52,6 +52,7 @@ extern "C" {
 #define ECT_MEM_DEVICE 1
 
 #define ECT_SETUP_HOST_ONLY 1   /* build geometry + decomposition only, no CUDA (inquire works) */
+#define ECT_SETUP_STREAM_GIVEN 2 /* opts.stream is valid even if it is 0 (the legacy default stream) */
 
 #define ECT_NCCL_UID_BYTES 128
 
@@ -91,6 +92,14 @@ typedef struct ect_info {
 #define ECT_ARR_SENDCNT 11  /* long long[nranks] TRMTOL send counts in (lat,m) records       */
 #define ECT_ARR_RECVCNT 12  /* long long[nranks]                                             */
 #define ECT_ARR_RACTHE  13  /* double[ndgl]  F%RACTHE                                        */
+/* Fourier-buffer record tables (what TRMTOL/TRLTOM move; NLTSGTB/NSTAGT0B/NPNTGTB1 in the reference) */
+#define ECT_ARR_MROW0   14  /* long long[nump+1]  start of local m in LEGRECN/LEGRECS          */
+#define ECT_ARR_LEGRECN 15  /* int[mrow0[nump]]   record of (local m, northern latitude i)     */
+#define ECT_ARR_LEGRECS 16  /* int[mrow0[nump]]   record of its southern mirror latitude       */
+#define ECT_ARR_LATROW0 17  /* long long[nlat+1]  start of local latitude in FFTREC            */
+#define ECT_ARR_FFTREC  18  /* int[latrow0[nlat]] record of (local latitude, m), -1 if m > NMEN */
+#define ECT_ARR_SENDOFF 19  /* long long[nranks]                                              */
+#define ECT_ARR_RECVOFF 20  /* long long[nranks]                                              */
 
 typedef struct ect_inv_args {
     int memspace;                 /* ECT_MEM_HOST / ECT_MEM_DEVICE                          */

@@ -493,6 +493,66 @@ def _spnsde(s: Setup, m: int, f: np.ndarray):
     return -(n - 1.0) * epsnm(m, n) * e[:, idx - 1] + (n + 2.0) * epsnm(m, n + 1) * e[:, idx + 1]
 
 
+
+def ltinv_m(s: Setup, m: int, spvor, spdiv, spscalar, scders=False, vorgp=False, divgp=False):
+    """LTINV for one zonal wavenumber: returns (north, south) Fourier coefficients
+    [ndglu(m), kf_out_lt] complex.  cpu/internal/ltinv_mod.F90:139-320."""
+    kf_uv = 0 if spvor is None else spvor.shape[0]
+    kf_sc = 0 if spscalar is None else spscalar.shape[0]
+    cols = []
+    if kf_uv:
+        vor = spec_m(s, spvor, m)
+        div = spec_m(s, spdiv, m)
+        u, v = _vdtuv(s, m, vor, div)
+        pad = np.zeros((kf_uv, 1), dtype=np.complex128)
+        if vorgp:
+            cols.append(np.concatenate([vor, pad], axis=1))
+        if divgp:
+            cols.append(np.concatenate([div, pad], axis=1))
+        cols += [u, v]
+    if kf_sc:
+        sc = spec_m(s, spscalar, m)
+        cols.append(np.concatenate([sc, np.zeros((kf_sc, 1), dtype=np.complex128)], axis=1))
+        if scders:
+            cols.append(_spnsde(s, m, sc))
+    x = np.concatenate(cols, axis=0).T  # [n=m..T+1, fld]
+    if m == 0:
+        x = x.real.astype(np.complex128)  # KM=0: imaginary columns skipped (leinv_mod.F90:103-110)
+    xs, xa = x[0::2], x[1::2]  # n-m even (symmetric), odd (antisymmetric)
+    pa, ps = s.pa[m], s.ps[m]
+    za = (pa @ xa.real) + 1j * (pa @ xa.imag)
+    zs = (ps @ xs.real) + 1j * (ps @ xs.imag)
+    return zs + za, zs - za
+
+
+def ledir_m(s: Setup, m: int, fn: np.ndarray, fs: np.ndarray, kf_uv: int):
+    """PRFI2B + LDFOU2 + LEDIR for one m: north/south Fourier coefficients [ndglu, nfld] ->
+    spectral coefficients [n = m..T+1, nfld].  prfi2b_mod.F90:84-94, ldfou2_mod.F90:90-96,
+    ledir_mod.F90:118-261."""
+    T = s.nsmax
+    ndglu = int(s.ndglu[m])
+    isl = s.ndgnh - ndglu
+    ila = (T - m + 2) // 2
+    ils = (T - m + 3) // 2
+    sym = fn + fs
+    asym = fn - fs
+    ract = s.racthe[isl:isl + ndglu][:, None]
+    sym[:, :2 * kf_uv] *= ract
+    asym[:, :2 * kf_uv] *= ract
+    wgt = s.rw[isl:isl + ndglu][:, None]
+    zb_a = asym * wgt
+    zb_s = sym * wgt
+    if m == 0:
+        zb_a = zb_a.real.astype(np.complex128)
+        zb_s = zb_s.real.astype(np.complex128)
+    pa, ps = s.pa[m], s.ps[m]
+    ca = (pa.T @ zb_a.real) + 1j * (pa.T @ zb_a.imag)  # n = m+1, m+3, ...
+    cs = (ps.T @ zb_s.real) + 1j * (ps.T @ zb_s.imag)  # n = m, m+2, ...
+    oa = np.zeros((T + 2 - m, fn.shape[1]), dtype=np.complex128)  # n = m..T+1
+    oa[0::2] = cs[:ils]
+    oa[1::2] = ca[:ila]
+    return oa
+
 # --------------------------------------------------------------------------
 #  Inverse transform
 # --------------------------------------------------------------------------
@@ -516,35 +576,11 @@ def inv_trans(s: Setup, spvor=None, spdiv=None, spscalar=None, scders=False,
     kf_out_lt = n_vor + n_div + 2 * kf_uv + kf_sc + n_nsd
     four = [np.zeros((int(s.nmen[j]) + 1, kf_out_lt), dtype=np.complex128) for j in range(s.ndgl)]
     for m in s.ms:
-        cols = []
-        if kf_uv:
-            vor = spec_m(s, spvor, m)
-            div = spec_m(s, spdiv, m)
-            u, v = _vdtuv(s, m, vor, div)
-            pad = np.zeros((kf_uv, 1), dtype=np.complex128)
-            if vorgp:
-                cols.append(np.concatenate([vor, pad], axis=1))
-            if divgp:
-                cols.append(np.concatenate([div, pad], axis=1))
-            cols += [u, v]
-        if kf_sc:
-            sc = spec_m(s, spscalar, m)
-            cols.append(np.concatenate([sc, np.zeros((kf_sc, 1), dtype=np.complex128)], axis=1))
-            if scders:
-                cols.append(_spnsde(s, m, sc))
-        x = np.concatenate(cols, axis=0).T  # [n=m..T+1, fld]
-        if m == 0:
-            x = x.real.astype(np.complex128)  # KM=0: imaginary columns skipped (leinv_mod.F90:103-110)
-        xs, xa = x[0::2], x[1::2]  # n-m even (symmetric), odd (antisymmetric)
         ndglu = int(s.ndglu[m])
         if ndglu == 0:
             continue
+        north, south = ltinv_m(s, m, spvor, spdiv, spscalar, scders, vorgp, divgp)
         isl = s.ndgnh - ndglu  # 0-based first northern latitude
-        pa, ps = s.pa[m], s.ps[m]
-        za = (pa @ xa.real) + 1j * (pa @ xa.imag)
-        zs = (ps @ xs.real) + 1j * (ps @ xs.imag)
-        north = zs + za
-        south = zs - za
         for i in range(ndglu):
             jn = isl + i
             js = s.ndgl - 1 - jn
@@ -619,23 +655,7 @@ def dir_trans(s: Setup, gp: np.ndarray, kf_uv: int = 0, kf_sc: int = 0):
             js = s.ndgl - 1 - jn
             fn[i] = four[jn][m]
             fs[i] = four[js][m]
-        sym = fn + fs
-        asym = fn - fs
-        ract = s.racthe[isl:isl + ndglu][:, None]
-        sym[:, :2 * kf_uv] *= ract
-        asym[:, :2 * kf_uv] *= ract
-        wgt = s.rw[isl:isl + ndglu][:, None]
-        zb_a = asym * wgt
-        zb_s = sym * wgt
-        if m == 0:
-            zb_a = zb_a.real.astype(np.complex128)
-            zb_s = zb_s.real.astype(np.complex128)
-        pa, ps = s.pa[m], s.ps[m]
-        ca = (pa.T @ zb_a.real) + 1j * (pa.T @ zb_a.imag)  # n = m+1, m+3, ...
-        cs = (ps.T @ zb_s.real) + 1j * (ps.T @ zb_s.imag)  # n = m, m+2, ...
-        oa = np.zeros((T + 2 - m, kf_fs), dtype=np.complex128)  # n = m..T+1
-        oa[0::2] = cs[:ils]
-        oa[1::2] = ca[:ila]
+        oa = ledir_m(s, m, fn, fs, kf_uv)
         o = int(s.nasm0[m])
         cnt = T - m + 1
 

@@ -1,0 +1,101 @@
+"""Index logic of the CUDA Fourier and table kernels, run on the CPU through the test-only harness
+tests/hostemu (same __host__ __device__ code the kernels call)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import ectrans_oracle as eo
+
+DP = ctypes.POINTER(ctypes.c_double)
+P = lambda a: a.ctypes.data_as(DP)
+
+
+def _smooth_lengths():
+    out = []
+    for n in list(range(2, 400, 2)) + [1024, 2310, 3596, 4096, 4 * 13 * 17, 7776, 10368]:
+        out.append(n)
+    return out
+
+
+def test_fft_all_small_even_lengths(emu):
+    rng = np.random.default_rng(0)
+    checked = 0
+    for n in _smooth_lengths():
+        if not emu.emu_smooth(n):
+            continue
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        xin = np.ascontiguousarray(np.stack([x.real, x.imag], 1))
+        out = np.zeros((n, 2))
+        assert emu.emu_fft(n, P(xin), P(out)) == 0
+        ref = np.fft.ifft(x) * n
+        assert np.abs(out[:, 0] + 1j * out[:, 1] - ref).max() <= 5e-15 * np.abs(ref).max() * max(1, np.log2(n))
+        checked += 1
+    assert checked > 120
+
+
+def _pair(emu, nlon, km, force, nthr, rng):
+    sa = rng.standard_normal(km + 1) + 1j * rng.standard_normal(km + 1)
+    sb = rng.standard_normal(km + 1) + 1j * rng.standard_normal(km + 1)
+    spec = np.ascontiguousarray(np.stack([sa.real, sa.imag, sb.real, sb.imag], 1))
+    oa, ob = np.zeros(nlon), np.zeros(nlon)
+    blue = emu.emu_ftinv_pair(nlon, km, P(spec), P(oa), P(ob), nthr, force)
+
+    def ref(s):
+        h = np.zeros(nlon // 2 + 1, complex)
+        h[:km + 1] = s
+        h[0] = h[0].real
+        return np.fft.irfft(h, n=nlon) * nlon
+
+    e1 = max(np.abs(oa - ref(sa)).max(), np.abs(ob - ref(sb)).max()) / np.abs(ref(sa)).max()
+    ra, rb = rng.standard_normal(nlon), rng.standard_normal(nlon)
+    sp = np.zeros((km + 1, 4))
+    emu.emu_ftdir_pair(nlon, km, P(ra), P(rb), P(sp), nthr, force)
+    fa, fb = np.fft.rfft(ra)[:km + 1] / nlon, np.fft.rfft(rb)[:km + 1] / nlon
+    e2 = max(np.abs(sp[:, 0] + 1j * sp[:, 1] - fa).max(), np.abs(sp[:, 2] + 1j * sp[:, 3] - fb).max()) / np.abs(fa).max()
+    return blue, e1, e2
+
+
+@pytest.mark.parametrize("nlon,km", [(20, 8), (24, 10), (18, 8), (30, 14), (300, 148), (336, 79), (656, 159),
+                                     (5136, 1279), (4 * 1283, 1279), (148, 40), (148, 73), (134, 50), (212, 60),
+                                     (20 + 4 * 399, 399), (4 * 97, 120)])
+def test_pair_transforms(emu, nlon, km):
+    rng = np.random.default_rng(nlon)
+    blue, e1, e2 = _pair(emu, nlon, km, 0, 7, rng)
+    assert e1 < 5e-15 and e2 < 5e-15, (blue, e1, e2)
+
+
+@pytest.mark.parametrize("nlon,km", [(20, 8), (24, 11), (18, 8), (300, 148), (336, 79)])
+def test_pair_transforms_forced_chirpz(emu, nlon, km):
+    rng = np.random.default_rng(nlon + 1)
+    blue, e1, e2 = _pair(emu, nlon, km, 1, 32, rng)
+    assert blue == 1 and e1 < 5e-15 and e2 < 5e-15
+
+
+def test_every_octahedral_length_has_a_plan(emu):
+    # O1280: nlon = 20 + 4 i ; lengths that are not <=31-smooth go through chirp-z, which must fit shared memory
+    rng = np.random.default_rng(5)
+    for i in (0, 1, 7, 330, 331, 777, 1000, 1279):
+        nlon = 20 + 4 * i
+        km = min(1279, max(2, nlon // 3 - 1))
+        blue, e1, e2 = _pair(emu, nlon, km, 0, 5, rng)
+        assert e1 < 1e-14 and e2 < 1e-14
+
+
+@pytest.mark.parametrize("T,N,ms", [(79, 80, None), (399, 400, [0, 1, 2, 3, 57, 200, 398, 399]),
+                                    (1279, 1280, [0, 1, 2, 641, 1277, 1278, 1279])])
+def test_supolf_column_bitwise(emu, T, N, ms):
+    """The table kernel's recurrence reproduces the oracle's SUPOLF restatement bit for bit on the CPU."""
+    mu, _ = eo.gauss_latitudes(2 * N)
+    mun = np.ascontiguousarray(mu[:N])
+    for m in (range(T + 1) if ms is None else ms):
+        imaxn = T + 1
+        ila, ils = (T - m + 2) // 2, (T - m + 3) // 2
+        even = (imaxn - m) % 2 == 0
+        for par, kc, kn in ((1, ila, imaxn + 1 if even else imaxn), (0, ils, imaxn if even else imaxn + 1)):
+            if kc == 0:
+                continue
+            ref = eo.supolf(m, kn, mun, kcheap=3 if par else 2)[m + par:m + par + 2 * kc:2]
+            out = np.zeros((kc, N))
+            emu.emu_supolf(m, par, kc, kn, N, P(mun), P(out))
+            assert np.array_equal(out, ref), (m, par)

@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): relative grid-point / spectral L2 difference <= 1e-12 in dp;
+golden vectors abs 1e-10 (tests/test_ectrans4py/test_ectrans4py.py:16); round trip <= 100 eps
+(src/programs/ectrans-benchmark.F90:847-871)."""
+import numpy as np
+import pytest
+
+import ectrans_oracle as eo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+T_ = lambda a: None if a is None else np.ascontiguousarray(a.T)
+
+
+def rel(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def eb(built):
+    import ectrans_b200
+    return ectrans_b200
+
+
+def unblock(gp, ngptot):
+    nblk, nf, npr = gp.shape
+    return gp.transpose(1, 0, 2).reshape(nf, nblk * npr)[:, :ngptot]
+
+
+def block(flat, nproma):
+    nf, n = flat.shape
+    nblk = (n + nproma - 1) // nproma
+    pad = np.zeros((nf, nblk * nproma))
+    pad[:, :n] = flat
+    return np.ascontiguousarray(pad.reshape(nf, nblk, nproma).transpose(1, 0, 2))
+
+
+# ---------------------------------------------------------------------------------------------
+def test_golden_vectors(eb, golden):
+    tr = eb.Transform(148, golden["nloen"])
+    nl = golden["nloen"]
+    gpref = np.concatenate([golden["gp_latlon"][i, :nl[i]] for i in range(150)])
+    gp = tr.inv_trans(spscalar=golden["sp"][:, None])
+    d = gp[0, 0] - gpref
+    assert abs(d.max()) < 1e-10 and abs(d.min()) < 1e-10
+    _, _, sp = tr.dir_trans(gpref[None, None, :], 0, 1)
+    d = sp[:, 0] - golden["sp"]
+    assert abs(d.max()) < 1e-10 and abs(d.min()) < 1e-10
+    assert (tr.ngptot, tr.nspec2 // 2) == (33052, 11175)
+    np.testing.assert_array_equal(tr.nmen, golden["nmen"])
+    tr.release()
+
+
+def test_legendre_table_matches_oracle(eb):
+    T, N = 159, 160
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen)
+    for ml in range(0, tr.nump, 7):
+        m = int(tr.myms[ml])
+        for par, ref in ((0, s.ps[m]), (1, s.pa[m])):
+            if ref.size == 0:
+                continue
+            got = tr.legendre_table(ml, par).T
+            # device FMA contraction only: a few ulp of the largest entry
+            assert np.abs(got - ref).max() <= 2e-13 * max(np.abs(ref).max(), 1.0)
+    tr.release()
+
+
+CASES = [
+    # T, N, nuv, nsc, options, nproma
+    (79, 80, 10, 11, {}, 0),                                                       # BASELINE config 0 (10 levels, 1 scalar field)
+    (79, 80, 0, 1, {}, 0),
+    (79, 80, 3, 0, dict(vorgp=True, divgp=True, uvder=True), 0),
+    (79, 80, 2, 3, dict(scders=True, vorgp=True, divgp=True, uvder=True), 1000),
+    (79, 80, 1, 1, dict(scders=True), 17),                                         # ragged last block, odd field counts
+    (159, 160, 5, 16, dict(scders=True, uvder=True), 0),                           # BASELINE config 1 shape, fewer levels
+    (47, 48, 130, 131, {}, 0),                                                     # many fields: several field tiles
+]
+
+
+@pytest.mark.parametrize("T,N,nuv,nsc,opts,nproma", CASES)
+def test_inv_dir_against_oracle(eb, T, N, nuv, nsc, opts, nproma):
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen)
+    vor = eo.random_spectral(s, nuv, 1, zero00=True) if nuv else None
+    div = eo.random_spectral(s, nuv, 2, zero00=True) if nuv else None
+    sc = eo.random_spectral(s, nsc, 3) if nsc else None
+    ref = eo.inv_trans(s, vor, div, sc, **opts)
+    gp = tr.inv_trans(T_(vor), T_(div), T_(sc), nproma=nproma, **opts)
+    got = unblock(gp, tr.ngptot)
+    assert got.shape == ref.shape
+    for i in range(ref.shape[0]):
+        assert rel(got[i], ref[i]) < TOL, (i, rel(got[i], ref[i]))
+    iu = (nuv if opts.get("vorgp") else 0) + (nuv if opts.get("divgp") else 0)
+    gin = ref[iu:iu + 2 * nuv + nsc]
+    rv, rd, rs = eo.dir_trans(s, gin, nuv, nsc)
+    npr = tr.ngptot if nproma <= 0 else nproma
+    ov, od, os_ = tr.dir_trans(block(gin, npr), nuv, nsc, nproma=nproma)
+    for a, b in ((ov, rv), (od, rd), (os_, rs)):
+        if b is not None:
+            assert rel(a.T, b) < TOL
+            # Im(m=0) = 0 and, for vor/div, coefficient (0,0) = 0  (updsp_mod.F90:120-133, updspb_mod.F90:98-117)
+            assert np.all(a[1:2 * (T + 1):2] == 0.0)
+    if nuv:
+        assert np.all(ov[0] == 0.0) and np.all(od[0] == 0.0)
+    if nsc:
+        assert rel(tr.specnorm(T_(sc)), eo.specnorm(s, sc)) < 1e-13
+    tr.release()
+
+
+def test_benchmark_input_roundtrip(eb):
+    """ectrans-benchmark's own check: Re psi(4,19) = 1 everywhere, inverse + direct, norm error <= 100 eps."""
+    T, N, nlev = 159, 160, 9
+    tr = eb.Transform(T, eb.octahedral_nloen(N))
+    s = eo.setup(T, 2 * N, eb.octahedral_nloen(N), tables=False)
+    sp = eo.benchmark_spectral(s, nlev)
+    z = T_(sp)
+    for it in range(2):
+        gp = tr.inv_trans(z, z, z)
+        ov, od, os_ = tr.dir_trans(gp[:, 2 * nlev:] if False else gp, nlev, nlev)
+        z = os_
+    n0 = eo.specnorm(s, sp)
+    n1 = tr.specnorm(os_)
+    assert np.abs(n1 / n0 - 1).max() <= 100 * np.finfo(float).eps
+    tr.release()
+
+
+def test_constant_field(eb):
+    # tests/transi/transi_test_program.c:76-81,150-164
+    tr = eb.Transform(47, eb.octahedral_nloen(48))
+    gp = np.stack([np.full(tr.ngptot, c) for c in (1.0, 2.0, 3.0, 4.0)])[None]
+    _, _, sp = tr.dir_trans(gp, 0, 4)
+    for i, c in enumerate((1.0, 2.0, 3.0, 4.0)):
+        assert abs(sp[0, i] - c) < 1e-13
+        assert np.abs(sp[1:, i]).max() < 1e-13
+    tr.release()
+
+
+def test_call_mode_2(eb):
+    """PGPUV / PGP3A / PGP2 layouts (inv_trans.h:84-104, trltog_mod.F90:579-731)."""
+    T, N, nlev, n3, n2 = 47, 48, 4, 2, 3
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen)
+    vor = eo.random_spectral(s, nlev, 1, zero00=True)
+    div = eo.random_spectral(s, nlev, 2, zero00=True)
+    sc2 = eo.random_spectral(s, n2, 3)
+    sc3 = eo.random_spectral(s, nlev * n3, 4)            # field index = j3 * nlev + lev
+    ref = eo.inv_trans(s, vor, div, np.concatenate([sc2, sc3]), scders=True, uvder=True, vorgp=True)
+    nproma = 500
+    nblk = (tr.ngptot + nproma - 1) // nproma
+    sp3 = np.ascontiguousarray(sc3.reshape(n3, nlev, s.nspec2).transpose(0, 2, 1))      # (fld, nspec2, lev)
+    gpuv = np.zeros((nblk, 5, nlev, nproma)); gp2 = np.zeros((nblk, 3 * n2, nproma)); gp3 = np.zeros((nblk, 3 * n3, nlev, nproma))
+    tr.inv_trans_raw(memspace=0, nproma=nproma, scders=1, vorgp=1, divgp=0, uvder=1,
+                     spvor=T_(vor), spdiv=T_(div), nuv=nlev, spsc2=T_(sc2), nsc2=n2,
+                     spsc3a=sp3, nsc3a_lev=nlev, nsc3a_fld=n3, gpuv=gpuv, gp2=gp2, gp3a=gp3)
+    flat = lambda a: a.reshape(nblk, -1, nproma).transpose(1, 0, 2).reshape(a.size // (nblk * nproma), -1)[:, :tr.ngptot]
+    # reference order: vor u v | sc2 sc3 | nsd(sc2) nsd(sc3) | du dv | ewd(sc2) ewd(sc3)
+    nsc = n2 + nlev * n3
+    o = 0
+    r_vor, r_u, r_v = ref[o:o + nlev], ref[o + nlev:o + 2 * nlev], ref[o + 2 * nlev:o + 3 * nlev]; o += 3 * nlev
+    r_sc = ref[o:o + nsc]; o += nsc
+    r_ns = ref[o:o + nsc]; o += nsc
+    r_du, r_dv = ref[o:o + nlev], ref[o + nlev:o + 2 * nlev]; o += 2 * nlev
+    r_ew = ref[o:o + nsc]
+    assert rel(flat(gpuv), np.concatenate([r_vor, r_u, r_v, r_du, r_dv])) < TOL
+    assert rel(flat(gp2), np.concatenate([r_sc[:n2], r_ns[:n2], r_ew[:n2]])) < TOL
+    assert rel(flat(gp3), np.concatenate([r_sc[n2:], r_ns[n2:], r_ew[n2:]])) < TOL
+    # direct, call mode 2
+    guv = np.ascontiguousarray(gpuv[:, 1:3]); g2 = np.ascontiguousarray(gp2[:, :n2]); g3 = np.ascontiguousarray(gp3[:, :n3])
+    ovor = np.zeros((s.nspec2, nlev)); odiv = np.zeros_like(ovor); o2 = np.zeros((s.nspec2, n2)); o3 = np.zeros((n3, s.nspec2, nlev))
+    tr.dir_trans_raw(memspace=0, nproma=nproma, nuv=nlev, gpuv=guv, gp2=g2, nsc2=n2, gp3a=g3, nsc3a_lev=nlev, nsc3a_fld=n3,
+                     spvor=ovor, spdiv=odiv, spsc2=o2, spsc3a=o3)
+    rv, rd, rs = eo.dir_trans(s, np.concatenate([r_u, r_v, r_sc]), nlev, nsc)
+    assert rel(ovor.T, rv) < TOL and rel(odiv.T, rd) < TOL and rel(o2.T, rs[:n2]) < TOL
+    assert rel(o3.transpose(0, 2, 1).reshape(n3 * nlev, -1), rs[n2:]) < TOL
+    tr.release()
+
+
+def test_device_memspace_matches_host(eb):
+    import torch
+    T, N = 79, 80
+    tr = eb.Transform(T, eb.octahedral_nloen(N), stream=torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(0)
+    sc = rng.uniform(-1, 1, (tr.nspec2, 6)); sc[1:2 * (T + 1):2] = 0
+    gp_h = tr.inv_trans(spscalar=sc)
+    gp_d = tr.inv_trans(spscalar=torch.from_numpy(sc).cuda())
+    # asynchronous back-to-back calls must not disturb each other (per-call tables live in a ring)
+    outs = [tr.dir_trans(gp_d, 0, 6)[2] for _ in range(6)]
+    tr.synchronize()
+    assert np.array_equal(gp_d.cpu().numpy(), gp_h)
+    sp_h = tr.dir_trans(gp_h, 0, 6)[2]
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), sp_h)
+    tr.release()
+
+
+def test_linearity_and_roundtrip_large(eb):
+    """Size-independent properties at a size the oracle is not run on (TCo639-class truncation)."""
+    T, N, nf = 639, 640, 4
+    tr = eb.Transform(T, eb.octahedral_nloen(N))
+    rng = np.random.default_rng(1)
+    n = np.concatenate([np.repeat(np.arange(m, T + 1), 2) for m in range(T + 1)]).astype(float)
+    a = rng.uniform(-1, 1, (tr.nspec2, nf)) / (1 + n[:, None]) ** 2
+    b = rng.uniform(-1, 1, (tr.nspec2, nf)) / (1 + n[:, None]) ** 2
+    for x in (a, b):
+        x[1:2 * (T + 1):2] = 0
+    ga, gb = tr.inv_trans(spscalar=a), tr.inv_trans(spscalar=b)
+    gab = tr.inv_trans(spscalar=2.0 * a - 3.0 * b)
+    assert rel(gab, 2.0 * ga - 3.0 * gb) < 1e-13
+    back = tr.dir_trans(ga, 0, nf)[2]
+    # cubic grid: low-order-dominated spectrum survives the round trip to rounding level
+    assert rel(back, a) < 1e-11
+    assert np.abs(tr.specnorm(back) / tr.specnorm(a) - 1).max() < 1e-12
+    tr.release()
+
+
+def test_errors_are_codes_not_aborts(eb):
+    import ctypes
+    tr = eb.Transform(47, eb.octahedral_nloen(48))
+    a = eb._InvArgs()
+    a.nuv = 2          # spvor / spdiv missing
+    assert eb.lib().ect_inv_trans(tr.handle, ctypes.byref(a)) == -3
+    a = eb._DirArgs(); a.nscalar = 1
+    assert eb.lib().ect_dir_trans(tr.handle, ctypes.byref(a)) == -3
+    tr.release()
+    assert eb.lib().ect_inv_trans(tr.handle, ctypes.byref(eb._InvArgs())) == -8

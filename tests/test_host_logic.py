@@ -1,0 +1,116 @@
+"""Host-side logic of the CUDA library through the C ABI, no GPU needed: the library loads and
+exports every symbol include/*.h declares, SETUP_TRANS geometry/decomposition agree with the oracle,
+errors come back as codes (never abort), and compute calls fail loudly without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ectrans_oracle as eo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def eb(built):
+    import ectrans_b200
+    return ectrans_b200
+
+
+def test_exports_match_headers(eb):
+    L = eb.lib()
+    names = set()
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        if not h.endswith(".h"):
+            continue
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"^\s*(?:const\s+)?(?:int|void|char\s*\*|const char\s*\*|struct\s+\w+\s*\*?|\w+_t\s*\*?)\s+\**((?:ect|trans)_\w+)\s*\(", src, flags=re.M))
+    assert len(names) >= 17
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in include/ but not exported"
+    for n in eb.EXPORTED_SYMBOLS:
+        assert n in names
+
+
+@pytest.mark.parametrize("T,N", [(47, 48), (79, 80), (159, 160), (399, 400)])
+def test_geometry_matches_oracle(eb, T, N):
+    nloen = eb.octahedral_nloen(N)
+    t = eb.Transform(T, nloen, host_only=True)
+    s = eo.setup(T, 2 * N, nloen, tables=False)
+    np.testing.assert_array_equal(t.nmen, s.nmen)
+    np.testing.assert_array_equal(t.ndglu, s.ndglu)
+    np.testing.assert_array_equal(t.nasm0, s.nasm0)
+    assert (t.nspec2, t.ngptot) == (s.nspec2, s.ngptot)
+    assert np.abs(t.rmu - s.rmu).max() < 1e-15
+    assert np.abs(t.rgw - s.rw).max() < 1e-15
+    assert abs(t.rgw.sum() - 1.0) < 1e-10
+    assert np.abs(t.racthe / s.racthe - 1).max() < 1e-14
+    t.release()
+
+
+def test_golden_grid_inquire(eb, golden):
+    # tests/test_ectrans4py/test_ectrans4py.py:123-131
+    t = eb.Transform(148, golden["nloen"], host_only=True)
+    assert (t.ngptot, t.nspec2 // 2) == (33052, 11175)
+    np.testing.assert_array_equal(t.nmen, golden["nmen"])
+    t.release()
+
+
+@pytest.mark.parametrize("P", [2, 3, 4, 8])
+def test_decomposition(eb, P):
+    T, N = 159, 160
+    nloen = eb.octahedral_nloen(N)
+    trs = [eb.Transform(T, nloen, nranks=P, rank=r, host_only=True) for r in range(P)]
+    nprocm, myms = eo.suwavedi(T, P)
+    first, count = eo.sumplatb_fourier(nloen, P)
+    for r, t in enumerate(trs):
+        np.testing.assert_array_equal(t.myms, myms[r])
+        np.testing.assert_array_equal(t.nprocm, nprocm)
+        assert list(t.lat_first) == first and list(t.lat_count) == count
+    assert sum(t.nspec2 for t in trs) == trs[0].nspec2g
+    assert sum(t.ngptot for t in trs) == trs[0].ngptotg
+    S = np.array([t.send_cnt for t in trs])
+    R = np.array([t.recv_cnt for t in trs])
+    np.testing.assert_array_equal(S, R.T)          # what a sends to b is what b expects from a
+    assert S.sum() == 2 * sum(int(trs[0].ndglu[m]) for m in range(T + 1))
+    # record tables: every (m, lat) pair appears exactly once on each side
+    for t in trs:
+        rt = t.record_tables()
+        n = int(t.send_cnt.sum())
+        recs = np.concatenate([rt["leg_rec_n"], rt["leg_rec_s"]])
+        assert sorted(recs.tolist()) == list(range(n))
+        f = rt["fft_rec"]
+        assert sorted(f[f >= 0].tolist()) == list(range(int(t.recv_cnt.sum())))
+    for t in trs:
+        t.release()
+
+
+def test_error_codes(eb):
+    L = eb.lib()
+    h = ctypes.c_int(0)
+    nl = eb.octahedral_nloen(8)
+    o = eb._SetupOpts(7, 15, nl.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 1, 0, 1, -1, None, None)
+    assert L.ect_setup(ctypes.byref(o), ctypes.byref(h)) == -4          # odd ndgl -> bad argument
+    assert b"bad arguments" in L.ect_last_error()
+    assert L.ect_setup(None, ctypes.byref(h)) == -3                     # missing
+    assert L.ect_inquire(12345, ctypes.byref(eb.Info())) == -8          # invalid handle
+    assert L.ect_release(12345) == -8
+    assert L.ect_strerror(-2) == b"not implemented"
+    odd = nl.copy(); odd[0] = odd[-1] = 21
+    o = eb._SetupOpts(7, 16, odd.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 1, 0, 1, -1, None, None)
+    assert L.ect_setup(ctypes.byref(o), ctypes.byref(h)) == -2          # odd nlon not implemented
+    t = eb.Transform(7, nl, host_only=True)
+    a = eb._InvArgs()
+    assert L.ect_inv_trans(t.handle, ctypes.byref(a)) == -6             # host-only handle has no device state
+    t.release()
+
+
+def test_no_cpu_fallback(eb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(eb.EctError, match="no CPU fallback"):
+        eb.Transform(47, eb.octahedral_nloen(48))

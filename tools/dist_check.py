@@ -1,0 +1,47 @@
+"""Run under torchrun: distributed INV_TRANS/DIR_TRANS (m over ranks, latitude bands, NCCL all-to-all)
+against the oracle on the same global input."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np
+import torch
+import torch.distributed as dist
+import ectrans_b200 as eb
+import ectrans_oracle as eo
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+buf = torch.zeros(eb.ECT_NCCL_UID_BYTES, dtype=torch.uint8, device=dev)
+if rank == 0:
+    buf.copy_(torch.frombuffer(bytearray(eb.nccl_unique_id()), dtype=torch.uint8))
+dist.broadcast(buf, 0)
+uid = bytes(buf.cpu().numpy().tobytes())
+T, N, nuv, nsc = 79, 80, 3, 4
+nloen = eb.octahedral_nloen(N)
+tr = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=uid)
+s = eo.setup(T, 2 * N, nloen)
+vor = eo.random_spectral(s, nuv, 1, zero00=True); div = eo.random_spectral(s, nuv, 2, zero00=True); sc = eo.random_spectral(s, nsc, 3)
+ref = eo.inv_trans(s, vor, div, sc, scders=True)
+# local spectral slices in MYMS order
+idx = np.concatenate([np.arange(s.nasm0[m], s.nasm0[m] + 2 * (T - m + 1)) for m in tr.myms]) if tr.nump else np.zeros(0, int)
+loc = lambda a: np.ascontiguousarray(a[:, idx].T)
+gp = tr.inv_trans(loc(vor), loc(div), loc(sc), scders=True)
+g0 = int(s.latoff[tr.info.lat0]) if tr.info.nlat else 0
+refloc = ref[:, g0:g0 + tr.ngptot]
+rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+e_inv = rel(gp[0], refloc)
+ov, od, os_ = tr.dir_trans(np.ascontiguousarray(gp[:, :2 * nuv + nsc]), nuv, nsc)
+rv, rd, rs = eo.dir_trans(s, ref[:2 * nuv + nsc], nuv, nsc)
+e_dir = max(rel(ov.T, rv[:, idx]), rel(od.T, rd[:, idx]), rel(os_.T, rs[:, idx])) if tr.nump else 0.0
+nrm = tr.specnorm(loc(sc))
+e_nrm = rel(nrm, eo.specnorm(s, sc))
+t = torch.tensor([e_inv, e_dir, e_nrm], device=dev, dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("dist errors inv %.2e dir %.2e norm %.2e" % tuple(t.cpu().tolist()), tr.timings())
+    ok = bool((t < 1e-12).all())
+    print("DIST_CHECK_OK" if ok else "DIST_CHECK_FAIL")
+tr.release()
+dist.destroy_process_group()
