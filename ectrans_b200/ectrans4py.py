@@ -1,0 +1,80 @@
+"""ectrans4py face (reference src/ectrans4py/__init__.py) on the B200 library.
+
+Same function names, argument order and return values as the reference's global (Gaussian-grid)
+entry points: ``trans_inq4py`` (:164), ``sp2gp_gauss4py`` (:305), ``gp2sp_gauss4py`` (:364),
+``get_legendre_assets`` (:89).  Single task, double precision, one field per call, handles cached per
+(truncation, nlat, nloen) like spec_setup4py.F90:100-159.  LAM entry points and LREORDER=True (the
+ARPEGE 'model' coefficient order) are out of scope and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import Transform
+
+_handles = {}
+
+
+def init_env(*args, **kwargs):
+    """Accepted for source compatibility (the reference sets OMP/stack limits here)."""
+    return None
+
+
+def _get(ktrunc, ksizej, kloen, knummaxresol):
+    key = (int(ktrunc), int(ksizej), hash(np.asarray(kloen, dtype=np.int64).tobytes()))
+    if key not in _handles:
+        if len(_handles) >= int(knummaxresol):
+            raise RuntimeError("ectrans4py: KNUMMAXRESOL handles exceeded")
+        _handles[key] = Transform(int(ktrunc), np.asarray(kloen, dtype=np.int32)[:int(ksizej)])
+    return _handles[key]
+
+
+def trans_inq4py(KSIZEJ, KTRUNC, KSLOEN, KLOEN, KNUMMAXRESOL):
+    """Returns (KGPTOT, KSPEC, KNMENG)."""
+    t = _get(KTRUNC, KSIZEJ, KLOEN, KNUMMAXRESOL)
+    return t.ngptot, t.nspec2 // 2, t.nmen.astype(np.int64)
+
+
+def sp2gp_gauss4py(KSIZEJ, KTRUNC, KNUMMAXRESOL, KGPTOT, KSLOEN, KLOEN, KSIZE, LGRADIENT, LREORDER, PSPEC):
+    """Returns (PGPT, PGPTM, PGPTL): field, N-S derivative, E-W derivative (zeros unless LGRADIENT)."""
+    if LREORDER:
+        raise NotImplementedError("LREORDER=True (model coefficient order) is not supported")
+    t = _get(KTRUNC, KSIZEJ, KLOEN, KNUMMAXRESOL)
+    sp = np.ascontiguousarray(PSPEC, dtype=np.float64).reshape(-1, 1)
+    assert sp.shape[0] == t.nspec2 == KSIZE and KGPTOT == t.ngptot
+    gp = t.inv_trans(spscalar=sp, scders=bool(LGRADIENT))
+    z = np.zeros(t.ngptot)
+    if LGRADIENT:
+        return gp[0, 0].copy(), gp[0, 1].copy(), gp[0, 2].copy()
+    return gp[0, 0].copy(), z, z.copy()
+
+
+def gp2sp_gauss4py(KSPEC, KSIZEJ, KTRUNC, KNUMMAXRESOL, KSLOEN, KLOEN, KSIZE, LREORDER, PGPT):
+    """Returns PSPEC (KSPEC real values: (re, im) pairs, m-major, n ascending)."""
+    if LREORDER:
+        raise NotImplementedError("LREORDER=True (model coefficient order) is not supported")
+    t = _get(KTRUNC, KSIZEJ, KLOEN, KNUMMAXRESOL)
+    assert KSPEC == t.nspec2 and KSIZE == t.ngptot
+    gp = np.ascontiguousarray(PGPT, dtype=np.float64).reshape(1, 1, -1)
+    return t.dir_trans(gp, 0, 1)[2][:, 0].copy()
+
+
+def get_legendre_assets(KSIZEJ, KTRUNC, KSLOEN, KSPOLEGL, KLOEN, KNUMMAXRESOL):
+    """Returns (KNMENG, PGW, PRPNM[KSLOEN//2, KSPOLEGL]).  PRPNM follows the F%RPNM order
+    (per m, n descending from T+1 to m, setup_dims_mod.F90:28-38); entries of latitudes that do not
+    carry m on the reduced grid (not resident in HBM) are returned as 0."""
+    t = _get(KTRUNC, KSIZEJ, KLOEN, KNUMMAXRESOL)
+    T = t.nsmax
+    ndgnh = t.ndgl // 2
+    rpnm = np.zeros((ndgnh, int(KSPOLEGL)))
+    col = 0
+    for ml, m in enumerate(t.myms):
+        nd = int(t.ndglu[m])
+        ps, pa = t.legendre_table(ml, 0), t.legendre_table(ml, 1)       # [k, i]
+        for n in range(T + 1, m - 1, -1):
+            k, par = divmod(n - m, 2)
+            src = pa if par else ps
+            if k < src.shape[0] and nd:
+                rpnm[ndgnh - nd:, col] = src[k]
+            col += 1
+    return t.nmen.astype(np.int64), t.rgw.copy(), rpnm

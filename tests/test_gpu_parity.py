@@ -228,3 +228,91 @@ def test_errors_are_codes_not_aborts(eb):
     assert eb.lib().ect_dir_trans(tr.handle, ctypes.byref(a)) == -3
     tr.release()
     assert eb.lib().ect_inv_trans(tr.handle, ctypes.byref(eb._InvArgs())) == -8
+
+
+def test_ectrans4py_face(eb, golden):
+    """The reference's own ectrans4py test, verbatim calls (tests/test_ectrans4py/test_ectrans4py.py:109-158)."""
+    from ectrans_b200 import ectrans4py
+    nl = golden["nloen"]
+    gpdata = np.concatenate([golden["gp_latlon"][i, :nl[i]] for i in range(150)])
+    sizes = ectrans4py.trans_inq4py(150, 148, len(nl), nl, 10)
+    assert sizes[0:2] == (33052, 11175)
+    np.testing.assert_array_equal(sizes[2], golden["nmen"])
+    gp = ectrans4py.sp2gp_gauss4py(150, 148, 10, int(sum(nl)), len(nl), nl, len(golden["sp"]), False, False, golden["sp"])[0]
+    assert np.abs(gp - gpdata).max() < 1e-10
+    sp = ectrans4py.gp2sp_gauss4py(11175 * 2, 150, 148, 10, len(nl), nl, len(gpdata), False, gpdata)
+    assert np.abs(sp - golden["sp"]).max() < 1e-10
+    nspec = sum(148 + 2 - im for im in range(149))
+    knmeng, weights, polys = ectrans4py.get_legendre_assets(150, 148, len(nl), nspec, nl, 10)
+    assert abs(sum(weights) - 1.0) < 1e-10
+    assert polys.shape == (75, nspec)
+
+
+def test_transi_face(eb):
+    """transi C API through ctypes: the reference's transi_test_program flow (tests/transi/transi_test_program.c:64-165)."""
+    import ctypes as C
+    L = eb.lib()
+
+    class Trans(C.Structure):
+        _fields_ = [("ndgl", C.c_int), ("nloen", C.POINTER(C.c_int)), ("nlon", C.c_int), ("nsmax", C.c_int),
+                    ("lsplit", C.c_int), ("llatlon", C.c_int), ("flt", C.c_int), ("fft", C.c_int),
+                    ("myproc", C.c_int), ("nproc", C.c_int), ("handle", C.c_int),
+                    ("nspec", C.c_int), ("nspec2", C.c_int), ("nspec2g", C.c_int), ("nspec2mx", C.c_int),
+                    ("nump", C.c_int), ("ngptot", C.c_int), ("ngptotg", C.c_int), ("ngptotmx", C.c_int),
+                    ("ngptotl", C.POINTER(C.c_int)), ("nmyms", C.POINTER(C.c_int)), ("nasm0", C.POINTER(C.c_int)),
+                    ("nprtrw", C.c_int), ("numpp", C.POINTER(C.c_int)), ("nallms", C.POINTER(C.c_int)),
+                    ("nptrms", C.POINTER(C.c_int)), ("nvalue", C.POINTER(C.c_int)), ("nultpp", C.POINTER(C.c_int)),
+                    ("nptrls", C.POINTER(C.c_int)), ("nnmeng", C.POINTER(C.c_int)),
+                    ("rmu", C.POINTER(C.c_double)), ("rgw", C.POINTER(C.c_double))]
+
+    class Inv(C.Structure):
+        _fields_ = [("rspscalar", C.c_void_p), ("rspvor", C.c_void_p), ("rspdiv", C.c_void_p), ("rmeanu", C.c_void_p),
+                    ("rmeanv", C.c_void_p), ("rgp", C.c_void_p), ("nproma", C.c_int), ("nscalar", C.c_int),
+                    ("nvordiv", C.c_int), ("lscalarders", C.c_int), ("luvder_EW", C.c_int), ("lvordivgp", C.c_int),
+                    ("ngpblks", C.c_int), ("lglobal", C.c_int), ("trans", C.POINTER(Trans)), ("count", C.c_int)]
+
+    class Dir(C.Structure):
+        _fields_ = [("rgp", C.c_void_p), ("rspscalar", C.c_void_p), ("rspvor", C.c_void_p), ("rspdiv", C.c_void_p),
+                    ("rmeanu", C.c_void_p), ("rmeanv", C.c_void_p), ("nproma", C.c_int), ("nscalar", C.c_int),
+                    ("nvordiv", C.c_int), ("ngpblks", C.c_int), ("lglobal", C.c_int), ("trans", C.POINTER(Trans)),
+                    ("count", C.c_int)]
+
+    L.new_invtrans.restype = Inv
+    L.new_invtrans.argtypes = [C.POINTER(Trans)]
+    L.new_dirtrans.restype = Dir
+    L.new_dirtrans.argtypes = [C.POINTER(Trans)]
+    L.trans_error_msg.restype = C.c_char_p
+    t = Trans()
+    assert L.trans_new(C.byref(t)) == 0
+    nl = eb.octahedral_nloen(24)
+    assert L.trans_set_resol(C.byref(t), 48, nl.ctypes.data_as(C.POINTER(C.c_int))) == 0
+    assert L.trans_set_trunc(C.byref(t), 23) == 0
+    assert L.trans_setup(C.byref(t)) == 0
+    assert t.nspec2 == 24 * 25 and t.ngptot == int(nl.sum())
+    assert L.trans_inquire(C.byref(t), b"nvalue,nmyms,nasm0,rgw") == 0
+    assert t.nvalue[0] == 0 and t.nvalue[2] == 1 and t.nasm0[0] == 1
+    assert L.trans_inquire(C.byref(t), b"bogus") == -4
+    nscalar = 2
+    rgp = np.zeros((nscalar, t.ngptot))
+    rgp[0] = 1.0
+    rgp[1] = 2.0
+    rsp = np.zeros((t.nspec2, nscalar))
+    d = L.new_dirtrans(C.byref(t))
+    d.nscalar = nscalar
+    d.rgp = rgp.ctypes.data
+    d.rspscalar = rsp.ctypes.data
+    assert L.trans_dirtrans(C.byref(d)) == 0
+    assert L.trans_dirtrans(C.byref(d)) == -5            # stale argument struct
+    assert abs(rsp[0, 0] - 1.0) < 1e-13 and abs(rsp[0, 1] - 2.0) < 1e-13 and np.abs(rsp[1:]).max() < 1e-13
+    out = np.zeros_like(rgp)
+    i = L.new_invtrans(C.byref(t))
+    i.nscalar = nscalar
+    i.rspscalar = rsp.ctypes.data
+    i.rgp = out.ctypes.data
+    assert L.trans_invtrans(C.byref(i)) == 0
+    assert np.abs(out - rgp).max() < 1e-13
+    i2 = L.new_invtrans(C.byref(t))
+    i2.nscalar = 1
+    assert L.trans_invtrans(C.byref(i2)) == -3           # missing rspscalar
+    assert b"missing" in L.trans_error_msg(-3)
+    assert L.trans_delete(C.byref(t)) == 0
