@@ -5,10 +5,15 @@
 // Everything here is __host__ __device__ so the index logic can be exercised on the
 // CPU by tests/ (tests/hostemu) -- the product only ever calls it from CUDA kernels.
 //
-// Data: double2 array of length n, processed in place.
+// Data: double2 array of length n processed in place; element i lives at ECT_PAD(i)
+// (one pad element every 16) so that the stride-R accesses of the innermost passes do not
+// pile onto the same shared-memory banks.
 //   DIT:  input at digit-reversed positions (perm table), output natural order.
 //   DIF:  input natural order, output at digit-reversed positions.
 // Stage s (0 = innermost) has radix r_s and sub-length L_s = prod_{j<s} r_j.
+// Twiddles: one table lookup per butterfly (w = exp(2 pi i k / (R L))), its powers by
+// multiplication -- the profile of the first version showed the shared-memory pipe, not the FP64
+// pipe, to be the limiter (profiles/r01_ncu_full_summary.txt).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,6 +21,8 @@
 #define ECT_HD __host__ __device__ __forceinline__
 #define ECT_MAX_STAGES 14
 #define ECT_MAX_RADIX 31
+#define ECT_PAD(i) ((i) + ((i) >> 4))
+#define ECT_PADDED_LEN(n) ((n) + ((n) >> 4) + 1)
 
 struct EctFftPlan {        // POD; one per transform length
     int n;                 // length (even)
@@ -23,6 +30,7 @@ struct EctFftPlan {        // POD; one per transform length
     int quarter;           // 1: n % 4 == 0, twiddle table holds exp(2 pi i j/n) for j <= n/4; 0: j < n/2
     int radix[ECT_MAX_STAGES];
     int sublen[ECT_MAX_STAGES];   // L_s
+    int lshift[ECT_MAX_STAGES];   // log2(L_s) if L_s is a power of two, else -1
     int perm_off;          // offset (elements) into the uint16 permutation pool: pos(i), i < n
     int tw_off;            // offset (double2) into the twiddle pool
     int tw_len;            // entries of the twiddle table
@@ -59,14 +67,56 @@ ECT_HD void bfly2(double2* v) {
     v[0] = c_add(a, b);
     v[1] = c_sub(a, b);
 }
-ECT_HD void bfly4(double2* v) {
-    double2 t0 = c_add(v[0], v[2]), t1 = c_sub(v[0], v[2]);
-    double2 t2 = c_add(v[1], v[3]), t3 = c_muli(c_sub(v[1], v[3]));
-    v[0] = c_add(t0, t2);
-    v[1] = c_add(t1, t3);
-    v[2] = c_sub(t0, t2);
-    v[3] = c_sub(t1, t3);
+ECT_HD void bfly4(double2& v0, double2& v1, double2& v2, double2& v3) {
+    double2 t0 = c_add(v0, v2), t1 = c_sub(v0, v2);
+    double2 t2 = c_add(v1, v3), t3 = c_muli(c_sub(v1, v3));
+    v0 = c_add(t0, t2);
+    v1 = c_add(t1, t3);
+    v2 = c_sub(t0, t2);
+    v3 = c_sub(t1, t3);
 }
+#define ECT_SQH 0.70710678118654752440
+#define ECT_C8 0.92387953251128675613
+#define ECT_S8 0.38268343236508977173
+// radix 8 = 4 x 2: q = 2a + b, p = p1 + 4 p2
+ECT_HD void bfly8(double2* v) {
+    bfly4(v[0], v[2], v[4], v[6]);          // b = 0: y[0][p1] in v[0], v[2], v[4], v[6]
+    bfly4(v[1], v[3], v[5], v[7]);          // b = 1
+    // twiddle y[1][p1] by W8^p1
+    v[3] = make_double2((v[3].x - v[3].y) * ECT_SQH, (v[3].x + v[3].y) * ECT_SQH);
+    v[5] = c_muli(v[5]);
+    v[7] = make_double2((-v[7].x - v[7].y) * ECT_SQH, (v[7].x - v[7].y) * ECT_SQH);
+    // 2-point DFTs over b: X[p1] = y0 + y1, X[p1 + 4] = y0 - y1
+    double2 x0 = c_add(v[0], v[1]), x4 = c_sub(v[0], v[1]);
+    double2 x1 = c_add(v[2], v[3]), x5 = c_sub(v[2], v[3]);
+    double2 x2 = c_add(v[4], v[5]), x6 = c_sub(v[4], v[5]);
+    double2 x3 = c_add(v[6], v[7]), x7 = c_sub(v[6], v[7]);
+    v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
+}
+// radix 16 = 4 x 4: q = 4a + b, p = p1 + 4 p2
+ECT_HD void bfly16(double2* v) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bfly4(v[b], v[4 + b], v[8 + b], v[12 + b]);   // y[b][p1] at v[4 p1 + b]
+    // twiddles W16^(b p1)
+    const double2 w1 = make_double2(ECT_C8, ECT_S8), w2 = make_double2(ECT_SQH, ECT_SQH), w3 = make_double2(ECT_S8, ECT_C8);
+    v[5] = c_mul(v[5], w1);                                     // b=1,p1=1
+    v[6] = c_mul(v[6], w2);                                     // b=2,p1=1
+    v[7] = c_mul(v[7], w3);                                     // b=3,p1=1
+    v[9] = c_mul(v[9], w2);                                     // b=1,p1=2
+    v[10] = c_muli(v[10]);                                      // b=2,p1=2 : W16^4 = i
+    v[11] = c_mul(v[11], make_double2(-ECT_SQH, ECT_SQH));      // b=3,p1=2 : W16^6
+    v[13] = c_mul(v[13], w3);                                   // b=1,p1=3
+    v[14] = c_mul(v[14], make_double2(-ECT_SQH, ECT_SQH));      // b=2,p1=3 : W16^6
+    v[15] = c_mul(v[15], make_double2(-ECT_C8, -ECT_S8));       // b=3,p1=3 : W16^9
+#pragma unroll
+    for (int p1 = 0; p1 < 4; ++p1) bfly4(v[4 * p1], v[4 * p1 + 1], v[4 * p1 + 2], v[4 * p1 + 3]);   // X[p1 + 4 p2] at v[4 p1 + p2]
+    // transpose 4x4 to natural order
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) { double2 t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
+}
+
 // odd radix R: rt[j] = (cos, sin)(2 pi j / R), j < R.  Outputs are handed to emit(p, value) as they are
 // produced so that only the R inputs live in registers.
 template <int R, typename Emit>
@@ -99,40 +149,74 @@ ECT_HD void bfly_odd(double2* v, const double2* __restrict__ rt, Emit emit) {
     }
 }
 
+template <int R>
+ECT_HD void bfly_pow2(double2* v) {
+    if constexpr (R == 2) bfly2(v);
+    else if constexpr (R == 4) bfly4(v[0], v[1], v[2], v[3]);
+    else if constexpr (R == 8) bfly8(v);
+    else bfly16(v);
+}
+
 // One stage over the whole array, executed cooperatively by nthr threads.
 // DIF == false: twiddle then butterfly (decimation in time stage B_s)
 // DIF == true : butterfly then twiddle (its transpose)
 template <int R, bool DIF>
-ECT_HD void fft_stage_r(double2* data, int n, int L, const double2* __restrict__ qt,
+ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const double2* __restrict__ qt,
                         const double2* __restrict__ rt, int tid, int nthr) {
     const int nb = n / R;
     const int n4 = (n & 3) ? -(n >> 1) : (n >> 2);
     const int tstride = n / (R * L);   // twiddle index stride: exp(2 pi i q k / (R L))
     for (int b = tid; b < nb; b += nthr) {
-        const int blk = b / L;
-        const int k = b - blk * L;
-        double2* p = data + (size_t)blk * R * L + k;
-        const int kt = k * tstride;
+        int blk, k;
+        if (lshift >= 0) { blk = b >> lshift; k = b & (L - 1); }
+        else { blk = b / L; k = b - blk * L; }
+        const int base = blk * R * L + k;
         double2 v[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = p[q * L];
-        if (!DIF && L > 1) {
+        for (int q = 0; q < R; ++q) v[q] = data[ECT_PAD(base + q * L)];
+        double2 w1 = make_double2(1.0, 0.0);
+        const bool tw = (L > 1) && (k > 0);
+        if (tw) w1 = tw_lookup(qt, k * tstride, n4);
+        if (!DIF && tw) {
+            double2 w = w1;
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = c_mul(v[q], tw_lookup(qt, q * kt, n4));
+            for (int q = 1; q < R; ++q) {
+                v[q] = c_mul(v[q], w);
+                if (q + 1 < R) w = c_mul(w, w1);
+            }
         }
-        if constexpr (R == 2 || R == 4) {
-            if constexpr (R == 2) bfly2(v); else bfly4(v);
-            if (DIF && L > 1) {
+        if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
+            bfly_pow2<R>(v);
+            if (DIF && tw) {
+                double2 w = w1;
 #pragma unroll
-                for (int q = 1; q < R; ++q) v[q] = c_mul(v[q], tw_lookup(qt, q * kt, n4));
+                for (int q = 1; q < R; ++q) {
+                    v[q] = c_mul(v[q], w);
+                    if (q + 1 < R) w = c_mul(w, w1);
+                }
             }
 #pragma unroll
-            for (int q = 0; q < R; ++q) p[q * L] = v[q];
+            for (int q = 0; q < R; ++q) data[ECT_PAD(base + q * L)] = v[q];
         } else {
-            bfly_odd<R>(v, rt, [&](int q, double2 val) {
-                if (DIF && L > 1 && q > 0) val = c_mul(val, tw_lookup(qt, q * kt, n4));
-                p[q * L] = val;
-            });
+            if (DIF && tw) {
+                // outputs arrive as (p, R-p) pairs: w^p by running product, w^(R-p) = w^R * conj(w^p)
+                const double2 wr = tw_lookup(qt, k * (n / L), n4);      // w^R = exp(2 pi i k / L)
+                double2 wp = make_double2(1.0, 0.0);
+                int last = 0;
+                bfly_odd<R>(v, rt, [&](int q, double2 val) {
+                    if (q > 0) {
+                        if (q <= (R - 1) / 2) {
+                            if (q != last) { wp = c_mul(wp, w1); last = q; }
+                            val = c_mul(val, wp);
+                        } else {
+                            val = c_mul(val, c_mul(wr, make_double2(wp.x, -wp.y)));
+                        }
+                    }
+                    data[ECT_PAD(base + q * L)] = val;
+                });
+            } else {
+                bfly_odd<R>(v, rt, [&](int q, double2 val) { data[ECT_PAD(base + q * L)] = val; });
+            }
         }
     }
 }
@@ -141,22 +225,52 @@ ECT_HD void fft_stage_r(double2* data, int n, int L, const double2* __restrict__
 #define ECT_ROOTS_OFF(R) ((R) * ((R) - 1) / 2)
 #define ECT_ROOTS_SIZE (ECT_MAX_RADIX * (ECT_MAX_RADIX + 1) / 2)
 template <bool DIF, int MAXR = ECT_MAX_RADIX>
-ECT_HD void fft_stage(double2* data, int n, int r, int L, const double2* __restrict__ qt,
+ECT_HD void fft_stage(double2* data, int n, int r, int L, int lshift, const double2* __restrict__ qt,
                       const double2* __restrict__ rt_all, int tid, int nthr) {
     const double2* rt = rt_all + ECT_ROOTS_OFF(r);
     switch (r) {
-        case 2:  fft_stage_r<2, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 4:  fft_stage_r<4, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 3:  fft_stage_r<3, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 5:  fft_stage_r<5, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 7:  fft_stage_r<7, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 11: if constexpr (MAXR >= 11) fft_stage_r<11, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 13: if constexpr (MAXR >= 13) fft_stage_r<13, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 17: if constexpr (MAXR >= 17) fft_stage_r<17, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 19: if constexpr (MAXR >= 19) fft_stage_r<19, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 23: if constexpr (MAXR >= 23) fft_stage_r<23, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 29: if constexpr (MAXR >= 29) fft_stage_r<29, DIF>(data, n, L, qt, rt, tid, nthr); break;
-        case 31: if constexpr (MAXR >= 31) fft_stage_r<31, DIF>(data, n, L, qt, rt, tid, nthr); break;
+        case 16: fft_stage_r<16, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 8:  fft_stage_r<8, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 4:  fft_stage_r<4, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 2:  fft_stage_r<2, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 3:  fft_stage_r<3, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 5:  fft_stage_r<5, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 7:  fft_stage_r<7, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 11: if constexpr (MAXR >= 11) fft_stage_r<11, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 13: if constexpr (MAXR >= 13) fft_stage_r<13, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 17: if constexpr (MAXR >= 17) fft_stage_r<17, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 19: if constexpr (MAXR >= 19) fft_stage_r<19, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 23: if constexpr (MAXR >= 23) fft_stage_r<23, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 29: if constexpr (MAXR >= 29) fft_stage_r<29, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 31: if constexpr (MAXR >= 31) fft_stage_r<31, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        default: break;
+    }
+}
+
+// Chirp-z middle step: the innermost DIF stage (L = 1, no twiddles), the pointwise product with the
+// (digit-reversed, 1/M-scaled) kernel spectrum and the innermost DIT stage fused into one pass.
+// The forward transform runs on swapped (re <-> im) data, the product un-swaps it.
+template <int R>
+ECT_HD void blue_middle_r(double2* data, int n, const double2* __restrict__ bhat, int tid, int nthr) {
+    const int nb = n / R;
+    for (int b = tid; b < nb; b += nthr) {
+        double2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = data[ECT_PAD(b * R + q)];
+        bfly_pow2<R>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = c_mul(make_double2(v[q].y, v[q].x), bhat[b * R + q]);
+        bfly_pow2<R>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) data[ECT_PAD(b * R + q)] = v[q];
+    }
+}
+ECT_HD void blue_middle(double2* data, int n, int r, const double2* __restrict__ bhat, int tid, int nthr) {
+    switch (r) {
+        case 16: blue_middle_r<16>(data, n, bhat, tid, nthr); break;
+        case 8:  blue_middle_r<8>(data, n, bhat, tid, nthr); break;
+        case 4:  blue_middle_r<4>(data, n, bhat, tid, nthr); break;
+        case 2:  blue_middle_r<2>(data, n, bhat, tid, nthr); break;
         default: break;
     }
 }

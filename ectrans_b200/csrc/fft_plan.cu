@@ -7,7 +7,7 @@
 int g_ect_force_bluestein = 0;   // test knob: route every length through the chirp-z path
 static const int kPrimes[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31};
 
-bool ect_fft_factorize(int n, std::vector<int>& radices) {
+bool ect_fft_factorize(int n, std::vector<int>& radices, bool pow2_inner) {
     radices.clear();
     if (n < 2 || n % 2 != 0) return false;
     int rem = n, twos = 0;
@@ -18,20 +18,31 @@ bool ect_fft_factorize(int n, std::vector<int>& radices) {
         while (rem % p == 0) { odd.push_back(p); rem /= p; }
     }
     if (rem != 1) return false;
-    // innermost first: odd radices (descending), then a single 2 if needed, then 4s outermost
     std::sort(odd.begin(), odd.end(), [](int a, int b) { return a > b; });
-    radices = odd;
-    if (twos % 2) radices.push_back(2);
-    for (int i = 0; i < twos / 2; ++i) radices.push_back(4);
+    std::vector<int> p2;                      // power-of-two part as 16s plus one smaller radix
+    for (int i = 0; i < twos / 4; ++i) p2.push_back(16);
+    if (twos % 4) p2.push_back(1 << (twos % 4));
+    if (pow2_inner) {
+        // chirp-z lengths r * 2^k: 16s innermost (fused middle step), small power of two next, odd r outermost
+        radices = p2;
+        radices.insert(radices.end(), odd.begin(), odd.end());
+    } else {
+        // direct lengths: odd radices innermost (descending; odd strides spread over the banks), powers of two outside
+        radices = odd;
+        std::reverse(p2.begin(), p2.end());
+        radices.insert(radices.end(), p2.begin(), p2.end());
+    }
     return (int)radices.size() <= ECT_MAX_STAGES;
 }
 
-int ect_fft_smooth_size(int need) {
-    for (int m = (need + 3) / 4 * 4;; m += 4) {
-        int r = m;
-        for (int p : {2, 3, 5, 7}) while (r % p == 0) r /= p;
-        if (r == 1) return m;
+int ect_fft_smooth_size(int need) {          // smallest r * 2^k >= need, r in {1, 3, 5, 7}, k >= 4
+    int best = 0;
+    for (int r : {1, 3, 5, 7}) {
+        int m = r * 16;
+        while (m < need) m *= 2;
+        if (best == 0 || m < best) best = m;
     }
+    return best;
 }
 
 static double2 expi2pi(long long num, long long den) {   // exp(2 pi i num/den), exact argument reduction
@@ -42,11 +53,12 @@ static double2 expi2pi(long long num, long long den) {   // exp(2 pi i num/den),
     return make_double2((double)cosl(a), (double)sinl(a));
 }
 
-int EctFftTables::get_plan(int n) {
-    auto it = plan_of_len.find(n);
+int EctFftTables::get_plan(int n, bool pow2_inner) {
+    const int key = pow2_inner ? -n : n;
+    auto it = plan_of_len.find(key);
     if (it != plan_of_len.end()) return it->second;
     std::vector<int> rad;
-    if (!ect_fft_factorize(n, rad)) return -1;
+    if (!ect_fft_factorize(n, rad, pow2_inner)) return -1;
     if (roots.empty()) {
         roots.assign(ECT_ROOTS_SIZE, make_double2(0.0, 0.0));
         for (int p : kPrimes) {
@@ -61,6 +73,8 @@ int EctFftTables::get_plan(int n) {
     for (int s = 0; s < p.nst; ++s) {
         p.radix[s] = rad[s];
         p.sublen[s] = L;
+        p.lshift[s] = -1;
+        if ((L & (L - 1)) == 0) { int sh = 0; while ((1 << sh) < L) ++sh; p.lshift[s] = sh; }
         L *= rad[s];
     }
     p.perm_off = (int)perm_pool.size();
@@ -79,18 +93,18 @@ int EctFftTables::get_plan(int n) {
     for (int j = 0; j < p.tw_len; ++j) tw_pool.push_back(expi2pi(j, n));
     plans.push_back(p);
     int id = (int)plans.size() - 1;
-    plan_of_len[n] = id;
+    plan_of_len[key] = id;
     return id;
 }
 
 void ect_fft_host(const EctFftTables& T, int plan, std::vector<double2>& data) {
     const EctFftPlan& p = T.plans[plan];
-    std::vector<double2> tmp(p.n);
-    for (int i = 0; i < p.n; ++i) tmp[T.perm_pool[p.perm_off + i]] = data[i];
+    std::vector<double2> tmp(ECT_PADDED_LEN(p.n));
+    for (int i = 0; i < p.n; ++i) tmp[ECT_PAD((int)T.perm_pool[p.perm_off + i])] = data[i];
     for (int s = 0; s < p.nst; ++s)
-        fft_stage<false>(tmp.data(), p.n, p.radix[s], p.sublen[s], T.tw_pool.data() + p.tw_off,
+        fft_stage<false>(tmp.data(), p.n, p.radix[s], p.sublen[s], p.lshift[s], T.tw_pool.data() + p.tw_off,
                          T.roots.data(), 0, 1);
-    data = tmp;
+    for (int i = 0; i < p.n; ++i) data[i] = tmp[ECT_PAD(i)];
 }
 
 int EctFftTables::get_latplan(int nlon, int km) {
@@ -100,21 +114,21 @@ int EctFftTables::get_latplan(int nlon, int km) {
     EctLatPlan lp{};
     lp.nlon = nlon;
     lp.km = km;
-    int direct = g_ect_force_bluestein ? -1 : get_plan(nlon);
+    int direct = g_ect_force_bluestein ? -1 : get_plan(nlon, false);
     if (direct >= 0) {
         lp.plan = direct;
         lp.bluestein = 0;
         lp.m = 0;
         lp.chirp_off = lp.bhat_inv_off = lp.bhat_dir_off = -1;
-        lp.smem_bytes = (nlon + plans[direct].tw_len) * (int)sizeof(double2);
+        lp.smem_bytes = ECT_PADDED_LEN(nlon) * (int)sizeof(double2);
     } else {
         const int N = nlon;
         const int ni_inv = 2 * km + 1, no_inv = N;       // inverse: inputs n in [-km, km], outputs k in [0, N)
         const int M = ect_fft_smooth_size(ni_inv + no_inv - 1);
         lp.bluestein = 1;
         lp.m = M;
-        lp.plan = get_plan(M);
-        lp.smem_bytes = (M + plans[lp.plan].tw_len) * (int)sizeof(double2);
+        lp.plan = get_plan(M, true);
+        lp.smem_bytes = ECT_PADDED_LEN(M) * (int)sizeof(double2);
         // chirp c[j] = exp(+i pi j^2 / N) = exp(2 pi i (j^2 mod 2N) / (2N)), j = 0 .. N/2
         lp.chirp_off = (int)cz_pool.size();
         for (int j = 0; j <= N / 2; ++j) {

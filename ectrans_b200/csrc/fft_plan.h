@@ -27,11 +27,11 @@ struct EctFftTables {
     std::vector<EctLatPlan> latplans;
     std::map<int, int> plan_of_len;
     std::map<std::pair<int, int>, int> latplan_of;
-    int get_plan(int n);                          // smooth n (multiple of 4)
+    int get_plan(int n, bool pow2_inner);         // smooth even n; pow2_inner: chirp-z stage order
     int get_latplan(int nlon, int km);
 };
 
-bool ect_fft_factorize(int n, std::vector<int>& radices);   // false if a prime factor > ECT_MAX_RADIX
-int ect_fft_smooth_size(int need);                           // smallest 7-smooth multiple of 4 >= need
+bool ect_fft_factorize(int n, std::vector<int>& radices, bool pow2_inner);   // false if a prime factor > ECT_MAX_RADIX
+int ect_fft_smooth_size(int need);                           // smallest r * 2^k >= need, r in {1,3,5,7}
 // reference host FFT (uses the same core single-threaded); sign +, unnormalised, natural order in/out
 void ect_fft_host(const EctFftTables& T, int plan, std::vector<double2>& data);

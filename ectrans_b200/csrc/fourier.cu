@@ -51,9 +51,8 @@ __global__ void k_fourier(FtArgs a) {
     c.cp = a.cp;
     const int len = c.plan.n;
     double2* data = sm;
-    double2* qt = sm + len;
+    const double2* qt = a.tw_pool + c.plan.tw_off;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int j = tid; j < c.plan.tw_len; j += nthr) qt[j] = a.tw_pool[c.plan.tw_off + j];
     for (int j = tid; j < ECT_ROOTS_SIZE; j += nthr) s_roots[j] = a.roots[j];
     c.qt = qt; c.roots = s_roots;
     const int g0 = a.gpoff[l];
@@ -81,16 +80,21 @@ __global__ void k_fourier(FtArgs a) {
         }
         __syncthreads();
         if (c.bluestein) {
-            for (int s = c.plan.nst - 1; s >= 0; --s) {
-                fft_stage<true, MAXR>(data, len, c.plan.radix[s], c.plan.sublen[s], qt, s_roots, tid, nthr);
+            for (int s = c.plan.nst - 1; s >= 1; --s) {
+                fft_stage<true, 7>(data, len, c.plan.radix[s], c.plan.sublen[s], c.plan.lshift[s], qt, s_roots, tid, nthr);
                 __syncthreads();
             }
-            blue_pointwise(data, c, tid, nthr);
+            blue_middle(data, len, c.plan.radix[0], c.bhat, tid, nthr);
             __syncthreads();
-        }
-        for (int s = 0; s < c.plan.nst; ++s) {
-            fft_stage<false, MAXR>(data, len, c.plan.radix[s], c.plan.sublen[s], qt, s_roots, tid, nthr);
-            __syncthreads();
+            for (int s = 1; s < c.plan.nst; ++s) {
+                fft_stage<false, 7>(data, len, c.plan.radix[s], c.plan.sublen[s], c.plan.lshift[s], qt, s_roots, tid, nthr);
+                __syncthreads();
+            }
+        } else {
+            for (int s = 0; s < c.plan.nst; ++s) {
+                fft_stage<false, MAXR>(data, len, c.plan.radix[s], c.plan.sublen[s], c.plan.lshift[s], qt, s_roots, tid, nthr);
+                __syncthreads();
+            }
         }
         if (INVERSE) {
             double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
@@ -193,7 +197,7 @@ int ect_fourier_setup(EctHandle* h) {
     int maxsm = 0;
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->dev);
     const int limits[] = {12 * 1024, 24 * 1024, 48 * 1024, 72 * 1024, 108 * 1024, maxsm - 9 * 1024};
-    const int threads[] = {64, 128, 256, 256, 256, 512};
+    const int threads[] = {64, 64, 128, 128, 128, 256};
     d->buckets.clear();
     for (int v = 0; v < 2; ++v)
         for (int i = 0; i < 6; ++i) {

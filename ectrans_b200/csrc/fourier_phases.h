@@ -22,7 +22,7 @@ struct EctPairCtx {
     // plan data
     EctFftPlan plan;              // length nlon (direct) or M (Bluestein)
     const uint16_t* perm;         // perm pool + plan.perm_off
-    const double2* qt;            // quarter twiddles (shared-memory copy in kernels)
+    const double2* qt;            // quarter twiddle table (global memory, L1/L2 resident)
     const double2* roots;
     const double2* chirp;         // Bluestein only
     const double2* bhat;          // Bluestein only (direction specific)
@@ -51,36 +51,28 @@ ECT_HD void ftinv_load(double2* data, const double* __restrict__ fb, const EctPa
     const int N = c.nlon, km = c.km;
     const double s1 = c.racthe, s2 = c.racthe * c.racthe;
     if (!c.bluestein) {
-        for (int k = km + 1 + tid; k < N - km; k += nthr) data[c.perm[k]] = make_double2(0.0, 0.0);
+        for (int k = km + 1 + tid; k < N - km; k += nthr) data[ECT_PAD((int)c.perm[k])] = make_double2(0.0, 0.0);
         for (int k = tid; k <= km; k += nthr) {
             const long long rb = (long long)c.rec[k] * c.cp;
             const double2 a = ect_load_fs(fb, c, rb, fa, k, s1, s2);
             const double2 b = ect_load_fs(fb, c, rb, fbd, k, s1, s2);
-            data[c.perm[k]] = make_double2(a.x - b.y, a.y + b.x);
-            if (k > 0) data[c.perm[N - k]] = make_double2(a.x + b.y, b.x - a.y);
+            data[ECT_PAD((int)c.perm[k])] = make_double2(a.x - b.y, a.y + b.x);
+            if (k > 0) data[ECT_PAD((int)c.perm[N - k])] = make_double2(a.x + b.y, b.x - a.y);
         }
     } else {
-        for (int u = 2 * km + 1 + tid; u < c.m; u += nthr) data[u] = make_double2(0.0, 0.0);
+        for (int u = 2 * km + 1 + tid; u < c.m; u += nthr) data[ECT_PAD(u)] = make_double2(0.0, 0.0);
         for (int k = tid; k <= km; k += nthr) {
             const long long rb = (long long)c.rec[k] * c.cp;
             const double2 a = ect_load_fs(fb, c, rb, fa, k, s1, s2);
             const double2 b = ect_load_fs(fb, c, rb, fbd, k, s1, s2);
             const double2 ch = c.chirp[k];
             const double2 xp = c_mul(make_double2(a.x - b.y, a.y + b.x), ch);
-            data[km + k] = make_double2(xp.y, xp.x);          // stored swapped for the sign-(-) FFT
+            data[ECT_PAD(km + k)] = make_double2(xp.y, xp.x);          // stored swapped for the sign-(-) FFT
             if (k > 0) {
                 const double2 xm = c_mul(make_double2(a.x + b.y, b.x - a.y), ch);
-                data[km - k] = make_double2(xm.y, xm.x);
+                data[ECT_PAD(km - k)] = make_double2(xm.y, xm.x);
             }
         }
-    }
-}
-
-// ---- Bluestein middle: forward stages (DIF), pointwise product, done by caller with syncs ----
-ECT_HD void blue_pointwise(double2* data, const EctPairCtx& c, int tid, int nthr) {
-    for (int i = tid; i < c.m; i += nthr) {
-        const double2 s = data[i];
-        data[i] = c_mul(make_double2(s.y, s.x), c.bhat[i]);
     }
 }
 
@@ -88,37 +80,37 @@ ECT_HD void blue_pointwise(double2* data, const EctPairCtx& c, int tid, int nthr
 // rowa/rowb: pointers to element j = 0 of the row in the (blocked) grid-point array; rows are
 // addressed through gp_index() by the caller, here they are plain contiguous segments
 ECT_HD double2 ftinv_out(const double2* data, const EctPairCtx& c, int j) {
-    if (!c.bluestein) return data[j];
+    if (!c.bluestein) return data[ECT_PAD(j)];
     long long jj = j;
     if (jj > c.nlon / 2) jj = c.nlon - jj;
-    return c_mul(c.chirp[jj], data[j]);   // t = k - o0 with o0 = 0
+    return c_mul(c.chirp[jj], data[ECT_PAD(j)]);   // t = k - o0 with o0 = 0
 }
 
 // ---- direct, phase 1: load two real rows (swapped: sign - transform on the sign + core) ----
 ECT_HD void ftdir_put(double2* data, const EctPairCtx& c, int j, double va, double vb) {
     if (!c.bluestein) {
-        data[c.perm[j]] = make_double2(vb, va);
+        data[ECT_PAD((int)c.perm[j])] = make_double2(vb, va);
     } else {
         long long jj = j;
         if (jj > c.nlon / 2) jj = c.nlon - jj;
         const double2 a = c_mul(make_double2(vb, va), c.chirp[jj]);
-        data[j] = make_double2(a.y, a.x);
+        data[ECT_PAD(j)] = make_double2(a.y, a.x);
     }
 }
 ECT_HD void ftdir_zero_tail(double2* data, const EctPairCtx& c, int tid, int nthr) {
     if (c.bluestein)
-        for (int u = c.nlon + tid; u < c.m; u += nthr) data[u] = make_double2(0.0, 0.0);
+        for (int u = c.nlon + tid; u < c.m; u += nthr) data[ECT_PAD(u)] = make_double2(0.0, 0.0);
 }
 
 // Z[k] for k in [-km, km] of the sign-(-) DFT of z = fa + i fb
 ECT_HD double2 ftdir_z(const double2* data, const EctPairCtx& c, int k) {
     if (!c.bluestein) {
         const int idx = k >= 0 ? k : c.nlon + k;
-        const double2 r = data[idx];
+        const double2 r = data[ECT_PAD(idx)];
         return make_double2(r.y, r.x);
     }
     const int ak = k >= 0 ? k : -k;
-    const double2 x = c_mul(c.chirp[ak], data[k + c.km]);
+    const double2 x = c_mul(c.chirp[ak], data[ECT_PAD(k + c.km)]);
     return make_double2(x.y, x.x);
 }
 

@@ -8,12 +8,15 @@ extern int g_ect_force_bluestein;
 
 static void run_stages(double2* data, const EctPairCtx& c, bool dif, int nthr) {
     const EctFftPlan& p = c.plan;
-    if (dif) {
-        for (int s = p.nst - 1; s >= 0; --s)
-            for (int t = 0; t < nthr; ++t) fft_stage<true>(data, p.n, p.radix[s], p.sublen[s], c.qt, c.roots, t, nthr);
+    if (dif) {       // chirp-z: DIF stages, fused middle, DIT stages
+        for (int s = p.nst - 1; s >= 1; --s)
+            for (int t = 0; t < nthr; ++t) fft_stage<true>(data, p.n, p.radix[s], p.sublen[s], p.lshift[s], c.qt, c.roots, t, nthr);
+        for (int t = 0; t < nthr; ++t) blue_middle(data, p.n, p.radix[0], c.bhat, t, nthr);
+        for (int s = 1; s < p.nst; ++s)
+            for (int t = 0; t < nthr; ++t) fft_stage<false>(data, p.n, p.radix[s], p.sublen[s], p.lshift[s], c.qt, c.roots, t, nthr);
     } else {
         for (int s = 0; s < p.nst; ++s)
-            for (int t = 0; t < nthr; ++t) fft_stage<false>(data, p.n, p.radix[s], p.sublen[s], c.qt, c.roots, t, nthr);
+            for (int t = 0; t < nthr; ++t) fft_stage<false>(data, p.n, p.radix[s], p.sublen[s], p.lshift[s], c.qt, c.roots, t, nthr);
     }
 }
 
@@ -34,12 +37,12 @@ static void make_ctx(EctFftTables& T, EctPairCtx& c, int nlon, int km, int dir, 
 }
 
 extern "C" {
-int emu_smooth(int n) { std::vector<int> r; return ect_fft_factorize(n, r) ? 1 : 0; }
+int emu_smooth(int n) { std::vector<int> r; return ect_fft_factorize(n, r, false) ? 1 : 0; }
 
 // complex sign-+ FFT of smooth length n
 int emu_fft(int n, const double* in, double* out) {
     EctFftTables T;
-    int id = T.get_plan(n);
+    int id = T.get_plan(n, false);
     if (id < 0) return -1;
     std::vector<double2> d(n);
     for (int i = 0; i < n; ++i) d[i] = make_double2(in[2 * i], in[2 * i + 1]);
@@ -53,14 +56,10 @@ int emu_ftinv_pair(int nlon, int km, const double* spec, double* outa, double* o
     g_ect_force_bluestein = force_blue;
     EctFftTables T; EctPairCtx c; std::vector<int> rec;
     make_ctx(T, c, nlon, km, 0, rec);
-    std::vector<double2> data(c.bluestein ? c.m : nlon);
+    std::vector<double2> data(ECT_PADDED_LEN(c.bluestein ? c.m : nlon));
     EctFsField fa{0, 0, 0}, fb{2, 0, 0};
     for (int t = 0; t < nthr; ++t) ftinv_load(data.data(), spec, c, fa, fb, t, nthr);
-    if (c.bluestein) {
-        run_stages(data.data(), c, true, nthr);
-        for (int t = 0; t < nthr; ++t) blue_pointwise(data.data(), c, t, nthr);
-    }
-    run_stages(data.data(), c, false, nthr);
+    run_stages(data.data(), c, c.bluestein != 0, nthr);
     for (int j = 0; j < nlon; ++j) { double2 x = ftinv_out(data.data(), c, j); outa[j] = x.x; outb[j] = x.y; }
     g_ect_force_bluestein = 0;
     return c.bluestein;
@@ -71,14 +70,10 @@ int emu_ftdir_pair(int nlon, int km, const double* rowa, const double* rowb, dou
     g_ect_force_bluestein = force_blue;
     EctFftTables T; EctPairCtx c; std::vector<int> rec;
     make_ctx(T, c, nlon, km, 1, rec);
-    std::vector<double2> data(c.bluestein ? c.m : nlon);
+    std::vector<double2> data(ECT_PADDED_LEN(c.bluestein ? c.m : nlon));
     for (int j = 0; j < nlon; ++j) ftdir_put(data.data(), c, j, rowa[j], rowb[j]);
     for (int t = 0; t < nthr; ++t) ftdir_zero_tail(data.data(), c, t, nthr);
-    if (c.bluestein) {
-        run_stages(data.data(), c, true, nthr);
-        for (int t = 0; t < nthr; ++t) blue_pointwise(data.data(), c, t, nthr);
-    }
-    run_stages(data.data(), c, false, nthr);
+    run_stages(data.data(), c, c.bluestein != 0, nthr);
     for (int t = 0; t < nthr; ++t) ftdir_store(data.data(), spec, c, 0, 2, t, nthr);
     g_ect_force_bluestein = 0;
     return c.bluestein;
