@@ -61,6 +61,21 @@ ECT_HD double2 tw_lookup(const double2* __restrict__ qt, int j, int n4) {
     return w;
 }
 
+// Two-level twiddle table (lives in shared memory in the kernels): exp(2 pi i j / n) = t1[j >> 7] * t2[j & 127]
+struct EctTw {
+    const double2* t1;     // exp(2 pi i 128 a / n), a <= n / 128
+    const double2* t2;     // exp(2 pi i b / n), b < 128
+};
+#define ECT_TW1_LEN(n) ((n) / 128 + 2)
+#define ECT_TW2_LEN 128
+ECT_HD double2 tw_get(const EctTw& t, int j) { return c_mul(t.t1[j >> 7], t.t2[j & 127]); }
+// fills the tables cooperatively from the per-length table qt (quarter / half wave, see tw_lookup)
+ECT_HD void tw_build(double2* t1, double2* t2, const double2* __restrict__ qt, int n, int tid, int nthr) {
+    const int n4 = (n & 3) ? -(n >> 1) : (n >> 2);
+    for (int a = tid; a < ECT_TW1_LEN(n); a += nthr) t1[a] = tw_lookup(qt, (128 * a) % n, n4);
+    for (int b = tid; b < ECT_TW2_LEN; b += nthr) t2[b] = tw_lookup(qt, b % n, n4);
+}
+
 // ---- butterflies: u[p] = sum_q v[q] exp(+2 pi i p q / R), in place on v[0..R) ----
 ECT_HD void bfly2(double2* v) {
     double2 a = v[0], b = v[1];
@@ -157,14 +172,39 @@ ECT_HD void bfly_pow2(double2* v) {
     else bfly16(v);
 }
 
+// v[q] *= w1^q, q = 1 .. R-1.  Powers 1..7 come from a shallow product tree, the rest as
+// w1^(8c) * w1^(q mod 8), so that only eight twiddles are live at a time.
+template <int R>
+ECT_HD void apply_twiddles(double2* v, double2 w1) {
+    constexpr int T = R < 8 ? R : 8;
+    double2 w[T];
+    w[0] = make_double2(1.0, 0.0);
+    w[1] = w1;
+#pragma unroll
+    for (int q = 2; q < T; ++q) w[q] = c_mul(w[q >> 1], w[q - (q >> 1)]);
+#pragma unroll
+    for (int q = 1; q < T; ++q) v[q] = c_mul(v[q], w[q]);
+    if constexpr (R > 8) {
+        const double2 w8 = c_mul(w[4], w[4]);
+        double2 base = w8;
+#pragma unroll
+        for (int c8 = 8; c8 < R; c8 += 8) {
+            v[c8] = c_mul(v[c8], base);
+#pragma unroll
+            for (int q = 1; q < 8; ++q)
+                if (c8 + q < R) v[c8 + q] = c_mul(v[c8 + q], c_mul(base, w[q]));
+            if (c8 + 8 < R) base = c_mul(base, w8);
+        }
+    }
+}
+
 // One stage over the whole array, executed cooperatively by nthr threads.
 // DIF == false: twiddle then butterfly (decimation in time stage B_s)
 // DIF == true : butterfly then twiddle (its transpose)
 template <int R, bool DIF>
-ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const double2* __restrict__ qt,
+ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const EctTw qt,
                         const double2* __restrict__ rt, int tid, int nthr) {
     const int nb = n / R;
-    const int n4 = (n & 3) ? -(n >> 1) : (n >> 2);
     const int tstride = n / (R * L);   // twiddle index stride: exp(2 pi i q k / (R L))
     for (int b = tid; b < nb; b += nthr) {
         int blk, k;
@@ -176,31 +216,17 @@ ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const double2* 
         for (int q = 0; q < R; ++q) v[q] = data[ECT_PAD(base + q * L)];
         double2 w1 = make_double2(1.0, 0.0);
         const bool tw = (L > 1) && (k > 0);
-        if (tw) w1 = tw_lookup(qt, k * tstride, n4);
-        if (!DIF && tw) {
-            double2 w = w1;
-#pragma unroll
-            for (int q = 1; q < R; ++q) {
-                v[q] = c_mul(v[q], w);
-                if (q + 1 < R) w = c_mul(w, w1);
-            }
-        }
+        if (tw) w1 = tw_get(qt, k * tstride);
+        if (!DIF && tw) apply_twiddles<R>(v, w1);
         if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
             bfly_pow2<R>(v);
-            if (DIF && tw) {
-                double2 w = w1;
-#pragma unroll
-                for (int q = 1; q < R; ++q) {
-                    v[q] = c_mul(v[q], w);
-                    if (q + 1 < R) w = c_mul(w, w1);
-                }
-            }
+            if (DIF && tw) apply_twiddles<R>(v, w1);
 #pragma unroll
             for (int q = 0; q < R; ++q) data[ECT_PAD(base + q * L)] = v[q];
         } else {
             if (DIF && tw) {
                 // outputs arrive as (p, R-p) pairs: w^p by running product, w^(R-p) = w^R * conj(w^p)
-                const double2 wr = tw_lookup(qt, k * (n / L), n4);      // w^R = exp(2 pi i k / L)
+                const double2 wr = tw_get(qt, k * (n / L));      // w^R = exp(2 pi i k / L)
                 double2 wp = make_double2(1.0, 0.0);
                 int last = 0;
                 bfly_odd<R>(v, rt, [&](int q, double2 val) {
@@ -225,7 +251,7 @@ ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const double2* 
 #define ECT_ROOTS_OFF(R) ((R) * ((R) - 1) / 2)
 #define ECT_ROOTS_SIZE (ECT_MAX_RADIX * (ECT_MAX_RADIX + 1) / 2)
 template <bool DIF, int MAXR = ECT_MAX_RADIX>
-ECT_HD void fft_stage(double2* data, int n, int r, int L, int lshift, const double2* __restrict__ qt,
+ECT_HD void fft_stage(double2* data, int n, int r, int L, int lshift, const EctTw qt,
                       const double2* __restrict__ rt_all, int tid, int nthr) {
     const double2* rt = rt_all + ECT_ROOTS_OFF(r);
     switch (r) {
@@ -259,7 +285,7 @@ ECT_HD void blue_middle_r(double2* data, int n, const double2* __restrict__ bhat
         for (int q = 0; q < R; ++q) v[q] = data[ECT_PAD(b * R + q)];
         bfly_pow2<R>(v);
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = c_mul(make_double2(v[q].y, v[q].x), bhat[b * R + q]);
+        for (int q = 0; q < R; ++q) v[q] = c_mul(make_double2(v[q].y, v[q].x), bhat[q * nb + b]);   // bhat stored [q][b]: coalesced
         bfly_pow2<R>(v);
 #pragma unroll
         for (int q = 0; q < R; ++q) data[ECT_PAD(b * R + q)] = v[q];

@@ -101,9 +101,11 @@ void ect_fft_host(const EctFftTables& T, int plan, std::vector<double2>& data) {
     const EctFftPlan& p = T.plans[plan];
     std::vector<double2> tmp(ECT_PADDED_LEN(p.n));
     for (int i = 0; i < p.n; ++i) tmp[ECT_PAD((int)T.perm_pool[p.perm_off + i])] = data[i];
+    std::vector<double2> t1(ECT_TW1_LEN(p.n)), t2(ECT_TW2_LEN);
+    tw_build(t1.data(), t2.data(), T.tw_pool.data() + p.tw_off, p.n, 0, 1);
+    EctTw tw{t1.data(), t2.data()};
     for (int s = 0; s < p.nst; ++s)
-        fft_stage<false>(tmp.data(), p.n, p.radix[s], p.sublen[s], p.lshift[s], T.tw_pool.data() + p.tw_off,
-                         T.roots.data(), 0, 1);
+        fft_stage<false>(tmp.data(), p.n, p.radix[s], p.sublen[s], p.lshift[s], tw, T.roots.data(), 0, 1);
     for (int i = 0; i < p.n; ++i) data[i] = tmp[ECT_PAD(i)];
 }
 
@@ -159,9 +161,10 @@ int EctFftTables::get_latplan(int nlon, int km) {
             int off = (int)cz_pool.size();
             cz_pool.resize(off + M);
             const double inv = 1.0 / (double)M;
+            const int r0 = pm.radix[0], nb0 = M / r0;       // middle step reads bhat[q * nb0 + b] for position b * r0 + q
             for (int n = 0; n < M; ++n) {
-                int pos = perm_pool[pm.perm_off + n];
-                cz_pool[off + pos] = make_double2(h[n].x * inv, h[n].y * inv);
+                const int pos = perm_pool[pm.perm_off + n];
+                cz_pool[off + (pos % r0) * nb0 + pos / r0] = make_double2(h[n].x * inv, h[n].y * inv);
             }
             if (dir == 0) lp.bhat_inv_off = off; else lp.bhat_dir_off = off;
         }

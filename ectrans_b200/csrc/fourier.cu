@@ -10,8 +10,13 @@
 #include "ect_internal.h"
 #include "fourier_phases.h"
 #include <algorithm>
+#include <cstdlib>
 
 #define FT_PAIRS_PER_CTA 8
+
+// phase timing probe (debug): cycles of block 0 at phase boundaries of its first pair
+__device__ long long g_ft_probe[64];
+#define FT_PROBE(i) do { if (blockIdx.x == 0 && tid == 0 && p == p0) g_ft_probe[i] = clock64(); } while (0)
 
 struct FtArgs {
     const EctLatPlan* latplans; const EctFftPlan* plans;
@@ -25,6 +30,7 @@ struct FtArgs {
     const EctFsField* fsf;        // inverse only
     const int2* pairs;            // (field a, field b or -1): only fields of one group share a transform
     int nproma; int ngptot;
+    int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum
 };
 
 __device__ __forceinline__ i64 gp_index(int g, int nproma, i64 blkstride) {
@@ -32,83 +38,246 @@ __device__ __forceinline__ i64 gp_index(int g, int nproma, i64 blkstride) {
     return (i64)blk * blkstride + (g - blk * nproma);
 }
 
+__device__ __forceinline__ void ft_cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void ft_cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void ft_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void ft_cp_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }
+
+// Shared memory of one CTA:
+//   data [ECT_PADDED_LEN(len)] double2   work array of the pair in flight
+//   stage                                raw inputs of the NEXT pair, filled by cp.async while this pair is transformed
+//                                        inverse: (km+1) x {field a, field b} double2 ; direct: 2 x nlon doubles
+//   t1, t2                               two-level twiddle table
+//   roots                                odd-radix root tables
 template <bool INVERSE, int MAXR>
-__global__ void k_fourier(FtArgs a) {
+__global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
     extern __shared__ __align__(16) double2 sm[];
-    __shared__ double2 s_roots[ECT_ROOTS_SIZE];
+    __shared__ EctFftPlan s_plan;        // stage list indexed at run time: keep it out of local memory
+    constexpr int NROOTS = MAXR <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE;
     const int item = blockIdx.x;
     const int l = a.lats[item / a.nchunks];
     const int chunk = item % a.nchunks;
     const EctLatPlan lp = a.latplans[a.lat_plan[l]];
     EctPairCtx c;
     c.nlon = lp.nlon; c.km = lp.km; c.racthe = a.racthe_loc[l];
-    c.plan = a.plans[lp.plan];
-    c.perm = a.perm_pool + c.plan.perm_off;
+    if (threadIdx.x == 0) s_plan = a.plans[lp.plan];
+    __syncthreads();
+    const int plan_n = s_plan.n, plan_nst = s_plan.nst;
+    c.perm = a.perm_pool + s_plan.perm_off;
     c.bluestein = lp.bluestein; c.m = lp.m;
     c.chirp = lp.bluestein ? a.cz_pool + lp.chirp_off : nullptr;
     c.bhat = lp.bluestein ? a.cz_pool + (INVERSE ? lp.bhat_inv_off : lp.bhat_dir_off) : nullptr;
     c.rec = a.fft_rec + a.latrow0[l];
     c.cp = a.cp;
-    const int len = c.plan.n;
+    const int len = plan_n;
+    const int N = c.nlon, km = c.km;
     double2* data = sm;
-    const double2* qt = a.tw_pool + c.plan.tw_off;
+    double2* stage = data + ECT_PADDED_LEN(len);
+    const int nstage = INVERSE ? 2 * (km + 1) : N;         // double2 elements
+    double2* t1 = stage + nstage;
+    double2* t2 = t1 + ECT_TW1_LEN(len);
+    double2* s_roots = t2 + ECT_TW2_LEN;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int j = tid; j < ECT_ROOTS_SIZE; j += nthr) s_roots[j] = a.roots[j];
+    tw_build(t1, t2, a.tw_pool + s_plan.tw_off, len, tid, nthr);
+    for (int j = tid; j < NROOTS; j += nthr) s_roots[j] = a.roots[j];
+    const EctTw qt{t1, t2};
     c.qt = qt; c.roots = s_roots;
     const int g0 = a.gpoff[l];
     const bool oneblk = a.nproma >= a.ngptot;
-    __syncthreads();
     const int p0 = chunk * FT_PAIRS_PER_CTA, p1 = min(p0 + FT_PAIRS_PER_CTA, a.npairs);
+    constexpr int NB = 4;      // global loads issued per thread before the first use (latency batching)
+    const double s1 = c.racthe, s2 = c.racthe * c.racthe;
+
+    auto prefetch = [&](int p) {       // raw inputs of pair p -> stage (asynchronous)
+        const int2 pr = a.pairs[p];
+        const int fa = pr.x, fb2 = pr.y;
+        if (INVERSE) {
+            const int ca = a.fsf[fa].src_c;
+            const int cb = fb2 >= 0 ? a.fsf[fb2].src_c : -1;
+            for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
+                int rk[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) { const int k = k0 + i * nthr; rk[i] = k <= km ? c.rec[k] : 0; }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int k = k0 + i * nthr;
+                    if (k > km) continue;
+                    const double* src = a.fb + (long long)rk[i] * c.cp;
+                    ft_cp_async16(stage + 2 * k, src + ca);
+                    if (cb >= 0) ft_cp_async16(stage + 2 * k + 1, src + cb);
+                }
+            }
+        } else {
+            const double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
+            const double* bb = fb2 >= 0 ? a.gp_base[fb2] : nullptr; const i64 sb = fb2 >= 0 ? a.gp_blk[fb2] : 0;
+            double* st = reinterpret_cast<double*>(stage);
+            for (int j = tid; j < N; j += nthr) {
+                const int g = g0 + j;
+                ft_cp_async8(st + j, ba + (oneblk ? (i64)g : gp_index(g, a.nproma, sa)));
+                if (bb) ft_cp_async8(st + N + j, bb + (oneblk ? (i64)g : gp_index(g, a.nproma, sb)));
+            }
+        }
+        ft_cp_commit();
+    };
+
+    if (p0 < p1) prefetch(p0);
     for (int p = p0; p < p1; ++p) {
         const int2 pr = a.pairs[p];
         const int fa = pr.x, fb2 = pr.y;
         const bool hasb = fb2 >= 0;
+        FT_PROBE(0);
+        ft_cp_wait_all();
+        __syncthreads();                 // staged inputs (and, first time, the twiddle tables) are visible
         if (INVERSE) {
+            // FOURIER_IN + FSC + zero padding (same arithmetic as fourier_phases.h ftinv_load)
             EctFsField sfa = a.fsf[fa], sfb;
             if (hasb) sfb = a.fsf[fb2]; else { sfb.src_c = -1; sfb.pw = 0; sfb.deriv = 0; }
-            ftinv_load(data, a.fb, c, sfa, sfb, tid, nthr);
+            if (!c.bluestein) { for (int k = km + 1 + tid; k < N - km; k += nthr) data[ECT_PAD((int)c.perm[k])] = make_double2(0.0, 0.0); }
+            else { for (int u = 2 * km + 1 + tid; u < c.m; u += nthr) data[ECT_PAD(u)] = make_double2(0.0, 0.0); }
+            const double sa_ = sfa.pw == 0 ? 1.0 : (sfa.pw == 1 ? s1 : s2);
+            const double sb_ = sfb.pw == 0 ? 1.0 : (sfb.pw == 1 ? s1 : s2);
+            for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
+                double2 ch[NB]; int pk[NB], pn[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int k = k0 + i * nthr;
+                    ch[i] = make_double2(1.0, 0.0); pk[i] = pn[i] = 0;
+                    if (k <= km) {
+                        if (c.bluestein) ch[i] = c.chirp[k];
+                        else { pk[i] = c.perm[k]; pn[i] = c.perm[k == 0 ? 0 : N - k]; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int k = k0 + i * nthr;
+                    if (k > km) continue;
+                    const double2 va = stage[2 * k];
+                    const double2 vb = hasb ? stage[2 * k + 1] : make_double2(0.0, 0.0);
+                    double2 fa_ = make_double2(va.x * sa_, k == 0 ? 0.0 : va.y * sa_);
+                    double2 fb_ = make_double2(vb.x * sb_, k == 0 ? 0.0 : vb.y * sb_);
+                    const double z = s1 * (double)k;
+                    if (sfa.deriv) fa_ = make_double2(-fa_.y * z, fa_.x * z);
+                    if (sfb.deriv) fb_ = make_double2(-fb_.y * z, fb_.x * z);
+                    const double2 zp = make_double2(fa_.x - fb_.y, fa_.y + fb_.x);      // Z[k]
+                    const double2 zm = make_double2(fa_.x + fb_.y, fb_.x - fa_.y);      // Z[-k]
+                    if (!c.bluestein) {
+                        data[ECT_PAD(pk[i])] = zp;
+                        if (k > 0) data[ECT_PAD(pn[i])] = zm;
+                    } else {
+                        const double2 xp = c_mul(zp, ch[i]);
+                        data[ECT_PAD(km + k)] = make_double2(xp.y, xp.x);
+                        if (k > 0) { const double2 xm = c_mul(zm, ch[i]); data[ECT_PAD(km - k)] = make_double2(xm.y, xm.x); }
+                    }
+                }
+            }
         } else {
-            const double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
-            const double* bb = hasb ? a.gp_base[fb2] : nullptr; const i64 sb = hasb ? a.gp_blk[fb2] : 0;
-            for (int j = tid; j < c.nlon; j += nthr) {
-                const int g = g0 + j;
-                const double va = ba[oneblk ? (i64)g : gp_index(g, a.nproma, sa)];
-                const double vb = hasb ? bb[oneblk ? (i64)g : gp_index(g, a.nproma, sb)] : 0.0;
-                ftdir_put(data, c, j, va, vb);
+            const double* st = reinterpret_cast<const double*>(stage);
+            for (int j0 = tid; j0 < N; j0 += NB * nthr) {
+                double2 ch[NB]; int pj[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int j = j0 + i * nthr;
+                    ch[i] = make_double2(1.0, 0.0); pj[i] = 0;
+                    if (j < N) {
+                        if (c.bluestein) ch[i] = c.chirp[j > N / 2 ? N - j : j];
+                        else pj[i] = c.perm[j];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int j = j0 + i * nthr;
+                    if (j >= N) continue;
+                    const double va = st[j], vb = hasb ? st[N + j] : 0.0;
+                    if (!c.bluestein) data[ECT_PAD(pj[i])] = make_double2(vb, va);
+                    else { const double2 t = c_mul(make_double2(vb, va), ch[i]); data[ECT_PAD(j)] = make_double2(t.y, t.x); }
+                }
             }
             ftdir_zero_tail(data, c, tid, nthr);
         }
-        __syncthreads();
+        __syncthreads();                 // work array complete, stage consumed
+        if (p + 1 < p1) prefetch(p + 1);
+        FT_PROBE(1);
         if (c.bluestein) {
-            for (int s = c.plan.nst - 1; s >= 1; --s) {
-                fft_stage<true, 7>(data, len, c.plan.radix[s], c.plan.sublen[s], c.plan.lshift[s], qt, s_roots, tid, nthr);
+            for (int s = plan_nst - 1; s >= 1; --s) {
+                fft_stage<true, 7>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, s_roots, tid, nthr);
                 __syncthreads();
+                FT_PROBE(2 + (plan_nst - 1 - s));
             }
-            blue_middle(data, len, c.plan.radix[0], c.bhat, tid, nthr);
+            blue_middle(data, len, s_plan.radix[0], c.bhat, tid, nthr);
             __syncthreads();
-            for (int s = 1; s < c.plan.nst; ++s) {
-                fft_stage<false, 7>(data, len, c.plan.radix[s], c.plan.sublen[s], c.plan.lshift[s], qt, s_roots, tid, nthr);
+            FT_PROBE(10);
+            for (int s = 1; s < plan_nst; ++s) {
+                fft_stage<false, 7>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, s_roots, tid, nthr);
                 __syncthreads();
+                FT_PROBE(10 + s);
             }
         } else {
-            for (int s = 0; s < c.plan.nst; ++s) {
-                fft_stage<false, MAXR>(data, len, c.plan.radix[s], c.plan.sublen[s], c.plan.lshift[s], qt, s_roots, tid, nthr);
+            for (int s = 0; s < plan_nst; ++s) {
+                fft_stage<false, MAXR>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, s_roots, tid, nthr);
                 __syncthreads();
             }
+            FT_PROBE(19);
         }
         if (INVERSE) {
             double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
             double* bb = hasb ? a.gp_base[fb2] : nullptr; const i64 sb = hasb ? a.gp_blk[fb2] : 0;
-            for (int j = tid; j < c.nlon; j += nthr) {
-                const double2 x = ftinv_out(data, c, j);
-                const int g = g0 + j;
-                ba[oneblk ? (i64)g : gp_index(g, a.nproma, sa)] = x.x;
-                if (hasb) bb[oneblk ? (i64)g : gp_index(g, a.nproma, sb)] = x.y;
+            for (int j0 = tid; j0 < N; j0 += NB * nthr) {
+                double2 x[NB], ch[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int j = j0 + i * nthr;
+                    if (j < N) {
+                        x[i] = data[ECT_PAD(j)];
+                        if (c.bluestein) ch[i] = (a.dbg & 1) ? make_double2(1.0, 0.0) : c.chirp[j > N / 2 ? N - j : j];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int j = j0 + i * nthr;
+                    if (j >= N) continue;
+                    const double2 y = c.bluestein ? c_mul(ch[i], x[i]) : x[i];
+                    if ((a.dbg & 2) && y.x != 12345.678) continue;
+                    const int g = g0 + j;
+                    ba[oneblk ? (i64)g : gp_index(g, a.nproma, sa)] = y.x;
+                    if (hasb) bb[oneblk ? (i64)g : gp_index(g, a.nproma, sb)] = y.y;
+                }
             }
         } else {
-            ftdir_store(data, a.fb, c, 2 * fa, hasb ? 2 * fb2 : -1, tid, nthr);
+            // 1/N + FOURIER_OUT (same arithmetic as fourier_phases.h ftdir_store)
+            const double sc = 0.5 / (double)N;
+            const int ca = 2 * fa, cb = hasb ? 2 * fb2 : -1;
+            for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
+                double2 zk[NB], zn[NB], ch[NB]; long long rb[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int k = k0 + i * nthr;
+                    if (k <= km) {
+                        rb[i] = (long long)c.rec[k] * c.cp;
+                        if (!c.bluestein) { zk[i] = data[ECT_PAD(k)]; zn[i] = data[ECT_PAD(k == 0 ? 0 : N - k)]; }
+                        else { zk[i] = data[ECT_PAD(km + k)]; zn[i] = data[ECT_PAD(km - k)]; ch[i] = c.chirp[k]; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int k = k0 + i * nthr;
+                    if (k > km) continue;
+                    double2 a_ = zk[i], b_ = zn[i];
+                    if (c.bluestein) { a_ = c_mul(ch[i], a_); b_ = c_mul(ch[i], b_); }
+                    // stored values are swapped (sign - transform on the sign + core): Z = (y, x)
+                    const double2 Zk = make_double2(a_.y, a_.x), Zn = make_double2(b_.y, b_.x);
+                    *reinterpret_cast<double2*>(a.fb + rb[i] + ca) = make_double2((Zk.x + Zn.x) * sc, (Zk.y - Zn.y) * sc);
+                    if (cb >= 0) *reinterpret_cast<double2*>(a.fb + rb[i] + cb) = make_double2((Zk.y + Zn.y) * sc, (Zn.x - Zk.x) * sc);
+                }
+            }
         }
         __syncthreads();
+        FT_PROBE(20);
     }
 }
 
@@ -122,13 +291,19 @@ static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     a.nfs = f.nfs; a.npairs = f.npairs;
     a.nchunks = (a.npairs + FT_PAIRS_PER_CTA - 1) / FT_PAIRS_PER_CTA;
     a.ngptot = h->hp.ngptot;
+    static const char* dbg = getenv("ECT_FFT_DBG");
+    a.dbg = dbg ? atoi(dbg) : 0;
 }
 
 template <bool INVERSE>
 static void launch_fourier(EctHandle* h, FtArgs& a) {
     EctDevice* d = h->d;
+    static const char* only = getenv("ECT_FFT_ONLY_BUCKET");     // debug: run a single shared-memory class
+    int bi = -1;
     for (auto& b : d->buckets) {
+        ++bi;
         if (b.lats.empty()) continue;
+        if (only && atoi(only) != bi) continue;
         a.lats = b.d_lats;
         const unsigned grid = (unsigned)(b.lats.size() * (size_t)a.nchunks);
         if (b.maxr <= 7) k_fourier<INVERSE, 7><<<grid, b.threads, b.smem, d->stream>>>(a);
@@ -196,23 +371,28 @@ int ect_fourier_setup(EctHandle* h) {
     // shared-memory classes
     int maxsm = 0;
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->dev);
-    const int limits[] = {12 * 1024, 24 * 1024, 48 * 1024, 72 * 1024, 108 * 1024, maxsm - 9 * 1024};
-    const int threads[] = {64, 64, 128, 128, 128, 256};
+    const int limits[] = {16 * 1024, 32 * 1024, 56 * 1024, 74 * 1024, 112 * 1024, maxsm - 1024};
+    const int threads[] = {64, 64, 128, 128, 256, 256};
     d->buckets.clear();
     for (int v = 0; v < 2; ++v)
         for (int i = 0; i < 6; ++i) {
             EctDevice::Bucket b;
             b.smem = limits[i];
-            b.threads = threads[i];
+            b.threads = v ? std::min(threads[i], 256) : threads[i];
             b.maxr = v ? ECT_MAX_RADIX : 7;
             d->buckets.push_back(b);
         }
+    std::vector<int> need_of(P.nlat, 0);
     for (int l = 0; l < P.nlat; ++l) {
         const EctLatPlan& lp = d->fft.latplans[d->h_lat_plan[l]];
         const EctFftPlan& pl = d->fft.plans[lp.plan];
-        const int need = lp.smem_bytes;
+        const int len_ = pl.n;
+        int need = (ECT_PADDED_LEN(len_) + std::max(2 * (lp.km + 1), lp.nlon) + ECT_TW1_LEN(len_) + ECT_TW2_LEN) * (int)sizeof(double2);
+
         int maxr = 2;
-        for (int s = 0; s < pl.nst; ++s) maxr = std::max(maxr, pl.radix[s]);
+        for (int s = 0; s < pl.nst; ++s) if (pl.radix[s] & 1) maxr = std::max(maxr, pl.radix[s]);   // 2,4,8,16 are in every variant
+        need += (maxr <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE) * (int)sizeof(double2);
+        need_of[l] = need;
         bool placed = false;
         for (auto& b : d->buckets)
             if (need <= b.smem && maxr <= b.maxr) { b.lats.push_back(l); placed = true; break; }
@@ -224,16 +404,21 @@ int ect_fourier_setup(EctHandle* h) {
     }
     for (auto& b : d->buckets) {
         // longest rows first; shrink the dynamic allocation to what the class needs
-        std::sort(b.lats.begin(), b.lats.end(), [&](int x, int y) {
-            return d->fft.latplans[d->h_lat_plan[x]].smem_bytes > d->fft.latplans[d->h_lat_plan[y]].smem_bytes;
-        });
+        std::sort(b.lats.begin(), b.lats.end(), [&](int x, int y) { return need_of[x] > need_of[y]; });
         if (b.lats.empty()) continue;
-        b.smem = d->fft.latplans[d->h_lat_plan[b.lats[0]]].smem_bytes;
+        b.smem = need_of[b.lats[0]];
         if ((rc = upload(b.d_lats, b.lats))) return rc;
     }
-    ECT_CUDA(cudaFuncSetAttribute(k_fourier<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 9 * 1024));
-    ECT_CUDA(cudaFuncSetAttribute(k_fourier<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 9 * 1024));
-    ECT_CUDA(cudaFuncSetAttribute(k_fourier<true, ECT_MAX_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 9 * 1024));
-    ECT_CUDA(cudaFuncSetAttribute(k_fourier<false, ECT_MAX_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 9 * 1024));
+    ECT_CUDA(cudaFuncSetAttribute(k_fourier<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024));
+    ECT_CUDA(cudaFuncSetAttribute(k_fourier<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024));
+    ECT_CUDA(cudaFuncSetAttribute(k_fourier<true, ECT_MAX_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024));
+    ECT_CUDA(cudaFuncSetAttribute(k_fourier<false, ECT_MAX_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024));
+    return ECT_SUCCESS;
+}
+
+// debug: phase cycle stamps of block 0 (first pair) of the last Fourier launch
+extern "C" int ect_debug_fft_probe(long long* out64) {
+    ECT_CUDA(cudaDeviceSynchronize());
+    ECT_CUDA(cudaMemcpyFromSymbol(out64, g_ft_probe, sizeof(long long) * 64));
     return ECT_SUCCESS;
 }

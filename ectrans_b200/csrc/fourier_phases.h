@@ -20,9 +20,8 @@ struct EctPairCtx {
     int nlon, km;
     double racthe;
     // plan data
-    EctFftPlan plan;              // length nlon (direct) or M (Bluestein)
     const uint16_t* perm;         // perm pool + plan.perm_off
-    const double2* qt;            // quarter twiddle table (global memory, L1/L2 resident)
+    EctTw qt;                     // two-level twiddle table (shared memory in the kernels)
     const double2* roots;
     const double2* chirp;         // Bluestein only
     const double2* bhat;          // Bluestein only (direction specific)

@@ -6,8 +6,9 @@
 #include <cstring>
 extern int g_ect_force_bluestein;
 
+static EctFftPlan g_plan;
 static void run_stages(double2* data, const EctPairCtx& c, bool dif, int nthr) {
-    const EctFftPlan& p = c.plan;
+    const EctFftPlan& p = g_plan;
     if (dif) {       // chirp-z: DIF stages, fused middle, DIT stages
         for (int s = p.nst - 1; s >= 1; --s)
             for (int t = 0; t < nthr; ++t) fft_stage<true>(data, p.n, p.radix[s], p.sublen[s], p.lshift[s], c.qt, c.roots, t, nthr);
@@ -20,13 +21,16 @@ static void run_stages(double2* data, const EctPairCtx& c, bool dif, int nthr) {
     }
 }
 
+static std::vector<double2> g_t1, g_t2;
 static void make_ctx(EctFftTables& T, EctPairCtx& c, int nlon, int km, int dir, std::vector<int>& rec) {
     int id = T.get_latplan(nlon, km);
     const EctLatPlan& lp = T.latplans[id];
     c.nlon = nlon; c.km = km; c.racthe = 1.0;
-    c.plan = T.plans[lp.plan];
-    c.perm = T.perm_pool.data() + c.plan.perm_off;
-    c.qt = T.tw_pool.data() + c.plan.tw_off;
+    g_plan = T.plans[lp.plan];
+    c.perm = T.perm_pool.data() + g_plan.perm_off;
+    g_t1.assign(ECT_TW1_LEN(g_plan.n), make_double2(0, 0)); g_t2.assign(ECT_TW2_LEN, make_double2(0, 0));
+    tw_build(g_t1.data(), g_t2.data(), T.tw_pool.data() + g_plan.tw_off, g_plan.n, 0, 1);
+    c.qt = EctTw{g_t1.data(), g_t2.data()};
     c.roots = T.roots.data();
     c.bluestein = lp.bluestein; c.m = lp.m;
     c.chirp = lp.bluestein ? T.cz_pool.data() + lp.chirp_off : nullptr;
