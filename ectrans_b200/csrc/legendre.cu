@@ -15,13 +15,14 @@
 #include "supolf.h"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------
 // small PTX helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -228,23 +229,23 @@ void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, 
 }
 
 // ------------------------------------------------------------------------------------------
-// DMMA contraction kernels.  CTA = 256 threads = 8 warps as 2 (M) x 4 (N); CTA tile 64 x 128,
-// warp tile 32 x 32 for each parity -> 2 x 16 m8n8 accumulators per thread.
+// DMMA contraction kernels.  CTA = 128 threads = 4 warps as 2 (M) x 2 (N); CTA tile 64 x 64 for BOTH
+// parities, warp tile 32 x 32 -> 2 x 16 m8n8 accumulators per thread; two CTAs per SM so that one CTA's
+// barrier / cp.async waits are covered by the other's DMMAs (the first version, one 256-thread CTA per
+// SM with a 64 x 128 tile, kept the DMMA pipe 75 % busy: profiles/r01_ncu_full_summary.txt).
+// 64-wide field tiles also remove the 6.5 -> 7 tile rounding at 412 fields (832 columns = 13 x 64).
 // Shared-memory pitches are = 4 (mod 16) doubles so that the fragment loads
 // (row = lane/4, k = lane%4) hit 16 distinct 8-byte banks per half warp.
 // ------------------------------------------------------------------------------------------
 #define LEG_BM 64
-#define LEG_BN 128
-#define INV_KC 8
-#define INV_STAGES 4
-#define INV_LDA (LEG_BM + 4)     // 68
-#define INV_LDB (LEG_BN + 4)     // 132
-#define INV_STAGE_DOUBLES (2 * INV_KC * INV_LDA + 2 * INV_KC * INV_LDB)
-#define DIR_KC 8
-#define DIR_NB (DIR_KC / 4)     // register-staged double2 per thread and hemisphere
-#define DIR_LDA (DIR_KC + 4)     // 20
-#define DIR_LDB (LEG_BN + 4)
-#define DIR_STAGE_DOUBLES (2 * LEG_BM * DIR_LDA + 2 * DIR_KC * DIR_LDB)
+#define LEG_BN 64
+#define LEG_THREADS 128
+#define LEG_KC 8
+#define LEG_STAGES 5
+#define LEG_LD (64 + 4)          // 68: pitch of the 8 x 64 tiles
+#define DIR_LDA (LEG_KC + 4)     // 12: pitch of the 64 x 8 polynomial tile of the direct kernel
+#define INV_STAGE_DOUBLES (4 * LEG_KC * LEG_LD)
+#define DIR_STAGE_DOUBLES (2 * LEG_BM * DIR_LDA + 2 * LEG_KC * LEG_LD)
 
 struct LegArgs {
     const EctLegM* legm;
@@ -257,9 +258,10 @@ struct LegArgs {
     const double* rw; const double* racthe;
     int cp;
     int c_uv_end;                 // direct: columns < c_uv_end are u,v (scaled by 1/(a cos))
+    int dbg;                      // ECT_LEG_DBG timing experiments: 1 skip B preparation, 2 contiguous (wrong) A loads
 };
 
-__global__ void __launch_bounds__(256, 1) k_leinv(LegArgs a) {
+__global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int tile = blockIdx.x / a.nct, ct = blockIdx.x - tile * a.nct;
     const int2 td = a.tiles[tile];
@@ -267,34 +269,29 @@ __global__ void __launch_bounds__(256, 1) k_leinv(LegArgs a) {
     const int i0 = td.y * LEG_BM, c0 = ct * LEG_BN;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
-    const int nchunks = (lm.ils + INV_KC - 1) / INV_KC;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int nchunks = (lm.ils + LEG_KC - 1) / LEG_KC;
     const double* ps = a.ptab + lm.ps_off + i0;
     const double* pa = a.ptab + lm.pa_off + i0;
     const double* xb = a.x + lm.xrow0 * (long long)a.cp + c0;
 
     auto load_chunk = [&](int chunk, int buf) {
         double* As = smem + (size_t)buf * INV_STAGE_DOUBLES;
-        double* Aa = As + INV_KC * INV_LDA;
-        double* Bs = Aa + INV_KC * INV_LDA;
-        double* Ba = Bs + INV_KC * INV_LDB;
-        const int k0 = chunk * INV_KC;
-        {   // polynomial tiles: 8 rows x 64 latitudes per parity, one 16 B piece per thread
-            const int row = tid >> 5, c2 = (tid & 31) * 2;
+        double* Aa = As + LEG_KC * LEG_LD;
+        double* Bs = Aa + LEG_KC * LEG_LD;
+        double* Ba = Bs + LEG_KC * LEG_LD;
+        const int k0 = chunk * LEG_KC;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {   // 8 rows x 64 columns = 256 16-byte pieces per tile
+            const int idx = tid + e * LEG_THREADS;
+            const int row = idx >> 5, c2 = (idx & 31) * 2;
             const int k = k0 + row;
             const bool vs = k < lm.ils, va = k < lm.ila;
-            cp_async16(As + row * INV_LDA + c2, ps + (long long)(vs ? k : 0) * lm.ldp + c2, vs);
-            cp_async16(Aa + row * INV_LDA + c2, pa + (long long)(va ? k : 0) * lm.ldp + c2, va);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {   // spectral tiles: 8 rows x 128 columns per parity
-            const int idx = tid + e * 256;
-            const int row = idx >> 6, c2 = (idx & 63) * 2;
-            const int k = k0 + row;
+            cp_async16(As + row * LEG_LD + c2, ps + (long long)(vs ? k : 0) * lm.ldp + c2, vs);
+            cp_async16(Aa + row * LEG_LD + c2, pa + (long long)(va ? k : 0) * lm.ldp + c2, va);
             const bool cv = (c0 + c2) < a.cp;
-            const bool vs = cv && k < lm.ils, va = cv && k < lm.ila;
-            cp_async16(Bs + row * INV_LDB + c2, xb + (long long)(vs ? 2 * k : 0) * a.cp + (cv ? c2 : 0), vs);
-            cp_async16(Ba + row * INV_LDB + c2, xb + (long long)(va ? 2 * k + 1 : 0) * a.cp + (cv ? c2 : 0), va);
+            cp_async16(Bs + row * LEG_LD + c2, xb + (long long)(vs ? 2 * k : 0) * a.cp + (cv ? c2 : 0), vs && cv);
+            cp_async16(Ba + row * LEG_LD + c2, xb + (long long)(va ? 2 * k + 1 : 0) * a.cp + (cv ? c2 : 0), va && cv);
         }
     };
 
@@ -305,31 +302,31 @@ __global__ void __launch_bounds__(256, 1) k_leinv(LegArgs a) {
         for (int j = 0; j < 4; ++j) { acs[i][j][0] = acs[i][j][1] = 0.0; aca[i][j][0] = aca[i][j][1] = 0.0; }
 
 #pragma unroll
-    for (int s = 0; s < INV_STAGES - 1; ++s) {
+    for (int s = 0; s < LEG_STAGES - 1; ++s) {
         if (s < nchunks) load_chunk(s, s);
         cp_async_commit();
     }
     for (int ch = 0; ch < nchunks; ++ch) {
-        cp_async_wait<INV_STAGES - 2>();
+        cp_async_wait<LEG_STAGES - 2>();
         __syncthreads();
         {
-            const int nx = ch + INV_STAGES - 1;
-            if (nx < nchunks) load_chunk(nx, nx % INV_STAGES);
+            const int nx = ch + LEG_STAGES - 1;
+            if (nx < nchunks) load_chunk(nx, nx % LEG_STAGES);
             cp_async_commit();
         }
-        const double* As = smem + (size_t)(ch % INV_STAGES) * INV_STAGE_DOUBLES;
-        const double* Aa = As + INV_KC * INV_LDA;
-        const double* Bs = Aa + INV_KC * INV_LDA;
-        const double* Ba = Bs + INV_KC * INV_LDB;
+        const double* As = smem + (size_t)(ch % LEG_STAGES) * INV_STAGE_DOUBLES;
+        const double* Aa = As + LEG_KC * LEG_LD;
+        const double* Bs = Aa + LEG_KC * LEG_LD;
+        const double* Ba = Bs + LEG_KC * LEG_LD;
 #pragma unroll
-        for (int kk = 0; kk < INV_KC; kk += 4) {
+        for (int kk = 0; kk < LEG_KC; kk += 4) {
             double fs[4], fa[4], bs[4], ba[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                fs[i] = As[(kk + t) * INV_LDA + wm * 32 + i * 8 + g];
-                fa[i] = Aa[(kk + t) * INV_LDA + wm * 32 + i * 8 + g];
-                bs[i] = Bs[(kk + t) * INV_LDB + wn * 32 + i * 8 + g];
-                ba[i] = Ba[(kk + t) * INV_LDB + wn * 32 + i * 8 + g];
+                fs[i] = As[(kk + t) * LEG_LD + wm * 32 + i * 8 + g];
+                fa[i] = Aa[(kk + t) * LEG_LD + wm * 32 + i * 8 + g];
+                bs[i] = Bs[(kk + t) * LEG_LD + wn * 32 + i * 8 + g];
+                ba[i] = Ba[(kk + t) * LEG_LD + wn * 32 + i * 8 + g];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -360,7 +357,10 @@ __global__ void __launch_bounds__(256, 1) k_leinv(LegArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(256, 1) k_ledir(LegArgs a) {
+// Direct: Psi[k][c] = sum_lat P[k][lat] * (w (N +- S))[lat][c].  Raw north / south records are staged
+// with cp.async; the N +- S combination, 1/(a cos theta) on u,v and the Gaussian weight are applied when
+// the B fragments are read from shared memory (prfi2b_mod.F90:91-92, ldfou2_mod.F90:90-96, ledir_mod.F90:122).
+__global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int tile = blockIdx.x / a.nct, ct = blockIdx.x - tile * a.nct;
     const int2 td = a.tiles[tile];
@@ -368,64 +368,47 @@ __global__ void __launch_bounds__(256, 1) k_ledir(LegArgs a) {
     const int kr0 = td.y * LEG_BM, c0 = ct * LEG_BN;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
-    const int nchunks = (lm.ndglu + DIR_KC - 1) / DIR_KC;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int nchunks = (lm.ndglu + LEG_KC - 1) / LEG_KC;
     const double* ps = a.ptab + lm.ps_off;
     const double* pa = a.ptab + lm.pa_off;
 
-    double2 rn_[DIR_NB], rs_[DIR_NB];     // register-staged north / south records of the next chunk
-
-    auto load_a = [&](int chunk, int buf) {      // polynomial tile P[k][lat chunk]: 64 rows x DIR_KC latitudes per parity
+    auto load_chunk = [&](int chunk, int buf) {
         double* As = smem + (size_t)buf * DIR_STAGE_DOUBLES;
         double* Aa = As + LEG_BM * DIR_LDA;
-        const int l0 = chunk * DIR_KC;
+        double* Bn = Aa + LEG_BM * DIR_LDA;
+        double* Bs = Bn + LEG_KC * LEG_LD;
+        const int l0 = chunk * LEG_KC;
 #pragma unroll
-        for (int e = 0; e < DIR_KC / 8; ++e) {
-            const int idx = tid + e * 256;
-            const int row = idx / (DIR_KC / 2), c2 = (idx % (DIR_KC / 2)) * 2;
-            const int k = kr0 + row;
-            const bool vs = k < lm.ils, va = k < lm.ila;
-            cp_async16(As + row * DIR_LDA + c2, ps + (long long)(vs ? k : 0) * lm.ldp + l0 + c2, vs);
-            cp_async16(Aa + row * DIR_LDA + c2, pa + (long long)(va ? k : 0) * lm.ldp + l0 + c2, va);
-        }
-    };
-    auto load_b_regs = [&](int chunk) {
-        const int l0 = chunk * DIR_KC;
-#pragma unroll
-        for (int e = 0; e < DIR_NB; ++e) {
-            const int idx = tid + e * 256;
-            const int lr = idx >> 6, c2 = (idx & 63) * 2;
-            const int li = l0 + lr;
-            if (li < lm.ndglu && (c0 + c2) < a.cp) {
-                const long long on = (long long)a.rec_n[lm.rec0 + li] * a.cp + c0 + c2;
-                const long long os = (long long)a.rec_s[lm.rec0 + li] * a.cp + c0 + c2;
-                rn_[e] = *reinterpret_cast<const double2*>(a.fb + on);
-                rs_[e] = *reinterpret_cast<const double2*>(a.fb + os);
-            } else {
-                rn_[e] = make_double2(0.0, 0.0);
-                rs_[e] = make_double2(0.0, 0.0);
+        for (int e = 0; e < 2; ++e) {
+            const int idx = tid + e * LEG_THREADS;
+            {   // polynomial tile P[k][lat chunk]: 64 rows x 8 latitudes = 256 pieces per parity
+                const int row = idx >> 2, c2 = (idx & 3) * 2;
+                const int k = kr0 + row;
+                const bool vs = k < lm.ils, va = k < lm.ila;
+                if (a.dbg & 2) {
+                    cp_async16(As + row * DIR_LDA + c2, ps + (long long)(chunk & 63) * lm.ldp + idx * 2, true);
+                    cp_async16(Aa + row * DIR_LDA + c2, pa + (long long)(chunk & 63) * lm.ldp + idx * 2, true);
+                } else {
+                cp_async16(As + row * DIR_LDA + c2, ps + (long long)(vs ? k : 0) * lm.ldp + l0 + c2, vs);
+                cp_async16(Aa + row * DIR_LDA + c2, pa + (long long)(va ? k : 0) * lm.ldp + l0 + c2, va);
+                }
+            }
+            {   // north / south records: 8 latitudes x 64 columns = 256 pieces per hemisphere
+                const int lr = idx >> 5, c2 = (idx & 31) * 2;
+                const int li = l0 + lr;
+                const bool v = li < lm.ndglu && (c0 + c2) < a.cp;
+                const long long on = v ? (long long)a.rec_n[lm.rec0 + li] * a.cp + c0 + c2 : 0;
+                const long long os = v ? (long long)a.rec_s[lm.rec0 + li] * a.cp + c0 + c2 : 0;
+                cp_async16(Bn + lr * LEG_LD + c2, a.fb + on, v);
+                cp_async16(Bs + lr * LEG_LD + c2, a.fb + os, v);
             }
         }
     };
-    auto store_b = [&](int chunk, int buf) {
-        double* Bs = smem + (size_t)buf * DIR_STAGE_DOUBLES + 2 * LEG_BM * DIR_LDA;
-        double* Ba = Bs + DIR_KC * DIR_LDB;
-        const int l0 = chunk * DIR_KC;
+
+    bool uvj[4];
 #pragma unroll
-        for (int e = 0; e < DIR_NB; ++e) {
-            const int idx = tid + e * 256;
-            const int lr = idx >> 6, c2 = (idx & 63) * 2;
-            const int li = l0 + lr;
-            double w = 0.0, ra = 1.0;
-            if (li < lm.ndglu) { w = a.rw[lm.isl + li]; ra = a.racthe[lm.isl + li]; }
-            double2 s = make_double2(rn_[e].x + rs_[e].x, rn_[e].y + rs_[e].y);    // prfi2b_mod.F90:91-92
-            double2 d = make_double2(rn_[e].x - rs_[e].x, rn_[e].y - rs_[e].y);
-            if (c0 + c2 < a.c_uv_end) { s.x *= ra; s.y *= ra; d.x *= ra; d.y *= ra; }   // ldfou2_mod.F90:90-96
-            s.x *= w; s.y *= w; d.x *= w; d.y *= w;                                  // ledir_mod.F90:122
-            *reinterpret_cast<double2*>(Bs + lr * DIR_LDB + c2) = s;
-            *reinterpret_cast<double2*>(Ba + lr * DIR_LDB + c2) = d;
-        }
-    };
+    for (int j = 0; j < 4; ++j) uvj[j] = (c0 + wn * 32 + j * 8 + g) < a.c_uv_end;
 
     double acs[4][4][2], aca[4][4][2];
 #pragma unroll
@@ -433,35 +416,47 @@ __global__ void __launch_bounds__(256, 1) k_ledir(LegArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acs[i][j][0] = acs[i][j][1] = 0.0; aca[i][j][0] = aca[i][j][1] = 0.0; }
 
-    if (nchunks > 0) {
-        load_a(0, 0);
-        cp_async_commit();
-        load_b_regs(0);
-        store_b(0, 0);
-        cp_async_wait<0>();
-    }
-    __syncthreads();
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int buf = ch & 1;
-        const bool more = ch + 1 < nchunks;
-        if (more) {
-            load_a(ch + 1, buf ^ 1);
-            cp_async_commit();
-            load_b_regs(ch + 1);
-        }
-        const double* As = smem + (size_t)buf * DIR_STAGE_DOUBLES;
-        const double* Aa = As + LEG_BM * DIR_LDA;
-        const double* Bs = Aa + LEG_BM * DIR_LDA;
-        const double* Ba = Bs + DIR_KC * DIR_LDB;
 #pragma unroll
-        for (int kk = 0; kk < DIR_KC; kk += 4) {
+    for (int s = 0; s < LEG_STAGES - 1; ++s) {
+        if (s < nchunks) load_chunk(s, s);
+        cp_async_commit();
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        // weights of this chunk's two fragment rows (kk + t, kk = 0, 4): issued before the wait
+        double wv[2], rv[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int li = ch * LEG_KC + 4 * h + t;
+            const bool v = li < lm.ndglu;
+            wv[h] = v ? a.rw[lm.isl + li] : 0.0;
+            rv[h] = v ? a.racthe[lm.isl + li] : 1.0;
+        }
+        cp_async_wait<LEG_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = ch + LEG_STAGES - 1;
+            if (nx < nchunks) load_chunk(nx, nx % LEG_STAGES);
+            cp_async_commit();
+        }
+        const double* As = smem + (size_t)(ch % LEG_STAGES) * DIR_STAGE_DOUBLES;
+        const double* Aa = As + LEG_BM * DIR_LDA;
+        const double* Bn = Aa + LEG_BM * DIR_LDA;
+        const double* Bs = Bn + LEG_KC * LEG_LD;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int kk = 4 * h;
             double fs[4], fa[4], bs[4], ba[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 fs[i] = As[(wm * 32 + i * 8 + g) * DIR_LDA + kk + t];
                 fa[i] = Aa[(wm * 32 + i * 8 + g) * DIR_LDA + kk + t];
-                bs[i] = Bs[(kk + t) * DIR_LDB + wn * 32 + i * 8 + g];
-                ba[i] = Ba[(kk + t) * DIR_LDB + wn * 32 + i * 8 + g];
+                const double vn = Bn[(kk + t) * LEG_LD + wn * 32 + i * 8 + g];
+                const double vs = Bs[(kk + t) * LEG_LD + wn * 32 + i * 8 + g];
+                double sy = vn + vs, as = vn - vs;
+                if (uvj[i]) { sy *= rv[h]; as *= rv[h]; }
+                bs[i] = sy * wv[h];
+                ba[i] = as * wv[h];
+                if (a.dbg & 1) { bs[i] = vn; ba[i] = vs; }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -471,12 +466,8 @@ __global__ void __launch_bounds__(256, 1) k_ledir(LegArgs a) {
                     dmma884(aca[i][j][0], aca[i][j][1], fa[i], ba[j]);
                 }
         }
-        if (more) {
-            store_b(ch + 1, buf ^ 1);
-            cp_async_wait<0>();
-        }
-        __syncthreads();
     }
+    cp_async_wait<0>();
     // epilogue: symmetric part -> rows n - m even, antisymmetric -> odd  (ledir_mod.F90:174-179, :248-253)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -499,9 +490,9 @@ static bool g_leg_attr_set = false;
 static void leg_set_attrs() {
     if (g_leg_attr_set) return;
     cudaFuncSetAttribute(k_leinv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         INV_STAGES * INV_STAGE_DOUBLES * (int)sizeof(double));
+                         LEG_STAGES * INV_STAGE_DOUBLES * (int)sizeof(double));
     cudaFuncSetAttribute(k_ledir, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         2 * DIR_STAGE_DOUBLES * (int)sizeof(double));
+                         LEG_STAGES * DIR_STAGE_DOUBLES * (int)sizeof(double));
     g_leg_attr_set = true;
 }
 
@@ -513,9 +504,9 @@ void ect_launch_leinv(EctHandle* h, const EctFieldCfg& f) {
     a.legm = d->legm; a.tiles = d->inv_tiles; a.nct = (f.cp + LEG_BN - 1) / LEG_BN;
     a.ptab = d->ptab; a.x = d->xwork; a.fb = d->fbuf_leg;
     a.rec_n = d->leg_rec_n; a.rec_s = d->leg_rec_s; a.rw = d->rw; a.racthe = d->racthe;
-    a.cp = f.cp; a.c_uv_end = 0;
-    const size_t smem = INV_STAGES * INV_STAGE_DOUBLES * sizeof(double);
-    k_leinv<<<(unsigned)((long long)d->n_inv_tiles * a.nct), 256, smem, d->stream>>>(a);
+    a.cp = f.cp; a.c_uv_end = 0; a.dbg = 0;
+    const size_t smem = LEG_STAGES * INV_STAGE_DOUBLES * sizeof(double);
+    k_leinv<<<(unsigned)((long long)d->n_inv_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
     d->launches++;
 }
 
@@ -528,8 +519,10 @@ void ect_launch_ledir(EctHandle* h, const EctFieldCfg& f) {
     a.ptab = d->ptab; a.x = d->xwork; a.fb = d->fbuf_leg;
     a.rec_n = d->leg_rec_n; a.rec_s = d->leg_rec_s; a.rw = d->rw; a.racthe = d->racthe;
     a.cp = f.cp; a.c_uv_end = 4 * f.kf_uv;
-    const size_t smem = 2 * DIR_STAGE_DOUBLES * sizeof(double);
-    k_ledir<<<(unsigned)((long long)d->n_dir_tiles * a.nct), 256, smem, d->stream>>>(a);
+    static const char* dbg = getenv("ECT_LEG_DBG");
+    a.dbg = dbg ? atoi(dbg) : 0;
+    const size_t smem = LEG_STAGES * DIR_STAGE_DOUBLES * sizeof(double);
+    k_ledir<<<(unsigned)((long long)d->n_dir_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
     d->launches++;
 }
 
