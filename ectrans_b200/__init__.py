@@ -26,6 +26,7 @@ ECT_MEM_HOST, ECT_MEM_DEVICE = 0, 1
 ECT_SETUP_HOST_ONLY = 1
 ECT_SETUP_STREAM_GIVEN = 2
 ECT_NCCL_UID_BYTES = 128
+ECT_PREC_DP, ECT_PREC_SP = 0, 1
 (ARR_NLOEN, ARR_NMEN, ARR_NDGLU, ARR_MYMS, ARR_NASM0, ARR_NPROCM, ARR_RMU, ARR_RGW, ARR_LATFIRST,
  ARR_LATCOUNT, ARR_SENDCNT, ARR_RECVCNT, ARR_RACTHE, ARR_MROW0, ARR_LEGRECN, ARR_LEGRECS, ARR_LATROW0,
  ARR_FFTREC, ARR_SENDOFF, ARR_RECVOFF) = range(1, 21)
@@ -38,7 +39,7 @@ class EctError(RuntimeError):
 class _SetupOpts(C.Structure):
     _fields_ = [("nsmax", C.c_int), ("ndgl", C.c_int), ("nloen", C.POINTER(C.c_int)), ("nranks", C.c_int),
                 ("rank", C.c_int), ("flags", C.c_int), ("device", C.c_int), ("stream", C.c_void_p),
-                ("nccl_uid", C.c_void_p)]
+                ("nccl_uid", C.c_void_p), ("precision", C.c_int)]
 
 
 class Info(C.Structure):
@@ -151,13 +152,14 @@ class PinnedArray:
     """float64 host array in page-locked memory from ect_host_alloc (the reference benchmark's
     pinned allocation, src/programs/util/ectrans_memory.c)."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, dtype=np.float64):
         self.shape = tuple(int(s) for s in shape)
         n = int(np.prod(self.shape)) if self.shape else 1
+        dt = np.dtype(dtype)
         self._p = C.c_void_p()
-        _check(lib().ect_host_alloc(C.byref(self._p), n * 8), "ect_host_alloc")
-        buf = (C.c_double * max(n, 1)).from_address(self._p.value)
-        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(self.shape)
+        _check(lib().ect_host_alloc(C.byref(self._p), n * dt.itemsize), "ect_host_alloc")
+        buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=n).reshape(self.shape)
 
     def free(self):
         if self._p:
@@ -175,14 +177,18 @@ class Transform:
     asynchronous on the handle's stream; call ``synchronize()``).
     """
 
-    def __init__(self, nsmax, nloen, nranks=1, rank=0, device=-1, stream=None, nccl_uid=None, host_only=False):
+    def __init__(self, nsmax, nloen, nranks=1, rank=0, device=-1, stream=None, nccl_uid=None, host_only=False,
+                 precision="dp"):
         L = lib()
+        self.precision = precision
+        self.dtype = np.float64 if precision == "dp" else np.float32
         nl = np.ascontiguousarray(nloen, dtype=np.int32)
         self._uid = C.create_string_buffer(nccl_uid, ECT_NCCL_UID_BYTES) if nccl_uid else None
         o = _SetupOpts(int(nsmax), int(nl.size), nl.ctypes.data_as(C.POINTER(C.c_int)), int(nranks), int(rank),
                        (ECT_SETUP_HOST_ONLY if host_only else 0) | (ECT_SETUP_STREAM_GIVEN if stream is not None else 0),
                        int(device), C.c_void_p(stream) if stream else None,
-                       C.cast(self._uid, C.c_void_p) if self._uid else None)
+                       C.cast(self._uid, C.c_void_p) if self._uid else None,
+                       ECT_PREC_DP if precision == "dp" else ECT_PREC_SP)
         h = C.c_int(0)
         _check(L.ect_setup(C.byref(o), C.byref(h)), "ect_setup")
         self.handle = h.value
@@ -237,6 +243,10 @@ class Transform:
             n += 2 * nuv
         return n
 
+    def _tdtype(self):
+        import torch
+        return torch.float64 if self.precision == "dp" else torch.float32
+
     def _blocks(self, nproma):
         nproma = self.ngptot if (nproma <= 0 or nproma >= self.ngptot) else nproma
         return nproma, (self.ngptot + nproma - 1) // max(nproma, 1)
@@ -256,11 +266,11 @@ class Transform:
             if dev:
                 import torch
                 ref = spvor if spvor is not None else spscalar
-                out = torch.empty((nblk, nfld, nproma), dtype=torch.float64, device=ref.device)
+                out = torch.empty((nblk, nfld, nproma), dtype=self._tdtype(), device=ref.device)
             else:
-                out = np.empty((nblk, nfld, nproma), dtype=np.float64)
+                out = np.empty((nblk, nfld, nproma), dtype=self.dtype)
         if not dev:
-            spvor, spdiv, spscalar = (None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+            spvor, spdiv, spscalar = (None if a is None else np.ascontiguousarray(a, dtype=self.dtype)
                                       for a in (spvor, spdiv, spscalar))
         a = _InvArgs()
         a.memspace = ECT_MEM_DEVICE if dev else ECT_MEM_HOST
@@ -281,10 +291,10 @@ class Transform:
         assert tuple(gp.shape) == (nblk, 2 * nuv + nscalar, nproma), (tuple(gp.shape), (nblk, 2 * nuv + nscalar, nproma))
         if dev:
             import torch
-            mk = lambda n: torch.empty((self.nspec2, n), dtype=torch.float64, device=gp.device) if n else None
+            mk = lambda n: torch.empty((self.nspec2, n), dtype=self._tdtype(), device=gp.device) if n else None
         else:
-            gp = np.ascontiguousarray(gp, dtype=np.float64)
-            mk = lambda n: np.empty((self.nspec2, n), dtype=np.float64) if n else None
+            gp = np.ascontiguousarray(gp, dtype=self.dtype)
+            mk = lambda n: np.empty((self.nspec2, n), dtype=self.dtype) if n else None
         if out is None:
             out = (mk(nuv), mk(nuv), mk(nscalar))
         spvor, spdiv, spsc = out
@@ -327,7 +337,7 @@ class Transform:
         dev = _is_torch(spec)
         nf = int(spec.shape[1])
         if not dev:
-            spec = np.ascontiguousarray(spec, dtype=np.float64)
+            spec = np.ascontiguousarray(spec, dtype=self.dtype)
         out = np.zeros(nf)
         _check(lib().ect_specnorm(self.handle, _ptr(spec), nf, ECT_MEM_DEVICE if dev else ECT_MEM_HOST,
                                   out.ctypes.data), "ect_specnorm")

@@ -128,6 +128,8 @@ extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
     EctHandle* h = new EctHandle();
     int rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, o->nranks < 1 ? 1 : o->nranks, o->rank);
     if (rc) { delete h; return rc; }
+    if (o->precision != ECT_PREC_DP && o->precision != ECT_PREC_SP) { delete h; ect_set_error("ect_setup: unknown precision %d", o->precision); return ECT_ERR_BADARG; }
+    h->precision = o->precision;
     if (!(o->flags & ECT_SETUP_HOST_ONLY)) {
         rc = ect_device_setup(h, (cudaStream_t)o->stream, (o->flags & ECT_SETUP_STREAM_GIVEN) != 0, o->device, o->nccl_uid);
         if (rc) { ect_device_free(h); delete h; return rc; }
@@ -302,6 +304,10 @@ struct CallLayout {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// pointer arithmetic on caller arrays in elements of the handle's precision (members are typed double*)
+template <typename T> static T* adv(T* p, i64 n, int es) { return (T*)((char*)p + n * es); }
+template <typename T> static const T* adv(const T* p, i64 n, int es) { return (const T*)((const char*)p + n * es); }
+
 static std::vector<int2> make_pairs(const std::vector<int>& groups) {
     std::vector<int2> pairs;
     int f0 = 0;
@@ -351,6 +357,8 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     f.nfs = f.nleg + (f.uvder ? 2 * kf_uv : 0) + n_nsd;
     if (f.nfs == 0) return ECT_SUCCESS;
     f.cp = round_up(2 * f.nleg, ECT_CPAD);
+    f.fp32 = (h->precision == ECT_PREC_SP);
+    const int es = f.fp32 ? 4 : 8;
     const int nproma = (a->nproma > 0 && a->nproma < P.ngptot) ? a->nproma : std::max(P.ngptot, 1);
     const int ngpblks = (P.ngptot + nproma - 1) / nproma;
     int rc;
@@ -367,8 +375,8 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
         double* p = d->stage_sp;
         auto stage = [&](const double*& ptr, i64 n) -> int {
             if (!ptr || n == 0) return ECT_SUCCESS;
-            ECT_CUDA(cudaMemcpyAsync(p, ptr, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, d->stream));
-            ptr = p; p += n;
+            ECT_CUDA(cudaMemcpyAsync(p, ptr, (size_t)n * es, cudaMemcpyHostToDevice, d->stream));
+            ptr = p; p = adv(p, n, es);
             return ECT_SUCCESS;
         };
         if (kf_uv) { if ((rc = stage(dvor, kf_uv * nsp))) return rc; if ((rc = stage(ddiv, kf_uv * nsp))) return rc; }
@@ -392,7 +400,7 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
         if ((rc = ensure(d->stage_gp, d->stage_gp_elems, tot, d->stream, false))) return rc;
         double* p = d->stage_gp;
         if (!mode2_gp) dgp = p;
-        else { dgpuv = p; p += sz_uv; dgp2 = p; p += sz_2; dgp3a = p; p += sz_3a; dgp3b = p; }
+        else { dgpuv = p; p = adv(p, sz_uv, es); dgp2 = p; p = adv(p, sz_2, es); dgp3a = p; p = adv(p, sz_3a, es); dgp3b = p; }
     }
     // ---- per-call tables ----
     const size_t n_spec = (size_t)(2 * kf_uv + kf_sc);
@@ -428,15 +436,15 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     int2* t_pairs = (int2*)(t_gps + f.nfs);
     EctFsField* t_fs = (EctFsField*)(t_pairs + pairs.size());
     memcpy(t_pairs, pairs.data(), pairs.size() * sizeof(int2));
-    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {dvor + j, kf_uv}; t_div[j] = {ddiv + j, kf_uv}; }
-    if (!mode2_sp) for (int s = 0; s < kf_sc; ++s) t_sc[s] = {dsc + s, kf_sc};
+    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {adv(dvor, j, es), kf_uv}; t_div[j] = {adv(ddiv, j, es), kf_uv}; }
+    if (!mode2_sp) for (int s = 0; s < kf_sc; ++s) t_sc[s] = {adv(dsc, s, es), kf_sc};
     else {
         int s = 0;
-        for (int j = 0; j < nsc2; ++j) t_sc[s++] = {dsc2 + j, nsc2};
+        for (int j = 0; j < nsc2; ++j) t_sc[s++] = {adv(dsc2, j, es), nsc2};
         for (int j3 = 0; j3 < (a->spsc3a ? a->nsc3a_fld : 0); ++j3)
-            for (int l = 0; l < a->nsc3a_lev; ++l) t_sc[s++] = {dsc3a + (i64)j3 * a->nsc3a_lev * nsp + l, a->nsc3a_lev};
+            for (int l = 0; l < a->nsc3a_lev; ++l) t_sc[s++] = {adv(dsc3a, (i64)j3 * a->nsc3a_lev * nsp + l, es), a->nsc3a_lev};
         for (int j3 = 0; j3 < (a->spsc3b ? a->nsc3b_fld : 0); ++j3)
-            for (int l = 0; l < a->nsc3b_lev; ++l) t_sc[s++] = {dsc3b + (i64)j3 * a->nsc3b_lev * nsp + l, a->nsc3b_lev};
+            for (int l = 0; l < a->nsc3b_lev; ++l) t_sc[s++] = {adv(dsc3b, (i64)j3 * a->nsc3b_lev * nsp + l, es), a->nsc3b_lev};
     }
     // Fourier-space field list: [vor][div] u v scalars [nsd] [du dv] [ewd]   (ftinv_ctl_mod.F90:144-166)
     {
@@ -451,23 +459,23 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     }
     // grid-point destinations (trltog_mod.F90:579-731)
     if (!mode2_gp) {
-        for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = dgp + (i64)i * nproma; t_gps[i] = (i64)f.nfs * nproma; }
+        for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = adv(dgp, (i64)i * nproma, es); t_gps[i] = (i64)f.nfs * nproma; }
     } else {
         int fi = 0, var = 0;
-        auto uvgroup = [&](int v) { for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = dgpuv + ((i64)v * kf_uv + l) * nproma; t_gps[fi] = (i64)nproma * kf_uv * nvar_uv; } };
+        auto uvgroup = [&](int v) { for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = adv(dgpuv, ((i64)v * kf_uv + l) * nproma, es); t_gps[fi] = (i64)nproma * kf_uv * nvar_uv; } };
         if (f.vorgp) uvgroup(var++);
         if (f.divgp) uvgroup(var++);
         if (kf_uv) { uvgroup(var++); uvgroup(var++); }
         auto scgroup = [&](int part) {   // part 0: fields, 1: N-S derivatives, 2: E-W derivatives
-            for (int j = 0; j < nsc2; ++j, ++fi) { t_gpb[fi] = dgp2 + ((i64)part * nsc2 + j) * nproma; t_gps[fi] = (i64)nproma * nsc2 * dfac; }
+            for (int j = 0; j < nsc2; ++j, ++fi) { t_gpb[fi] = adv(dgp2, ((i64)part * nsc2 + j) * nproma, es); t_gps[fi] = (i64)nproma * nsc2 * dfac; }
             for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3)
                 for (int l = 0; l < a->nsc3a_lev; ++l, ++fi) {
-                    t_gpb[fi] = dgp3a + (((i64)part * a->nsc3a_fld + j3) * a->nsc3a_lev + l) * nproma;
+                    t_gpb[fi] = adv(dgp3a, (((i64)part * a->nsc3a_fld + j3) * a->nsc3a_lev + l) * nproma, es);
                     t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld * dfac;
                 }
             for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3)
                 for (int l = 0; l < a->nsc3b_lev; ++l, ++fi) {
-                    t_gpb[fi] = dgp3b + (((i64)part * a->nsc3b_fld + j3) * a->nsc3b_lev + l) * nproma;
+                    t_gpb[fi] = adv(dgp3b, (((i64)part * a->nsc3b_fld + j3) * a->nsc3b_lev + l) * nproma, es);
                     t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld * dfac;
                 }
         };
@@ -497,12 +505,12 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     ECT_CUDA(cudaGetLastError());
     if ((rc = release_callbuf(d))) return rc;
     if (host) {
-        if (!mode2_gp) ECT_CUDA(cudaMemcpyAsync(a->gp, dgp, (size_t)sz_gp * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+        if (!mode2_gp) ECT_CUDA(cudaMemcpyAsync(a->gp, dgp, (size_t)sz_gp * es, cudaMemcpyDeviceToHost, d->stream));
         else {
-            if (sz_uv) ECT_CUDA(cudaMemcpyAsync(a->gpuv, dgpuv, (size_t)sz_uv * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
-            if (sz_2) ECT_CUDA(cudaMemcpyAsync(a->gp2, dgp2, (size_t)sz_2 * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
-            if (sz_3a) ECT_CUDA(cudaMemcpyAsync(a->gp3a, dgp3a, (size_t)sz_3a * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
-            if (sz_3b) ECT_CUDA(cudaMemcpyAsync(a->gp3b, dgp3b, (size_t)sz_3b * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+            if (sz_uv) ECT_CUDA(cudaMemcpyAsync(a->gpuv, dgpuv, (size_t)sz_uv * es, cudaMemcpyDeviceToHost, d->stream));
+            if (sz_2) ECT_CUDA(cudaMemcpyAsync(a->gp2, dgp2, (size_t)sz_2 * es, cudaMemcpyDeviceToHost, d->stream));
+            if (sz_3a) ECT_CUDA(cudaMemcpyAsync(a->gp3a, dgp3a, (size_t)sz_3a * es, cudaMemcpyDeviceToHost, d->stream));
+            if (sz_3b) ECT_CUDA(cudaMemcpyAsync(a->gp3b, dgp3b, (size_t)sz_3b * es, cudaMemcpyDeviceToHost, d->stream));
         }
     }
     ECT_CUDA(cudaEventRecord(d->ev[6], d->stream));
@@ -542,6 +550,8 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
     f.nleg = f.nfs = 2 * kf_uv + kf_sc;
     if (f.nfs == 0) return ECT_SUCCESS;
     f.cp = round_up(2 * f.nleg, ECT_CPAD);
+    f.fp32 = (h->precision == ECT_PREC_SP);
+    const int es = f.fp32 ? 4 : 8;
     const int nproma = (a->nproma > 0 && a->nproma < P.ngptot) ? a->nproma : std::max(P.ngptot, 1);
     const int ngpblks = (P.ngptot + nproma - 1) / nproma;
     int rc;
@@ -558,8 +568,8 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
         double* p = d->stage_gp;
         auto stage = [&](const double*& ptr, i64 n) -> int {
             if (!ptr || n == 0) return ECT_SUCCESS;
-            ECT_CUDA(cudaMemcpyAsync(p, ptr, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, d->stream));
-            ptr = p; p += n;
+            ECT_CUDA(cudaMemcpyAsync(p, ptr, (size_t)n * es, cudaMemcpyHostToDevice, d->stream));
+            ptr = p; p = adv(p, n, es);
             return ECT_SUCCESS;
         };
         if (!mode2) { if ((rc = stage(dgp, sz_gp))) return rc; }
@@ -576,9 +586,9 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
         const i64 tot = (2 * (i64)kf_uv + kf_sc) * nsp;
         if ((rc = ensure(d->stage_sp, d->stage_sp_elems, tot, d->stream, false))) return rc;
         double* p = d->stage_sp;
-        dvor = p; p += kf_uv * nsp; ddiv = p; p += kf_uv * nsp;
+        dvor = p; p = adv(p, kf_uv * nsp, es); ddiv = p; p = adv(p, kf_uv * nsp, es);
         if (!mode2) { dsc = p; }
-        else { dsc2 = p; p += nsc2 * nsp; dsc3a = p; p += n3a * nsp; dsc3b = p; }
+        else { dsc2 = p; p = adv(p, nsc2 * nsp, es); dsc3a = p; p = adv(p, n3a * nsp, es); dsc3b = p; }
     }
     const size_t n_spec = (size_t)(2 * kf_uv + kf_sc);
     std::vector<int> groups;
@@ -602,27 +612,27 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
     i64* t_gps = (i64*)(t_gpb + f.nfs);
     int2* t_pairs = (int2*)(t_gps + f.nfs);
     memcpy(t_pairs, pairs.data(), pairs.size() * sizeof(int2));
-    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {dvor + j, kf_uv}; t_div[j] = {ddiv + j, kf_uv}; }
+    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {adv(dvor, j, es), kf_uv}; t_div[j] = {adv(ddiv, j, es), kf_uv}; }
     if (!mode2) {
-        for (int s = 0; s < kf_sc; ++s) t_sc[s] = {dsc + s, kf_sc};
-        for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = (double*)dgp + (i64)i * nproma; t_gps[i] = (i64)f.nfs * nproma; }
+        for (int s = 0; s < kf_sc; ++s) t_sc[s] = {adv(dsc, s, es), kf_sc};
+        for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = adv((double*)dgp, (i64)i * nproma, es); t_gps[i] = (i64)f.nfs * nproma; }
     } else {
         int s = 0, fi = 0;
         for (int v = 0; v < (kf_uv ? 2 : 0); ++v)
-            for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = (double*)dgpuv + ((i64)v * kf_uv + l) * nproma; t_gps[fi] = (i64)nproma * kf_uv * 2; }
+            for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = adv((double*)dgpuv, ((i64)v * kf_uv + l) * nproma, es); t_gps[fi] = (i64)nproma * kf_uv * 2; }
         for (int j = 0; j < nsc2; ++j, ++fi) {
-            t_sc[s++] = {dsc2 + j, nsc2};
-            t_gpb[fi] = (double*)dgp2 + (i64)j * nproma; t_gps[fi] = (i64)nproma * nsc2;
+            t_sc[s++] = {adv(dsc2, j, es), nsc2};
+            t_gpb[fi] = adv((double*)dgp2, (i64)j * nproma, es); t_gps[fi] = (i64)nproma * nsc2;
         }
         for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3)
             for (int l = 0; l < a->nsc3a_lev; ++l, ++fi) {
-                t_sc[s++] = {dsc3a + (i64)j3 * a->nsc3a_lev * nsp + l, a->nsc3a_lev};
-                t_gpb[fi] = (double*)dgp3a + ((i64)j3 * a->nsc3a_lev + l) * nproma; t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld;
+                t_sc[s++] = {adv(dsc3a, (i64)j3 * a->nsc3a_lev * nsp + l, es), a->nsc3a_lev};
+                t_gpb[fi] = adv((double*)dgp3a, ((i64)j3 * a->nsc3a_lev + l) * nproma, es); t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld;
             }
         for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3)
             for (int l = 0; l < a->nsc3b_lev; ++l, ++fi) {
-                t_sc[s++] = {dsc3b + (i64)j3 * a->nsc3b_lev * nsp + l, a->nsc3b_lev};
-                t_gpb[fi] = (double*)dgp3b + ((i64)j3 * a->nsc3b_lev + l) * nproma; t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld;
+                t_sc[s++] = {adv(dsc3b, (i64)j3 * a->nsc3b_lev * nsp + l, es), a->nsc3b_lev};
+                t_gpb[fi] = adv((double*)dgp3b, ((i64)j3 * a->nsc3b_lev + l) * nproma, es); t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld;
             }
     }
     ECT_CUDA(cudaMemcpyAsync(d->callbuf, d->h_callbuf, bytes, cudaMemcpyHostToDevice, d->stream));
@@ -646,7 +656,7 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
     if (host) {
         auto back = [&](double* dst, const double* src, i64 n) -> int {
             if (!dst || n == 0) return ECT_SUCCESS;
-            ECT_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+            ECT_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * es, cudaMemcpyDeviceToHost, d->stream));
             return ECT_SUCCESS;
         };
         if ((rc = back(a->spvor, dvor, kf_uv * nsp))) return rc;
@@ -695,6 +705,7 @@ extern "C" int ect_get_timings(int handle, ect_timings* t) {
 // ---------------------------------------------------------------------------------------
 // SPECNORM: cpu/internal/spnormd_mod.F90:36-51, spnorm_ctl_mod.F90:56-57
 // ---------------------------------------------------------------------------------------
+template <bool FP32>
 __global__ void k_specnorm(const double* __restrict__ sp, int nfld, int nspec2, int z0, int z1, int chunk,
                            double* __restrict__ acc) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -702,7 +713,7 @@ __global__ void k_specnorm(const double* __restrict__ sp, int nfld, int nspec2, 
     const int i0 = blockIdx.y * chunk, i1 = min(i0 + chunk, nspec2);
     double s = 0.0;
     for (int i = i0; i < i1; ++i) {
-        const double v = sp[(long long)i * nfld + f];
+        const double v = FP32 ? (double)reinterpret_cast<const float*>(sp)[(long long)i * nfld + f] : sp[(long long)i * nfld + f];
         const bool zonal = (i >= z0 && i < z1);
         if (zonal) { if (((i - z0) & 1) == 0) s += v * v; }
         else s += 2.0 * v * v;
@@ -721,7 +732,7 @@ extern "C" int ect_specnorm(int handle, const double* spec, int nfld, int memspa
     int rc;
     if (memspace == ECT_MEM_HOST) {
         if ((rc = ensure(d->stage_sp, d->stage_sp_elems, (i64)nfld * P.nspec2, d->stream, false))) return rc;
-        ECT_CUDA(cudaMemcpyAsync(d->stage_sp, spec, (size_t)nfld * P.nspec2 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        ECT_CUDA(cudaMemcpyAsync(d->stage_sp, spec, (size_t)nfld * P.nspec2 * (h->precision == ECT_PREC_SP ? 4 : 8), cudaMemcpyHostToDevice, d->stream));
         dsp = d->stage_sp;
     }
     if (d->normbuf_n < nfld) {
@@ -734,7 +745,8 @@ extern "C" int ect_specnorm(int handle, const double* spec, int nfld, int memspa
     if (P.nspec2 > 0) {
         const int chunk = 2048;
         dim3 grid((nfld + 127) / 128, (P.nspec2 + chunk - 1) / chunk);
-        k_specnorm<<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nspec2, z0, z1, chunk, d->normbuf);
+        if (h->precision == ECT_PREC_SP) k_specnorm<true><<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nspec2, z0, z1, chunk, d->normbuf);
+        else k_specnorm<false><<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nspec2, z0, z1, chunk, d->normbuf);
     }
     if (P.nranks > 1) ECT_NCCL(ncclAllReduce(d->normbuf, d->normbuf, nfld, ncclDouble, ncclSum, (ncclComm_t)d->comm, d->stream));
     ECT_CUDA(cudaMemcpyAsync(norms, d->normbuf, nfld * sizeof(double), cudaMemcpyDeviceToHost, d->stream));

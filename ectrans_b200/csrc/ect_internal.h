@@ -71,6 +71,7 @@ struct EctFieldCfg {       // field bookkeeping of one call (INV_TRANS inv_trans
     int nfs = 0;           // Fourier / grid-point fields
     int cp = 0;            // record pitch in doubles = roundup(2*nleg, ECT_CPAD)
     int npairs = 0;        // field pairs of the Fourier stage
+    int fp32 = 0;          // caller arrays are float
 };
 
 struct EctDevice {

@@ -30,6 +30,7 @@ struct FtArgs {
     const EctFsField* fsf;        // inverse only
     const int2* pairs;            // (field a, field b or -1): only fields of one group share a transform
     int nproma; int ngptot;
+    int fp32;                     // grid-point arrays are float
     int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum
 };
 
@@ -45,6 +46,10 @@ __device__ __forceinline__ void ft_cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void ft_cp_async8(void* smem, const void* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void ft_cp_async4(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void ft_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void ft_cp_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }
@@ -116,11 +121,21 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
         } else {
             const double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
             const double* bb = fb2 >= 0 ? a.gp_base[fb2] : nullptr; const i64 sb = fb2 >= 0 ? a.gp_blk[fb2] : 0;
-            double* st = reinterpret_cast<double*>(stage);
-            for (int j = tid; j < N; j += nthr) {
-                const int g = g0 + j;
-                ft_cp_async8(st + j, ba + (oneblk ? (i64)g : gp_index(g, a.nproma, sa)));
-                if (bb) ft_cp_async8(st + N + j, bb + (oneblk ? (i64)g : gp_index(g, a.nproma, sb)));
+            if (a.fp32) {
+                float* st = reinterpret_cast<float*>(stage);
+                const float* fa_ = reinterpret_cast<const float*>(ba); const float* fb_ = reinterpret_cast<const float*>(bb);
+                for (int j = tid; j < N; j += nthr) {
+                    const int g = g0 + j;
+                    ft_cp_async4(st + j, fa_ + (oneblk ? (i64)g : gp_index(g, a.nproma, sa)));
+                    if (bb) ft_cp_async4(st + N + j, fb_ + (oneblk ? (i64)g : gp_index(g, a.nproma, sb)));
+                }
+            } else {
+                double* st = reinterpret_cast<double*>(stage);
+                for (int j = tid; j < N; j += nthr) {
+                    const int g = g0 + j;
+                    ft_cp_async8(st + j, ba + (oneblk ? (i64)g : gp_index(g, a.nproma, sa)));
+                    if (bb) ft_cp_async8(st + N + j, bb + (oneblk ? (i64)g : gp_index(g, a.nproma, sb)));
+                }
             }
         }
         ft_cp_commit();
@@ -178,6 +193,7 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
             }
         } else {
             const double* st = reinterpret_cast<const double*>(stage);
+            const float* stf = reinterpret_cast<const float*>(stage);
             for (int j0 = tid; j0 < N; j0 += NB * nthr) {
                 double2 ch[NB]; int pj[NB];
 #pragma unroll
@@ -193,7 +209,8 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
                 for (int i = 0; i < NB; ++i) {
                     const int j = j0 + i * nthr;
                     if (j >= N) continue;
-                    const double va = st[j], vb = hasb ? st[N + j] : 0.0;
+                    const double va = a.fp32 ? (double)stf[j] : st[j];
+                    const double vb = hasb ? (a.fp32 ? (double)stf[N + j] : st[N + j]) : 0.0;
                     if (!c.bluestein) data[ECT_PAD(pj[i])] = make_double2(vb, va);
                     else { const double2 t = c_mul(make_double2(vb, va), ch[i]); data[ECT_PAD(j)] = make_double2(t.y, t.x); }
                 }
@@ -244,8 +261,13 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
                     const double2 y = c.bluestein ? c_mul(ch[i], x[i]) : x[i];
                     if ((a.dbg & 2) && y.x != 12345.678) continue;
                     const int g = g0 + j;
-                    ba[oneblk ? (i64)g : gp_index(g, a.nproma, sa)] = y.x;
-                    if (hasb) bb[oneblk ? (i64)g : gp_index(g, a.nproma, sb)] = y.y;
+                    if (a.fp32) {
+                        reinterpret_cast<float*>(ba)[oneblk ? (i64)g : gp_index(g, a.nproma, sa)] = (float)y.x;
+                        if (hasb) reinterpret_cast<float*>(bb)[oneblk ? (i64)g : gp_index(g, a.nproma, sb)] = (float)y.y;
+                    } else {
+                        ba[oneblk ? (i64)g : gp_index(g, a.nproma, sa)] = y.x;
+                        if (hasb) bb[oneblk ? (i64)g : gp_index(g, a.nproma, sb)] = y.y;
+                    }
                 }
             }
         } else {
@@ -291,6 +313,7 @@ static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     a.nfs = f.nfs; a.npairs = f.npairs;
     a.nchunks = (a.npairs + FT_PAIRS_PER_CTA - 1) / FT_PAIRS_PER_CTA;
     a.ngptot = h->hp.ngptot;
+    a.fp32 = f.fp32;
     static const char* dbg = getenv("ECT_FFT_DBG");
     a.dbg = dbg ? atoi(dbg) : 0;
 }

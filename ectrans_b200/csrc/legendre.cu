@@ -60,7 +60,7 @@ struct ProArgs {
     const EctLegM* legm; const int* nasm0;
     const EctSpecField* vor; const EctSpecField* div; const EctSpecField* sc;
     double* x; int cp; int nsmax;
-    int kf_uv, kf_sc, scders, vorgp, divgp;
+    int kf_uv, kf_sc, scders, vorgp, divgp, fp32;
 };
 
 __device__ __forceinline__ double d_eps(int m, int n) {     // pre_suleg_mod.F90:46-65
@@ -70,13 +70,21 @@ __device__ __forceinline__ double d_eps(int m, int n) {     // pre_suleg_mod.F90
 __device__ __forceinline__ double d_lap(int n) {            // RLAPIN
     return n >= 1 ? -(ECT_RA * ECT_RA / ((double)n * (double)(n + 1))) : 0.0;
 }
+template <bool FP32>
 __device__ __forceinline__ double2 ld_spec(const EctSpecField f, int idx, bool valid, bool m0) {
     if (!valid) return make_double2(0.0, 0.0);
+    if (FP32) {
+        const float* b = reinterpret_cast<const float*>(f.base);
+        const double re = (double)b[(long long)idx * f.stride];
+        const double im = m0 ? 0.0 : (double)b[(long long)(idx + 1) * f.stride];
+        return make_double2(re, im);
+    }
     const double re = f.base[(long long)idx * f.stride];
     const double im = m0 ? 0.0 : f.base[(long long)(idx + 1) * f.stride];
     return make_double2(re, im);
 }
 
+template <bool FP32>
 __global__ void k_ltinv_prologue(ProArgs a) {
     const EctLegM lm = a.legm[blockIdx.y];
     const int m = lm.m, T = a.nsmax;
@@ -104,8 +112,8 @@ __global__ void k_ltinv_prologue(ProArgs a) {
     for (int j = threadIdx.x; j < a.kf_uv + a.kf_sc; j += blockDim.x) {
         if (j < a.kf_uv) {
             const EctSpecField fv = a.vor[j], fd = a.div[j];
-            const double2 z0 = ld_spec(fv, idx, v0, m0), zm = ld_spec(fv, idx - 2, vm, m0), zp = ld_spec(fv, idx + 2, vp, m0);
-            const double2 d0 = ld_spec(fd, idx, v0, m0), dm = ld_spec(fd, idx - 2, vm, m0), dp = ld_spec(fd, idx + 2, vp, m0);
+            const double2 z0 = ld_spec<FP32>(fv, idx, v0, m0), zm = ld_spec<FP32>(fv, idx - 2, vm, m0), zp = ld_spec<FP32>(fv, idx + 2, vp, m0);
+            const double2 d0 = ld_spec<FP32>(fd, idx, v0, m0), dm = ld_spec<FP32>(fd, idx - 2, vm, m0), dp = ld_spec<FP32>(fd, idx + 2, vp, m0);
             // vdtuv_mod.F90:121-139
             double2 u, v;
             u.x = -zl * d0.y + c1 * zm.x - c2 * zp.x;
@@ -120,10 +128,10 @@ __global__ void k_ltinv_prologue(ProArgs a) {
         } else {
             const int s = j - a.kf_uv;
             const EctSpecField f = a.sc[s];
-            const double2 f0 = ld_spec(f, idx, v0, m0);
+            const double2 f0 = ld_spec<FP32>(f, idx, v0, m0);
             *reinterpret_cast<double2*>(row + 2 * (o_sc + s)) = f0;
             if (a.scders) {
-                const double2 fm = ld_spec(f, idx - 2, vm, m0), fp = ld_spec(f, idx + 2, vp, m0);
+                const double2 fm = ld_spec<FP32>(f, idx - 2, vm, m0), fp = ld_spec<FP32>(f, idx + 2, vp, m0);
                 *reinterpret_cast<double2*>(row + 2 * (o_nsd + s)) =
                     make_double2(-e1 * fm.x + e2 * fp.x, -e1 * fm.y + e2 * fp.y);
             }
@@ -143,7 +151,9 @@ void ect_launch_ltinv_prologue(EctHandle* h, const EctFieldCfg& f, const void* d
     dim3 grid(h->hp.nsmax + 2, h->hp.nump);
     int items = f.kf_uv + f.kf_sc;
     int threads = items >= 192 ? 256 : (items >= 96 ? 128 : 64);
-    k_ltinv_prologue<<<grid, threads, 0, d->stream>>>(a);
+    a.fp32 = f.fp32;
+    if (f.fp32) k_ltinv_prologue<true><<<grid, threads, 0, d->stream>>>(a);
+    else k_ltinv_prologue<false><<<grid, threads, 0, d->stream>>>(a);
     d->launches++;
 }
 
@@ -157,6 +167,20 @@ struct EpiArgs {
     int kf_uv, kf_sc;
 };
 
+template <bool FP32>
+__device__ __forceinline__ void st_spec(const EctSpecField f, int idx, double re, double im) {
+    if (FP32) {
+        float* b = reinterpret_cast<float*>(const_cast<double*>(f.base));
+        b[(long long)idx * f.stride] = (float)re;
+        b[(long long)(idx + 1) * f.stride] = (float)im;
+    } else {
+        double* b = const_cast<double*>(f.base);
+        b[(long long)idx * f.stride] = re;
+        b[(long long)(idx + 1) * f.stride] = im;
+    }
+}
+
+template <bool FP32>
 __global__ void k_ltdir_epilogue(EpiArgs a) {
     const EctLegM lm = a.legm[blockIdx.y];
     const int m = lm.m, T = a.nsmax;
@@ -194,21 +218,13 @@ __global__ void k_ltdir_epilogue(EpiArgs a) {
             div.x = -zkm * u0.y + c1 * vp.x - c2 * vm.x;
             div.y = zkm * u0.x + c1 * vp.y - c2 * vm.y;
             if (m0) { vor.y = 0.0; div.y = 0.0; if (n == 0) { vor.x = 0.0; div.x = 0.0; } }
-            const EctSpecField fv = a.vor[j], fd = a.div[j];
-            double* bv = const_cast<double*>(fv.base);
-            double* bd = const_cast<double*>(fd.base);
-            bv[(long long)idx * fv.stride] = vor.x;
-            bv[(long long)(idx + 1) * fv.stride] = vor.y;
-            bd[(long long)idx * fd.stride] = div.x;
-            bd[(long long)(idx + 1) * fd.stride] = div.y;
+            st_spec<FP32>(a.vor[j], idx, vor.x, vor.y);
+            st_spec<FP32>(a.div[j], idx, div.x, div.y);
         } else {
             const int s = j - a.kf_uv;
             double2 f0 = *reinterpret_cast<const double2*>(row + 2 * (o_sc + s));
             if (m0) f0.y = 0.0;
-            const EctSpecField f = a.sc[s];
-            double* b = const_cast<double*>(f.base);
-            b[(long long)idx * f.stride] = f0.x;
-            b[(long long)(idx + 1) * f.stride] = f0.y;
+            st_spec<FP32>(a.sc[s], idx, f0.x, f0.y);
         }
     }
 }
@@ -224,7 +240,8 @@ void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, 
     dim3 grid(h->hp.nsmax + 1, h->hp.nump);
     int items = f.kf_uv + f.kf_sc;
     int threads = items >= 192 ? 256 : (items >= 96 ? 128 : 64);
-    k_ltdir_epilogue<<<grid, threads, 0, d->stream>>>(a);
+    if (f.fp32) k_ltdir_epilogue<true><<<grid, threads, 0, d->stream>>>(a);
+    else k_ltdir_epilogue<false><<<grid, threads, 0, d->stream>>>(a);
     d->launches++;
 }
 

@@ -73,7 +73,7 @@ int trans_setup(struct Trans_t* t) {
     if (t->nsmax < 0) t->nsmax = (2 * t->ndgl - 1) / 2;      // linear-grid default as in transi_module.F90
     ect_setup_opts o;
     memset(&o, 0, sizeof(o));
-    o.nsmax = t->nsmax; o.ndgl = t->ndgl; o.nloen = nloen; o.nranks = 1; o.rank = 0; o.device = -1;
+    o.nsmax = t->nsmax; o.ndgl = t->ndgl; o.nloen = nloen; o.nranks = 1; o.rank = 0; o.device = -1; o.precision = ECT_PREC_DP;
     int h = 0;
     int rc = ect_setup(&o, &h);
     if (rc) return rc;

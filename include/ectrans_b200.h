@@ -56,6 +56,13 @@ extern "C" {
 
 #define ECT_NCCL_UID_BYTES 128
 
+/* Precision of the caller's arrays (the reference builds one library per precision, src/trans/CMakeLists.txt:9-39).
+   ECT_PREC_SP: every field array in ect_inv_args / ect_dir_args / ect_specnorm is float although the members are
+   typed double*; the contraction and the FFT run in fp64 internally (so the reference's fp64 treatment of m = 0,
+   ledir_mod.F90:133-171, holds for every m), inputs are widened on load and results rounded once on store. */
+#define ECT_PREC_DP 0
+#define ECT_PREC_SP 1
+
 typedef struct ect_setup_opts {
     int nsmax;            /* KSMAX: spectral truncation                                  */
     int ndgl;             /* KDGL : number of Gaussian latitudes (even)                  */
@@ -66,6 +73,7 @@ typedef struct ect_setup_opts {
     int device;           /* CUDA device ordinal, -1 = current                           */
     void* stream;         /* cudaStream_t to run on, NULL = library-owned stream         */
     const void* nccl_uid; /* ECT_NCCL_UID_BYTES from ect_nccl_unique_id() of rank 0; NULL if nranks == 1 */
+    int precision;        /* ECT_PREC_DP (JPRB = real64, trans_*_dp) or ECT_PREC_SP (JPRB = real32, trans_*_sp) */
 } ect_setup_opts;
 
 typedef struct ect_info {

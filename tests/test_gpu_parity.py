@@ -316,3 +316,27 @@ def test_transi_face(eb):
     assert L.trans_invtrans(C.byref(i2)) == -3           # missing rspscalar
     assert b"missing" in L.trans_error_msg(-3)
     assert L.trans_delete(C.byref(t)) == 0
+
+
+@pytest.mark.parametrize("T,N,nuv,nsc,opts", [(79, 80, 3, 4, dict(scders=True, uvder=True)), (159, 160, 2, 5, {})])
+def test_single_precision_face(eb, T, N, nuv, nsc, opts):
+    """sp build (BASELINE configs 2 and 4 are sp): float arrays at the boundary, tolerance 1e-5 relative
+    (north_star); the reference keeps m = 0 in fp64 for sp (ledir_mod.F90:133-171), here every m is."""
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen, precision="sp")
+    s = eo.setup(T, 2 * N, nloen)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    vor = f32(eo.random_spectral(s, nuv, 1, zero00=True)); div = f32(eo.random_spectral(s, nuv, 2, zero00=True))
+    sc = f32(eo.random_spectral(s, nsc, 3))
+    ref = eo.inv_trans(s, vor, div, sc, **opts)
+    gp = tr.inv_trans(T_(vor).astype(np.float32), T_(div).astype(np.float32), T_(sc).astype(np.float32), **opts)
+    assert gp.dtype == np.float32
+    for i in range(ref.shape[0]):
+        assert rel(gp[0, i].astype(np.float64), ref[i]) < 1e-6
+    gin = f32(ref[:2 * nuv + nsc])
+    rv, rd, rs = eo.dir_trans(s, gin, nuv, nsc)
+    ov, od, os_ = tr.dir_trans(gin[None].astype(np.float32), nuv, nsc)
+    for a, b in ((ov, rv), (od, rd), (os_, rs)):
+        assert a.dtype == np.float32 and rel(a.T.astype(np.float64), b) < 1e-6
+    assert rel(tr.specnorm(T_(sc).astype(np.float32)), eo.specnorm(s, sc)) < 1e-6
+    tr.release()
