@@ -29,7 +29,8 @@ ECT_NCCL_UID_BYTES = 128
 ECT_PREC_DP, ECT_PREC_SP = 0, 1
 (ARR_NLOEN, ARR_NMEN, ARR_NDGLU, ARR_MYMS, ARR_NASM0, ARR_NPROCM, ARR_RMU, ARR_RGW, ARR_LATFIRST,
  ARR_LATCOUNT, ARR_SENDCNT, ARR_RECVCNT, ARR_RACTHE, ARR_MROW0, ARR_LEGRECN, ARR_LEGRECS, ARR_LATROW0,
- ARR_FFTREC, ARR_SENDOFF, ARR_RECVOFF) = range(1, 21)
+ ARR_FFTREC, ARR_SENDOFF, ARR_RECVOFF, ARR_LEGDSTRANKN, ARR_LEGDSTRECN, ARR_LEGDSTRANKS, ARR_LEGDSTRECS,
+ ARR_FFTDSTRANK, ARR_FFTDSTREC) = range(1, 27)
 
 
 class EctError(RuntimeError):
@@ -222,7 +223,13 @@ class Transform:
         return {"mrow0": mrow0, "latrow0": latrow0,
                 "leg_rec_n": self._arr(ARR_LEGRECN, np.int32, int(mrow0[-1])),
                 "leg_rec_s": self._arr(ARR_LEGRECS, np.int32, int(mrow0[-1])),
-                "fft_rec": self._arr(ARR_FFTREC, np.int32, int(latrow0[-1]))}
+                "fft_rec": self._arr(ARR_FFTREC, np.int32, int(latrow0[-1])),
+                "leg_dst_rank_n": self._arr(ARR_LEGDSTRANKN, np.int32, int(mrow0[-1])),
+                "leg_dst_rec_n": self._arr(ARR_LEGDSTRECN, np.int32, int(mrow0[-1])),
+                "leg_dst_rank_s": self._arr(ARR_LEGDSTRANKS, np.int32, int(mrow0[-1])),
+                "leg_dst_rec_s": self._arr(ARR_LEGDSTRECS, np.int32, int(mrow0[-1])),
+                "fft_dst_rank": self._arr(ARR_FFTDSTRANK, np.int32, int(latrow0[-1])),
+                "fft_dst_rec": self._arr(ARR_FFTDSTREC, np.int32, int(latrow0[-1]))}
 
     def _arr(self, which, dtype, n):
         out = np.zeros(max(int(n), 1), dtype=dtype)

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 
 struct EctSpecFieldH { const double* base; long long stride; };
 
@@ -96,6 +97,30 @@ int ect_device_setup(EctHandle* h, cudaStream_t stream, bool use_given_stream, i
         ncclComm_t comm;
         ECT_NCCL(ncclCommInitRank(&comm, P.nranks, id, P.rank));
         d->comm = comm;
+        const char* nop2p = getenv("ECT_NO_P2P");
+        d->p2p = !(nop2p && atoi(nop2p) != 0);
+        ECT_CUDA(cudaMalloc(&d->barrier_buf, 64));
+        ECT_CUDA(cudaMemset(d->barrier_buf, 0, 64));
+    }
+    // destination tables of the transposition-fused stores.  One rank or NCCL mode: everything stays local
+    // (rank 0 of a one-entry pointer table, record = local record); peer mode: consumer rank + its record.
+    {
+        const bool fused = d->p2p;
+        const size_t nl = P.leg_rec_n.size(), nf = P.fft_rec.size();
+        std::vector<int> zl(nl, 0), zf(nf, 0);
+        auto up = [&](int*& dst, const std::vector<int>& v) -> int {
+            ECT_CUDA(cudaMalloc(&dst, std::max<size_t>(v.size(), 1) * sizeof(int)));
+            if (!v.empty()) ECT_CUDA(cudaMemcpy(dst, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+            return ECT_SUCCESS;
+        };
+        if ((rc = up(d->leg_dst_rank_n, fused ? P.leg_dst_rank_n : zl))) return rc;
+        if ((rc = up(d->leg_dst_rank_s, fused ? P.leg_dst_rank_s : zl))) return rc;
+        if ((rc = up(d->leg_dst_rec_n, fused ? P.leg_dst_rec_n : P.leg_rec_n))) return rc;
+        if ((rc = up(d->leg_dst_rec_s, fused ? P.leg_dst_rec_s : P.leg_rec_s))) return rc;
+        if ((rc = up(d->fft_dst_rank, fused ? P.fft_dst_rank : zf))) return rc;
+        if ((rc = up(d->fft_dst_rec, fused ? P.fft_dst_rec : P.fft_rec))) return rc;
+        ECT_CUDA(cudaMalloc(&d->peer_fft, P.nranks * sizeof(double*)));
+        ECT_CUDA(cudaMalloc(&d->peer_leg, P.nranks * sizeof(double*)));
     }
     return ECT_SUCCESS;
 }
@@ -104,11 +129,13 @@ void ect_device_free(EctHandle* h) {
     EctDevice* d = h->d;
     if (!d) return;
     cudaStreamSynchronize(d->stream);
+    for (void* m : d->ipc_open) cudaIpcCloseMemHandle(m);
     if (d->comm) ncclCommDestroy((ncclComm_t)d->comm);
     void* ptrs[] = {d->rw, d->racthe, d->racthe_loc, d->nloen, d->gpoff, d->ptab, d->legm, d->leg_rec_n, d->leg_rec_s,
                     d->nasm0, d->inv_tiles, d->dir_tiles, d->plans, d->latplans, d->perm_pool, d->tw_pool,
                     d->cz_pool, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->xwork, d->fbuf_leg,
-                    d->stage_sp, d->stage_gp, d->normbuf};
+                    d->stage_sp, d->stage_gp, d->normbuf, d->leg_dst_rank_n, d->leg_dst_rank_s, d->leg_dst_rec_n,
+                    d->leg_dst_rec_s, d->fft_dst_rank, d->fft_dst_rec, d->peer_fft, d->peer_leg, d->barrier_buf};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < EctDevice::kSlots; ++i) {
         if (d->ring_d[i]) cudaFree(d->ring_d[i]);
@@ -212,6 +239,12 @@ extern "C" int ect_inquire_array(int handle, int which, void* out, long long cap
         case ECT_ARR_LEGRECS: return copy_out<int>(out, cap, P.leg_rec_s);
         case ECT_ARR_LATROW0: return copy_out<long long>(out, cap, P.latrow0);
         case ECT_ARR_FFTREC: return copy_out<int>(out, cap, P.fft_rec);
+        case ECT_ARR_LEGDSTRANKN: return copy_out<int>(out, cap, P.leg_dst_rank_n);
+        case ECT_ARR_LEGDSTRECN: return copy_out<int>(out, cap, P.leg_dst_rec_n);
+        case ECT_ARR_LEGDSTRANKS: return copy_out<int>(out, cap, P.leg_dst_rank_s);
+        case ECT_ARR_LEGDSTRECS: return copy_out<int>(out, cap, P.leg_dst_rec_s);
+        case ECT_ARR_FFTDSTRANK: return copy_out<int>(out, cap, P.fft_dst_rank);
+        case ECT_ARR_FFTDSTREC: return copy_out<int>(out, cap, P.fft_dst_rec);
         default: ect_set_error("ect_inquire_array: unknown array id %d", which); return ECT_ERR_BADARG;
     }
 }
@@ -229,17 +262,64 @@ static int ensure(double*& p, i64& have, i64 need, cudaStream_t s, bool zero) {
     return ECT_SUCCESS;
 }
 
+// Publishes the (re)allocated Fourier buffers: pointer tables for the transposition-fused stores.  In peer mode
+// the buffers of all ranks are mapped through CUDA IPC; the handles travel through an NCCL all-gather.
+static int publish_buffers(EctHandle* h) {
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    std::vector<double*> pf(P.nranks, nullptr), pl(P.nranks, nullptr);
+    if (!d->p2p) {
+        // inverse stores go to the local Legendre-side buffer (then NCCL moves them), direct stores to the local
+        // Fourier-side buffer; with one rank both are the same memory
+        for (int r = 0; r < P.nranks; ++r) { pf[r] = d->fbuf_leg; pl[r] = d->fbuf_fft; }
+    } else {
+        for (void* m : d->ipc_open) ECT_CUDA(cudaIpcCloseMemHandle(m));
+        d->ipc_open.clear();
+        cudaIpcMemHandle_t mine[2];
+        ECT_CUDA(cudaIpcGetMemHandle(&mine[0], d->fbuf_fft));
+        ECT_CUDA(cudaIpcGetMemHandle(&mine[1], d->fbuf_leg));
+        const size_t hb = sizeof(mine);
+        char *dsend = nullptr, *drecv = nullptr;
+        ECT_CUDA(cudaMalloc(&dsend, hb));
+        ECT_CUDA(cudaMalloc(&drecv, hb * P.nranks));
+        ECT_CUDA(cudaMemcpyAsync(dsend, mine, hb, cudaMemcpyHostToDevice, d->stream));
+        ECT_NCCL(ncclAllGather(dsend, drecv, hb, ncclChar, (ncclComm_t)d->comm, d->stream));
+        std::vector<cudaIpcMemHandle_t> all(2 * P.nranks);
+        ECT_CUDA(cudaMemcpyAsync(all.data(), drecv, hb * P.nranks, cudaMemcpyDeviceToHost, d->stream));
+        ECT_CUDA(cudaStreamSynchronize(d->stream));
+        cudaFree(dsend); cudaFree(drecv);
+        for (int r = 0; r < P.nranks; ++r) {
+            if (r == P.rank) { pf[r] = d->fbuf_fft; pl[r] = d->fbuf_leg; continue; }
+            void *a = nullptr, *b = nullptr;
+            ECT_CUDA(cudaIpcOpenMemHandle(&a, all[2 * r], cudaIpcMemLazyEnablePeerAccess));
+            ECT_CUDA(cudaIpcOpenMemHandle(&b, all[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+            d->ipc_open.push_back(a); d->ipc_open.push_back(b);
+            pf[r] = (double*)a; pl[r] = (double*)b;
+        }
+    }
+    ECT_CUDA(cudaMemcpyAsync(d->peer_fft, pf.data(), P.nranks * sizeof(double*), cudaMemcpyHostToDevice, d->stream));
+    ECT_CUDA(cudaMemcpyAsync(d->peer_leg, pl.data(), P.nranks * sizeof(double*), cudaMemcpyHostToDevice, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    return ECT_SUCCESS;
+}
+
 static int ensure_work(EctHandle* h, const EctFieldCfg& f) {
     EctDevice* d = h->d;
     const EctHostPlan& P = h->hp;
     int rc;
     if ((rc = ensure(d->xwork, d->xwork_elems, (d->xrows + 2) * (i64)f.cp, d->stream, true))) return rc;
-    if ((rc = ensure(d->fbuf_leg, d->fbuf_leg_elems, (P.nrec_leg + 1) * (i64)f.cp, d->stream, true))) return rc;
-    if (P.nranks > 1) {
-        if ((rc = ensure(d->fbuf_fft, d->fbuf_fft_elems, (P.nrec_fft + 1) * (i64)f.cp, d->stream, true))) return rc;
-    } else {
-        d->fbuf_fft = d->fbuf_leg;
-        d->fbuf_fft_elems = d->fbuf_leg_elems;
+    // the Fourier buffers grow by record pitch only (same decision on every rank: the IPC exchange is collective)
+    if (f.cp > d->cp_alloc) {
+        if (d->p2p) { for (void* m : d->ipc_open) ECT_CUDA(cudaIpcCloseMemHandle(m)); d->ipc_open.clear(); }
+        if ((rc = ensure(d->fbuf_leg, d->fbuf_leg_elems, (P.nrec_leg + 1) * (i64)f.cp, d->stream, true))) return rc;
+        if (P.nranks > 1) {
+            if ((rc = ensure(d->fbuf_fft, d->fbuf_fft_elems, (P.nrec_fft + 1) * (i64)f.cp, d->stream, true))) return rc;
+        } else {
+            d->fbuf_fft = d->fbuf_leg;
+            d->fbuf_fft_elems = d->fbuf_leg_elems;
+        }
+        d->cp_alloc = f.cp;
+        if ((rc = publish_buffers(h))) return rc;
     }
     return ECT_SUCCESS;
 }
@@ -274,6 +354,12 @@ int ect_transpose(EctHandle* h, const EctFieldCfg& f, int to_fft) {
     EctDevice* d = h->d;
     if (P.nranks == 1) return ECT_SUCCESS;
     ncclComm_t comm = (ncclComm_t)d->comm;
+    if (d->p2p) {
+        // the producing kernels already wrote every record into its consumer's buffer over NVLink: all that is
+        // left of TRMTOL / TRLTOM is "everybody has finished writing"
+        ECT_NCCL(ncclAllReduce(d->barrier_buf, d->barrier_buf + 8, 1, ncclInt, ncclSum, comm, d->stream));
+        return ECT_SUCCESS;
+    }
     const i64 cp = f.cp;
     ECT_NCCL(ncclGroupStart());
     for (int p = 0; p < P.nranks; ++p) {

@@ -42,6 +42,9 @@ struct EctHostPlan {
     std::vector<i64> latrow0;                // local lat -> start in fft_rec (length nmen+1)
     std::vector<int> fft_rec;
     std::vector<i64> send_cnt, send_off, recv_cnt, recv_off;   // records, per peer (leg -> fft direction)
+    // fused transposition: destination rank and record index in the destination's buffer
+    std::vector<int> leg_dst_rank_n, leg_dst_rank_s, leg_dst_rec_n, leg_dst_rec_s;   // per (local m, northern lat i)
+    std::vector<int> fft_dst_rank, fft_dst_rec;                                      // per (local lat, m)
     i64 nrec_leg = 0, nrec_fft = 0;
     std::string err;
 };
@@ -120,8 +123,16 @@ struct EctDevice {
     void* ring_d[kSlots] = {}; void* ring_h[kSlots] = {}; size_t ring_bytes[kSlots] = {};
     cudaEvent_t ring_ev[kSlots] = {}; bool ring_used[kSlots] = {}; int ring_next = 0; int ring_cur = 0;
     double* normbuf = nullptr; int normbuf_n = 0;
-    // NCCL
+    // NCCL + fused (peer-memory) transposition
     void* comm = nullptr;
+    bool p2p = false;                     // kernels write records straight into the consumer rank's buffer
+    int *leg_dst_rank_n = nullptr, *leg_dst_rank_s = nullptr, *leg_dst_rec_n = nullptr, *leg_dst_rec_s = nullptr;
+    int *fft_dst_rank = nullptr, *fft_dst_rec = nullptr;
+    double** peer_fft = nullptr;          // device array [nranks]: Fourier-side buffer of every rank
+    double** peer_leg = nullptr;          // device array [nranks]: Legendre-side buffer of every rank
+    std::vector<void*> ipc_open;          // mappings to close on reallocation / release
+    int cp_alloc = 0;                     // record pitch the Fourier buffers were sized for
+    int* barrier_buf = nullptr;
     // timing
     cudaEvent_t ev[16] = {};
     int last_dir = 0; bool timed = false;

@@ -30,6 +30,8 @@ struct FtArgs {
     const EctFsField* fsf;        // inverse only
     const int2* pairs;            // (field a, field b or -1): only fields of one group share a transform
     int nproma; int ngptot;
+    // direct store destinations: rank owning m + record in its Legendre-side buffer (TRLTOM fused)
+    double* const* peer; const int* dst_rank; const int* dst_rec;
     int fp32;                     // grid-point arrays are float
     int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum
 };
@@ -274,13 +276,15 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
             // 1/N + FOURIER_OUT (same arithmetic as fourier_phases.h ftdir_store)
             const double sc = 0.5 / (double)N;
             const int ca = 2 * fa, cb = hasb ? 2 * fb2 : -1;
+            const int* drank = a.dst_rank + a.latrow0[l];
+            const int* drec = a.dst_rec + a.latrow0[l];
             for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
-                double2 zk[NB], zn[NB], ch[NB]; long long rb[NB];
+                double2 zk[NB], zn[NB], ch[NB]; double* rb[NB];
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int k = k0 + i * nthr;
                     if (k <= km) {
-                        rb[i] = (long long)c.rec[k] * c.cp;
+                        rb[i] = a.peer[drank[k]] + (long long)drec[k] * c.cp;
                         if (!c.bluestein) { zk[i] = data[ECT_PAD(k)]; zn[i] = data[ECT_PAD(k == 0 ? 0 : N - k)]; }
                         else { zk[i] = data[ECT_PAD(km + k)]; zn[i] = data[ECT_PAD(km - k)]; ch[i] = c.chirp[k]; }
                     }
@@ -293,8 +297,8 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
                     if (c.bluestein) { a_ = c_mul(ch[i], a_); b_ = c_mul(ch[i], b_); }
                     // stored values are swapped (sign - transform on the sign + core): Z = (y, x)
                     const double2 Zk = make_double2(a_.y, a_.x), Zn = make_double2(b_.y, b_.x);
-                    *reinterpret_cast<double2*>(a.fb + rb[i] + ca) = make_double2((Zk.x + Zn.x) * sc, (Zk.y - Zn.y) * sc);
-                    if (cb >= 0) *reinterpret_cast<double2*>(a.fb + rb[i] + cb) = make_double2((Zk.y + Zn.y) * sc, (Zn.x - Zk.x) * sc);
+                    *reinterpret_cast<double2*>(rb[i] + ca) = make_double2((Zk.x + Zn.x) * sc, (Zk.y - Zn.y) * sc);
+                    if (cb >= 0) *reinterpret_cast<double2*>(rb[i] + cb) = make_double2((Zk.y + Zn.y) * sc, (Zn.x - Zk.x) * sc);
                 }
             }
         }
@@ -310,6 +314,7 @@ static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     a.lat_plan = d->lat_plan; a.latrow0 = d->latrow0; a.fft_rec = d->fft_rec;
     a.gpoff = d->gpoff; a.nloen_loc = d->nloen; a.racthe_loc = d->racthe_loc;
     a.fb = d->fbuf_fft; a.cp = f.cp;
+    a.peer = d->peer_leg; a.dst_rank = d->fft_dst_rank; a.dst_rec = d->fft_dst_rec;
     a.nfs = f.nfs; a.npairs = f.npairs;
     a.nchunks = (a.npairs + FT_PAIRS_PER_CTA - 1) / FT_PAIRS_PER_CTA;
     a.ngptot = h->hp.ngptot;

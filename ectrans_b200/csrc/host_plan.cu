@@ -261,6 +261,52 @@ int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, i
         P.recv_cnt[s] = rec - P.recv_off[s];
     }
     P.nrec_fft = rec;
+    // Destination tables for the fused (peer-memory) transpositions: where a record produced on this rank
+    // lives in the buffer of the rank that consumes it.
+    //   inverse: (local m, lat) -> rank owning lat, index in ITS Fourier-side buffer  [src][lat][m of src]
+    //   direct : (local lat, m) -> rank owning m,   index in ITS Legendre-side buffer [dest][lat of dest][local m]
+    std::vector<int> rank_of_lat(ndgl, 0);
+    for (int b = 0; b < nranks; ++b)
+        for (int g = P.lat_first[b]; g < P.lat_first[b] + P.lat_count[b]; ++g) rank_of_lat[g] = b;
+    P.leg_dst_rank_n.assign(P.leg_rec_n.size(), 0); P.leg_dst_rank_s.assign(P.leg_rec_n.size(), 0);
+    P.leg_dst_rec_n.assign(P.leg_rec_n.size(), -1); P.leg_dst_rec_s.assign(P.leg_rec_n.size(), -1);
+    {
+        // position of m inside ms_of[rank] restricted to m <= nmen[g] is not closed-form: walk every rank's buffer
+        std::vector<int> mloc(nsmax + 1, -1);
+        for (int ml = 0; ml < P.nump; ++ml) mloc[P.myms[ml]] = ml;
+        for (int b = 0; b < nranks; ++b) {
+            i64 r = 0;
+            for (int sr = 0; sr < nranks; ++sr)
+                for (int g = P.lat_first[b]; g < P.lat_first[b] + P.lat_count[b]; ++g)
+                    for (int m : P.ms_of[sr]) {
+                        if (m > P.nmen[g]) continue;
+                        if (sr == rank) {
+                            const int ml = mloc[m];
+                            const int gn = g < P.ndgnh ? g : ndgl - 1 - g;
+                            const size_t at = (size_t)(P.mrow0[ml] + gn - (P.ndgnh - P.ndglu[m]));
+                            if (g < P.ndgnh) { P.leg_dst_rank_n[at] = b; P.leg_dst_rec_n[at] = (int)r; }
+                            else { P.leg_dst_rank_s[at] = b; P.leg_dst_rec_s[at] = (int)r; }
+                        }
+                        ++r;
+                    }
+        }
+    }
+    P.fft_dst_rank.assign(P.fft_rec.size(), 0);
+    P.fft_dst_rec.assign(P.fft_rec.size(), -1);
+    for (int r = 0; r < nranks; ++r) {          // rank r's Legendre-side buffer
+        i64 q = 0;
+        for (int d = 0; d < nranks; ++d)
+            for (int g = P.lat_first[d]; g < P.lat_first[d] + P.lat_count[d]; ++g)
+                for (int m : P.ms_of[r]) {
+                    if (m > P.nmen[g]) continue;
+                    if (d == rank) {
+                        const size_t at = (size_t)(P.latrow0[g - P.lat0] + m);
+                        P.fft_dst_rank[at] = r;
+                        P.fft_dst_rec[at] = (int)q;
+                    }
+                    ++q;
+                }
+    }
     if (P.nrec_leg >= (1LL << 31) || P.nrec_fft >= (1LL << 31)) {
         ect_set_error("ect_setup: record count overflows int32");
         return ECT_ERR_NOTIMPL;

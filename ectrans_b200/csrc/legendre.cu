@@ -276,6 +276,8 @@ struct LegArgs {
     int cp;
     int c_uv_end;                 // direct: columns < c_uv_end are u,v (scaled by 1/(a cos))
     int dbg;                      // ECT_LEG_DBG timing experiments: 1 skip B preparation, 2 contiguous (wrong) A loads
+    // inverse epilogue destinations: rank + record in that rank's Fourier-side buffer (self when one rank / NCCL mode)
+    double* const* peer; const int* dst_rank_n; const int* dst_rank_s; const int* dst_rec_n; const int* dst_rec_s;
 };
 
 __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
@@ -360,15 +362,16 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
     for (int i = 0; i < 4; ++i) {
         const int li = i0 + wm * 32 + i * 8 + g;
         if (li >= lm.ndglu) continue;
-        const long long rn = (long long)a.rec_n[lm.rec0 + li] * a.cp;
-        const long long rs = (long long)a.rec_s[lm.rec0 + li] * a.cp;
+        // TRMTOL fused: the record goes straight into the buffer of the rank that owns the latitude
+        double* pn = a.peer[a.dst_rank_n[lm.rec0 + li]] + (long long)a.dst_rec_n[lm.rec0 + li] * a.cp;
+        double* psth = a.peer[a.dst_rank_s[lm.rec0 + li]] + (long long)a.dst_rec_s[lm.rec0 + li] * a.cp;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + wn * 32 + j * 8 + 2 * t;
             if (c >= a.cp) continue;
-            *reinterpret_cast<double2*>(a.fb + rn + c) =
+            *reinterpret_cast<double2*>(pn + c) =
                 make_double2(acs[i][j][0] + aca[i][j][0], acs[i][j][1] + aca[i][j][1]);
-            *reinterpret_cast<double2*>(a.fb + rs + c) =
+            *reinterpret_cast<double2*>(psth + c) =
                 make_double2(acs[i][j][0] - aca[i][j][0], acs[i][j][1] - aca[i][j][1]);
         }
     }
@@ -522,6 +525,8 @@ void ect_launch_leinv(EctHandle* h, const EctFieldCfg& f) {
     a.ptab = d->ptab; a.x = d->xwork; a.fb = d->fbuf_leg;
     a.rec_n = d->leg_rec_n; a.rec_s = d->leg_rec_s; a.rw = d->rw; a.racthe = d->racthe;
     a.cp = f.cp; a.c_uv_end = 0; a.dbg = 0;
+    a.peer = d->peer_fft; a.dst_rank_n = d->leg_dst_rank_n; a.dst_rank_s = d->leg_dst_rank_s;
+    a.dst_rec_n = d->leg_dst_rec_n; a.dst_rec_s = d->leg_dst_rec_s;
     const size_t smem = LEG_STAGES * INV_STAGE_DOUBLES * sizeof(double);
     k_leinv<<<(unsigned)((long long)d->n_inv_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
     d->launches++;
@@ -538,6 +543,7 @@ void ect_launch_ledir(EctHandle* h, const EctFieldCfg& f) {
     a.cp = f.cp; a.c_uv_end = 4 * f.kf_uv;
     static const char* dbg = getenv("ECT_LEG_DBG");
     a.dbg = dbg ? atoi(dbg) : 0;
+    a.peer = nullptr; a.dst_rank_n = a.dst_rank_s = a.dst_rec_n = a.dst_rec_s = nullptr;
     const size_t smem = LEG_STAGES * DIR_STAGE_DOUBLES * sizeof(double);
     k_ledir<<<(unsigned)((long long)d->n_dir_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
     d->launches++;

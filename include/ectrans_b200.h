@@ -108,6 +108,13 @@ typedef struct ect_info {
 #define ECT_ARR_FFTREC  18  /* int[latrow0[nlat]] record of (local latitude, m), -1 if m > NMEN */
 #define ECT_ARR_SENDOFF 19  /* long long[nranks]                                              */
 #define ECT_ARR_RECVOFF 20  /* long long[nranks]                                              */
+/* fused (peer-memory) transposition: destination rank / record of what this rank produces */
+#define ECT_ARR_LEGDSTRANKN 21 /* int[mrow0[nump]]   rank owning the northern latitude                 */
+#define ECT_ARR_LEGDSTRECN  22 /* int[mrow0[nump]]   record in that rank's Fourier-side buffer          */
+#define ECT_ARR_LEGDSTRANKS 23
+#define ECT_ARR_LEGDSTRECS  24
+#define ECT_ARR_FFTDSTRANK  25 /* int[latrow0[nlat]] rank owning m                                      */
+#define ECT_ARR_FFTDSTREC   26 /* int[latrow0[nlat]] record in that rank's Legendre-side buffer         */
 
 typedef struct ect_inv_args {
     int memspace;                 /* ECT_MEM_HOST / ECT_MEM_DEVICE                          */

@@ -84,6 +84,32 @@ def test_decomposition(eb, P):
         assert sorted(recs.tolist()) == list(range(n))
         f = rt["fft_rec"]
         assert sorted(f[f >= 0].tolist()) == list(range(int(t.recv_cnt.sum())))
+    # fused transposition: what rank a says about the destination of its records is what the destination expects
+    tabs = [t.record_tables() for t in trs]
+    ndgnh = trs[0].ndgl // 2
+    for a, t in enumerate(trs):
+        rt = tabs[a]
+        for ml, m in enumerate(t.myms):
+            nd = int(t.ndglu[m]); isl = ndgnh - nd
+            for i in range(0, nd, 7):
+                at = rt["mrow0"][ml] + i
+                for g, rk, rc in ((isl + i, rt["leg_dst_rank_n"][at], rt["leg_dst_rec_n"][at]),
+                                  (t.ndgl - 1 - (isl + i), rt["leg_dst_rank_s"][at], rt["leg_dst_rec_s"][at])):
+                    b = trs[rk]
+                    l = g - int(b.info.lat0)
+                    assert 0 <= l < int(b.info.nlat)
+                    assert tabs[rk]["fft_rec"][tabs[rk]["latrow0"][l] + m] == rc
+        for l in range(0, int(t.info.nlat), 5):
+            g = int(t.info.lat0) + l
+            for m in range(0, int(t.nmen[g]) + 1, 3):
+                at = rt["latrow0"][l] + m
+                rk, rc = rt["fft_dst_rank"][at], rt["fft_dst_rec"][at]
+                assert rk == t.nprocm[m]
+                ml = list(trs[rk].myms).index(m)
+                gn = g if g < ndgnh else t.ndgl - 1 - g
+                i = gn - (ndgnh - int(t.ndglu[m]))
+                key = "leg_rec_n" if g < ndgnh else "leg_rec_s"
+                assert tabs[rk][key][tabs[rk]["mrow0"][ml] + i] == rc
     for t in trs:
         t.release()
 
