@@ -145,6 +145,8 @@ void ect_device_free(EctHandle* h) {
     if (d->fbuf_fft && d->fbuf_fft != d->fbuf_leg) cudaFree(d->fbuf_fft);
     for (auto& b : d->buckets) if (b.d_lats) cudaFree(b.d_lats);
     for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    for (int k = 0; k < EctDevice::kSide; ++k) { if (d->ev_join[k]) cudaEventDestroy(d->ev_join[k]); if (d->side[k]) cudaStreamDestroy(d->side[k]); }
     if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
     delete d;
     h->d = nullptr;

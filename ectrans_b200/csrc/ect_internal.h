@@ -133,6 +133,10 @@ struct EctDevice {
     std::vector<void*> ipc_open;          // mappings to close on reallocation / release
     int cp_alloc = 0;                     // record pitch the Fourier buffers were sized for
     int* barrier_buf = nullptr;
+    // side streams: the shared-memory classes of the Fourier stage run concurrently so that small classes fill the
+    // tails of large ones
+    static const int kSide = 3;
+    cudaStream_t side[kSide] = {}; cudaEvent_t ev_fork = nullptr; cudaEvent_t ev_join[kSide] = {};
     // timing
     cudaEvent_t ev[16] = {};
     int last_dir = 0; bool timed = false;

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 
 int g_ect_force_bluestein = 0;   // test knob: route every length through the chirp-z path
 static const int kPrimes[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31};
@@ -19,9 +20,11 @@ bool ect_fft_factorize(int n, std::vector<int>& radices, bool pow2_inner) {
     }
     if (rem != 1) return false;
     std::sort(odd.begin(), odd.end(), [](int a, int b) { return a > b; });
-    std::vector<int> p2;                      // power-of-two part as 16s plus one smaller radix
-    for (int i = 0; i < twos / 4; ++i) p2.push_back(16);
-    if (twos % 4) p2.push_back(1 << (twos % 4));
+    std::vector<int> p2;                      // power-of-two part as 16s (or 8s) plus one smaller radix
+    static const char* r8 = getenv("ECT_FFT_R8");
+    const int lg = (pow2_inner && r8 && atoi(r8)) ? 3 : 4;
+    for (int i = 0; i < twos / lg; ++i) p2.push_back(1 << lg);
+    if (twos % lg) p2.push_back(1 << (twos % lg));
     if (pow2_inner) {
         // chirp-z lengths r * 2^k: 16s innermost (fused middle step), small power of two next, odd r outermost
         radices = p2;
@@ -121,7 +124,7 @@ int EctFftTables::get_latplan(int nlon, int km) {
         lp.plan = direct;
         lp.bluestein = 0;
         lp.m = 0;
-        lp.chirp_off = lp.bhat_inv_off = lp.bhat_dir_off = -1;
+        lp.chirp_off = lp.bhat_inv_off = lp.bhat_dir_off = lp.ctw_off = -1;
         lp.smem_bytes = ECT_PADDED_LEN(nlon) * (int)sizeof(double2);
     } else {
         const int N = nlon;
@@ -137,6 +140,9 @@ int EctFftTables::get_latplan(int nlon, int km) {
             long long jj = ((long long)j * j) % (2LL * N);
             cz_pool.push_back(expi2pi(jj, 2LL * N));
         }
+        lp.ctw_off = (int)cz_pool.size();
+        for (int a = 0; a < ECT_TW1_LEN(2 * N); ++a) cz_pool.push_back(expi2pi((128LL * a) % (2LL * N), 2LL * N));
+        for (int b = 0; b < ECT_TW2_LEN; ++b) cz_pool.push_back(expi2pi(b % (2LL * N), 2LL * N));
         auto chirp = [&](long long d) -> double2 {   // c[d] for any integer d (even N: period N, even symmetry)
             long long j = std::llabs(d) % N;
             if (j > N / 2) j = N - j;

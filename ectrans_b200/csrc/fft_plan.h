@@ -13,6 +13,7 @@ struct EctLatPlan {        // one per distinct (nlon, nmen)
     int bluestein;         // 0 / 1
     int m;                 // Bluestein convolution length (0 if direct)
     int chirp_off;         // double2 pool: c[j] = exp(+i pi j^2 / nlon), j = 0 .. nlon/2
+    int ctw_off;           // double2 pool: two-level table of exp(2 pi i t / (2 nlon)): [ECT_TW1_LEN(2 nlon)] then [128]
     int bhat_inv_off;      // double2 pool: permuted spectrum of the inverse-direction kernel (includes 1/M)
     int bhat_dir_off;      // same for the direct direction
     int smem_bytes;        // dynamic shared memory for one field pair + twiddle table

@@ -16,7 +16,7 @@
 
 // phase timing probe (debug): cycles of block 0 at phase boundaries of its first pair
 __device__ long long g_ft_probe[64];
-#define FT_PROBE(i) do { if (blockIdx.x == 0 && tid == 0 && p == p0) g_ft_probe[i] = clock64(); } while (0)
+#define FT_PROBE(i) do { if (blockIdx.x == 0 && tid == 0 && p == p0 + ((a.dbg >> 8) & 15)) g_ft_probe[i] = clock64(); } while (0)
 
 struct FtArgs {
     const EctLatPlan* latplans; const EctFftPlan* plans;
@@ -62,8 +62,8 @@ __device__ __forceinline__ void ft_cp_wait_all() { asm volatile("cp.async.wait_a
 //                                        inverse: (km+1) x {field a, field b} double2 ; direct: 2 x nlon doubles
 //   t1, t2                               two-level twiddle table
 //   roots                                odd-radix root tables
-template <bool INVERSE, int MAXR>
-__global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
+template <bool INVERSE, int MAXR, int TB, bool FP32>
+__global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
     extern __shared__ __align__(16) double2 sm[];
     __shared__ EctFftPlan s_plan;        // stage list indexed at run time: keep it out of local memory
     constexpr int NROOTS = MAXR <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE;
@@ -86,13 +86,22 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
     const int N = c.nlon, km = c.km;
     double2* data = sm;
     double2* stage = data + ECT_PADDED_LEN(len);
-    const int nstage = INVERSE ? 2 * (km + 1) : N;         // double2 elements
+    // inverse chirp-z rows keep the chirp c[0 .. N/2] in shared memory behind the staged records (both fit in
+    // the space the direct transform needs for its two staged rows whenever 2 (km+1) + N/2 + 1 <= N)
+    const bool chirp_sm = INVERSE && lp.bluestein;
+    const int nstage = INVERSE ? 2 * (km + 1) + (chirp_sm ? N / 2 + 1 : 0) : N;         // double2 elements
+    double2* s_chirp = stage + 2 * (km + 1);
     double2* t1 = stage + nstage;
     double2* t2 = t1 + ECT_TW1_LEN(len);
     double2* s_roots = t2 + ECT_TW2_LEN;
+    int* s_rec = reinterpret_cast<int*>(s_roots + NROOTS);   // per m: inverse local record, direct (dest rank << 24 | dest record)
     const int tid = threadIdx.x, nthr = blockDim.x;
     tw_build(t1, t2, a.tw_pool + s_plan.tw_off, len, tid, nthr);
     for (int j = tid; j < NROOTS; j += nthr) s_roots[j] = a.roots[j];
+    if (chirp_sm) for (int j = tid; j <= N / 2; j += nthr) s_chirp[j] = c.chirp[j];
+    for (int k = tid; k <= km; k += nthr)
+        s_rec[k] = INVERSE ? c.rec[k] : ((a.dst_rank[a.latrow0[l] + k] << 24) | a.dst_rec[a.latrow0[l] + k]);
+    const double2* chirp_tab = chirp_sm ? s_chirp : c.chirp;
     const EctTw qt{t1, t2};
     c.qt = qt; c.roots = s_roots;
     const int g0 = a.gpoff[l];
@@ -108,14 +117,11 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
             const int ca = a.fsf[fa].src_c;
             const int cb = fb2 >= 0 ? a.fsf[fb2].src_c : -1;
             for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
-                int rk[NB];
-#pragma unroll
-                for (int i = 0; i < NB; ++i) { const int k = k0 + i * nthr; rk[i] = k <= km ? c.rec[k] : 0; }
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int k = k0 + i * nthr;
                     if (k > km) continue;
-                    const double* src = a.fb + (long long)rk[i] * c.cp;
+                    const double* src = a.fb + (long long)s_rec[k] * c.cp;
                     ft_cp_async16(stage + 2 * k, src + ca);
                     if (cb >= 0) ft_cp_async16(stage + 2 * k + 1, src + cb);
                 }
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
         } else {
             const double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
             const double* bb = fb2 >= 0 ? a.gp_base[fb2] : nullptr; const i64 sb = fb2 >= 0 ? a.gp_blk[fb2] : 0;
-            if (a.fp32) {
+            if (FP32) {
                 float* st = reinterpret_cast<float*>(stage);
                 const float* fa_ = reinterpret_cast<const float*>(ba); const float* fb_ = reinterpret_cast<const float*>(bb);
                 for (int j = tid; j < N; j += nthr) {
@@ -143,6 +149,7 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
         ft_cp_commit();
     };
 
+    __syncthreads();                    // s_rec visible
     if (p0 < p1) prefetch(p0);
     for (int p = p0; p < p1; ++p) {
         const int2 pr = a.pairs[p];
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
                     const int k = k0 + i * nthr;
                     ch[i] = make_double2(1.0, 0.0); pk[i] = pn[i] = 0;
                     if (k <= km) {
-                        if (c.bluestein) ch[i] = c.chirp[k];
+                        if (c.bluestein) ch[i] = chirp_tab[k];
                         else { pk[i] = c.perm[k]; pn[i] = c.perm[k == 0 ? 0 : N - k]; }
                     }
                 }
@@ -196,8 +203,9 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
         } else {
             const double* st = reinterpret_cast<const double*>(stage);
             const float* stf = reinterpret_cast<const float*>(stage);
-            for (int j0 = tid; j0 < N; j0 += NB * nthr) {
-                double2 ch[NB]; int pj[NB];
+            // chirp factors come from global memory (no shared memory left next to two staged rows): the loads of
+            // batch i+1 are in flight while batch i is scattered
+            auto ld_batch = [&](int j0, double2* ch, int* pj) {
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int j = j0 + i * nthr;
@@ -207,15 +215,25 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
                         else pj[i] = c.perm[j];
                     }
                 }
+            };
+            auto put_batch = [&](int j0, const double2* ch, const int* pj) {
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int j = j0 + i * nthr;
                     if (j >= N) continue;
-                    const double va = a.fp32 ? (double)stf[j] : st[j];
-                    const double vb = hasb ? (a.fp32 ? (double)stf[N + j] : st[N + j]) : 0.0;
+                    const double va = FP32 ? (double)stf[j] : st[j];
+                    const double vb = hasb ? (FP32 ? (double)stf[N + j] : st[N + j]) : 0.0;
                     if (!c.bluestein) data[ECT_PAD(pj[i])] = make_double2(vb, va);
                     else { const double2 t = c_mul(make_double2(vb, va), ch[i]); data[ECT_PAD(j)] = make_double2(t.y, t.x); }
                 }
+            };
+            double2 chA[NB], chB[NB]; int pjA[NB], pjB[NB];
+            ld_batch(tid, chA, pjA);
+            for (int j0 = tid; j0 < N; j0 += 2 * NB * nthr) {
+                ld_batch(j0 + NB * nthr, chB, pjB);
+                put_batch(j0, chA, pjA);
+                ld_batch(j0 + 2 * NB * nthr, chA, pjA);
+                put_batch(j0 + NB * nthr, chB, pjB);
             }
             ftdir_zero_tail(data, c, tid, nthr);
         }
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
                 __syncthreads();
                 FT_PROBE(2 + (plan_nst - 1 - s));
             }
-            blue_middle(data, len, s_plan.radix[0], c.bhat, tid, nthr);
+            blue_middle(data, len, s_plan.radix[0], (a.dbg & 4) ? a.cz_pool : c.bhat, tid, nthr);
             __syncthreads();
             FT_PROBE(10);
             for (int s = 1; s < plan_nst; ++s) {
@@ -253,7 +271,7 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
                     const int j = j0 + i * nthr;
                     if (j < N) {
                         x[i] = data[ECT_PAD(j)];
-                        if (c.bluestein) ch[i] = (a.dbg & 1) ? make_double2(1.0, 0.0) : c.chirp[j > N / 2 ? N - j : j];
+                        if (c.bluestein) ch[i] = chirp_tab[j > N / 2 ? N - j : j];
                     }
                 }
 #pragma unroll
@@ -263,7 +281,7 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
                     const double2 y = c.bluestein ? c_mul(ch[i], x[i]) : x[i];
                     if ((a.dbg & 2) && y.x != 12345.678) continue;
                     const int g = g0 + j;
-                    if (a.fp32) {
+                    if (FP32) {
                         reinterpret_cast<float*>(ba)[oneblk ? (i64)g : gp_index(g, a.nproma, sa)] = (float)y.x;
                         if (hasb) reinterpret_cast<float*>(bb)[oneblk ? (i64)g : gp_index(g, a.nproma, sb)] = (float)y.y;
                     } else {
@@ -276,15 +294,14 @@ __global__ void __launch_bounds__(256) k_fourier(FtArgs a) {
             // 1/N + FOURIER_OUT (same arithmetic as fourier_phases.h ftdir_store)
             const double sc = 0.5 / (double)N;
             const int ca = 2 * fa, cb = hasb ? 2 * fb2 : -1;
-            const int* drank = a.dst_rank + a.latrow0[l];
-            const int* drec = a.dst_rec + a.latrow0[l];
             for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
                 double2 zk[NB], zn[NB], ch[NB]; double* rb[NB];
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int k = k0 + i * nthr;
                     if (k <= km) {
-                        rb[i] = a.peer[drank[k]] + (long long)drec[k] * c.cp;
+                        const int pk_ = s_rec[k];
+                        rb[i] = a.peer[pk_ >> 24] + (long long)(pk_ & 0xffffff) * c.cp;
                         if (!c.bluestein) { zk[i] = data[ECT_PAD(k)]; zn[i] = data[ECT_PAD(k == 0 ? 0 : N - k)]; }
                         else { zk[i] = data[ECT_PAD(km + k)]; zn[i] = data[ECT_PAD(km - k)]; ch[i] = c.chirp[k]; }
                     }
@@ -327,17 +344,42 @@ template <bool INVERSE>
 static void launch_fourier(EctHandle* h, FtArgs& a) {
     EctDevice* d = h->d;
     static const char* only = getenv("ECT_FFT_ONLY_BUCKET");     // debug: run a single shared-memory class
-    int bi = -1;
-    for (auto& b : d->buckets) {
-        ++bi;
+    static const char* serial = getenv("ECT_FFT_SERIAL");        // debug: one stream
+    static const char* conc = getenv("ECT_FFT_CONCURRENT");   // side streams did not pay off in measurements: off by default
+    const bool fork = conc && atoi(conc) && !(serial && atoi(serial)) && d->ev_fork != nullptr;
+    if (fork) {
+        cudaEventRecord(d->ev_fork, d->stream);
+        for (int k = 0; k < EctDevice::kSide; ++k) cudaStreamWaitEvent(d->side[k], d->ev_fork, 0);
+    }
+    // largest classes first, round-robin over main + side streams
+    std::vector<int> order;
+    for (int i = (int)d->buckets.size() - 1; i >= 0; --i) order.push_back(i);
+    static const char* oldorder = getenv("ECT_FFT_OLDORDER");
+    if (oldorder && atoi(oldorder)) std::reverse(order.begin(), order.end());
+    else std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return d->buckets[x].smem > d->buckets[y].smem; });
+    int slot = 0;
+    for (int bi : order) {
+        auto& b = d->buckets[bi];
         if (b.lats.empty()) continue;
         if (only && atoi(only) != bi) continue;
         a.lats = b.d_lats;
         const unsigned grid = (unsigned)(b.lats.size() * (size_t)a.nchunks);
-        if (b.maxr <= 7) k_fourier<INVERSE, 7><<<grid, b.threads, b.smem, d->stream>>>(a);
-        else k_fourier<INVERSE, ECT_MAX_RADIX><<<grid, b.threads, b.smem, d->stream>>>(a);
+        cudaStream_t st = d->stream;
+        if (fork) { const int k = slot % (EctDevice::kSide + 1); st = k == 0 ? d->stream : d->side[k - 1]; }
+        ++slot;
+        if (a.fp32) {
+            if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, true><<<grid, std::min(b.threads, 256), b.smem, st>>>(a);
+            else k_fourier<INVERSE, ECT_MAX_RADIX, 256, true><<<grid, b.threads, b.smem, st>>>(a);
+        } else if (b.maxr <= 7 && b.threads == 512) k_fourier<INVERSE, 7, 512, false><<<grid, b.threads, b.smem, st>>>(a);
+        else if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, false><<<grid, b.threads, b.smem, st>>>(a);
+        else k_fourier<INVERSE, ECT_MAX_RADIX, 256, false><<<grid, b.threads, b.smem, st>>>(a);
         d->launches++;
     }
+    if (fork)
+        for (int k = 0; k < EctDevice::kSide; ++k) {
+            cudaEventRecord(d->ev_join[k], d->side[k]);
+            cudaStreamWaitEvent(d->stream, d->ev_join[k], 0);
+        }
 }
 
 void ect_launch_ftinv(EctHandle* h, const EctFieldCfg& f, double* const* d_gp_base, const i64* d_gp_blkstride,
@@ -407,6 +449,8 @@ int ect_fourier_setup(EctHandle* h) {
             EctDevice::Bucket b;
             b.smem = limits[i];
             b.threads = v ? std::min(threads[i], 256) : threads[i];
+            static const char* t512 = getenv("ECT_FFT_T512");
+            if (!v && i >= 4 && t512 && atoi(t512)) b.threads = 512;
             b.maxr = v ? ECT_MAX_RADIX : 7;
             d->buckets.push_back(b);
         }
@@ -415,11 +459,12 @@ int ect_fourier_setup(EctHandle* h) {
         const EctLatPlan& lp = d->fft.latplans[d->h_lat_plan[l]];
         const EctFftPlan& pl = d->fft.plans[lp.plan];
         const int len_ = pl.n;
-        int need = (ECT_PADDED_LEN(len_) + std::max(2 * (lp.km + 1), lp.nlon) + ECT_TW1_LEN(len_) + ECT_TW2_LEN) * (int)sizeof(double2);
+        int need = (ECT_PADDED_LEN(len_) + std::max(2 * (lp.km + 1) + (lp.bluestein ? lp.nlon / 2 + 1 : 0), lp.nlon) + ECT_TW1_LEN(len_) + ECT_TW2_LEN) * (int)sizeof(double2);
 
         int maxr = 2;
         for (int s = 0; s < pl.nst; ++s) if (pl.radix[s] & 1) maxr = std::max(maxr, pl.radix[s]);   // 2,4,8,16 are in every variant
         need += (maxr <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE) * (int)sizeof(double2);
+        need += ((lp.km + 1) * (int)sizeof(int) + 15) / 16 * 16;
         need_of[l] = need;
         bool placed = false;
         for (auto& b : d->buckets)
@@ -437,10 +482,18 @@ int ect_fourier_setup(EctHandle* h) {
         b.smem = need_of[b.lats[0]];
         if ((rc = upload(b.d_lats, b.lats))) return rc;
     }
-    ECT_CUDA(cudaFuncSetAttribute(k_fourier<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024));
-    ECT_CUDA(cudaFuncSetAttribute(k_fourier<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024));
-    ECT_CUDA(cudaFuncSetAttribute(k_fourier<true, ECT_MAX_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024));
-    ECT_CUDA(cudaFuncSetAttribute(k_fourier<false, ECT_MAX_RADIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024));
+    ECT_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < EctDevice::kSide; ++k) {
+        ECT_CUDA(cudaStreamCreateWithFlags(&d->side[k], cudaStreamNonBlocking));
+        ECT_CUDA(cudaEventCreateWithFlags(&d->ev_join[k], cudaEventDisableTiming));
+    }
+#define FT_ATTR(...) ECT_CUDA(cudaFuncSetAttribute(k_fourier<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024))
+    FT_ATTR(true, 7, 512, false); FT_ATTR(false, 7, 512, false);
+    FT_ATTR(true, 7, 256, false); FT_ATTR(false, 7, 256, false);
+    FT_ATTR(true, ECT_MAX_RADIX, 256, false); FT_ATTR(false, ECT_MAX_RADIX, 256, false);
+    FT_ATTR(true, 7, 256, true); FT_ATTR(false, 7, 256, true);
+    FT_ATTR(true, ECT_MAX_RADIX, 256, true); FT_ATTR(false, ECT_MAX_RADIX, 256, true);
+#undef FT_ATTR
     return ECT_SUCCESS;
 }
 

@@ -307,8 +307,8 @@ int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, i
                     ++q;
                 }
     }
-    if (P.nrec_leg >= (1LL << 31) || P.nrec_fft >= (1LL << 31)) {
-        ect_set_error("ect_setup: record count overflows int32");
+    if (P.nrec_leg >= (1LL << 24) || P.nrec_fft >= (1LL << 24) || nranks > 127) {
+        ect_set_error("ect_setup: record count overflows the packed (rank, record) table (2^24 records per rank)");
         return ECT_ERR_NOTIMPL;
     }
     return ECT_SUCCESS;
