@@ -304,6 +304,15 @@ def run_ours(args):
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         hbm_peak = 6650.0
+    traffic = None
+    try:   # DRAM bytes of one k_leinv launch from the committed ncu --set full capture of this workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if tj.get("workload") == args.config and world == 1:
+            traffic = {"k_leinv_dram_bytes_per_launch": tj["dram_bytes_per_launch"],
+                       "algorithmic_bytes_per_launch": int(tr.info.table_bytes + 8 * (nf * 2) * (sum(T - m + 2 for m in range(T + 1)) + 2 * sum(int(x) for x in tr.ndglu))),
+                       "source": tj["source"]}
+    except Exception:
+        traffic = None
     fb = 2.0 * fft_bytes(tr.nloen, nf)
     ft_ach = fb / world / (ft_ms * 1e-3) / 1e9
     line = {
@@ -315,7 +324,7 @@ def run_ours(args):
         "stages_ms": {"legendre": leg_ms, "fourier": ft_ms, "transpose": tp_ms,
                       "prologue": med("inv", "prologue"), "epilogue": med("dir", "epilogue")},
         "roofline": {"bound": "tensor", "kernel": "k_leinv+k_ledir (FP64 DMMA m8n8k4)", "achieved": ach,
-                     "peak": peak_dmma, "unit": "TFLOP/s", "frac": ach / peak_dmma, "traffic": None,
+                     "peak": peak_dmma, "unit": "TFLOP/s", "frac": ach / peak_dmma, "traffic": traffic,
                      "peak_source": "ect_measure_fp64_peak(DMMA) measured live in this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "dfma_peak": peak_dfma},
         "roofline_fourier": {"bound": "hbm", "kernel": "k_fourier<inv>+k_fourier<dir>", "achieved": ft_ach,
