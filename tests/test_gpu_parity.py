@@ -340,3 +340,37 @@ def test_single_precision_face(eb, T, N, nuv, nsc, opts):
         assert a.dtype == np.float32 and rel(a.T.astype(np.float64), b) < 1e-6
     assert rel(tr.specnorm(T_(sc).astype(np.float32)), eo.specnorm(s, sc)) < 1e-6
     tr.release()
+
+
+def test_full_size_grid_properties(eb):
+    """BASELINE headline grid (TCo1279 / O1280, every row length 20..5136 incl. all chirp-z classes) with a
+    reduced field count: linearity, round trip, norm preservation, and the benchmark's single-harmonic
+    input against its analytic answer 2 P_19^4(mu) cos(4 lambda) (ectrans-benchmark.F90:1389-1415)."""
+    T, N = 1279, 1280
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    nf = 6
+    rng = np.random.default_rng(7)
+    n = np.concatenate([np.repeat(np.arange(m, T + 1), 2) for m in range(T + 1)]).astype(float)
+    a = rng.uniform(-1, 1, (tr.nspec2, nf)) / (1 + n[:, None]) ** 2
+    a[1:2 * (T + 1):2] = 0
+    b = np.zeros_like(a)
+    b[int(tr.nasm0[4]) + 2 * (19 - 4)] = 1.0                      # Re psi(4, 19) = 1 in every field
+    ga, gb = tr.inv_trans(spscalar=a), tr.inv_trans(spscalar=b)
+    gab = tr.inv_trans(spscalar=a - 2.5 * b)
+    assert rel(gab, ga - 2.5 * gb) < 1e-13
+    off = np.concatenate([[0], np.cumsum(nloen)])
+    for j in (0, 3, 500, 1023, 1279, 1280, 2000, 2559):            # pole, chirp-z and smooth rows, both hemispheres
+        nlon = int(nloen[j])
+        row = gb[0, 0, off[j]:off[j] + nlon]
+        if tr.nmen[j] >= 4:
+            p = eo.supolf(4, 19, tr.rmu[j])[19, 0]
+            assert np.abs(row - 2 * p * np.cos(2 * np.pi * 4 * np.arange(nlon) / nlon)).max() < 1e-12
+        else:
+            assert np.abs(row).max() == 0.0
+    back = tr.dir_trans(ga, 0, nf)[2]
+    assert rel(back, a) < 1e-11
+    assert np.abs(tr.specnorm(back) / tr.specnorm(a) - 1).max() < 1e-12
+    bb = tr.dir_trans(gb, 0, nf)[2]
+    assert np.abs(tr.specnorm(bb) / tr.specnorm(b) - 1).max() <= 100 * np.finfo(float).eps
+    tr.release()
