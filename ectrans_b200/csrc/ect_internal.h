@@ -84,6 +84,7 @@ struct EctDevice {
     // geometry
     double *rw = nullptr, *racthe = nullptr;      // indexed by global latitude
     double* racthe_loc = nullptr;                 // indexed by local latitude
+    double* rw_loc = nullptr;
     int *nloen = nullptr, *nmen = nullptr, *gpoff = nullptr;
     // Legendre
     double* ptab = nullptr;  i64 ptab_elems = 0;

@@ -32,6 +32,8 @@ struct FtArgs {
     int nproma; int ngptot;
     // direct store destinations: rank owning m + record in its Legendre-side buffer (TRLTOM fused)
     double* const* peer; const int* dst_rank; const int* dst_rec;
+    const double* rw_loc;         // Gaussian weight per local latitude (direct: folded into the stored records)
+    int n_uv_fields;              // direct: fields < n_uv_fields are u, v (also scaled by 1/(a cos theta), LDFOU2)
     int fp32;                     // grid-point arrays are float
     int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum
 };
@@ -292,7 +294,11 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
             }
         } else {
             // 1/N + FOURIER_OUT (same arithmetic as fourier_phases.h ftdir_store)
-            const double sc = 0.5 / (double)N;
+            // 1/N (tpm_fftw.F90:317-321), Gaussian weight (ledir_mod.F90:122) and, for u and v, 1/(a cos theta)
+            // (ldfou2_mod.F90:90-96) in one factor, so that the Legendre loader only forms N +- S
+            const double wl = a.rw_loc[l];
+            const double sca = 0.5 / (double)N * wl * (fa < a.n_uv_fields ? s1 : 1.0);
+            const double scb = 0.5 / (double)N * wl * (fb2 >= 0 && fb2 < a.n_uv_fields ? s1 : 1.0);
             const int ca = 2 * fa, cb = hasb ? 2 * fb2 : -1;
             for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
                 double2 zk[NB], zn[NB], ch[NB]; double* rb[NB];
@@ -314,8 +320,8 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
                     if (c.bluestein) { a_ = c_mul(ch[i], a_); b_ = c_mul(ch[i], b_); }
                     // stored values are swapped (sign - transform on the sign + core): Z = (y, x)
                     const double2 Zk = make_double2(a_.y, a_.x), Zn = make_double2(b_.y, b_.x);
-                    *reinterpret_cast<double2*>(rb[i] + ca) = make_double2((Zk.x + Zn.x) * sc, (Zk.y - Zn.y) * sc);
-                    if (cb >= 0) *reinterpret_cast<double2*>(rb[i] + cb) = make_double2((Zk.y + Zn.y) * sc, (Zn.x - Zk.x) * sc);
+                    *reinterpret_cast<double2*>(rb[i] + ca) = make_double2((Zk.x + Zn.x) * sca, (Zk.y - Zn.y) * sca);
+                    if (cb >= 0) *reinterpret_cast<double2*>(rb[i] + cb) = make_double2((Zk.y + Zn.y) * scb, (Zn.x - Zk.x) * scb);
                 }
             }
         }
@@ -336,6 +342,7 @@ static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     a.nchunks = (a.npairs + FT_PAIRS_PER_CTA - 1) / FT_PAIRS_PER_CTA;
     a.ngptot = h->hp.ngptot;
     a.fp32 = f.fp32;
+    a.rw_loc = d->rw_loc; a.n_uv_fields = 2 * f.kf_uv;
     static const char* dbg = getenv("ECT_FFT_DBG");
     a.dbg = dbg ? atoi(dbg) : 0;
 }
@@ -437,6 +444,11 @@ int ect_fourier_setup(EctHandle* h) {
     for (int l = 0; l < P.nlat; ++l) { nl[l] = P.nloen[P.lat0 + l]; ra[l] = P.racthe[P.lat0 + l]; }
     if ((rc = upload(d->nloen, nl))) return rc;
     if ((rc = upload(d->racthe_loc, ra))) return rc;
+    {
+        std::vector<double> wl(P.nlat);
+        for (int l = 0; l < P.nlat; ++l) wl[l] = P.rw[P.lat0 + l];
+        if ((rc = upload(d->rw_loc, wl))) return rc;
+    }
     if ((rc = upload(d->gpoff, P.gpoff))) return rc;
     // shared-memory classes
     int maxsm = 0;

@@ -377,9 +377,9 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
     }
 }
 
-// Direct: Psi[k][c] = sum_lat P[k][lat] * (w (N +- S))[lat][c].  Raw north / south records are staged
-// with cp.async; the N +- S combination, 1/(a cos theta) on u,v and the Gaussian weight are applied when
-// the B fragments are read from shared memory (prfi2b_mod.F90:91-92, ldfou2_mod.F90:90-96, ledir_mod.F90:122).
+// Direct: Psi[k][c] = sum_lat P[k][lat] * (w (N +- S))[lat][c].  North / south records arrive already scaled by
+// the Gaussian weight (and 1/(a cos theta) for u, v) from the Fourier stage's store; they are staged with
+// cp.async and only the N +- S combination (prfi2b_mod.F90:91-92) is formed when the B fragments are read.
 __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int tile = blockIdx.x / a.nct, ct = blockIdx.x - tile * a.nct;
@@ -426,10 +426,6 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
         }
     };
 
-    bool uvj[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) uvj[j] = (c0 + wn * 32 + j * 8 + g) < a.c_uv_end;
-
     double acs[4][4][2], aca[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -442,15 +438,6 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
         cp_async_commit();
     }
     for (int ch = 0; ch < nchunks; ++ch) {
-        // weights of this chunk's two fragment rows (kk + t, kk = 0, 4): issued before the wait
-        double wv[2], rv[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int li = ch * LEG_KC + 4 * h + t;
-            const bool v = li < lm.ndglu;
-            wv[h] = v ? a.rw[lm.isl + li] : 0.0;
-            rv[h] = v ? a.racthe[lm.isl + li] : 1.0;
-        }
         cp_async_wait<LEG_STAGES - 2>();
         __syncthreads();
         {
@@ -472,11 +459,8 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
                 fa[i] = Aa[(wm * 32 + i * 8 + g) * DIR_LDA + kk + t];
                 const double vn = Bn[(kk + t) * LEG_LD + wn * 32 + i * 8 + g];
                 const double vs = Bs[(kk + t) * LEG_LD + wn * 32 + i * 8 + g];
-                double sy = vn + vs, as = vn - vs;
-                if (uvj[i]) { sy *= rv[h]; as *= rv[h]; }
-                bs[i] = sy * wv[h];
-                ba[i] = as * wv[h];
-                if (a.dbg & 1) { bs[i] = vn; ba[i] = vs; }
+                bs[i] = vn + vs;
+                ba[i] = vn - vs;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)

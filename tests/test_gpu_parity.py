@@ -374,3 +374,39 @@ def test_full_size_grid_properties(eb):
     bb = tr.dir_trans(gb, 0, nf)[2]
     assert np.abs(tr.specnorm(bb) / tr.specnorm(b) - 1).max() <= 100 * np.finfo(float).eps
     tr.release()
+
+
+# the reference's own benchmark-as-test matrix (tests/CMakeLists.txt:219-326): T47 / O48, --niter 2 --check 100
+BENCH_MATRIX = [
+    dict(nlev=1, nfld=0),
+    dict(nlev=20, nfld=10),
+    dict(nlev=20, nfld=10, scders=True, uvder=True),
+    dict(nlev=20, nfld=10, scders=True, uvder=True, vordiv=True),
+    dict(nlev=20, nfld=10, nproma=16),
+]
+
+
+@pytest.mark.parametrize("cfg", BENCH_MATRIX)
+def test_reference_benchmark_matrix(eb, cfg):
+    T, N = 47, 48
+    nlev, nfld = cfg["nlev"], cfg["nfld"]
+    nuv, nsc = nlev, nlev * nfld + 1                     # ectrans-benchmark.F90:450-478
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen, tables=False)
+    vor = T_(eo.benchmark_spectral(s, nuv)); div = vor.copy(); sc = T_(eo.benchmark_spectral(s, nsc))
+    n0v, n0s = tr.specnorm(vor), tr.specnorm(sc)
+    opts = dict(scders=cfg.get("scders", False), uvder=cfg.get("uvder", False),
+                vorgp=cfg.get("vordiv", False), divgp=cfg.get("vordiv", False))
+    nproma = cfg.get("nproma", 0)
+    for it in range(2):                                   # --niter 2
+        gp = tr.inv_trans(vor, div, sc, nproma=nproma, **opts)
+        iu = (nuv if opts["vorgp"] else 0) + (nuv if opts["divgp"] else 0)
+        gin = np.ascontiguousarray(gp[:, iu:iu + 2 * nuv + nsc])
+        vor, div, sc = tr.dir_trans(gin, nuv, nsc, nproma=nproma)
+    eps = np.finfo(float).eps
+    # criterion of ectrans-benchmark.F90:847-871 (--check 100): relative spectral-norm error <= 100 eps
+    assert np.abs(tr.specnorm(vor) / n0v - 1).max() <= 100 * eps
+    assert np.abs(tr.specnorm(div) / n0v - 1).max() <= 100 * eps
+    assert np.abs(tr.specnorm(sc) / n0s - 1).max() <= 100 * eps
+    tr.release()
