@@ -20,7 +20,7 @@ EXTRA_legendre :=
 
 $(LIB): $(OBJS)
 	@mkdir -p ectrans_b200/lib
-	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -lnccl
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -ldl
 
 emu:
 	@mkdir -p tests/hostemu/_build

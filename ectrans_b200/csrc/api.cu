@@ -7,6 +7,7 @@
 #include "ect_internal.h"
 #include "fourier_phases.h"
 #include <nccl.h>
+#include <dlfcn.h>
 #include <mutex>
 #include <map>
 #include <cstring>
@@ -41,6 +42,49 @@ extern "C" const char* ect_strerror(int code) {
     }
 }
 
+// NCCL is bound at run time (dlopen) and only when more than one rank is used: a DT_NEEDED libnccl.so.2 would
+// pin whichever copy the loader finds first and break hosts that ship their own (PyTorch bundles a newer one
+// under the same soname).  An already loaded libnccl.so.2 is reused.
+struct EctNccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static EctNccl g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return ECT_SUCCESS;
+    void* L = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!L) L = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!L) L = dlopen("libnccl.so", RTLD_NOW);
+    if (!L) { ect_set_error("NCCL: cannot load libnccl.so.2 (%s)", dlerror()); return ECT_ERR_NCCL; }
+#define ECT_SYM(field, name) do { *(void**)(&g_nccl.field) = dlsym(L, name); \
+        if (!g_nccl.field) { ect_set_error("NCCL: symbol %s not found", name); return ECT_ERR_NCCL; } } while (0)
+    ECT_SYM(GetUniqueId, "ncclGetUniqueId"); ECT_SYM(CommInitRank, "ncclCommInitRank"); ECT_SYM(CommDestroy, "ncclCommDestroy");
+    ECT_SYM(GroupStart, "ncclGroupStart"); ECT_SYM(GroupEnd, "ncclGroupEnd"); ECT_SYM(Send, "ncclSend"); ECT_SYM(Recv, "ncclRecv");
+    ECT_SYM(AllReduce, "ncclAllReduce"); ECT_SYM(AllGather, "ncclAllGather"); ECT_SYM(GetErrorString, "ncclGetErrorString");
+#undef ECT_SYM
+    g_nccl.lib = L;
+    return ECT_SUCCESS;
+}
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclAllReduce g_nccl.AllReduce
+#define ncclAllGather g_nccl.AllGather
+#define ncclGetErrorString g_nccl.GetErrorString
+
 #define ECT_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) { \
     ect_set_error("%s:%d: NCCL: %s", __FILE__, __LINE__, ncclGetErrorString(r__)); return ECT_ERR_NCCL; } } while (0)
 
@@ -48,6 +92,7 @@ extern "C" int ect_nccl_unique_id(void* out_bytes) {
     if (!out_bytes) return ECT_ERR_MISSING;
     static_assert(sizeof(ncclUniqueId) <= ECT_NCCL_UID_BYTES, "uid size");
     ncclUniqueId id;
+    { int lrc = nccl_load(); if (lrc) return lrc; }
     ECT_NCCL(ncclGetUniqueId(&id));
     memset(out_bytes, 0, ECT_NCCL_UID_BYTES);
     memcpy(out_bytes, &id, sizeof(id));
@@ -92,6 +137,7 @@ int ect_device_setup(EctHandle* h, cudaStream_t stream, bool use_given_stream, i
     if ((rc = ect_fourier_setup(h))) return rc;
     if (P.nranks > 1) {
         if (!uid) { ect_set_error("ect_setup: nranks > 1 needs nccl_uid"); return ECT_ERR_MISSING; }
+        if ((rc = nccl_load())) return rc;
         ncclUniqueId id;
         memcpy(&id, uid, sizeof(id));
         ncclComm_t comm;

@@ -261,7 +261,13 @@ void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, 
 #define LEG_STAGES 5
 #define LEG_LD (64 + 4)          // 68: pitch of the 8 x 64 tiles
 #define DIR_LDA (LEG_KC + 4)     // 12: pitch of the 64 x 8 polynomial tile of the direct kernel
-#define INV_STAGE_DOUBLES (4 * LEG_KC * LEG_LD)
+#ifndef INV_KC
+#define INV_KC 8
+#endif
+#ifndef INV_STAGES
+#define INV_STAGES 5
+#endif
+#define INV_STAGE_DOUBLES (4 * INV_KC * LEG_LD)
 #define DIR_STAGE_DOUBLES (2 * LEG_BM * DIR_LDA + 2 * LEG_KC * LEG_LD)
 
 struct LegArgs {
@@ -289,19 +295,19 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
-    const int nchunks = (lm.ils + LEG_KC - 1) / LEG_KC;
+    const int nchunks = (lm.ils + INV_KC - 1) / INV_KC;
     const double* ps = a.ptab + lm.ps_off + i0;
     const double* pa = a.ptab + lm.pa_off + i0;
     const double* xb = a.x + lm.xrow0 * (long long)a.cp + c0;
 
     auto load_chunk = [&](int chunk, int buf) {
         double* As = smem + (size_t)buf * INV_STAGE_DOUBLES;
-        double* Aa = As + LEG_KC * LEG_LD;
-        double* Bs = Aa + LEG_KC * LEG_LD;
-        double* Ba = Bs + LEG_KC * LEG_LD;
-        const int k0 = chunk * LEG_KC;
+        double* Aa = As + INV_KC * LEG_LD;
+        double* Bs = Aa + INV_KC * LEG_LD;
+        double* Ba = Bs + INV_KC * LEG_LD;
+        const int k0 = chunk * INV_KC;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {   // 8 rows x 64 columns = 256 16-byte pieces per tile
+        for (int e = 0; e < INV_KC / 4; ++e) {   // INV_KC rows x 64 columns = INV_KC * 32 16-byte pieces per tile
             const int idx = tid + e * LEG_THREADS;
             const int row = idx >> 5, c2 = (idx & 31) * 2;
             const int k = k0 + row;
@@ -321,24 +327,24 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
         for (int j = 0; j < 4; ++j) { acs[i][j][0] = acs[i][j][1] = 0.0; aca[i][j][0] = aca[i][j][1] = 0.0; }
 
 #pragma unroll
-    for (int s = 0; s < LEG_STAGES - 1; ++s) {
+    for (int s = 0; s < INV_STAGES - 1; ++s) {
         if (s < nchunks) load_chunk(s, s);
         cp_async_commit();
     }
     for (int ch = 0; ch < nchunks; ++ch) {
-        cp_async_wait<LEG_STAGES - 2>();
+        cp_async_wait<INV_STAGES - 2>();
         __syncthreads();
         {
-            const int nx = ch + LEG_STAGES - 1;
-            if (nx < nchunks) load_chunk(nx, nx % LEG_STAGES);
+            const int nx = ch + INV_STAGES - 1;
+            if (nx < nchunks) load_chunk(nx, nx % INV_STAGES);
             cp_async_commit();
         }
-        const double* As = smem + (size_t)(ch % LEG_STAGES) * INV_STAGE_DOUBLES;
-        const double* Aa = As + LEG_KC * LEG_LD;
-        const double* Bs = Aa + LEG_KC * LEG_LD;
-        const double* Ba = Bs + LEG_KC * LEG_LD;
+        const double* As = smem + (size_t)(ch % INV_STAGES) * INV_STAGE_DOUBLES;
+        const double* Aa = As + INV_KC * LEG_LD;
+        const double* Bs = Aa + INV_KC * LEG_LD;
+        const double* Ba = Bs + INV_KC * LEG_LD;
 #pragma unroll
-        for (int kk = 0; kk < LEG_KC; kk += 4) {
+        for (int kk = 0; kk < INV_KC; kk += 4) {
             double fs[4], fa[4], bs[4], ba[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -494,7 +500,7 @@ static bool g_leg_attr_set = false;
 static void leg_set_attrs() {
     if (g_leg_attr_set) return;
     cudaFuncSetAttribute(k_leinv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         LEG_STAGES * INV_STAGE_DOUBLES * (int)sizeof(double));
+                         INV_STAGES * INV_STAGE_DOUBLES * (int)sizeof(double));
     cudaFuncSetAttribute(k_ledir, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          LEG_STAGES * DIR_STAGE_DOUBLES * (int)sizeof(double));
     g_leg_attr_set = true;
@@ -511,7 +517,7 @@ void ect_launch_leinv(EctHandle* h, const EctFieldCfg& f) {
     a.cp = f.cp; a.c_uv_end = 0; a.dbg = 0;
     a.peer = d->peer_fft; a.dst_rank_n = d->leg_dst_rank_n; a.dst_rank_s = d->leg_dst_rank_s;
     a.dst_rec_n = d->leg_dst_rec_n; a.dst_rec_s = d->leg_dst_rec_s;
-    const size_t smem = LEG_STAGES * INV_STAGE_DOUBLES * sizeof(double);
+    const size_t smem = INV_STAGES * INV_STAGE_DOUBLES * sizeof(double);
     k_leinv<<<(unsigned)((long long)d->n_inv_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
     d->launches++;
 }

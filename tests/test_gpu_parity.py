@@ -410,3 +410,16 @@ def test_reference_benchmark_matrix(eb, cfg):
     assert np.abs(tr.specnorm(div) / n0v - 1).max() <= 100 * eps
     assert np.abs(tr.specnorm(sc) / n0s - 1).max() <= 100 * eps
     tr.release()
+
+
+def test_benchmark_driver_config0(built):
+    """BASELINE config 0 through the ectrans-benchmark mirror: T79 / O80, 10 levels, 1 scalar field,
+    inverse + direct, --norms --check 100 (the reference's own pass criterion)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "tools", "ectrans_benchmark.py"), "-t", "79", "-g", "O80", "-l", "10",
+           "-f", "1", "-n", "3", "--niter-warmup", "1", "--norms", "--check", "100"]
+    for extra in ([], ["--vordiv", "--scders", "--uvders", "--nproma", "16"], ["--device-resident"]):
+        out = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert "Inverse-direct transforms" in out.stdout and "Correctness test failed" not in out.stdout
