@@ -179,7 +179,7 @@ void ect_device_free(EctHandle* h) {
     if (d->comm) ncclCommDestroy((ncclComm_t)d->comm);
     void* ptrs[] = {d->rw, d->racthe, d->racthe_loc, d->rw_loc, d->nloen, d->gpoff, d->ptab, d->legm, d->leg_rec_n, d->leg_rec_s,
                     d->nasm0, d->inv_tiles, d->dir_tiles, d->plans, d->latplans, d->perm_pool, d->tw_pool,
-                    d->cz_pool, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->xwork, d->fbuf_leg,
+                    d->cz_pool, d->cz_pool_f, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->xwork, d->fbuf_leg,
                     d->stage_sp, d->stage_gp, d->normbuf, d->leg_dst_rank_n, d->leg_dst_rank_s, d->leg_dst_rec_n,
                     d->leg_dst_rec_s, d->fft_dst_rank, d->fft_dst_rec, d->peer_fft, d->peer_leg, d->barrier_buf};
     for (void* p : ptrs) if (p) cudaFree(p);

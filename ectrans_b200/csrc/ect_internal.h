@@ -102,12 +102,13 @@ struct EctDevice {
     EctLatPlan* latplans = nullptr;
     uint16_t* perm_pool = nullptr;
     double2 *tw_pool = nullptr, *cz_pool = nullptr, *roots = nullptr;
+    float2* cz_pool_f = nullptr;                        // sp handles: chirp tables in float (cz_pool stays null)
     int* lat_plan = nullptr;              // local lat -> latplan id
     i64* latrow0 = nullptr;
     int* fft_rec = nullptr;
     std::vector<int> h_lat_plan;
     // per smem-class work lists (latitudes sorted by cost)
-    struct Bucket { int smem; int threads; int maxr; std::vector<int> lats; int* d_lats = nullptr; };
+    struct Bucket { int smem; int threads; int maxr; int nostage = 0; std::vector<int> lats; int* d_lats = nullptr; };
     std::vector<Bucket> buckets;
     // workspaces (grow only)
     double* xwork = nullptr; i64 xwork_elems = 0;       // X (inverse input) / POA (direct output)

@@ -42,6 +42,20 @@ ECT_HD double2 c_mul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 ECT_HD double2 c_muli(double2 a) { return make_double2(-a.y, a.x); }   // a * i
+// single-precision arithmetic (sp handles): the same core on float2
+ECT_HD float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+ECT_HD float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+ECT_HD float2 c_mul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+ECT_HD float2 c_muli(float2 a) { return make_float2(-a.y, a.x); }
+template <typename C> struct EctReal;
+template <> struct EctReal<double2> { typedef double type; };
+template <> struct EctReal<float2> { typedef float type; };
+template <typename C, typename A, typename B>
+ECT_HD C c_make(A x, B y) { C c; c.x = (typename EctReal<C>::type)x; c.y = (typename EctReal<C>::type)y; return c; }
+template <typename C, typename S>
+ECT_HD C c_cvt(S a) { return c_make<C>(a.x, a.y); }
 
 // exp(+2 pi i j / n) for 0 <= j < n from the quarter table qt[0 .. n/4] (n4 = n/4 > 0)
 // or from the half table qt[0 .. n/2) (n4 = -(n/2))
@@ -62,29 +76,36 @@ ECT_HD double2 tw_lookup(const double2* __restrict__ qt, int j, int n4) {
 }
 
 // Two-level twiddle table (lives in shared memory in the kernels): exp(2 pi i j / n) = t1[j >> 7] * t2[j & 127]
-struct EctTw {
-    const double2* t1;     // exp(2 pi i 128 a / n), a <= n / 128
-    const double2* t2;     // exp(2 pi i b / n), b < 128
+template <typename C>
+struct EctTwT {
+    const C* t1;           // exp(2 pi i 128 a / n), a <= n / 128
+    const C* t2;           // exp(2 pi i b / n), b < 128
 };
+typedef EctTwT<double2> EctTw;
 #define ECT_TW1_LEN(n) ((n) / 128 + 2)
 #define ECT_TW2_LEN 128
-ECT_HD double2 tw_get(const EctTw& t, int j) { return c_mul(t.t1[j >> 7], t.t2[j & 127]); }
+template <typename C>
+ECT_HD C tw_get(const EctTwT<C>& t, int j) { return c_mul(t.t1[j >> 7], t.t2[j & 127]); }
 // fills the tables cooperatively from the per-length table qt (quarter / half wave, see tw_lookup)
-ECT_HD void tw_build(double2* t1, double2* t2, const double2* __restrict__ qt, int n, int tid, int nthr) {
+template <typename C>
+ECT_HD void tw_build(C* t1, C* t2, const double2* __restrict__ qt, int n, int tid, int nthr) {
     const int n4 = (n & 3) ? -(n >> 1) : (n >> 2);
-    for (int a = tid; a < ECT_TW1_LEN(n); a += nthr) t1[a] = tw_lookup(qt, (128 * a) % n, n4);
-    for (int b = tid; b < ECT_TW2_LEN; b += nthr) t2[b] = tw_lookup(qt, b % n, n4);
+    for (int a = tid; a < ECT_TW1_LEN(n); a += nthr) t1[a] = c_cvt<C>(tw_lookup(qt, (128 * a) % n, n4));
+    for (int b = tid; b < ECT_TW2_LEN; b += nthr) t2[b] = c_cvt<C>(tw_lookup(qt, b % n, n4));
 }
 
 // ---- butterflies: u[p] = sum_q v[q] exp(+2 pi i p q / R), in place on v[0..R) ----
-ECT_HD void bfly2(double2* v) {
-    double2 a = v[0], b = v[1];
+// C = double2 (dp handles) or float2 (sp handles)
+template <typename C>
+ECT_HD void bfly2(C* v) {
+    C a = v[0], b = v[1];
     v[0] = c_add(a, b);
     v[1] = c_sub(a, b);
 }
-ECT_HD void bfly4(double2& v0, double2& v1, double2& v2, double2& v3) {
-    double2 t0 = c_add(v0, v2), t1 = c_sub(v0, v2);
-    double2 t2 = c_add(v1, v3), t3 = c_muli(c_sub(v1, v3));
+template <typename C>
+ECT_HD void bfly4(C& v0, C& v1, C& v2, C& v3) {
+    C t0 = c_add(v0, v2), t1 = c_sub(v0, v2);
+    C t2 = c_add(v1, v3), t3 = c_muli(c_sub(v1, v3));
     v0 = c_add(t0, t2);
     v1 = c_add(t1, t3);
     v2 = c_sub(t0, t2);
@@ -94,54 +115,59 @@ ECT_HD void bfly4(double2& v0, double2& v1, double2& v2, double2& v3) {
 #define ECT_C8 0.92387953251128675613
 #define ECT_S8 0.38268343236508977173
 // radix 8 = 4 x 2: q = 2a + b, p = p1 + 4 p2
-ECT_HD void bfly8(double2* v) {
+template <typename C>
+ECT_HD void bfly8(C* v) {
+    typedef typename EctReal<C>::type R_;
+    const R_ sqh = (R_)ECT_SQH;
     bfly4(v[0], v[2], v[4], v[6]);          // b = 0: y[0][p1] in v[0], v[2], v[4], v[6]
     bfly4(v[1], v[3], v[5], v[7]);          // b = 1
     // twiddle y[1][p1] by W8^p1
-    v[3] = make_double2((v[3].x - v[3].y) * ECT_SQH, (v[3].x + v[3].y) * ECT_SQH);
+    v[3] = c_make<C>((v[3].x - v[3].y) * sqh, (v[3].x + v[3].y) * sqh);
     v[5] = c_muli(v[5]);
-    v[7] = make_double2((-v[7].x - v[7].y) * ECT_SQH, (v[7].x - v[7].y) * ECT_SQH);
+    v[7] = c_make<C>((-v[7].x - v[7].y) * sqh, (v[7].x - v[7].y) * sqh);
     // 2-point DFTs over b: X[p1] = y0 + y1, X[p1 + 4] = y0 - y1
-    double2 x0 = c_add(v[0], v[1]), x4 = c_sub(v[0], v[1]);
-    double2 x1 = c_add(v[2], v[3]), x5 = c_sub(v[2], v[3]);
-    double2 x2 = c_add(v[4], v[5]), x6 = c_sub(v[4], v[5]);
-    double2 x3 = c_add(v[6], v[7]), x7 = c_sub(v[6], v[7]);
+    C x0 = c_add(v[0], v[1]), x4 = c_sub(v[0], v[1]);
+    C x1 = c_add(v[2], v[3]), x5 = c_sub(v[2], v[3]);
+    C x2 = c_add(v[4], v[5]), x6 = c_sub(v[4], v[5]);
+    C x3 = c_add(v[6], v[7]), x7 = c_sub(v[6], v[7]);
     v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
 }
 // radix 16 = 4 x 4: q = 4a + b, p = p1 + 4 p2
-ECT_HD void bfly16(double2* v) {
+template <typename C>
+ECT_HD void bfly16(C* v) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) bfly4(v[b], v[4 + b], v[8 + b], v[12 + b]);   // y[b][p1] at v[4 p1 + b]
     // twiddles W16^(b p1)
-    const double2 w1 = make_double2(ECT_C8, ECT_S8), w2 = make_double2(ECT_SQH, ECT_SQH), w3 = make_double2(ECT_S8, ECT_C8);
+    const C w1 = c_make<C>(ECT_C8, ECT_S8), w2 = c_make<C>(ECT_SQH, ECT_SQH), w3 = c_make<C>(ECT_S8, ECT_C8);
     v[5] = c_mul(v[5], w1);                                     // b=1,p1=1
     v[6] = c_mul(v[6], w2);                                     // b=2,p1=1
     v[7] = c_mul(v[7], w3);                                     // b=3,p1=1
     v[9] = c_mul(v[9], w2);                                     // b=1,p1=2
     v[10] = c_muli(v[10]);                                      // b=2,p1=2 : W16^4 = i
-    v[11] = c_mul(v[11], make_double2(-ECT_SQH, ECT_SQH));      // b=3,p1=2 : W16^6
+    v[11] = c_mul(v[11], c_make<C>(-ECT_SQH, ECT_SQH));         // b=3,p1=2 : W16^6
     v[13] = c_mul(v[13], w3);                                   // b=1,p1=3
-    v[14] = c_mul(v[14], make_double2(-ECT_SQH, ECT_SQH));      // b=2,p1=3 : W16^6
-    v[15] = c_mul(v[15], make_double2(-ECT_C8, -ECT_S8));       // b=3,p1=3 : W16^9
+    v[14] = c_mul(v[14], c_make<C>(-ECT_SQH, ECT_SQH));         // b=2,p1=3 : W16^6
+    v[15] = c_mul(v[15], c_make<C>(-ECT_C8, -ECT_S8));          // b=3,p1=3 : W16^9
 #pragma unroll
     for (int p1 = 0; p1 < 4; ++p1) bfly4(v[4 * p1], v[4 * p1 + 1], v[4 * p1 + 2], v[4 * p1 + 3]);   // X[p1 + 4 p2] at v[4 p1 + p2]
     // transpose 4x4 to natural order
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = a + 1; b < 4; ++b) { double2 t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
+        for (int b = a + 1; b < 4; ++b) { C t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
 }
 
 // odd radix R: rt[j] = (cos, sin)(2 pi j / R), j < R.  Outputs are handed to emit(p, value) as they are
 // produced so that only the R inputs live in registers.
-template <int R, typename Emit>
-ECT_HD void bfly_odd(double2* v, const double2* __restrict__ rt, Emit emit) {
+template <int R, typename C, typename Emit>
+ECT_HD void bfly_odd(C* v, const C* __restrict__ rt, Emit emit) {
+    typedef typename EctReal<C>::type R_;
     constexpr int H = (R - 1) / 2;
     // in place: v[q] <- v[q] + v[R-q] (t_q), v[R-q] <- v[q] - v[R-q] (d_q)
-    double2 s0 = v[0];
+    C s0 = v[0];
 #pragma unroll
     for (int q = 1; q <= H; ++q) {
-        const double2 a = v[q], b = v[R - q];
+        const C a = v[q], b = v[R - q];
         v[q] = c_add(a, b);
         v[R - q] = c_sub(a, b);
         s0 = c_add(s0, v[q]);
@@ -149,23 +175,23 @@ ECT_HD void bfly_odd(double2* v, const double2* __restrict__ rt, Emit emit) {
     emit(0, s0);
 #pragma unroll
     for (int p = 1; p <= H; ++p) {
-        double mx = v[0].x, my = v[0].y, nx = 0.0, ny = 0.0;
+        R_ mx = v[0].x, my = v[0].y, nx = 0, ny = 0;
 #pragma unroll
         for (int q = 1; q <= H; ++q) {
-            const double2 w = rt[(p * q) % R];
+            const C w = rt[(p * q) % R];
             mx += w.x * v[q].x;
             my += w.x * v[q].y;
             nx += w.y * v[R - q].x;
             ny += w.y * v[R - q].y;
         }
         // n = i * (nx + i ny) = (-ny, nx)
-        emit(p, make_double2(mx - ny, my + nx));
-        emit(R - p, make_double2(mx + ny, my - nx));
+        emit(p, c_make<C>(mx - ny, my + nx));
+        emit(R - p, c_make<C>(mx + ny, my - nx));
     }
 }
 
-template <int R>
-ECT_HD void bfly_pow2(double2* v) {
+template <int R, typename C>
+ECT_HD void bfly_pow2(C* v) {
     if constexpr (R == 2) bfly2(v);
     else if constexpr (R == 4) bfly4(v[0], v[1], v[2], v[3]);
     else if constexpr (R == 8) bfly8(v);
@@ -174,19 +200,19 @@ ECT_HD void bfly_pow2(double2* v) {
 
 // v[q] *= w1^q, q = 1 .. R-1.  Powers 1..7 come from a shallow product tree, the rest as
 // w1^(8c) * w1^(q mod 8), so that only eight twiddles are live at a time.
-template <int R>
-ECT_HD void apply_twiddles(double2* v, double2 w1) {
+template <int R, typename C>
+ECT_HD void apply_twiddles(C* v, C w1) {
     constexpr int T = R < 8 ? R : 8;
-    double2 w[T];
-    w[0] = make_double2(1.0, 0.0);
+    C w[T];
+    w[0] = c_make<C>(1, 0);
     w[1] = w1;
 #pragma unroll
     for (int q = 2; q < T; ++q) w[q] = c_mul(w[q >> 1], w[q - (q >> 1)]);
 #pragma unroll
     for (int q = 1; q < T; ++q) v[q] = c_mul(v[q], w[q]);
     if constexpr (R > 8) {
-        const double2 w8 = c_mul(w[4], w[4]);
-        double2 base = w8;
+        const C w8 = c_mul(w[4], w[4]);
+        C base = w8;
 #pragma unroll
         for (int c8 = 8; c8 < R; c8 += 8) {
             v[c8] = c_mul(v[c8], base);
@@ -201,9 +227,9 @@ ECT_HD void apply_twiddles(double2* v, double2 w1) {
 // One stage over the whole array, executed cooperatively by nthr threads.
 // DIF == false: twiddle then butterfly (decimation in time stage B_s)
 // DIF == true : butterfly then twiddle (its transpose)
-template <int R, bool DIF>
-ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const EctTw qt,
-                        const double2* __restrict__ rt, int tid, int nthr) {
+template <int R, bool DIF, typename C>
+ECT_HD void fft_stage_r(C* data, int n, int L, int lshift, const EctTwT<C> qt,
+                        const C* __restrict__ rt, int tid, int nthr) {
     const int nb = n / R;
     const int tstride = n / (R * L);   // twiddle index stride: exp(2 pi i q k / (R L))
     for (int b = tid; b < nb; b += nthr) {
@@ -211,10 +237,10 @@ ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const EctTw qt,
         if (lshift >= 0) { blk = b >> lshift; k = b & (L - 1); }
         else { blk = b / L; k = b - blk * L; }
         const int base = blk * R * L + k;
-        double2 v[R];
+        C v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = data[ECT_PAD(base + q * L)];
-        double2 w1 = make_double2(1.0, 0.0);
+        C w1 = c_make<C>(1, 0);
         const bool tw = (L > 1) && (k > 0);
         if (tw) w1 = tw_get(qt, k * tstride);
         if (!DIF && tw) apply_twiddles<R>(v, w1);
@@ -226,22 +252,22 @@ ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const EctTw qt,
         } else {
             if (DIF && tw) {
                 // outputs arrive as (p, R-p) pairs: w^p by running product, w^(R-p) = w^R * conj(w^p)
-                const double2 wr = tw_get(qt, k * (n / L));      // w^R = exp(2 pi i k / L)
-                double2 wp = make_double2(1.0, 0.0);
+                const C wr = tw_get(qt, k * (n / L));      // w^R = exp(2 pi i k / L)
+                C wp = c_make<C>(1, 0);
                 int last = 0;
-                bfly_odd<R>(v, rt, [&](int q, double2 val) {
+                bfly_odd<R>(v, rt, [&](int q, C val) {
                     if (q > 0) {
                         if (q <= (R - 1) / 2) {
                             if (q != last) { wp = c_mul(wp, w1); last = q; }
                             val = c_mul(val, wp);
                         } else {
-                            val = c_mul(val, c_mul(wr, make_double2(wp.x, -wp.y)));
+                            val = c_mul(val, c_mul(wr, c_make<C>(wp.x, -wp.y)));
                         }
                     }
                     data[ECT_PAD(base + q * L)] = val;
                 });
             } else {
-                bfly_odd<R>(v, rt, [&](int q, double2 val) { data[ECT_PAD(base + q * L)] = val; });
+                bfly_odd<R>(v, rt, [&](int q, C val) { data[ECT_PAD(base + q * L)] = val; });
             }
         }
     }
@@ -250,10 +276,10 @@ ECT_HD void fft_stage_r(double2* data, int n, int L, int lshift, const EctTw qt,
 // rt_all: concatenated root tables; the table of odd radix R occupies [R(R-1)/2, R(R+1)/2)
 #define ECT_ROOTS_OFF(R) ((R) * ((R) - 1) / 2)
 #define ECT_ROOTS_SIZE (ECT_MAX_RADIX * (ECT_MAX_RADIX + 1) / 2)
-template <bool DIF, int MAXR = ECT_MAX_RADIX>
-ECT_HD void fft_stage(double2* data, int n, int r, int L, int lshift, const EctTw qt,
-                      const double2* __restrict__ rt_all, int tid, int nthr) {
-    const double2* rt = rt_all + ECT_ROOTS_OFF(r);
+template <bool DIF, int MAXR = ECT_MAX_RADIX, typename C>
+ECT_HD void fft_stage(C* data, int n, int r, int L, int lshift, const EctTwT<C> qt,
+                      const C* __restrict__ rt_all, int tid, int nthr) {
+    const C* rt = rt_all + ECT_ROOTS_OFF(r);
     switch (r) {
         case 16: fft_stage_r<16, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
         case 8:  fft_stage_r<8, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
@@ -276,22 +302,23 @@ ECT_HD void fft_stage(double2* data, int n, int r, int L, int lshift, const EctT
 // Chirp-z middle step: the innermost DIF stage (L = 1, no twiddles), the pointwise product with the
 // (digit-reversed, 1/M-scaled) kernel spectrum and the innermost DIT stage fused into one pass.
 // The forward transform runs on swapped (re <-> im) data, the product un-swaps it.
-template <int R>
-ECT_HD void blue_middle_r(double2* data, int n, const double2* __restrict__ bhat, int tid, int nthr) {
+template <int R, typename C>
+ECT_HD void blue_middle_r(C* data, int n, const C* __restrict__ bhat, int tid, int nthr) {
     const int nb = n / R;
     for (int b = tid; b < nb; b += nthr) {
-        double2 v[R];
+        C v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = data[ECT_PAD(b * R + q)];
         bfly_pow2<R>(v);
 #pragma unroll
-        for (int q = 0; q < R; ++q) v[q] = c_mul(make_double2(v[q].y, v[q].x), bhat[q * nb + b]);   // bhat stored [q][b]: coalesced
+        for (int q = 0; q < R; ++q) v[q] = c_mul(c_make<C>(v[q].y, v[q].x), bhat[q * nb + b]);   // bhat stored [q][b]: coalesced
         bfly_pow2<R>(v);
 #pragma unroll
         for (int q = 0; q < R; ++q) data[ECT_PAD(b * R + q)] = v[q];
     }
 }
-ECT_HD void blue_middle(double2* data, int n, int r, const double2* __restrict__ bhat, int tid, int nthr) {
+template <typename C>
+ECT_HD void blue_middle(C* data, int n, int r, const C* __restrict__ bhat, int tid, int nthr) {
     switch (r) {
         case 16: blue_middle_r<16>(data, n, bhat, tid, nthr); break;
         case 8:  blue_middle_r<8>(data, n, bhat, tid, nthr); break;

@@ -11,6 +11,7 @@
 #include "fourier_phases.h"
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #define FT_PAIRS_PER_CTA 8
 
@@ -20,7 +21,7 @@ __device__ long long g_ft_probe[64];
 
 struct FtArgs {
     const EctLatPlan* latplans; const EctFftPlan* plans;
-    const uint16_t* perm_pool; const double2* tw_pool; const double2* cz_pool; const double2* roots;
+    const uint16_t* perm_pool; const double2* tw_pool; const void* cz_pool; const double2* roots;   // cz_pool: double2 (dp) or float2 (sp)
     const int* lat_plan; const i64* latrow0; const int* fft_rec;
     const int* lats;              // latitudes (local index) of this launch
     const int* gpoff; const int* nloen_loc; const double* racthe_loc;
@@ -34,7 +35,8 @@ struct FtArgs {
     double* const* peer; const int* dst_rank; const int* dst_rec;
     const double* rw_loc;         // Gaussian weight per local latitude (direct: folded into the stored records)
     int n_uv_fields;              // direct: fields < n_uv_fields are u, v (also scaled by 1/(a cos theta), LDFOU2)
-    int fp32;                     // grid-point arrays are float
+    int fp32;                     // sp handle: grid-point arrays are float and the FFT arithmetic is float
+    int nostage;                  // this launch's rows do not fit with a staging area: inputs are read straight from HBM
     int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum
 };
 
@@ -58,6 +60,23 @@ __device__ __forceinline__ void ft_cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void ft_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void ft_cp_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }
 
+// Byte offsets of the shared-memory areas of one CTA (host: class sizing, device: carve-up)
+struct FtLayout { int stage, chirp, t1, t2, roots, rec, total; };
+__host__ __device__ inline int ft_al16(int b) { return (b + 15) & ~15; }
+__host__ __device__ inline FtLayout ft_layout(bool inverse, bool bluestein, int len, int N, int km, int nroots,
+                                              int csize, int iosize, bool nostage) {
+    FtLayout L;
+    L.stage = ft_al16(ECT_PADDED_LEN(len) * csize);
+    const int nst = nostage ? 0 : (inverse ? 2 * (km + 1) * (int)sizeof(double2) : 2 * N * iosize);
+    L.chirp = L.stage + ft_al16(nst);
+    L.t1 = L.chirp + ((inverse && bluestein) ? ft_al16((N / 2 + 1) * csize) : 0);
+    L.t2 = L.t1 + ft_al16(ECT_TW1_LEN(len) * csize);
+    L.roots = L.t2 + ECT_TW2_LEN * csize;
+    L.rec = L.roots + ft_al16(nroots * csize);
+    L.total = L.rec + ft_al16((km + 1) * (int)sizeof(int));
+    return L;
+}
+
 // Shared memory of one CTA:
 //   data [ECT_PADDED_LEN(len)] double2   work array of the pair in flight
 //   stage                                raw inputs of the NEXT pair, filled by cp.async while this pair is transformed
@@ -66,53 +85,55 @@ __device__ __forceinline__ void ft_cp_wait_all() { asm volatile("cp.async.wait_a
 //   roots                                odd-radix root tables
 template <bool INVERSE, int MAXR, int TB, bool FP32>
 __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
-    extern __shared__ __align__(16) double2 sm[];
+    typedef typename std::conditional<FP32, float2, double2>::type C;     // arithmetic / work-array type
+    typedef typename EctReal<C>::type R_;
+    extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ EctFftPlan s_plan;        // stage list indexed at run time: keep it out of local memory
     constexpr int NROOTS = MAXR <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE;
     const int item = blockIdx.x;
     const int l = a.lats[item / a.nchunks];
     const int chunk = item % a.nchunks;
     const EctLatPlan lp = a.latplans[a.lat_plan[l]];
-    EctPairCtx c;
-    c.nlon = lp.nlon; c.km = lp.km; c.racthe = a.racthe_loc[l];
     if (threadIdx.x == 0) s_plan = a.plans[lp.plan];
     __syncthreads();
     const int plan_n = s_plan.n, plan_nst = s_plan.nst;
-    c.perm = a.perm_pool + s_plan.perm_off;
-    c.bluestein = lp.bluestein; c.m = lp.m;
-    c.chirp = lp.bluestein ? a.cz_pool + lp.chirp_off : nullptr;
-    c.bhat = lp.bluestein ? a.cz_pool + (INVERSE ? lp.bhat_inv_off : lp.bhat_dir_off) : nullptr;
-    c.rec = a.fft_rec + a.latrow0[l];
-    c.cp = a.cp;
+    const uint16_t* perm = a.perm_pool + s_plan.perm_off;
+    const bool blue = lp.bluestein != 0;
+    const C* czp = reinterpret_cast<const C*>(a.cz_pool);
+    const C* g_chirp = blue ? czp + lp.chirp_off : nullptr;
+    const C* bhat = blue ? czp + (INVERSE ? lp.bhat_inv_off : lp.bhat_dir_off) : nullptr;
+    const int* recs = a.fft_rec + a.latrow0[l];
+    const int cp = a.cp;
     const int len = plan_n;
-    const int N = c.nlon, km = c.km;
-    double2* data = sm;
-    double2* stage = data + ECT_PADDED_LEN(len);
-    // inverse chirp-z rows keep the chirp c[0 .. N/2] in shared memory behind the staged records (both fit in
-    // the space the direct transform needs for its two staged rows whenever 2 (km+1) + N/2 + 1 <= N)
-    const bool chirp_sm = INVERSE && lp.bluestein;
-    const int nstage = INVERSE ? 2 * (km + 1) + (chirp_sm ? N / 2 + 1 : 0) : N;         // double2 elements
-    double2* s_chirp = stage + 2 * (km + 1);
-    double2* t1 = stage + nstage;
-    double2* t2 = t1 + ECT_TW1_LEN(len);
-    double2* s_roots = t2 + ECT_TW2_LEN;
-    int* s_rec = reinterpret_cast<int*>(s_roots + NROOTS);   // per m: inverse local record, direct (dest rank << 24 | dest record)
+    const int N = lp.nlon, km = lp.km;
+    const bool staged = !a.nostage;
+    const FtLayout lay = ft_layout(INVERSE, blue, len, N, km, NROOTS, (int)sizeof(C), FP32 ? 4 : 8, !staged);
+    C* data = reinterpret_cast<C*>(smraw);
+    double2* stage = reinterpret_cast<double2*>(smraw + lay.stage);
+    // inverse chirp-z rows keep the chirp c[0 .. N/2] in shared memory
+    const bool chirp_sm = INVERSE && blue;
+    C* s_chirp = reinterpret_cast<C*>(smraw + lay.chirp);
+    C* t1 = reinterpret_cast<C*>(smraw + lay.t1);
+    C* t2 = reinterpret_cast<C*>(smraw + lay.t2);
+    C* s_roots = reinterpret_cast<C*>(smraw + lay.roots);
+    int* s_rec = reinterpret_cast<int*>(smraw + lay.rec);   // per m: inverse local record, direct (dest rank << 24 | dest record)
     const int tid = threadIdx.x, nthr = blockDim.x;
     tw_build(t1, t2, a.tw_pool + s_plan.tw_off, len, tid, nthr);
-    for (int j = tid; j < NROOTS; j += nthr) s_roots[j] = a.roots[j];
-    if (chirp_sm) for (int j = tid; j <= N / 2; j += nthr) s_chirp[j] = c.chirp[j];
+    for (int j = tid; j < NROOTS; j += nthr) s_roots[j] = c_cvt<C>(a.roots[j]);
+    if (chirp_sm) for (int j = tid; j <= N / 2; j += nthr) s_chirp[j] = g_chirp[j];
     for (int k = tid; k <= km; k += nthr)
-        s_rec[k] = INVERSE ? c.rec[k] : ((a.dst_rank[a.latrow0[l] + k] << 24) | a.dst_rec[a.latrow0[l] + k]);
-    const double2* chirp_tab = chirp_sm ? s_chirp : c.chirp;
-    const EctTw qt{t1, t2};
-    c.qt = qt; c.roots = s_roots;
+        s_rec[k] = INVERSE ? recs[k] : ((a.dst_rank[a.latrow0[l] + k] << 24) | a.dst_rec[a.latrow0[l] + k]);
+    const C* chirp_tab = chirp_sm ? s_chirp : g_chirp;
+    const EctTwT<C> qt{t1, t2};
     const int g0 = a.gpoff[l];
     const bool oneblk = a.nproma >= a.ngptot;
     const int p0 = chunk * FT_PAIRS_PER_CTA, p1 = min(p0 + FT_PAIRS_PER_CTA, a.npairs);
     constexpr int NB = 4;      // global loads issued per thread before the first use (latency batching)
-    const double s1 = c.racthe, s2 = c.racthe * c.racthe;
+    const double racthe = a.racthe_loc[l];
+    const R_ s1 = (R_)racthe, s2 = (R_)(racthe * racthe);
 
     auto prefetch = [&](int p) {       // raw inputs of pair p -> stage (asynchronous)
+        if (!staged) return;
         const int2 pr = a.pairs[p];
         const int fa = pr.x, fb2 = pr.y;
         if (INVERSE) {
@@ -123,7 +144,7 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
                 for (int i = 0; i < NB; ++i) {
                     const int k = k0 + i * nthr;
                     if (k > km) continue;
-                    const double* src = a.fb + (long long)s_rec[k] * c.cp;
+                    const double* src = a.fb + (long long)s_rec[k] * cp;
                     ft_cp_async16(stage + 2 * k, src + ca);
                     if (cb >= 0) ft_cp_async16(stage + 2 * k + 1, src + cb);
                 }
@@ -164,101 +185,122 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
             // FOURIER_IN + FSC + zero padding (same arithmetic as fourier_phases.h ftinv_load)
             EctFsField sfa = a.fsf[fa], sfb;
             if (hasb) sfb = a.fsf[fb2]; else { sfb.src_c = -1; sfb.pw = 0; sfb.deriv = 0; }
-            if (!c.bluestein) { for (int k = km + 1 + tid; k < N - km; k += nthr) data[ECT_PAD((int)c.perm[k])] = make_double2(0.0, 0.0); }
-            else { for (int u = 2 * km + 1 + tid; u < c.m; u += nthr) data[ECT_PAD(u)] = make_double2(0.0, 0.0); }
-            const double sa_ = sfa.pw == 0 ? 1.0 : (sfa.pw == 1 ? s1 : s2);
-            const double sb_ = sfb.pw == 0 ? 1.0 : (sfb.pw == 1 ? s1 : s2);
+            if (!blue) { for (int k = km + 1 + tid; k < N - km; k += nthr) data[ECT_PAD((int)perm[k])] = c_make<C>(0, 0); }
+            else { for (int u = 2 * km + 1 + tid; u < lp.m; u += nthr) data[ECT_PAD(u)] = c_make<C>(0, 0); }
+            const R_ sa_ = sfa.pw == 0 ? (R_)1 : (sfa.pw == 1 ? s1 : s2);
+            const R_ sb_ = sfb.pw == 0 ? (R_)1 : (sfb.pw == 1 ? s1 : s2);
             for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
-                double2 ch[NB]; int pk[NB], pn[NB];
+                C ch[NB]; int pk[NB], pn[NB]; double2 ra[NB], rb[NB];
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int k = k0 + i * nthr;
-                    ch[i] = make_double2(1.0, 0.0); pk[i] = pn[i] = 0;
+                    ch[i] = c_make<C>(1, 0); pk[i] = pn[i] = 0;
+                    ra[i] = rb[i] = make_double2(0.0, 0.0);
                     if (k <= km) {
-                        if (c.bluestein) ch[i] = chirp_tab[k];
-                        else { pk[i] = c.perm[k]; pn[i] = c.perm[k == 0 ? 0 : N - k]; }
+                        if (blue) ch[i] = chirp_tab[k];
+                        else { pk[i] = perm[k]; pn[i] = perm[k == 0 ? 0 : N - k]; }
+                        if (staged) { ra[i] = stage[2 * k]; if (hasb) rb[i] = stage[2 * k + 1]; }
+                        else {
+                            const double* src = a.fb + (long long)s_rec[k] * cp;
+                            ra[i] = *reinterpret_cast<const double2*>(src + sfa.src_c);
+                            if (hasb) rb[i] = *reinterpret_cast<const double2*>(src + sfb.src_c);
+                        }
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int k = k0 + i * nthr;
                     if (k > km) continue;
-                    const double2 va = stage[2 * k];
-                    const double2 vb = hasb ? stage[2 * k + 1] : make_double2(0.0, 0.0);
-                    double2 fa_ = make_double2(va.x * sa_, k == 0 ? 0.0 : va.y * sa_);
-                    double2 fb_ = make_double2(vb.x * sb_, k == 0 ? 0.0 : vb.y * sb_);
-                    const double z = s1 * (double)k;
-                    if (sfa.deriv) fa_ = make_double2(-fa_.y * z, fa_.x * z);
-                    if (sfb.deriv) fb_ = make_double2(-fb_.y * z, fb_.x * z);
-                    const double2 zp = make_double2(fa_.x - fb_.y, fa_.y + fb_.x);      // Z[k]
-                    const double2 zm = make_double2(fa_.x + fb_.y, fb_.x - fa_.y);      // Z[-k]
-                    if (!c.bluestein) {
+                    const C va = c_cvt<C>(ra[i]), vb = c_cvt<C>(rb[i]);
+                    C fa_ = c_make<C>(va.x * sa_, k == 0 ? (R_)0 : va.y * sa_);
+                    C fb_ = c_make<C>(vb.x * sb_, k == 0 ? (R_)0 : vb.y * sb_);
+                    const R_ z = s1 * (R_)k;
+                    if (sfa.deriv) fa_ = c_make<C>(-fa_.y * z, fa_.x * z);
+                    if (sfb.deriv) fb_ = c_make<C>(-fb_.y * z, fb_.x * z);
+                    const C zp = c_make<C>(fa_.x - fb_.y, fa_.y + fb_.x);      // Z[k]
+                    const C zm = c_make<C>(fa_.x + fb_.y, fb_.x - fa_.y);      // Z[-k]
+                    if (!blue) {
                         data[ECT_PAD(pk[i])] = zp;
                         if (k > 0) data[ECT_PAD(pn[i])] = zm;
                     } else {
-                        const double2 xp = c_mul(zp, ch[i]);
-                        data[ECT_PAD(km + k)] = make_double2(xp.y, xp.x);
-                        if (k > 0) { const double2 xm = c_mul(zm, ch[i]); data[ECT_PAD(km - k)] = make_double2(xm.y, xm.x); }
+                        const C xp = c_mul(zp, ch[i]);
+                        data[ECT_PAD(km + k)] = c_make<C>(xp.y, xp.x);
+                        if (k > 0) { const C xm = c_mul(zm, ch[i]); data[ECT_PAD(km - k)] = c_make<C>(xm.y, xm.x); }
                     }
                 }
             }
         } else {
             const double* st = reinterpret_cast<const double*>(stage);
             const float* stf = reinterpret_cast<const float*>(stage);
+            const double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
+            const double* bb = hasb ? a.gp_base[fb2] : nullptr; const i64 sb = hasb ? a.gp_blk[fb2] : 0;
             // chirp factors come from global memory (no shared memory left next to two staged rows): the loads of
             // batch i+1 are in flight while batch i is scattered
-            auto ld_batch = [&](int j0, double2* ch, int* pj) {
+            auto ld_batch = [&](int j0, C* ch, int* pj, R_* xa, R_* xb) {
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int j = j0 + i * nthr;
-                    ch[i] = make_double2(1.0, 0.0); pj[i] = 0;
+                    ch[i] = c_make<C>(1, 0); pj[i] = 0; xa[i] = xb[i] = 0;
                     if (j < N) {
-                        if (c.bluestein) ch[i] = c.chirp[j > N / 2 ? N - j : j];
-                        else pj[i] = c.perm[j];
+                        if (blue) ch[i] = g_chirp[j > N / 2 ? N - j : j];
+                        else pj[i] = perm[j];
+                        if (!staged) {
+                            const int g = g0 + j;
+                            const i64 ia = oneblk ? (i64)g : gp_index(g, a.nproma, sa);
+                            xa[i] = FP32 ? (R_)reinterpret_cast<const float*>(ba)[ia] : (R_)ba[ia];
+                            if (hasb) {
+                                const i64 ib = oneblk ? (i64)g : gp_index(g, a.nproma, sb);
+                                xb[i] = FP32 ? (R_)reinterpret_cast<const float*>(bb)[ib] : (R_)bb[ib];
+                            }
+                        }
                     }
                 }
             };
-            auto put_batch = [&](int j0, const double2* ch, const int* pj) {
+            auto put_batch = [&](int j0, const C* ch, const int* pj, const R_* xa, const R_* xb) {
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int j = j0 + i * nthr;
                     if (j >= N) continue;
-                    const double va = FP32 ? (double)stf[j] : st[j];
-                    const double vb = hasb ? (FP32 ? (double)stf[N + j] : st[N + j]) : 0.0;
-                    if (!c.bluestein) data[ECT_PAD(pj[i])] = make_double2(vb, va);
-                    else { const double2 t = c_mul(make_double2(vb, va), ch[i]); data[ECT_PAD(j)] = make_double2(t.y, t.x); }
+                    R_ va = xa[i], vb = xb[i];
+                    if (staged) {
+                        va = FP32 ? (R_)stf[j] : (R_)st[j];
+                        vb = hasb ? (FP32 ? (R_)stf[N + j] : (R_)st[N + j]) : (R_)0;
+                    }
+                    if (!blue) data[ECT_PAD(pj[i])] = c_make<C>(vb, va);
+                    else { const C t = c_mul(c_make<C>(vb, va), ch[i]); data[ECT_PAD(j)] = c_make<C>(t.y, t.x); }
                 }
             };
-            double2 chA[NB], chB[NB]; int pjA[NB], pjB[NB];
-            ld_batch(tid, chA, pjA);
+            C chA[NB], chB[NB]; int pjA[NB], pjB[NB]; R_ xaA[NB], xbA[NB], xaB[NB], xbB[NB];
+            ld_batch(tid, chA, pjA, xaA, xbA);
             for (int j0 = tid; j0 < N; j0 += 2 * NB * nthr) {
-                ld_batch(j0 + NB * nthr, chB, pjB);
-                put_batch(j0, chA, pjA);
-                ld_batch(j0 + 2 * NB * nthr, chA, pjA);
-                put_batch(j0 + NB * nthr, chB, pjB);
+                ld_batch(j0 + NB * nthr, chB, pjB, xaB, xbB);
+                put_batch(j0, chA, pjA, xaA, xbA);
+                ld_batch(j0 + 2 * NB * nthr, chA, pjA, xaA, xbA);
+                put_batch(j0 + NB * nthr, chB, pjB, xaB, xbB);
             }
-            ftdir_zero_tail(data, c, tid, nthr);
+            // zero tail of the chirp-z work array (fourier_phases.h ftdir_zero_tail)
+            if (blue) for (int u = N + tid; u < lp.m; u += nthr) data[ECT_PAD(u)] = c_make<C>(0, 0);
         }
         __syncthreads();                 // work array complete, stage consumed
         if (p + 1 < p1) prefetch(p + 1);
         FT_PROBE(1);
-        if (c.bluestein) {
+        if (blue) {
             for (int s = plan_nst - 1; s >= 1; --s) {
-                fft_stage<true, 7>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, s_roots, tid, nthr);
+                fft_stage<true, 7>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
                 __syncthreads();
                 FT_PROBE(2 + (plan_nst - 1 - s));
             }
-            blue_middle(data, len, s_plan.radix[0], (a.dbg & 4) ? a.cz_pool : c.bhat, tid, nthr);
+            blue_middle(data, len, s_plan.radix[0], (a.dbg & 4) ? czp : bhat, tid, nthr);
             __syncthreads();
             FT_PROBE(10);
             for (int s = 1; s < plan_nst; ++s) {
-                fft_stage<false, 7>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, s_roots, tid, nthr);
+                fft_stage<false, 7>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
                 __syncthreads();
                 FT_PROBE(10 + s);
             }
         } else {
             for (int s = 0; s < plan_nst; ++s) {
-                fft_stage<false, MAXR>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, s_roots, tid, nthr);
+                fft_stage<false, MAXR>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
                 __syncthreads();
             }
             FT_PROBE(19);
@@ -267,21 +309,21 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
             double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
             double* bb = hasb ? a.gp_base[fb2] : nullptr; const i64 sb = hasb ? a.gp_blk[fb2] : 0;
             for (int j0 = tid; j0 < N; j0 += NB * nthr) {
-                double2 x[NB], ch[NB];
+                C x[NB], ch[NB];
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int j = j0 + i * nthr;
                     if (j < N) {
                         x[i] = data[ECT_PAD(j)];
-                        if (c.bluestein) ch[i] = chirp_tab[j > N / 2 ? N - j : j];
+                        if (blue) ch[i] = chirp_tab[j > N / 2 ? N - j : j];
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int j = j0 + i * nthr;
                     if (j >= N) continue;
-                    const double2 y = c.bluestein ? c_mul(ch[i], x[i]) : x[i];
-                    if ((a.dbg & 2) && y.x != 12345.678) continue;
+                    const C y = blue ? c_mul(ch[i], x[i]) : x[i];
+                    if ((a.dbg & 2) && y.x != (R_)12345.678) continue;
                     const int g = g0 + j;
                     if (FP32) {
                         reinterpret_cast<float*>(ba)[oneblk ? (i64)g : gp_index(g, a.nproma, sa)] = (float)y.x;
@@ -297,31 +339,31 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
             // 1/N (tpm_fftw.F90:317-321), Gaussian weight (ledir_mod.F90:122) and, for u and v, 1/(a cos theta)
             // (ldfou2_mod.F90:90-96) in one factor, so that the Legendre loader only forms N +- S
             const double wl = a.rw_loc[l];
-            const double sca = 0.5 / (double)N * wl * (fa < a.n_uv_fields ? s1 : 1.0);
-            const double scb = 0.5 / (double)N * wl * (fb2 >= 0 && fb2 < a.n_uv_fields ? s1 : 1.0);
+            const R_ sca = (R_)(0.5 / (double)N * wl * (fa < a.n_uv_fields ? racthe : 1.0));
+            const R_ scb = (R_)(0.5 / (double)N * wl * (fb2 >= 0 && fb2 < a.n_uv_fields ? racthe : 1.0));
             const int ca = 2 * fa, cb = hasb ? 2 * fb2 : -1;
             for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
-                double2 zk[NB], zn[NB], ch[NB]; double* rb[NB];
+                C zk[NB], zn[NB], ch[NB]; double* rb[NB];
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int k = k0 + i * nthr;
                     if (k <= km) {
                         const int pk_ = s_rec[k];
-                        rb[i] = a.peer[pk_ >> 24] + (long long)(pk_ & 0xffffff) * c.cp;
-                        if (!c.bluestein) { zk[i] = data[ECT_PAD(k)]; zn[i] = data[ECT_PAD(k == 0 ? 0 : N - k)]; }
-                        else { zk[i] = data[ECT_PAD(km + k)]; zn[i] = data[ECT_PAD(km - k)]; ch[i] = c.chirp[k]; }
+                        rb[i] = a.peer[pk_ >> 24] + (long long)(pk_ & 0xffffff) * cp;
+                        if (!blue) { zk[i] = data[ECT_PAD(k)]; zn[i] = data[ECT_PAD(k == 0 ? 0 : N - k)]; }
+                        else { zk[i] = data[ECT_PAD(km + k)]; zn[i] = data[ECT_PAD(km - k)]; ch[i] = g_chirp[k]; }
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int k = k0 + i * nthr;
                     if (k > km) continue;
-                    double2 a_ = zk[i], b_ = zn[i];
-                    if (c.bluestein) { a_ = c_mul(ch[i], a_); b_ = c_mul(ch[i], b_); }
+                    C a_ = zk[i], b_ = zn[i];
+                    if (blue) { a_ = c_mul(ch[i], a_); b_ = c_mul(ch[i], b_); }
                     // stored values are swapped (sign - transform on the sign + core): Z = (y, x)
-                    const double2 Zk = make_double2(a_.y, a_.x), Zn = make_double2(b_.y, b_.x);
-                    *reinterpret_cast<double2*>(rb[i] + ca) = make_double2((Zk.x + Zn.x) * sca, (Zk.y - Zn.y) * sca);
-                    if (cb >= 0) *reinterpret_cast<double2*>(rb[i] + cb) = make_double2((Zk.y + Zn.y) * scb, (Zn.x - Zk.x) * scb);
+                    const C Zk = c_make<C>(a_.y, a_.x), Zn = c_make<C>(b_.y, b_.x);
+                    *reinterpret_cast<double2*>(rb[i] + ca) = make_double2((double)((Zk.x + Zn.x) * sca), (double)((Zk.y - Zn.y) * sca));
+                    if (cb >= 0) *reinterpret_cast<double2*>(rb[i] + cb) = make_double2((double)((Zk.y + Zn.y) * scb), (double)((Zn.x - Zk.x) * scb));
                 }
             }
         }
@@ -333,7 +375,8 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
 static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     EctDevice* d = h->d;
     a.latplans = d->latplans; a.plans = d->plans;
-    a.perm_pool = d->perm_pool; a.tw_pool = d->tw_pool; a.cz_pool = d->cz_pool; a.roots = d->roots;
+    a.perm_pool = d->perm_pool; a.tw_pool = d->tw_pool; a.roots = d->roots;
+    a.cz_pool = f.fp32 ? (const void*)d->cz_pool_f : (const void*)d->cz_pool;
     a.lat_plan = d->lat_plan; a.latrow0 = d->latrow0; a.fft_rec = d->fft_rec;
     a.gpoff = d->gpoff; a.nloen_loc = d->nloen; a.racthe_loc = d->racthe_loc;
     a.fb = d->fbuf_fft; a.cp = f.cp;
@@ -370,12 +413,14 @@ static void launch_fourier(EctHandle* h, FtArgs& a) {
         if (b.lats.empty()) continue;
         if (only && atoi(only) != bi) continue;
         a.lats = b.d_lats;
+        a.nostage = b.nostage;
         const unsigned grid = (unsigned)(b.lats.size() * (size_t)a.nchunks);
         cudaStream_t st = d->stream;
         if (fork) { const int k = slot % (EctDevice::kSide + 1); st = k == 0 ? d->stream : d->side[k - 1]; }
         ++slot;
         if (a.fp32) {
-            if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, true><<<grid, std::min(b.threads, 256), b.smem, st>>>(a);
+            if (b.maxr <= 7 && b.threads == 512) k_fourier<INVERSE, 7, 512, true><<<grid, b.threads, b.smem, st>>>(a);
+            else if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, true><<<grid, b.threads, b.smem, st>>>(a);
             else k_fourier<INVERSE, ECT_MAX_RADIX, 256, true><<<grid, b.threads, b.smem, st>>>(a);
         } else if (b.maxr <= 7 && b.threads == 512) k_fourier<INVERSE, 7, 512, false><<<grid, b.threads, b.smem, st>>>(a);
         else if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, false><<<grid, b.threads, b.smem, st>>>(a);
@@ -433,7 +478,11 @@ int ect_fourier_setup(EctHandle* h) {
     if ((rc = upload(d->latplans, d->fft.latplans))) return rc;
     if ((rc = upload(d->perm_pool, d->fft.perm_pool))) return rc;
     if ((rc = upload(d->tw_pool, d->fft.tw_pool))) return rc;
-    if ((rc = upload(d->cz_pool, d->fft.cz_pool))) return rc;
+    if (h->precision == ECT_PREC_SP) {
+        std::vector<float2> czf(d->fft.cz_pool.size());
+        for (size_t i = 0; i < czf.size(); ++i) czf[i] = make_float2((float)d->fft.cz_pool[i].x, (float)d->fft.cz_pool[i].y);
+        if ((rc = upload(d->cz_pool_f, czf))) return rc;
+    } else if ((rc = upload(d->cz_pool, d->fft.cz_pool))) return rc;
     if (d->fft.roots.empty()) d->fft.roots.assign(ECT_ROOTS_SIZE, make_double2(0.0, 0.0));
     if ((rc = upload(d->roots, d->fft.roots))) return rc;
     if ((rc = upload(d->lat_plan, d->h_lat_plan))) return rc;
@@ -453,34 +502,38 @@ int ect_fourier_setup(EctHandle* h) {
     // shared-memory classes
     int maxsm = 0;
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->dev);
-    const int limits[] = {16 * 1024, 32 * 1024, 56 * 1024, 74 * 1024, 112 * 1024, maxsm - 1024};
-    const int threads[] = {64, 64, 128, 128, 256, 256};
+    const int limits[] = {16 * 1024, 32 * 1024, 56 * 1024, 74 * 1024, 112 * 1024, maxsm - 1024, maxsm - 1024};
+    const int threads[] = {64, 64, 128, 128, 256, 256, 256};
+    const bool sp = h->precision == ECT_PREC_SP;
+    const int csize = sp ? (int)sizeof(float2) : (int)sizeof(double2), iosize = sp ? 4 : 8;
     d->buckets.clear();
     for (int v = 0; v < 2; ++v)
-        for (int i = 0; i < 6; ++i) {
+        for (int i = 0; i < 7; ++i) {
             EctDevice::Bucket b;
             b.smem = limits[i];
             b.threads = v ? std::min(threads[i], 256) : threads[i];
             static const char* t512 = getenv("ECT_FFT_T512");
             if (!v && i >= 4 && t512 && atoi(t512)) b.threads = 512;
+            if (sp && !v && i >= 5) b.threads = 512;      // float work arrays: 128 registers/thread, 16 warps fit
             b.maxr = v ? ECT_MAX_RADIX : 7;
+            b.nostage = i == 6;        // last class: rows too long for a staging area next to the work array
             d->buckets.push_back(b);
         }
     std::vector<int> need_of(P.nlat, 0);
     for (int l = 0; l < P.nlat; ++l) {
         const EctLatPlan& lp = d->fft.latplans[d->h_lat_plan[l]];
         const EctFftPlan& pl = d->fft.plans[lp.plan];
-        const int len_ = pl.n;
-        int need = (ECT_PADDED_LEN(len_) + std::max(2 * (lp.km + 1) + (lp.bluestein ? lp.nlon / 2 + 1 : 0), lp.nlon) + ECT_TW1_LEN(len_) + ECT_TW2_LEN) * (int)sizeof(double2);
-
         int maxr = 2;
         for (int s = 0; s < pl.nst; ++s) if (pl.radix[s] & 1) maxr = std::max(maxr, pl.radix[s]);   // 2,4,8,16 are in every variant
-        need += (maxr <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE) * (int)sizeof(double2);
-        need += ((lp.km + 1) * (int)sizeof(int) + 15) / 16 * 16;
-        need_of[l] = need;
+        const int nroots = maxr <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE;
         bool placed = false;
-        for (auto& b : d->buckets)
+        int need = 0;
+        for (auto& b : d->buckets) {
+            need = std::max(ft_layout(true, lp.bluestein != 0, pl.n, lp.nlon, lp.km, nroots, csize, iosize, b.nostage).total,
+                            ft_layout(false, lp.bluestein != 0, pl.n, lp.nlon, lp.km, nroots, csize, iosize, b.nostage).total);
             if (need <= b.smem && maxr <= b.maxr) { b.lats.push_back(l); placed = true; break; }
+        }
+        need_of[l] = need;
         if (!placed) {
             ect_set_error("ect_setup: latitude with nlon=%d needs %d bytes of shared memory (max %d)",
                           P.nloen[P.lat0 + l], need, maxsm);
@@ -504,6 +557,7 @@ int ect_fourier_setup(EctHandle* h) {
     FT_ATTR(true, 7, 256, false); FT_ATTR(false, 7, 256, false);
     FT_ATTR(true, ECT_MAX_RADIX, 256, false); FT_ATTR(false, ECT_MAX_RADIX, 256, false);
     FT_ATTR(true, 7, 256, true); FT_ATTR(false, 7, 256, true);
+    FT_ATTR(true, 7, 512, true); FT_ATTR(false, 7, 512, true);
     FT_ATTR(true, ECT_MAX_RADIX, 256, true); FT_ATTR(false, ECT_MAX_RADIX, 256, true);
 #undef FT_ATTR
     return ECT_SUCCESS;

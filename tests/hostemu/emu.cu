@@ -55,6 +55,38 @@ int emu_fft(int n, const double* in, double* out) {
     return 0;
 }
 
+// float instantiation of the same core (sp handles): complex sign-+ FFT of smooth length n, and with
+// chirpz = 1 the DIF / fused middle / DIT chain on length n against an all-ones kernel spectrum
+// (= forward FFT on swapped data then inverse, i.e. n * swap(x) reproduced), exercising blue_middle<float2>
+int emu_fft_float(int n, const double* in, double* out, int chirpz) {
+    EctFftTables T;
+    int id = T.get_plan(n, chirpz != 0);
+    if (id < 0) return -1;
+    const EctFftPlan& p = T.plans[id];
+    std::vector<float2> t1(ECT_TW1_LEN(n)), t2(ECT_TW2_LEN), roots(T.roots.size()), data(ECT_PADDED_LEN(n));
+    tw_build(t1.data(), t2.data(), T.tw_pool.data() + p.tw_off, n, 0, 1);
+    for (size_t i = 0; i < roots.size(); ++i) roots[i] = c_cvt<float2>(T.roots[i]);
+    const EctTwT<float2> tw{t1.data(), t2.data()};
+    const uint16_t* perm = T.perm_pool.data() + p.perm_off;
+    const int nthr = 3;
+    if (!chirpz) {
+        for (int i = 0; i < n; ++i) data[ECT_PAD((int)perm[i])] = make_float2((float)in[2 * i], (float)in[2 * i + 1]);
+        for (int s = 0; s < p.nst; ++s)
+            for (int t = 0; t < nthr; ++t) fft_stage<false>(data.data(), n, p.radix[s], p.sublen[s], p.lshift[s], tw, (const float2*)roots.data(), t, nthr);
+    } else {
+        if (p.radix[0] & 1) return -2;
+        std::vector<float2> ones(n, make_float2(1.f, 0.f));
+        for (int i = 0; i < n; ++i) data[ECT_PAD(i)] = make_float2((float)in[2 * i], (float)in[2 * i + 1]);
+        for (int s = p.nst - 1; s >= 1; --s)
+            for (int t = 0; t < nthr; ++t) fft_stage<true>(data.data(), n, p.radix[s], p.sublen[s], p.lshift[s], tw, (const float2*)roots.data(), t, nthr);
+        for (int t = 0; t < nthr; ++t) blue_middle(data.data(), n, p.radix[0], (const float2*)ones.data(), t, nthr);
+        for (int s = 1; s < p.nst; ++s)
+            for (int t = 0; t < nthr; ++t) fft_stage<false>(data.data(), n, p.radix[s], p.sublen[s], p.lshift[s], tw, (const float2*)roots.data(), t, nthr);
+    }
+    for (int i = 0; i < n; ++i) { out[2 * i] = data[ECT_PAD(i)].x; out[2 * i + 1] = data[ECT_PAD(i)].y; }
+    return 0;
+}
+
 // inverse pair: spec [km+1][4] = (reA, imA, reB, imB) records; out rows [nlon] each
 int emu_ftinv_pair(int nlon, int km, const double* spec, double* outa, double* outb, int nthr, int force_blue) {
     g_ect_force_bluestein = force_blue;

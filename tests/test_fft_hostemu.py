@@ -34,6 +34,31 @@ def test_fft_all_small_even_lengths(emu):
     assert checked > 120
 
 
+def test_fft_float_core(emu):
+    """The same templated core instantiated on float2 (sp handles): smooth lengths directly, and the
+    chirp-z chain (DIF stages, fused middle, DIT stages) with a unit kernel, which must return n * swap(x)."""
+    rng = np.random.default_rng(1)
+    for n in (20, 48, 336, 1024, 1616, 2310, 4096, 10368, 16384):
+        if not emu.emu_smooth(n):
+            continue
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        xin = np.ascontiguousarray(np.stack([x.real, x.imag], 1))
+        out = np.zeros((n, 2))
+        assert emu.emu_fft_float(n, P(xin), P(out), 0) == 0
+        ref = np.fft.ifft(x) * n
+        err = np.linalg.norm(out[:, 0] + 1j * out[:, 1] - ref) / np.linalg.norm(ref)
+        assert err < 1e-6, (n, err)
+    for n in (64, 1024, 3 * 512, 5 * 1024, 7 * 2048, 16384):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        xin = np.ascontiguousarray(np.stack([x.real, x.imag], 1))
+        out = np.zeros((n, 2))
+        assert emu.emu_fft_float(n, P(xin), P(out), 1) == 0
+        # F+(swap(F+(x))) = i conj(F-(F+(x))) = n swap(x)   (swap(z) = i conj(z); the kernels swap on load)
+        want = n * (x.imag + 1j * x.real)
+        err = np.linalg.norm(out[:, 0] + 1j * out[:, 1] - want) / np.linalg.norm(want)
+        assert err < 2e-6, (n, err)
+
+
 def _pair(emu, nlon, km, force, nthr, rng):
     sa = rng.standard_normal(km + 1) + 1j * rng.standard_normal(km + 1)
     sb = rng.standard_normal(km + 1) + 1j * rng.standard_normal(km + 1)

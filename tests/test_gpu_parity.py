@@ -331,14 +331,46 @@ def test_single_precision_face(eb, T, N, nuv, nsc, opts):
     ref = eo.inv_trans(s, vor, div, sc, **opts)
     gp = tr.inv_trans(T_(vor).astype(np.float32), T_(div).astype(np.float32), T_(sc).astype(np.float32), **opts)
     assert gp.dtype == np.float32
+    # sp handles compute the Fourier stage in float (as the reference's sp build does); stated tolerance 1e-5
     for i in range(ref.shape[0]):
-        assert rel(gp[0, i].astype(np.float64), ref[i]) < 1e-6
+        assert rel(gp[0, i].astype(np.float64), ref[i]) < 5e-6
     gin = f32(ref[:2 * nuv + nsc])
     rv, rd, rs = eo.dir_trans(s, gin, nuv, nsc)
     ov, od, os_ = tr.dir_trans(gin[None].astype(np.float32), nuv, nsc)
     for a, b in ((ov, rv), (od, rd), (os_, rs)):
-        assert a.dtype == np.float32 and rel(a.T.astype(np.float64), b) < 1e-6
+        assert a.dtype == np.float32 and rel(a.T.astype(np.float64), b) < 5e-6
     assert rel(tr.specnorm(T_(sc).astype(np.float32)), eo.specnorm(s, sc)) < 1e-6
+    tr.release()
+
+
+def test_tco2559_rows_sp(eb):
+    """BASELINE config 4 grid (TCo2559 / O2560, sp; rows up to 10256 points, chirp-z length 16384 in float,
+    the longest rows without a staging area) on one GPU with a reduced field count: the benchmark's
+    single-harmonic input against its analytic answer, linearity and the round trip, tolerance 1e-5."""
+    T, N = 2559, 2560
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen, precision="sp")
+    nf = 4
+    rng = np.random.default_rng(11)
+    n = np.concatenate([np.repeat(np.arange(m, T + 1), 2) for m in range(T + 1)]).astype(float)
+    a = (rng.uniform(-1, 1, (tr.nspec2, nf)) / (1 + n[:, None]) ** 1.5).astype(np.float32)
+    a[1:2 * (T + 1):2] = 0
+    b = np.zeros_like(a)
+    b[int(tr.nasm0[4]) + 2 * (19 - 4)] = 1.0
+    ga, gb = tr.inv_trans(spscalar=a), tr.inv_trans(spscalar=b)
+    assert ga.dtype == np.float32
+    off = np.concatenate([[0], np.cumsum(nloen)])
+    for j in (0, 5, 1000, 2047, 2559, 2560, 4000, 5119):
+        nlon = int(nloen[j])
+        row = gb[0, 0, off[j]:off[j] + nlon].astype(np.float64)
+        if tr.nmen[j] >= 4:
+            p = eo.supolf(4, 19, tr.rmu[j])[19, 0]
+            assert np.abs(row - 2 * p * np.cos(2 * np.pi * 4 * np.arange(nlon) / nlon)).max() < 1e-5
+    gab = tr.inv_trans(spscalar=(a - 2.5 * b).astype(np.float32))
+    assert rel(gab.astype(np.float64), ga.astype(np.float64) - 2.5 * gb) < 1e-5
+    back = tr.dir_trans(ga, 0, nf)[2]
+    assert rel(back.astype(np.float64), a.astype(np.float64)) < 1e-5
+    assert np.abs(tr.specnorm(back) / tr.specnorm(a) - 1).max() < 1e-5
     tr.release()
 
 
