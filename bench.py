@@ -35,7 +35,10 @@ CONFIGS = {
     "T159_O160_L137": (159, 160, 137, 3),
     "TCo399_O400_L137": (399, 400, 137, 1),
     "TCo1279_O1280_L137": (1279, 1280, 137, 1),
+    "TCo2559_O2560_L137": (2559, 2560, 137, 1),
 }
+# BASELINE.json configs 2 and 4 are single precision builds (JPRB = real32)
+PRECISION = {"TCo399_O400_L137": "sp", "TCo2559_O2560_L137": "sp"}
 
 
 def legendre_flops(T, ndglu, nfields):
@@ -167,7 +170,8 @@ def run_reference(args):
               f"{2 * nuv + nsc} fields, scaled by sampled flops / grid points; oracle port (NumPy+OpenBLAS GEMM, scipy pocketfft with all cores)")
     line = {"impl": "reference", "metric": "ms per INV_TRANS+DIR_TRANS step", "value": v, "unit": "ms",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v,
-            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if prec == "dp" else "f32 at the boundary and in the Fourier stage, f64 DMMA contraction", "data": "synthetic",
             "config": {"workload": args.config, "fields": 2 * nuv + nsc},
             "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample, "detail": detail},
             "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -199,12 +203,15 @@ def run_ours(args):
     nf = 2 * nuv + nsc
     stream = torch.cuda.current_stream().cuda_stream
     t0 = time.time()
-    tr = eb.Transform(T, eb.octahedral_nloen(N), nranks=world, rank=rank, device=local, stream=stream, nccl_uid=uid)
+    prec = args.precision or PRECISION.get(args.config, "dp")
+    tdt, ndt, esz = (torch.float32, np.float32, 4) if prec == "sp" else (torch.float64, np.float64, 8)
+    tr = eb.Transform(T, eb.octahedral_nloen(N), nranks=world, rank=rank, device=local, stream=stream, nccl_uid=uid,
+                      precision=prec)
     setup_s = time.time() - t0
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
-    mk = lambda n: (torch.rand((tr.nspec2, n), generator=g, device=dev, dtype=torch.float64) - 0.5) * 0.2
+    mk = lambda n: (torch.rand((tr.nspec2, n), generator=g, device=dev, dtype=tdt) - 0.5) * 0.2
     spvor, spdiv, spsc = mk(nuv), mk(nuv), mk(nsc)
-    gp = torch.empty((1, nf, tr.ngptot), dtype=torch.float64, device=dev)
+    gp = torch.empty((1, nf, tr.ngptot), dtype=tdt, device=dev)
     o_vor, o_div, o_sc = (torch.empty_like(spvor), torch.empty_like(spdiv), torch.empty_like(spsc))
 
     def barrier():
@@ -261,13 +268,13 @@ def run_ours(args):
     if not args.no_e2e:
         del gp, o_vor, o_div, o_sc
         torch.cuda.empty_cache()
-        h_in = [eb.PinnedArray((tr.nspec2, n)) for n in (nuv, nuv, nsc)]
+        h_in = [eb.PinnedArray((tr.nspec2, n), dtype=ndt) for n in (nuv, nuv, nsc)]
         for hp, dv in zip(h_in, (spvor, spdiv, spsc)):
             hp.array[...] = dv.cpu().numpy()
         del spvor, spdiv, spsc
         torch.cuda.empty_cache()
-        h_gp = eb.PinnedArray((1, nf, tr.ngptot))
-        h_out = [eb.PinnedArray((tr.nspec2, n)) for n in (nuv, nuv, nsc)]
+        h_gp = eb.PinnedArray((1, nf, tr.ngptot), dtype=ndt)
+        h_out = [eb.PinnedArray((tr.nspec2, n), dtype=ndt) for n in (nuv, nuv, nsc)]
 
         def step_host():
             tr.inv_trans(h_in[0].array, h_in[1].array, h_in[2].array, out=h_gp.array)
@@ -288,8 +295,8 @@ def run_ours(args):
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        bytes_in = 8 * (tr.nspec2 * nf + tr.ngptot * nf)
-        bytes_out = 8 * (tr.ngptot * nf + tr.nspec2 * nf)
+        bytes_in = esz * (tr.nspec2 * nf + tr.ngptot * nf)
+        bytes_out = esz * (tr.ngptot * nf + tr.nspec2 * nf)
         e2e = {"value": float(te.cpu()[0]), "unit": "ms", "h2d_bytes_per_step": int(bytes_in),
                "d2h_bytes_per_step": int(bytes_out), "steps": ne}
     if rank != 0:
@@ -313,12 +320,13 @@ def run_ours(args):
                        "source": tj["source"]}
     except Exception:
         traffic = None
-    fb = 2.0 * fft_bytes(tr.nloen, nf)
+    fb = 2.0 * fft_bytes(tr.nloen, nf) * esz / 8
     ft_ach = fb / world / (ft_ms * 1e-3) / 1e9
     line = {
         "metric": "ms per INV_TRANS+DIR_TRANS step", "value": ms_dev, "unit": "ms", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if prec == "dp" else "f32 at the boundary and in the Fourier stage, f64 DMMA contraction", "data": "synthetic",
         "config": {"workload": args.config, "truncation": T, "grid": f"O{N}", "levels": nlev, "fields": nf,
                    "decomposition": f"nprtrw={world},nprtrv=1", "l2": "inputs (GBs) larger than L2, no flush needed"},
         "stages_ms": {"legendre": leg_ms, "fourier": ft_ms, "transpose": tp_ms,
@@ -351,6 +359,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="TCo1279_O1280_L137", choices=list(CONFIGS))
+    ap.add_argument("--precision", default=None, choices=["dp", "sp"], help="default: the config's (TCo399, TCo2559: sp)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -190,6 +190,9 @@ void ect_device_free(EctHandle* h) {
     }
     if (d->fbuf_fft && d->fbuf_fft != d->fbuf_leg) cudaFree(d->fbuf_fft);
     for (auto& b : d->buckets) if (b.d_lats) cudaFree(b.d_lats);
+    if (d->cin) { cudaStreamDestroy(d->cin); cudaStreamDestroy(d->cout); cudaEventDestroy(d->ev_c0); cudaEventDestroy(d->ev_c1); }
+    for (int i = 0; i < 2; ++i) for (cudaEvent_t e : {d->ev_in_ready[i], d->ev_cmp_done[i], d->ev_out_done[i]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : d->ev_sp) if (e) cudaEventDestroy(e);
     for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
     for (int k = 0; k < EctDevice::kSide; ++k) { if (d->ev_join[k]) cudaEventDestroy(d->ev_join[k]); if (d->side[k]) cudaStreamDestroy(d->side[k]); }
@@ -372,6 +375,21 @@ static int ensure_work(EctHandle* h, const EctFieldCfg& f) {
     return ECT_SUCCESS;
 }
 
+// Per-call tables go to the device through a tiny kernel that reads the pinned (mapped) host buffer, not through
+// cudaMemcpyAsync: a DMA copy would queue behind the multi-GB field copies of the chunked host path in the same
+// copy engine and stall the compute stream until they finish (measured: 16 ms of kernels took 60 ms per chunk).
+__global__ void k_upload_tables(int4* __restrict__ dst, const int4* __restrict__ src, int n16) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static int upload_callbuf(EctDevice* d, size_t bytes) {
+    const int n16 = (int)((bytes + 15) / 16);
+    void* hdev = nullptr;
+    ECT_CUDA(cudaHostGetDevicePointer(&hdev, d->h_callbuf, 0));
+    k_upload_tables<<<std::min(64, (n16 + 255) / 256), 256, 0, d->stream>>>((int4*)d->callbuf, (const int4*)hdev, n16);
+    d->launches++;
+    return ECT_SUCCESS;
+}
+
 static int ensure_callbuf(EctDevice* d, size_t bytes) {
     const int i = d->ring_next;
     d->ring_next = (i + 1) % EctDevice::kSlots;
@@ -382,7 +400,7 @@ static int ensure_callbuf(EctDevice* d, size_t bytes) {
         if (d->ring_d[i]) { ECT_CUDA(cudaFree(d->ring_d[i])); ECT_CUDA(cudaFreeHost(d->ring_h[i])); }
         bytes = (bytes + 4095) / 4096 * 4096;
         ECT_CUDA(cudaMalloc(&d->ring_d[i], bytes));
-        ECT_CUDA(cudaHostAlloc(&d->ring_h[i], bytes, cudaHostAllocDefault));
+        ECT_CUDA(cudaHostAlloc(&d->ring_h[i], bytes, cudaHostAllocMapped));
         d->ring_bytes[i] = bytes;
     }
     d->callbuf = d->ring_d[i];
@@ -452,7 +470,342 @@ static std::vector<int2> make_pairs(const std::vector<int>& groups) {
     return pairs;
 }
 
-extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
+
+// ---------------------------------------------------------------------------------------
+// Host-pointer calls on large field sets: the call is split into field chunks and pipelined -- chunk c+1's
+// inputs travel host->device and chunk c-1's results device->host (each on its own copy stream) while chunk c
+// is transformed, so that the PCIe time of the larger side hides everything else.  A chunk is an ordinary
+// device-pointer call on dense staging arrays; chunks never mix scalar fields of different caller arrays
+// (fields of one array share complex transforms, see make_pairs).  The chunk plan depends on global sizes only,
+// so every rank issues the same sequence of (collective) sub-calls.
+// ---------------------------------------------------------------------------------------
+// sub-call view: the chunk's spectral fields live inside larger staged arrays (row pitch in fields)
+struct SubView { int uv_stride, sc_stride; };
+static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view);
+static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view);
+struct HostChunk { int j0, nj; int seg, s0, ns; };   // uv levels [j0, j0+nj), scalars [s0, s0+ns) (flattened index) of segment seg
+// one caller array slice: fields [start, start+count) contiguous with pitch = count; arr = which caller array,
+// dev = the slice inside the staged copy of that array
+struct ScSeg { double* base; int start, count; int arr; double* dev; };
+
+static int host_chunk_target() {          // Legendre fields per chunk; ECT_HOST_CHUNK_FIELDS=0 disables chunking
+    const char* e = getenv("ECT_HOST_CHUNK_FIELDS");
+    return e ? atoi(e) : 32;
+}
+static int host_chunk_count(EctHandle* h, int nleg) {
+    const int target = host_chunk_target();
+    if (target <= 0) return 1;
+    const char* mb = getenv("ECT_HOST_CHUNK_MIN_BYTES");
+    const double minb = mb ? atof(mb) : 256e6;
+    if ((double)h->hp.ngptotg * nleg * 8.0 < minb || nleg < 2 * target) return 1;
+    return (nleg + target - 1) / target;
+}
+
+static std::vector<HostChunk> plan_chunks(int kf_uv, int w_uv, const std::vector<ScSeg>& segs, int w_sc) {
+    const int target = std::max(1, host_chunk_target());
+    std::vector<HostChunk> out;
+    auto split = [&](int n, int per, auto emit) {
+        if (n <= 0) return;
+        const int nc = (n + per - 1) / per;
+        int i0 = 0;
+        for (int c = 0; c < nc; ++c) { const int cnt = n / nc + (c < n % nc ? 1 : 0); emit(i0, cnt); i0 += cnt; }
+    };
+    split(kf_uv, std::max(1, target / w_uv), [&](int i0, int cnt) { out.push_back({i0, cnt, -1, 0, 0}); });
+    for (int g = 0; g < (int)segs.size(); ++g)
+        split(segs[g].count, std::max(1, target / w_sc), [&](int i0, int cnt) { out.push_back({0, 0, g, segs[g].start + i0, cnt}); });
+    return out;
+}
+
+static int copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                  cudaMemcpyKind kind, cudaStream_t st) {
+    if (width == 0 || height == 0) return ECT_SUCCESS;
+    if (height == 1 || (dpitch == width && spitch == width)) {
+        ECT_CUDA(cudaMemcpyAsync(dst, src, width * height, kind, st));
+        return ECT_SUCCESS;
+    }
+    const size_t maxp = (size_t)1 << 31;
+    if (dpitch >= maxp || spitch >= maxp) {
+        for (size_t r = 0; r < height; ++r)
+            ECT_CUDA(cudaMemcpyAsync((char*)dst + r * dpitch, (const char*)src + r * spitch, width, kind, st));
+        return ECT_SUCCESS;
+    }
+    ECT_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, st));
+    return ECT_SUCCESS;
+}
+
+// dense chunk array (nproma, nf_c, ngpblks) on the device <-> the caller's fields gidx[0..nf_c) (runs of fields that
+// are neighbours in the caller's array move as one 2-D copy)
+static int copy_gp_fields(bool to_host, char* dev, const std::vector<int>& gidx, const std::vector<double*>& hb,
+                          const std::vector<i64>& hs, int nproma, int ngpblks, int es, cudaStream_t st) {
+    const int nfc = (int)gidx.size();
+    int rc;
+    for (int i = 0; i < nfc;) {
+        int j = i + 1;
+        while (j < nfc && hs[gidx[j]] == hs[gidx[i]] &&
+               (char*)hb[gidx[j]] == (char*)hb[gidx[i]] + (size_t)(j - i) * nproma * es) ++j;
+        const size_t width = (size_t)(j - i) * nproma * es;
+        char* dp = dev + (size_t)i * nproma * es;
+        const size_t dpitch = (size_t)nfc * nproma * es, hpitch = (size_t)hs[gidx[i]] * es;
+        if (to_host) rc = copy2d(hb[gidx[i]], hpitch, dp, dpitch, width, ngpblks, cudaMemcpyDeviceToHost, st);
+        else rc = copy2d(dp, dpitch, hb[gidx[i]], hpitch, width, ngpblks, cudaMemcpyHostToDevice, st);
+        if (rc) return rc;
+        i = j;
+    }
+    return ECT_SUCCESS;
+}
+
+// ECT_HOST_CHUNK_DBG=1: per-chunk timeline (ms after the start of the call) on stderr
+struct ChunkTrace {
+    bool on; cudaEvent_t t0; std::vector<cudaEvent_t> ev; std::vector<const char*> tag; std::vector<int> chunk;
+    explicit ChunkTrace(cudaEvent_t start) : t0(start) { const char* e = getenv("ECT_HOST_CHUNK_DBG"); on = e && atoi(e); }
+    void mark(const char* what, int c, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+        ev.push_back(e); tag.push_back(what); chunk.push_back(c);
+    }
+    void dump(const char* name) {
+        if (!on) return;
+        for (size_t i = 0; i < ev.size(); ++i) {
+            float ms = 0.f; cudaEventElapsedTime(&ms, t0, ev[i]);
+            fprintf(stderr, "[%s] chunk %2d %-9s %8.2f ms\n", name, chunk[i], tag[i], ms);
+            cudaEventDestroy(ev[i]);
+        }
+    }
+};
+
+static int ensure_pipe(EctDevice* d) {
+    if (d->cin) return ECT_SUCCESS;
+    ECT_CUDA(cudaStreamCreateWithFlags(&d->cin, cudaStreamNonBlocking));
+    ECT_CUDA(cudaStreamCreateWithFlags(&d->cout, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        ECT_CUDA(cudaEventCreateWithFlags(&d->ev_in_ready[i], cudaEventDisableTiming));
+        ECT_CUDA(cudaEventCreateWithFlags(&d->ev_cmp_done[i], cudaEventDisableTiming));
+        ECT_CUDA(cudaEventCreateWithFlags(&d->ev_out_done[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 4; ++i) ECT_CUDA(cudaEventCreateWithFlags(&d->ev_sp[i], cudaEventDisableTiming));
+    ECT_CUDA(cudaEventCreate(&d->ev_c0));
+    ECT_CUDA(cudaEventCreate(&d->ev_c1));
+    return ECT_SUCCESS;
+}
+
+// The spectral arrays are (nspec2, fields) with the field index fastest: a field chunk is a column block, whose
+// narrow-row 2-D copies run far below PCIe speed.  They are therefore staged whole (they are the small side,
+// 1/5 of the bytes) -- array by array in the order the chunks need them -- and the sub-calls address their
+// columns inside the staged arrays (SubView); the grid-point side moves chunk by chunk.
+struct SpStage {
+    double* dev[5] = {};       // staged vor, div, scalar arrays (mode 1: spscalar; mode 2: sc2, sc3a, sc3b)
+    double* host[5] = {};
+    i64 elems[5] = {};
+};
+
+static std::vector<ScSeg> scalar_segments(bool mode2, const SpStage& st, int kf_sc, int nsc2, int lev_a, int fld_a,
+                                          int lev_b, int fld_b, i64 nsp, int es) {
+    std::vector<ScSeg> segs;
+    if (!mode2) { if (kf_sc) segs.push_back({st.host[2], 0, kf_sc, 2, st.dev[2]}); return segs; }
+    int s0 = 0;
+    if (nsc2) { segs.push_back({st.host[2], s0, nsc2, 2, st.dev[2]}); s0 += nsc2; }
+    for (int j3 = 0; j3 < fld_a; ++j3) {
+        segs.push_back({adv(st.host[3], (i64)j3 * lev_a * nsp, es), s0, lev_a, 3, adv(st.dev[3], (i64)j3 * lev_a * nsp, es)});
+        s0 += lev_a;
+    }
+    for (int j3 = 0; j3 < fld_b; ++j3) {
+        segs.push_back({adv(st.host[4], (i64)j3 * lev_b * nsp, es), s0, lev_b, 4, adv(st.dev[4], (i64)j3 * lev_b * nsp, es)});
+        s0 += lev_b;
+    }
+    return segs;
+}
+
+static int layout_sp_stage(EctDevice* d, SpStage& st, int es) {
+    i64 tot = 0;
+    for (int i = 0; i < 5; ++i) tot += (st.elems[i] + 31) / 32 * 32;
+    int rc;
+    if ((rc = ensure(d->stage_sp, d->stage_sp_elems, tot, d->stream, false))) return rc;
+    double* p = d->stage_sp;
+    for (int i = 0; i < 5; ++i) { st.dev[i] = st.elems[i] ? p : nullptr; p = adv(p, (st.elems[i] + 31) / 32 * 32, es); }
+    return ECT_SUCCESS;
+}
+
+template <typename Fill>
+static int inv_trans_chunked(int handle, EctHandle* h, const ect_inv_args* a, const EctFieldCfg& f, bool mode2_sp,
+                             int nsc2, int n3a, int n3b, int nproma, int ngpblks, Fill& fill_gp_table) {
+    EctDevice* d = h->d;
+    const EctHostPlan& P = h->hp;
+    const int es = f.fp32 ? 4 : 8;
+    const i64 nsp = P.nspec2, blk = (i64)nproma * ngpblks;
+    const int kf_uv = f.kf_uv, kf_sc = f.kf_sc;
+    int rc;
+    if ((rc = ensure_pipe(d))) return rc;
+    SpStage st;
+    st.host[0] = (double*)a->spvor; st.host[1] = (double*)a->spdiv; st.elems[0] = st.elems[1] = (i64)kf_uv * nsp;
+    if (!mode2_sp) { st.host[2] = (double*)a->spscalar; st.elems[2] = (i64)kf_sc * nsp; }
+    else {
+        st.host[2] = (double*)a->spsc2; st.elems[2] = (i64)nsc2 * nsp;
+        st.host[3] = (double*)a->spsc3a; st.elems[3] = (i64)n3a * nsp;
+        st.host[4] = (double*)a->spsc3b; st.elems[4] = (i64)n3b * nsp;
+    }
+    if ((rc = layout_sp_stage(d, st, es))) return rc;
+    const std::vector<ScSeg> segs = scalar_segments(mode2_sp, st, kf_sc, nsc2, a->nsc3a_lev, n3a ? a->nsc3a_fld : 0,
+                                                    a->nsc3b_lev, n3b ? a->nsc3b_fld : 0, nsp, es);
+    std::vector<double*> hgpb(f.nfs);
+    std::vector<i64> hgps(f.nfs);
+    fill_gp_table(a->gp, a->gpuv, a->gp2, a->gp3a, a->gp3b, hgpb.data(), hgps.data());
+    // global Fourier-field index of each kind (order: [vor][div] u v scalars [nsd] [du dv] [ewd])
+    const int n_vor = f.vorgp ? kf_uv : 0, n_div = f.divgp ? kf_uv : 0, n_nsd = f.scders ? kf_sc : 0;
+    const int g_vor = 0, g_div = n_vor, g_u = n_vor + n_div, g_v = g_u + kf_uv, g_sc = g_v + kf_uv, g_nsd = g_sc + kf_sc,
+              g_du = g_nsd + n_nsd, g_dv = g_du + kf_uv, g_ewd = g_du + (f.uvder ? 2 * kf_uv : 0);
+    const int w_uv = 2 + (f.vorgp ? 1 : 0) + (f.divgp ? 1 : 0), w_sc = 1 + (f.scders ? 1 : 0);
+    // scalar chunks first: their arrays are the smaller ones, so the first results leave sooner
+    std::vector<HostChunk> chunks = plan_chunks(kf_uv, w_uv, segs, w_sc);
+    std::stable_partition(chunks.begin(), chunks.end(), [](const HostChunk& c) { return c.ns > 0; });
+    i64 max_out = 0;
+    for (const HostChunk& c : chunks)
+        max_out = std::max(max_out, (i64)(c.nj * (w_uv + (f.uvder ? 2 : 0)) + c.ns * (f.scders ? 3 : 1)) * blk);
+    max_out = (max_out + 31) / 32 * 32;
+    if ((rc = ensure(d->stage_gp, d->stage_gp_elems, 2 * max_out, d->stream, false))) return rc;
+    ECT_CUDA(cudaEventRecord(d->ev_c0, d->stream));
+    ECT_CUDA(cudaStreamWaitEvent(d->cin, d->ev_c0, 0));
+    ChunkTrace trace(d->ev_c0);
+    // ---- spectral inputs, whole arrays in the order of use (copy-in stream) ----
+    for (int i : {2, 3, 4, 0, 1}) {
+        if (st.elems[i]) ECT_CUDA(cudaMemcpyAsync(st.dev[i], st.host[i], (size_t)st.elems[i] * es, cudaMemcpyHostToDevice, d->cin));
+        if (i >= 1) ECT_CUDA(cudaEventRecord(d->ev_sp[i - 1], d->cin));       // ev_sp[0]: vor and div, ev_sp[1..3]: scalar arrays
+        trace.mark("sp_in", i, d->cin);
+    }
+    i64 launches = 0;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+        const HostChunk& c = chunks[ic];
+        const int slot = (int)(ic & 1);
+        double* out = adv(d->stage_gp, slot * max_out, es);
+        // ---- transform (handle stream): a device-pointer call on columns of the staged arrays ----
+        ECT_CUDA(cudaStreamWaitEvent(d->stream, d->ev_sp[c.nj ? 0 : segs[c.seg].arr - 1], 0));
+        if (ic >= 2) ECT_CUDA(cudaStreamWaitEvent(d->stream, d->ev_out_done[slot], 0));
+        ect_inv_args sub;
+        memset(&sub, 0, sizeof(sub));
+        sub.memspace = ECT_MEM_DEVICE; sub.nproma = a->nproma;
+        sub.scders = a->scders; sub.vorgp = a->vorgp; sub.divgp = a->divgp; sub.uvder = a->uvder;
+        SubView view{kf_uv, 0};
+        if (c.nj) { sub.spvor = adv(st.dev[0], c.j0, es); sub.spdiv = adv(st.dev[1], c.j0, es); sub.nuv = c.nj; }
+        if (c.ns) {
+            const ScSeg& sg = segs[c.seg];
+            sub.spscalar = adv(sg.dev, c.s0 - sg.start, es); sub.nscalar = c.ns; view.sc_stride = sg.count;
+        }
+        sub.gp = out;
+        trace.mark("cmp_start", (int)ic, d->stream);
+        if ((rc = inv_trans_impl(handle, &sub, &view))) return rc;
+        launches += d->launches;
+        ECT_CUDA(cudaEventRecord(d->ev_cmp_done[slot], d->stream));
+        trace.mark("cmp_done", (int)ic, d->stream);
+        // ---- results (copy-out stream) ----
+        std::vector<int> gidx;
+        auto add = [&](int g0, int i0, int n) { for (int i = 0; i < n; ++i) gidx.push_back(g0 + i0 + i); };
+        if (f.vorgp) add(g_vor, c.j0, c.nj);
+        if (f.divgp) add(g_div, c.j0, c.nj);
+        add(g_u, c.j0, c.nj); add(g_v, c.j0, c.nj);
+        add(g_sc, c.s0, c.ns);
+        if (f.scders) add(g_nsd, c.s0, c.ns);
+        if (f.uvder) { add(g_du, c.j0, c.nj); add(g_dv, c.j0, c.nj); }
+        if (f.scders) add(g_ewd, c.s0, c.ns);
+        ECT_CUDA(cudaStreamWaitEvent(d->cout, d->ev_cmp_done[slot], 0));
+        if ((rc = copy_gp_fields(true, (char*)out, gidx, hgpb, hgps, nproma, ngpblks, es, d->cout))) return rc;
+        ECT_CUDA(cudaEventRecord(d->ev_out_done[slot], d->cout));
+        trace.mark("out_done", (int)ic, d->cout);
+    }
+    for (int i = 0; i < 2 && i < (int)chunks.size(); ++i) ECT_CUDA(cudaStreamWaitEvent(d->stream, d->ev_out_done[i], 0));
+    ECT_CUDA(cudaEventRecord(d->ev_c1, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    ECT_CUDA(cudaEventElapsedTime(&d->chunked_ms, d->ev_c0, d->ev_c1));
+    trace.dump("inv");
+    d->launches = launches;
+    d->last_dir = 0;
+    return ECT_SUCCESS;
+}
+
+template <typename Fill>
+static int dir_trans_chunked(int handle, EctHandle* h, const ect_dir_args* a, const EctFieldCfg& f, bool mode2,
+                             int nsc2, int n3a, int n3b, int nproma, int ngpblks, Fill& fill_gp_table) {
+    EctDevice* d = h->d;
+    const EctHostPlan& P = h->hp;
+    const int es = f.fp32 ? 4 : 8;
+    const i64 nsp = P.nspec2, blk = (i64)nproma * ngpblks;
+    const int kf_uv = f.kf_uv, kf_sc = f.kf_sc;
+    int rc;
+    if ((rc = ensure_pipe(d))) return rc;
+    SpStage st;
+    st.host[0] = a->spvor; st.host[1] = a->spdiv; st.elems[0] = st.elems[1] = (i64)kf_uv * nsp;
+    if (!mode2) { st.host[2] = a->spscalar; st.elems[2] = (i64)kf_sc * nsp; }
+    else {
+        st.host[2] = a->spsc2; st.elems[2] = (i64)nsc2 * nsp;
+        st.host[3] = a->spsc3a; st.elems[3] = (i64)n3a * nsp;
+        st.host[4] = a->spsc3b; st.elems[4] = (i64)n3b * nsp;
+    }
+    if ((rc = layout_sp_stage(d, st, es))) return rc;
+    const std::vector<ScSeg> segs = scalar_segments(mode2, st, kf_sc, nsc2, a->nsc3a_lev, n3a ? a->nsc3a_fld : 0,
+                                                    a->nsc3b_lev, n3b ? a->nsc3b_fld : 0, nsp, es);
+    std::vector<double*> hgpb(f.nfs);
+    std::vector<i64> hgps(f.nfs);
+    fill_gp_table((double*)a->gp, (double*)a->gpuv, (double*)a->gp2, (double*)a->gp3a, (double*)a->gp3b, hgpb.data(), hgps.data());
+    const std::vector<HostChunk> chunks = plan_chunks(kf_uv, 2, segs, 1);
+    i64 max_in = 0;
+    for (const HostChunk& c : chunks) max_in = std::max(max_in, (2 * (i64)c.nj + c.ns) * blk);
+    max_in = (max_in + 31) / 32 * 32;
+    if ((rc = ensure(d->stage_gp, d->stage_gp_elems, 2 * max_in, d->stream, false))) return rc;
+    ECT_CUDA(cudaEventRecord(d->ev_c0, d->stream));
+    ECT_CUDA(cudaStreamWaitEvent(d->cin, d->ev_c0, 0));
+    ECT_CUDA(cudaStreamWaitEvent(d->cout, d->ev_c0, 0));
+    ChunkTrace trace(d->ev_c0);
+    i64 launches = 0;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+        const HostChunk& c = chunks[ic];
+        const int slot = (int)(ic & 1);
+        double* in = adv(d->stage_gp, slot * max_in, es);
+        // ---- grid-point inputs of the chunk (copy-in stream) ----
+        if (ic >= 2) ECT_CUDA(cudaStreamWaitEvent(d->cin, d->ev_cmp_done[slot], 0));
+        std::vector<int> gidx;     // global input field of each chunk field: u levels, v levels, scalars
+        for (int i = 0; i < c.nj; ++i) gidx.push_back(c.j0 + i);
+        for (int i = 0; i < c.nj; ++i) gidx.push_back(kf_uv + c.j0 + i);
+        for (int i = 0; i < c.ns; ++i) gidx.push_back(2 * kf_uv + c.s0 + i);
+        if ((rc = copy_gp_fields(false, (char*)in, gidx, hgpb, hgps, nproma, ngpblks, es, d->cin))) return rc;
+        ECT_CUDA(cudaEventRecord(d->ev_in_ready[slot], d->cin));
+        trace.mark("in_done", (int)ic, d->cin);
+        // ---- transform: results go to columns of the staged spectral arrays ----
+        ECT_CUDA(cudaStreamWaitEvent(d->stream, d->ev_in_ready[slot], 0));
+        ect_dir_args sub;
+        memset(&sub, 0, sizeof(sub));
+        sub.memspace = ECT_MEM_DEVICE; sub.nproma = a->nproma;
+        sub.nuv = c.nj; sub.nscalar = c.ns; sub.gp = in;
+        SubView view{kf_uv, 0};
+        if (c.nj) { sub.spvor = adv(st.dev[0], c.j0, es); sub.spdiv = adv(st.dev[1], c.j0, es); }
+        if (c.ns) { const ScSeg& sg = segs[c.seg]; sub.spscalar = adv(sg.dev, c.s0 - sg.start, es); view.sc_stride = sg.count; }
+        trace.mark("cmp_start", (int)ic, d->stream);
+        if ((rc = dir_trans_impl(handle, &sub, &view))) return rc;
+        launches += d->launches;
+        ECT_CUDA(cudaEventRecord(d->ev_cmp_done[slot], d->stream));
+        trace.mark("cmp_done", (int)ic, d->stream);
+        // ---- a spectral array goes back as soon as its last chunk is done (copy-out stream) ----
+        const bool last = ic + 1 == chunks.size();
+        const int arr_now = c.nj ? 0 : segs[c.seg].arr, arr_next = last ? -1 : (chunks[ic + 1].nj ? 0 : segs[chunks[ic + 1].seg].arr);
+        if (arr_now != arr_next) {
+            ECT_CUDA(cudaStreamWaitEvent(d->cout, d->ev_cmp_done[slot], 0));
+            for (int i = (arr_now == 0 ? 0 : arr_now); i <= (arr_now == 0 ? 1 : arr_now); ++i)
+                if (st.elems[i]) ECT_CUDA(cudaMemcpyAsync(st.host[i], st.dev[i], (size_t)st.elems[i] * es, cudaMemcpyDeviceToHost, d->cout));
+            trace.mark("sp_out", arr_now, d->cout);
+        }
+    }
+    ECT_CUDA(cudaEventRecord(d->ev_out_done[0], d->cout));
+    ECT_CUDA(cudaStreamWaitEvent(d->stream, d->ev_out_done[0], 0));
+    ECT_CUDA(cudaEventRecord(d->ev_c1, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    ECT_CUDA(cudaEventElapsedTime(&d->chunked_ms, d->ev_c0, d->ev_c1));
+    trace.dump("dir");
+    d->launches = launches;
+    d->last_dir = 1;
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) { return inv_trans_impl(handle, a, nullptr); }
+extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) { return dir_trans_impl(handle, a, nullptr); }
+
+static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view) {
     EctHandle* h = get_handle(handle);
     if (!h) { ect_set_error("ect_inv_trans: invalid handle %d", handle); return ECT_ERR_HANDLE; }
     if (!a) return ECT_ERR_MISSING;
@@ -496,9 +849,47 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     const int nproma = (a->nproma > 0 && a->nproma < P.ngptot) ? a->nproma : std::max(P.ngptot, 1);
     const int ngpblks = (P.ngptot + nproma - 1) / nproma;
     int rc;
+    const bool host = (a->memspace == ECT_MEM_HOST);
+    // grid-point field table: base pointer and block stride of every Fourier field (trltog_mod.F90:579-731);
+    // pure address arithmetic, used with device pointers (kernel tables) and with the caller's host pointers
+    // (chunked host path)
+    const int nvar_uv = (f.vorgp ? 1 : 0) + (f.divgp ? 1 : 0) + 2 + (f.uvder ? 2 : 0);
+    const int dfac = f.scders ? 3 : 1;
+    auto fill_gp_table = [&](double* q_gp, double* q_uv, double* q_2, double* q_3a, double* q_3b, double** t_gpb, i64* t_gps) {
+        if (!mode2_gp) {
+            for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = adv(q_gp, (i64)i * nproma, es); t_gps[i] = (i64)f.nfs * nproma; }
+        } else {
+            int fi = 0, var = 0;
+            auto uvgroup = [&](int v) { for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = adv(q_uv, ((i64)v * kf_uv + l) * nproma, es); t_gps[fi] = (i64)nproma * kf_uv * nvar_uv; } };
+            if (f.vorgp) uvgroup(var++);
+            if (f.divgp) uvgroup(var++);
+            if (kf_uv) { uvgroup(var++); uvgroup(var++); }
+            auto scgroup = [&](int part) {   // part 0: fields, 1: N-S derivatives, 2: E-W derivatives
+                for (int j = 0; j < nsc2; ++j, ++fi) { t_gpb[fi] = adv(q_2, ((i64)part * nsc2 + j) * nproma, es); t_gps[fi] = (i64)nproma * nsc2 * dfac; }
+                for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3)
+                    for (int l = 0; l < a->nsc3a_lev; ++l, ++fi) {
+                        t_gpb[fi] = adv(q_3a, (((i64)part * a->nsc3a_fld + j3) * a->nsc3a_lev + l) * nproma, es);
+                        t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld * dfac;
+                    }
+                for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3)
+                    for (int l = 0; l < a->nsc3b_lev; ++l, ++fi) {
+                        t_gpb[fi] = adv(q_3b, (((i64)part * a->nsc3b_fld + j3) * a->nsc3b_lev + l) * nproma, es);
+                        t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld * dfac;
+                    }
+            };
+            scgroup(0);
+            if (f.scders) scgroup(1);
+            if (f.uvder) { uvgroup(var++); uvgroup(var++); }
+            if (f.scders) scgroup(2);
+        }
+    };
+    if (host) {
+        const int nch = host_chunk_count(h, f.nleg);
+        if (nch > 1) return inv_trans_chunked(handle, h, a, f, mode2_sp, nsc2, n3a, n3b, nproma, ngpblks, fill_gp_table);
+    }
     if ((rc = ensure_work(h, f))) return rc;
     d->launches = 0;
-    const bool host = (a->memspace == ECT_MEM_HOST);
+    d->chunked_ms = -1.f;
     ECT_CUDA(cudaEventRecord(d->ev[0], d->stream));
     // ---- spectral inputs on the device ----
     const i64 nsp = P.nspec2;
@@ -524,8 +915,6 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     ECT_CUDA(cudaEventRecord(d->ev[1], d->stream));
     // ---- grid-point outputs on the device ----
     double *dgp = a->gp, *dgpuv = a->gpuv, *dgp2 = a->gp2, *dgp3a = a->gp3a, *dgp3b = a->gp3b;
-    const int nvar_uv = (f.vorgp ? 1 : 0) + (f.divgp ? 1 : 0) + 2 + (f.uvder ? 2 : 0);
-    const int dfac = f.scders ? 3 : 1;
     const i64 blk = (i64)nproma * ngpblks;
     const i64 sz_gp = (i64)f.nfs * blk, sz_uv = (i64)kf_uv * nvar_uv * blk, sz_2 = (i64)nsc2 * dfac * blk,
               sz_3a = (i64)n3a * dfac * blk, sz_3b = (i64)n3b * dfac * blk;
@@ -570,8 +959,9 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     int2* t_pairs = (int2*)(t_gps + f.nfs);
     EctFsField* t_fs = (EctFsField*)(t_pairs + pairs.size());
     memcpy(t_pairs, pairs.data(), pairs.size() * sizeof(int2));
-    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {adv(dvor, j, es), kf_uv}; t_div[j] = {adv(ddiv, j, es), kf_uv}; }
-    if (!mode2_sp) for (int s = 0; s < kf_sc; ++s) t_sc[s] = {adv(dsc, s, es), kf_sc};
+    const int st_uv = view ? view->uv_stride : kf_uv, st_sc = view ? view->sc_stride : kf_sc;
+    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {adv(dvor, j, es), st_uv}; t_div[j] = {adv(ddiv, j, es), st_uv}; }
+    if (!mode2_sp) for (int s = 0; s < kf_sc; ++s) t_sc[s] = {adv(dsc, s, es), st_sc};
     else {
         int s = 0;
         for (int j = 0; j < nsc2; ++j) t_sc[s++] = {adv(dsc2, j, es), nsc2};
@@ -592,33 +982,8 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
         for (int j = 0; j < n_nsd; ++j, ++fi) t_fs[fi] = {2 * (l_sc + j), 0, 1};
     }
     // grid-point destinations (trltog_mod.F90:579-731)
-    if (!mode2_gp) {
-        for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = adv(dgp, (i64)i * nproma, es); t_gps[i] = (i64)f.nfs * nproma; }
-    } else {
-        int fi = 0, var = 0;
-        auto uvgroup = [&](int v) { for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = adv(dgpuv, ((i64)v * kf_uv + l) * nproma, es); t_gps[fi] = (i64)nproma * kf_uv * nvar_uv; } };
-        if (f.vorgp) uvgroup(var++);
-        if (f.divgp) uvgroup(var++);
-        if (kf_uv) { uvgroup(var++); uvgroup(var++); }
-        auto scgroup = [&](int part) {   // part 0: fields, 1: N-S derivatives, 2: E-W derivatives
-            for (int j = 0; j < nsc2; ++j, ++fi) { t_gpb[fi] = adv(dgp2, ((i64)part * nsc2 + j) * nproma, es); t_gps[fi] = (i64)nproma * nsc2 * dfac; }
-            for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3)
-                for (int l = 0; l < a->nsc3a_lev; ++l, ++fi) {
-                    t_gpb[fi] = adv(dgp3a, (((i64)part * a->nsc3a_fld + j3) * a->nsc3a_lev + l) * nproma, es);
-                    t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld * dfac;
-                }
-            for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3)
-                for (int l = 0; l < a->nsc3b_lev; ++l, ++fi) {
-                    t_gpb[fi] = adv(dgp3b, (((i64)part * a->nsc3b_fld + j3) * a->nsc3b_lev + l) * nproma, es);
-                    t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld * dfac;
-                }
-        };
-        scgroup(0);
-        if (f.scders) scgroup(1);
-        if (f.uvder) { uvgroup(var++); uvgroup(var++); }
-        if (f.scders) scgroup(2);
-    }
-    ECT_CUDA(cudaMemcpyAsync(d->callbuf, d->h_callbuf, bytes, cudaMemcpyHostToDevice, d->stream));
+    fill_gp_table(dgp, dgpuv, dgp2, dgp3a, dgp3b, t_gpb, t_gps);
+    if ((rc = upload_callbuf(d, bytes))) return rc;
     char* db = (char*)d->callbuf;
     const void* d_vor = db;
     const void* d_div = db + ((char*)t_div - hb);
@@ -654,7 +1019,7 @@ extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) {
     return ECT_SUCCESS;
 }
 
-extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
+static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view) {
     EctHandle* h = get_handle(handle);
     if (!h) { ect_set_error("ect_dir_trans: invalid handle %d", handle); return ECT_ERR_HANDLE; }
     if (!a) return ECT_ERR_MISSING;
@@ -689,9 +1054,33 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
     const int nproma = (a->nproma > 0 && a->nproma < P.ngptot) ? a->nproma : std::max(P.ngptot, 1);
     const int ngpblks = (P.ngptot + nproma - 1) / nproma;
     int rc;
+    const bool host = (a->memspace == ECT_MEM_HOST);
+    // grid-point field table (trgtol_mod.F90): base pointer and block stride of every input field, order u v scalars
+    auto fill_gp_table = [&](double* q_gp, double* q_uv, double* q_2, double* q_3a, double* q_3b, double** t_gpb, i64* t_gps) {
+        if (!mode2) {
+            for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = adv(q_gp, (i64)i * nproma, es); t_gps[i] = (i64)f.nfs * nproma; }
+            return;
+        }
+        int fi = 0;
+        for (int v = 0; v < (kf_uv ? 2 : 0); ++v)
+            for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = adv(q_uv, ((i64)v * kf_uv + l) * nproma, es); t_gps[fi] = (i64)nproma * kf_uv * 2; }
+        for (int j = 0; j < nsc2; ++j, ++fi) { t_gpb[fi] = adv(q_2, (i64)j * nproma, es); t_gps[fi] = (i64)nproma * nsc2; }
+        for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3)
+            for (int l = 0; l < a->nsc3a_lev; ++l, ++fi) {
+                t_gpb[fi] = adv(q_3a, ((i64)j3 * a->nsc3a_lev + l) * nproma, es); t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld;
+            }
+        for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3)
+            for (int l = 0; l < a->nsc3b_lev; ++l, ++fi) {
+                t_gpb[fi] = adv(q_3b, ((i64)j3 * a->nsc3b_lev + l) * nproma, es); t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld;
+            }
+    };
+    if (host) {
+        const int nch = host_chunk_count(h, f.nleg);
+        if (nch > 1) return dir_trans_chunked(handle, h, a, f, mode2, nsc2, n3a, n3b, nproma, ngpblks, fill_gp_table);
+    }
     if ((rc = ensure_work(h, f))) return rc;
     d->launches = 0;
-    const bool host = (a->memspace == ECT_MEM_HOST);
+    d->chunked_ms = -1.f;
     const i64 nsp = P.nspec2, blk = (i64)nproma * ngpblks;
     const i64 sz_gp = (i64)f.nfs * blk, sz_uv = (i64)kf_uv * 2 * blk, sz_2 = (i64)nsc2 * blk, sz_3a = (i64)n3a * blk, sz_3b = (i64)n3b * blk;
     ECT_CUDA(cudaEventRecord(d->ev[0], d->stream));
@@ -746,30 +1135,20 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) {
     i64* t_gps = (i64*)(t_gpb + f.nfs);
     int2* t_pairs = (int2*)(t_gps + f.nfs);
     memcpy(t_pairs, pairs.data(), pairs.size() * sizeof(int2));
-    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {adv(dvor, j, es), kf_uv}; t_div[j] = {adv(ddiv, j, es), kf_uv}; }
+    const int st_uv = view ? view->uv_stride : kf_uv, st_sc = view ? view->sc_stride : kf_sc;
+    for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {adv(dvor, j, es), st_uv}; t_div[j] = {adv(ddiv, j, es), st_uv}; }
     if (!mode2) {
-        for (int s = 0; s < kf_sc; ++s) t_sc[s] = {adv(dsc, s, es), kf_sc};
-        for (int i = 0; i < f.nfs; ++i) { t_gpb[i] = adv((double*)dgp, (i64)i * nproma, es); t_gps[i] = (i64)f.nfs * nproma; }
+        for (int s = 0; s < kf_sc; ++s) t_sc[s] = {adv(dsc, s, es), st_sc};
     } else {
-        int s = 0, fi = 0;
-        for (int v = 0; v < (kf_uv ? 2 : 0); ++v)
-            for (int l = 0; l < kf_uv; ++l, ++fi) { t_gpb[fi] = adv((double*)dgpuv, ((i64)v * kf_uv + l) * nproma, es); t_gps[fi] = (i64)nproma * kf_uv * 2; }
-        for (int j = 0; j < nsc2; ++j, ++fi) {
-            t_sc[s++] = {adv(dsc2, j, es), nsc2};
-            t_gpb[fi] = adv((double*)dgp2, (i64)j * nproma, es); t_gps[fi] = (i64)nproma * nsc2;
-        }
+        int s = 0;
+        for (int j = 0; j < nsc2; ++j) t_sc[s++] = {adv(dsc2, j, es), nsc2};
         for (int j3 = 0; j3 < (n3a ? a->nsc3a_fld : 0); ++j3)
-            for (int l = 0; l < a->nsc3a_lev; ++l, ++fi) {
-                t_sc[s++] = {adv(dsc3a, (i64)j3 * a->nsc3a_lev * nsp + l, es), a->nsc3a_lev};
-                t_gpb[fi] = adv((double*)dgp3a, ((i64)j3 * a->nsc3a_lev + l) * nproma, es); t_gps[fi] = (i64)nproma * a->nsc3a_lev * a->nsc3a_fld;
-            }
+            for (int l = 0; l < a->nsc3a_lev; ++l) t_sc[s++] = {adv(dsc3a, (i64)j3 * a->nsc3a_lev * nsp + l, es), a->nsc3a_lev};
         for (int j3 = 0; j3 < (n3b ? a->nsc3b_fld : 0); ++j3)
-            for (int l = 0; l < a->nsc3b_lev; ++l, ++fi) {
-                t_sc[s++] = {adv(dsc3b, (i64)j3 * a->nsc3b_lev * nsp + l, es), a->nsc3b_lev};
-                t_gpb[fi] = adv((double*)dgp3b, ((i64)j3 * a->nsc3b_lev + l) * nproma, es); t_gps[fi] = (i64)nproma * a->nsc3b_lev * a->nsc3b_fld;
-            }
+            for (int l = 0; l < a->nsc3b_lev; ++l) t_sc[s++] = {adv(dsc3b, (i64)j3 * a->nsc3b_lev * nsp + l, es), a->nsc3b_lev};
     }
-    ECT_CUDA(cudaMemcpyAsync(d->callbuf, d->h_callbuf, bytes, cudaMemcpyHostToDevice, d->stream));
+    fill_gp_table((double*)dgp, (double*)dgpuv, (double*)dgp2, (double*)dgp3a, (double*)dgp3b, t_gpb, t_gps);
+    if ((rc = upload_callbuf(d, bytes))) return rc;
     char* db = (char*)d->callbuf;
     void* d_vor = db;
     void* d_div = db + ((char*)t_div - hb);
@@ -824,6 +1203,11 @@ extern "C" int ect_get_timings(int handle, ect_timings* t) {
     memset(t, 0, sizeof(*t));
     if (!d->timed) return ECT_SUCCESS;
     ECT_CUDA(cudaStreamSynchronize(d->stream));
+    if (d->chunked_ms >= 0.f) {       // chunked host call: copies and stages of different chunks overlap, only the total is defined
+        t->total = d->chunked_ms;
+        t->launches = d->launches;
+        return ECT_SUCCESS;
+    }
     float ms[6];
     for (int i = 0; i < 6; ++i) ECT_CUDA(cudaEventElapsedTime(&ms[i], d->ev[i], d->ev[i + 1]));
     ECT_CUDA(cudaEventElapsedTime(&t->total, d->ev[0], d->ev[6]));

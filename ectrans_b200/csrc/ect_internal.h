@@ -117,6 +117,10 @@ struct EctDevice {
     // staging for host-pointer calls
     double* stage_sp = nullptr; i64 stage_sp_elems = 0;
     double* stage_gp = nullptr; i64 stage_gp_elems = 0;
+    // chunked host path: copy streams and per-slot events
+    cudaStream_t cin = nullptr, cout = nullptr;
+    cudaEvent_t ev_in_ready[2] = {}, ev_cmp_done[2] = {}, ev_out_done[2] = {}, ev_sp[4] = {}, ev_c0 = nullptr, ev_c1 = nullptr;
+    float chunked_ms = -1.f;
     // per-call small tables
     // per-call small tables: ring of slots, each (pinned host, device) pair guarded by an event recorded
     // after the last kernel of the call that used it (calls are asynchronous in ECT_MEM_DEVICE mode)

@@ -180,6 +180,47 @@ def test_call_mode_2(eb):
     tr.release()
 
 
+@pytest.fixture
+def forced_chunks(monkeypatch):
+    """Host-pointer calls split into many small pipelined field chunks (normally only multi-GB calls are)."""
+    monkeypatch.setenv("ECT_HOST_CHUNK_FIELDS", "3")
+    monkeypatch.setenv("ECT_HOST_CHUNK_MIN_BYTES", "0")
+
+
+def test_call_mode_2_chunked(eb, forced_chunks):
+    test_call_mode_2(eb)
+
+
+@pytest.mark.parametrize("nproma", [0, 777])
+def test_host_chunked_pipeline(eb, forced_chunks, nproma):
+    """The pipelined host path (field chunks, copy streams) against the oracle and against the single-shot path:
+    every option that changes the field lists, blocked and unblocked."""
+    T, N, nuv, nsc = 79, 80, 7, 10
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen)
+    vor = eo.random_spectral(s, nuv, 1, zero00=True); div = eo.random_spectral(s, nuv, 2, zero00=True)
+    sc = eo.random_spectral(s, nsc, 3)
+    opts = dict(scders=True, uvder=True, vorgp=True, divgp=True)
+    ref = eo.inv_trans(s, vor, div, sc, **opts)
+    gp = tr.inv_trans(T_(vor), T_(div), T_(sc), nproma=nproma, **opts)
+    assert tr.timings()["launches"] > 60          # several chunks ran
+    flat = gp.transpose(1, 0, 2).reshape(gp.shape[1], -1)[:, :tr.ngptot]
+    for i in range(ref.shape[0]):
+        assert rel(flat[i], ref[i]) < TOL, i
+    iu = 2 * nuv
+    gin = np.ascontiguousarray(gp[:, iu:iu + 2 * nuv + nsc])
+    ov, od, os_ = tr.dir_trans(gin, nuv, nsc, nproma=nproma)
+    rv, rd, rs = eo.dir_trans(s, ref[iu:iu + 2 * nuv + nsc], nuv, nsc)
+    assert rel(ov.T, rv) < TOL and rel(od.T, rd) < TOL and rel(os_.T, rs) < TOL
+    import os
+    os.environ["ECT_HOST_CHUNK_FIELDS"] = "0"      # single shot
+    gp1 = tr.inv_trans(T_(vor), T_(div), T_(sc), nproma=nproma, **opts)
+    flat1 = gp1.transpose(1, 0, 2).reshape(gp1.shape[1], -1)[:, :tr.ngptot]
+    assert rel(flat, flat1) < 1e-13
+    tr.release()
+
+
 def test_device_memspace_matches_host(eb):
     import torch
     T, N = 79, 80

@@ -6,10 +6,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np, torch
     import ectrans_b200 as eb
     L = eb.lib()
-    T, N, nf = 1279, 1280, 32
-    tr = eb.Transform(T, eb.octahedral_nloen(N), stream=torch.cuda.current_stream().cuda_stream)
-    sc = (torch.rand((tr.nspec2, nf), device="cuda", dtype=torch.float64) - 0.5)
-    gp = torch.empty((1, nf, tr.ngptot), dtype=torch.float64, device="cuda")
+    T, N, nf = int(os.environ.get("PROBE_T", 1279)), int(os.environ.get("PROBE_N", 1280)), 32
+    prec = os.environ.get("PROBE_PREC", "dp")
+    tdt = torch.float32 if prec == "sp" else torch.float64
+    tr = eb.Transform(T, eb.octahedral_nloen(N), stream=torch.cuda.current_stream().cuda_stream, precision=prec)
+    sc = (torch.rand((tr.nspec2, nf), device="cuda", dtype=tdt) - 0.5)
+    gp = torch.empty((1, nf, tr.ngptot), dtype=tdt, device="cuda")
     for direction in ("inv", "dir"):
         for it in range(2):
             if direction == "inv": tr.inv_trans(spscalar=sc, out=gp)
@@ -29,6 +31,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         d["store"] = int(v[20] - prev); d["total"] = int(v[20] - v[0])
         print("bucket", os.environ.get("ECT_FFT_ONLY_BUCKET"), direction, "fourier ms %.3f" % t["fourier"], d, flush=True)
 else:
-    for b in range(12):
+    for b in range(14):
         env = dict(os.environ, ECT_FFT_ONLY_BUCKET=str(b))
         subprocess.run([sys.executable, __file__, "child"], env=env)
