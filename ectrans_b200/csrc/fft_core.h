@@ -227,29 +227,40 @@ ECT_HD void apply_twiddles(C* v, C w1) {
 // One stage over the whole array, executed cooperatively by nthr threads.
 // DIF == false: twiddle then butterfly (decimation in time stage B_s)
 // DIF == true : butterfly then twiddle (its transpose)
+template <int R, typename C>
+ECT_HD void stage_addr(int b, int L, int lshift, int& base, int& k) {
+    int blk;
+    if (lshift >= 0) { blk = b >> lshift; k = b & (L - 1); }
+    else { blk = b / L; k = b - blk * L; }
+    base = blk * R * L + k;
+}
+// power-of-two radix: twiddles + butterfly on a register-resident column
+template <int R, bool DIF, typename C>
+ECT_HD void stage_math_pow2(C* v, bool tw, C w1) {
+    if (!DIF && tw) apply_twiddles<R>(v, w1);
+    bfly_pow2<R>(v);
+    if (DIF && tw) apply_twiddles<R>(v, w1);
+}
 template <int R, bool DIF, typename C>
 ECT_HD void fft_stage_r(C* data, int n, int L, int lshift, const EctTwT<C> qt,
                         const C* __restrict__ rt, int tid, int nthr) {
     const int nb = n / R;
     const int tstride = n / (R * L);   // twiddle index stride: exp(2 pi i q k / (R L))
     for (int b = tid; b < nb; b += nthr) {
-        int blk, k;
-        if (lshift >= 0) { blk = b >> lshift; k = b & (L - 1); }
-        else { blk = b / L; k = b - blk * L; }
-        const int base = blk * R * L + k;
+        int base, k;
+        stage_addr<R, C>(b, L, lshift, base, k);
         C v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = data[ECT_PAD(base + q * L)];
         C w1 = c_make<C>(1, 0);
         const bool tw = (L > 1) && (k > 0);
         if (tw) w1 = tw_get(qt, k * tstride);
-        if (!DIF && tw) apply_twiddles<R>(v, w1);
         if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
-            bfly_pow2<R>(v);
-            if (DIF && tw) apply_twiddles<R>(v, w1);
+            stage_math_pow2<R, DIF>(v, tw, w1);
 #pragma unroll
             for (int q = 0; q < R; ++q) data[ECT_PAD(base + q * L)] = v[q];
         } else {
+            if (!DIF && tw) apply_twiddles<R>(v, w1);
             if (DIF && tw) {
                 // outputs arrive as (p, R-p) pairs: w^p by running product, w^(R-p) = w^R * conj(w^p)
                 const C wr = tw_get(qt, k * (n / L));      // w^R = exp(2 pi i k / L)
