@@ -84,6 +84,7 @@ EXPORTED_SYMBOLS = [
     "ect_setup", "ect_inquire", "ect_inquire_array", "ect_inv_trans", "ect_dir_trans", "ect_specnorm",
     "ect_get_timings", "ect_synchronize", "ect_release", "ect_finalize", "ect_strerror", "ect_last_error",
     "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
+    "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec",
 ]
 
 
@@ -109,6 +110,10 @@ def lib():
         L.ect_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_longlong]
         L.ect_host_free.argtypes = [C.c_void_p]
         L.ect_nccl_unique_id.argtypes = [C.c_void_p]
+        L.ect_gath_grid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ect_dist_grid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ect_gath_spec.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ect_dist_spec.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -348,6 +353,46 @@ class Transform:
         out = np.zeros(nf)
         _check(lib().ect_specnorm(self.handle, _ptr(spec), nf, ECT_MEM_DEVICE if dev else ECT_MEM_HOST,
                                   out.ctypes.data), "ect_specnorm")
+        return out
+
+    # ---- GATH_GRID / DIST_GRID / GATH_SPEC / DIST_SPEC (host arrays; collective over the ranks of the handle) ----
+    def _owners(self, nfld, owner):
+        own = np.zeros(nfld, dtype=np.int32) if owner is None else np.ascontiguousarray(np.broadcast_to(owner, (nfld,)), dtype=np.int32)
+        return own, int((own == self.rank).sum())
+
+    def gath_grid(self, gp, kto=None, nproma=0):
+        """GATH_GRID: gp (ngpblks, nfld, nproma) local -> (nfld_owned, ngptotg) on the owning ranks (kto: 0-based, default 0)."""
+        gp = np.ascontiguousarray(gp, dtype=self.dtype)
+        nfld = int(gp.shape[1])
+        own, mine = self._owners(nfld, kto)
+        out = np.zeros((mine, self.ngptotg), dtype=self.dtype)
+        _check(lib().ect_gath_grid(self.handle, gp.ctypes.data, nfld, nproma, own.ctypes.data, out.ctypes.data if mine else None), "ect_gath_grid")
+        return out
+
+    def dist_grid(self, gpg, nfld, kfrom=None, nproma=0):
+        """DIST_GRID: (nfld_owned, ngptotg) on the owning ranks -> local (ngpblks, nfld, nproma)."""
+        own, mine = self._owners(nfld, kfrom)
+        gpg = None if gpg is None else np.ascontiguousarray(gpg, dtype=self.dtype)
+        npr, nblk = self._blocks(nproma)
+        out = np.zeros((nblk, nfld, npr), dtype=self.dtype)
+        _check(lib().ect_dist_grid(self.handle, gpg.ctypes.data if mine else None, nfld, nproma, own.ctypes.data, out.ctypes.data), "ect_dist_grid")
+        return out
+
+    def gath_spec(self, sp, kto=None):
+        """GATH_SPEC: sp (nspec2, nfld) local -> (nspec2g, nfld_owned), m ascending then n ascending, Im(m = 0) zeroed."""
+        sp = np.ascontiguousarray(sp, dtype=self.dtype)
+        nfld = int(sp.shape[1])
+        own, mine = self._owners(nfld, kto)
+        out = np.zeros((self.nspec2g, mine), dtype=self.dtype)
+        _check(lib().ect_gath_spec(self.handle, sp.ctypes.data, nfld, own.ctypes.data, out.ctypes.data if mine else None), "ect_gath_spec")
+        return out
+
+    def dist_spec(self, spg, nfld, kfrom=None):
+        """DIST_SPEC: (nspec2g, nfld_owned) on the owning ranks -> local (nspec2, nfld)."""
+        own, mine = self._owners(nfld, kfrom)
+        spg = None if spg is None else np.ascontiguousarray(spg, dtype=self.dtype)
+        out = np.zeros((self.nspec2, nfld), dtype=self.dtype)
+        _check(lib().ect_dist_spec(self.handle, spg.ctypes.data if mine else None, nfld, own.ctypes.data, out.ctypes.data), "ect_dist_spec")
         return out
 
     def legendre_table(self, ml, parity):

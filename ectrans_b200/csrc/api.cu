@@ -1344,3 +1344,167 @@ extern "C" int ect_measure_fp64_peak(int which, double* tflops) {
     *tflops = best;
     return ECT_SUCCESS;
 }
+
+// ---------------------------------------------------------------------------------------
+// GATH_GRID / DIST_GRID / GATH_SPEC / DIST_SPEC: global <-> distributed arrays on host memory.
+// Reference: cpu/internal/gath_grid_ctl_mod.F90, dist_grid_ctl_mod.F90, gath_spec_control_mod.F90,
+// dist_spec_control_mod.F90 (interfaces include/ectrans/gath_grid.h:12-60 ...).  Field f of the global array
+// lives on rank kto[f] / kfrom[f] (0-based); a rank's global array holds the fields it owns, in order.
+// Grid points: rank r owns the global range of its latitude band; spectral: global order is m ascending,
+// n ascending (IASM0G, gath_spec_control_mod.F90:111-114) whatever the wave distribution.
+// The pieces travel as NCCL send/recv on device staging buffers; with one rank it is a host-side reorder.
+// ---------------------------------------------------------------------------------------
+struct PieceMap { std::vector<i64> off, cnt; };
+
+static PieceMap grid_pieces(const EctHostPlan& P) {
+    PieceMap g; g.off.assign(P.nranks, 0); g.cnt.assign(P.nranks, 0);
+    i64 pos = 0;
+    for (int r = 0; r < P.nranks; ++r) {
+        i64 n = 0;
+        for (int j = 0; j < P.lat_count[r]; ++j) n += P.nloen[P.lat_first[r] + j];
+        g.off[r] = pos; g.cnt[r] = n; pos += n;
+    }
+    return g;
+}
+static PieceMap spec_pieces(const EctHostPlan& P) {
+    PieceMap g; g.off.assign(P.nranks, 0); g.cnt.assign(P.nranks, 0);
+    i64 pos = 0;
+    for (int r = 0; r < P.nranks; ++r) {
+        i64 n = 0;
+        for (int m : P.ms_of[r]) n += 2 * (P.nsmax - m + 1);
+        g.off[r] = pos; g.cnt[r] = n; pos += n;
+    }
+    return g;
+}
+
+// exchange of per-rank pieces: gather (everybody -> owners) or scatter (owners -> everybody).
+// sendbytes[t] bytes at sendoff[t] of h_send go to rank t; recvbytes[s] bytes from rank s land at recvoff[s] of h_recv.
+static int exchange_host(EctHandle* h, const char* h_send, const std::vector<i64>& sendoff, const std::vector<i64>& sendbytes,
+                         char* h_recv, const std::vector<i64>& recvoff, const std::vector<i64>& recvbytes) {
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    i64 stot = 0, rtot = 0;
+    for (int r = 0; r < P.nranks; ++r) { stot = std::max(stot, sendoff[r] + sendbytes[r]); rtot = std::max(rtot, recvoff[r] + recvbytes[r]); }
+    if (P.nranks == 1) {
+        if (sendbytes[0] != recvbytes[0]) { ect_set_error("gath/dist: inconsistent piece sizes"); return ECT_ERR_GENERIC; }
+        memcpy(h_recv + recvoff[0], h_send + sendoff[0], (size_t)sendbytes[0]);
+        return ECT_SUCCESS;
+    }
+    int rc;
+    if ((rc = ensure(d->stage_sp, d->stage_sp_elems, (stot + 7) / 8 + 1, d->stream, false))) return rc;
+    if ((rc = ensure(d->stage_gp, d->stage_gp_elems, (rtot + 7) / 8 + 1, d->stream, false))) return rc;
+    char* ds = (char*)d->stage_sp; char* dr = (char*)d->stage_gp;
+    if (stot) ECT_CUDA(cudaMemcpyAsync(ds, h_send, (size_t)stot, cudaMemcpyHostToDevice, d->stream));
+    ncclComm_t comm = (ncclComm_t)d->comm;
+    ECT_NCCL(ncclGroupStart());
+    for (int r = 0; r < P.nranks; ++r) {
+        if (sendbytes[r]) ECT_NCCL(ncclSend(ds + sendoff[r], (size_t)sendbytes[r], ncclChar, r, comm, d->stream));
+        if (recvbytes[r]) ECT_NCCL(ncclRecv(dr + recvoff[r], (size_t)recvbytes[r], ncclChar, r, comm, d->stream));
+    }
+    ECT_NCCL(ncclGroupEnd());
+    if (rtot) ECT_CUDA(cudaMemcpyAsync(h_recv, dr, (size_t)rtot, cudaMemcpyDeviceToHost, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    return ECT_SUCCESS;
+}
+
+static int check_owner(const EctHostPlan& P, const int* own, int nfld, const char* who) {
+    if (nfld < 0 || (nfld > 0 && !own)) { ect_set_error("%s: owner list missing", who); return ECT_ERR_MISSING; }
+    for (int f = 0; f < nfld; ++f)
+        if (own[f] < 0 || own[f] >= P.nranks) { ect_set_error("%s: field %d owner %d outside 0..%d", who, f, own[f], P.nranks - 1); return ECT_ERR_BADARG; }
+    return ECT_SUCCESS;
+}
+
+// gather = true : local (blocked grid / local spectral) -> global arrays on the owners
+// gather = false: global arrays on the owners -> local
+static int gath_dist(int handle, bool grid, bool gather, void* v_local, void* v_global, int nfld, int nproma_in, const int* own) {
+    EctHandle* h = get_handle(handle);
+    if (!h) { ect_set_error("gath/dist: invalid handle %d", handle); return ECT_ERR_HANDLE; }
+    const EctHostPlan& P = h->hp;
+    if (!h->d && P.nranks > 1) { ect_set_error("gath/dist: handle was set up host-only"); return ECT_ERR_CUDA; }
+    const char* who = grid ? (gather ? "ect_gath_grid" : "ect_dist_grid") : (gather ? "ect_gath_spec" : "ect_dist_spec");
+    int rc;
+    if ((rc = check_owner(P, own, nfld, who))) return rc;
+    if (nfld == 0) return ECT_SUCCESS;
+    if (h->d) ECT_CUDA(cudaSetDevice(h->d->dev));
+    const int es = h->precision == ECT_PREC_SP ? 4 : 8;
+    const PieceMap pm = grid ? grid_pieces(P) : spec_pieces(P);
+    const i64 nloc = pm.cnt[P.rank];
+    const i64 nglob = grid ? (i64)P.ngptotg : (i64)P.nspec2_g;
+    std::vector<int> nown(P.nranks, 0), slot(nfld, 0);      // fields per owner, position of f among its owner's fields
+    for (int f = 0; f < nfld; ++f) slot[f] = nown[own[f]]++;
+    const int mine = nown[P.rank];
+    if (nloc > 0 && !v_local) { ect_set_error("%s: local array missing", who); return ECT_ERR_MISSING; }
+    if (mine > 0 && !v_global) { ect_set_error("%s: this rank owns %d field(s) but the global array is missing", who, mine); return ECT_ERR_MISSING; }
+    char* loc = (char*)v_local; char* glob = (char*)v_global;
+    const int nproma = (nproma_in > 0 && nproma_in < P.ngptot) ? nproma_in : std::max(P.ngptot, 1);
+    // "wire" layout between rank s (data of its piece) and owner t: grid (fields of t, n_s) ; spectral (n_s, fields of t)
+    // local-side buffer: for every owner t a block of nown[t] * nloc elements; owner-side buffer: for every source s a block
+    // of mine * cnt[s] elements
+    std::vector<i64> loff(P.nranks), lbytes(P.nranks), goff(P.nranks), gbytes(P.nranks);
+    i64 lp = 0, gp = 0;
+    for (int r = 0; r < P.nranks; ++r) {
+        loff[r] = lp; lbytes[r] = (i64)nown[r] * nloc * es; lp += lbytes[r];
+        goff[r] = gp; gbytes[r] = (i64)mine * pm.cnt[r] * es; gp += gbytes[r];
+    }
+    std::vector<char> lbuf((size_t)lp + 8), gbuf((size_t)gp + 8);
+    // element (field f, local index i) in the local-side buffer / in the caller's local array
+    auto lwire = [&](int f, i64 i) -> char* {
+        const int t = own[f];
+        const i64 e = grid ? (i64)slot[f] * nloc + i : i * nown[t] + slot[f];
+        return lbuf.data() + loff[t] + e * es;
+    };
+    auto lcaller = [&](int f, i64 i) -> char* {
+        if (!grid) return loc + (i * nfld + f) * es;                    // PSPEC(nfld, nspec2)
+        const i64 b = i / nproma, k = i - b * nproma;                  // PGP(nproma, nfld, ngpblks)
+        return loc + ((b * nfld + f) * nproma + k) * es;
+    };
+    // element (owned field slot q, source rank s, index i within the piece of s) on the owner side
+    auto gwire = [&](int q, int s, i64 i) -> char* {
+        const i64 e = grid ? (i64)q * pm.cnt[s] + i : i * mine + q;
+        return gbuf.data() + goff[s] + e * es;
+    };
+    // global position of element i of the piece of rank s
+    std::vector<i64> gpos;      // spectral only: global index of every local index, per source rank, concatenated
+    std::vector<i64> gpos0(P.nranks + 1, 0);
+    if (!grid) {
+        gpos.reserve((size_t)nglob);
+        std::vector<i64> iasm0g(P.nsmax + 2, 0);
+        for (int m = 0; m <= P.nsmax; ++m) iasm0g[m + 1] = iasm0g[m] + 2 * (P.nsmax - m + 1);
+        for (int s = 0; s < P.nranks; ++s) {
+            gpos0[s] = (i64)gpos.size();
+            for (int m : P.ms_of[s]) for (int i = 0; i < 2 * (P.nsmax - m + 1); ++i) gpos.push_back(iasm0g[m] + i);
+        }
+        gpos0[P.nranks] = (i64)gpos.size();
+    }
+    auto gcaller = [&](int q, int s, i64 i) -> char* {
+        if (grid) return glob + ((i64)q * nglob + pm.off[s] + i) * es;   // PGPG(ngptotg, nfld)
+        return glob + (gpos[gpos0[s] + i] * mine + q) * es;              // PSPECG(nfld, nspec2g)
+    };
+    if (gather) {
+        for (int f = 0; f < nfld; ++f) for (i64 i = 0; i < nloc; ++i) memcpy(lwire(f, i), lcaller(f, i), es);
+        if ((rc = exchange_host(h, lbuf.data(), loff, lbytes, gbuf.data(), goff, gbytes))) return rc;
+        for (int q = 0; q < mine; ++q) for (int s = 0; s < P.nranks; ++s) for (i64 i = 0; i < pm.cnt[s]; ++i) memcpy(gcaller(q, s, i), gwire(q, s, i), es);
+        if (!grid && mine > 0) {
+            // LDZA0IP: imaginary parts of the zonal coefficients are zero in the global array (gath_spec_control_mod.F90:178-184)
+            for (int n = 0; n <= P.nsmax; ++n) for (int q = 0; q < mine; ++q) memset(glob + ((i64)(2 * n + 1) * mine + q) * es, 0, es);
+        }
+    } else {
+        for (int q = 0; q < mine; ++q) for (int s = 0; s < P.nranks; ++s) for (i64 i = 0; i < pm.cnt[s]; ++i) memcpy(gwire(q, s, i), gcaller(q, s, i), es);
+        if ((rc = exchange_host(h, gbuf.data(), goff, gbytes, lbuf.data(), loff, lbytes))) return rc;
+        for (int f = 0; f < nfld; ++f) for (i64 i = 0; i < nloc; ++i) memcpy(lcaller(f, i), lwire(f, i), es);
+    }
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_gath_grid(int handle, const void* gp_local, int nfld, int nproma, const int* kto, void* gp_global) {
+    return gath_dist(handle, true, true, (void*)gp_local, gp_global, nfld, nproma, kto);
+}
+extern "C" int ect_dist_grid(int handle, const void* gp_global, int nfld, int nproma, const int* kfrom, void* gp_local) {
+    return gath_dist(handle, true, false, gp_local, (void*)gp_global, nfld, nproma, kfrom);
+}
+extern "C" int ect_gath_spec(int handle, const void* sp_local, int nfld, const int* kto, void* sp_global) {
+    return gath_dist(handle, false, true, (void*)sp_local, sp_global, nfld, 0, kto);
+}
+extern "C" int ect_dist_spec(int handle, const void* sp_global, int nfld, const int* kfrom, void* sp_local) {
+    return gath_dist(handle, false, false, sp_local, (void*)sp_global, nfld, 0, kfrom);
+}

@@ -169,6 +169,18 @@ int ect_inv_trans(int handle, const ect_inv_args* args);
 int ect_dir_trans(int handle, const ect_dir_args* args);
 int ect_specnorm(int handle, const double* spec, int nfld, int memspace, double* norms /* host, nfld */);
 int ect_get_timings(int handle, ect_timings* t);
+/* GATH_GRID / DIST_GRID / GATH_SPEC / DIST_SPEC: host arrays, every rank of the handle calls (collective).
+ * Replaces src/trans/include/ectrans/gath_grid.h:12-60, dist_grid.h:12-68, gath_spec.h:12-70, dist_spec.h:12-71.
+ *   gp_local  PGP(nproma, nfld, ngpblks)       gp_global PGPG(ngptotg, nfld_owned)
+ *   sp_local  PSPEC(nfld, nspec2)              sp_global PSPECG(nfld_owned, nspec2g), m ascending then n ascending
+ * kto[f] / kfrom[f] = rank (0-based, the reference's KTO/KFROM minus 1) that holds field f of the global array; a
+ * rank's global array carries the fields it holds, in order (may be NULL on ranks that hold none).
+ * GATH_SPEC zeroes the imaginary parts of the zonal (m = 0) coefficients (LDZA0IP default). */
+int ect_gath_grid(int handle, const void* gp_local, int nfld, int nproma, const int* kto, void* gp_global);
+int ect_dist_grid(int handle, const void* gp_global, int nfld, int nproma, const int* kfrom, void* gp_local);
+int ect_gath_spec(int handle, const void* sp_local, int nfld, const int* kto, void* sp_global);
+int ect_dist_spec(int handle, const void* sp_global, int nfld, const int* kfrom, void* sp_local);
+
 int ect_synchronize(int handle);   /* wait for asynchronous ECT_MEM_DEVICE calls on this handle */
 int ect_release(int handle);
 int ect_finalize(void);

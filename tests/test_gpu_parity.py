@@ -496,3 +496,20 @@ def test_benchmark_driver_config0(built):
         out = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
         assert "Inverse-direct transforms" in out.stdout and "Correctness test failed" not in out.stdout
+
+
+def test_benchmark_checksums_reproducible(built, tmp_path):
+    """--dump-checksums (ectrans-benchmark.F90:1455-1638 harness): host arrays and device-resident runs, blocked and
+    unblocked, give identical per-field checksums at every iteration."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = [sys.executable, os.path.join(root, "tools", "ectrans_benchmark.py"), "-t", "47", "-g", "O48", "-l", "3",
+            "-f", "2", "-n", "2", "--niter-warmup", "0"]
+    dumps = []
+    for i, extra in enumerate(([], ["--device-resident"], ["--nproma", "33"])):
+        f = tmp_path / f"crc{i}.txt"
+        out = subprocess.run(base + extra + ["--dump-checksums", str(f)], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        dumps.append(f.read_text())
+    assert dumps[0].count("zgp (") == 2 * (2 * 3 + 3 * 2 + 1) and "zspscalar (7)" in dumps[0]
+    assert dumps[0] == dumps[1] == dumps[2]

@@ -140,3 +140,29 @@ def test_no_cpu_fallback(eb):
         pytest.skip("GPU present")
     with pytest.raises(eb.EctError, match="no CPU fallback"):
         eb.Transform(47, eb.octahedral_nloen(48))
+
+
+def test_gath_dist_single_rank(built):
+    """GATH_GRID / DIST_GRID / GATH_SPEC / DIST_SPEC on one rank (host-only handle): unblocking of PGP(nproma, nfld,
+    ngpblks) into PGPG(ngptotg, nfld), identity spectral order, zeroed Im(m = 0) (gath_spec_control_mod.F90:178-184),
+    field ownership checks."""
+    import ectrans_b200 as eb
+    T, N = 21, 24
+    tr = eb.Transform(T, eb.octahedral_nloen(N), host_only=True)
+    rng = np.random.default_rng(0)
+    sp = rng.standard_normal((tr.nspec2, 3))
+    g = tr.gath_spec(sp)
+    exp = sp.copy(); exp[1:2 * (T + 1):2] = 0
+    assert np.array_equal(g, exp)
+    assert np.array_equal(tr.dist_spec(g, 3), exp)
+    for npr in (0, 100, 7):
+        nproma, nblk = tr._blocks(npr)
+        gp = rng.standard_normal((nblk, 4, nproma))
+        G = tr.gath_grid(gp, nproma=npr)
+        flat = gp.transpose(1, 0, 2).reshape(4, -1)[:, :tr.ngptot]
+        assert G.shape == (4, tr.ngptotg) and np.array_equal(G, flat)
+        back = tr.dist_grid(G, 4, nproma=npr)
+        assert np.array_equal(back.transpose(1, 0, 2).reshape(4, -1)[:, :tr.ngptot], flat)
+    with pytest.raises(eb.EctError):
+        tr.gath_spec(sp, kto=[0, 1, 0])              # rank 1 does not exist
+    tr.release()

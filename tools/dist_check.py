@@ -37,11 +37,39 @@ rv, rd, rs = eo.dir_trans(s, ref[:2 * nuv + nsc], nuv, nsc)
 e_dir = max(rel(ov.T, rv[:, idx]), rel(od.T, rd[:, idx]), rel(os_.T, rs[:, idx])) if tr.nump else 0.0
 nrm = tr.specnorm(loc(sc))
 e_nrm = rel(nrm, eo.specnorm(s, sc))
-t = torch.tensor([e_inv, e_dir, e_nrm], device=dev, dtype=torch.float64)
+tim = tr.timings()
+# ---- GATH_GRID / GATH_SPEC / DIST_* and reproducibility across decompositions (the property behind the reference's
+# --dump-checksums harness, ectrans-benchmark.F90:1455-1638): the gathered results must equal, bit for bit, those of
+# one rank transforming the same global input ----
+nfg = gp.shape[1]
+kto = np.arange(nfg, dtype=np.int32) % world                       # field f gathered on rank f % world
+gg = tr.gath_grid(gp, kto=kto)
+gv, gd, gs = tr.gath_spec(ov, kto=0), tr.gath_spec(od, kto=0), tr.gath_spec(os_, kto=np.arange(nsc) % world)
+T_ = lambda a: np.ascontiguousarray(a.T)
+dv = tr.dist_spec(T_(vor) if rank == 0 else None, nuv, kfrom=0)
+e_dist = float(np.abs(dv - loc(vor)).max()) if tr.nump else 0.0
+dg = tr.dist_grid(ref[:nfg] if rank == 0 else None, nfg, kfrom=0)
+e_dist = max(e_dist, float(np.abs(dg[0] - refloc[:nfg]).max()))
+bit = 1.0
+tr1 = eb.Transform(T, nloen, device=local)                          # the same transform on one rank
+g1 = tr1.inv_trans(T_(vor), T_(div), T_(sc), scders=True)
+mine = [f for f in range(nfg) if kto[f] == rank]
+bit = min(bit, float(np.array_equal(gg, g1[0][mine])))
+e_gath = rel(gg, ref[mine]) if mine else 0.0
+v1, d1, s1 = tr1.dir_trans(np.ascontiguousarray(g1[:, :2 * nuv + nsc]), nuv, nsc)
+def z(a):                                                            # GATH_SPEC zeroes Im(m = 0)
+    b = a.copy(); b[1:2 * (T + 1):2] = 0
+    return b
+if rank == 0:
+    bit = min(bit, float(np.array_equal(gv, z(v1))), float(np.array_equal(gd, z(d1))))
+smine = [f for f in range(nsc) if f % world == rank]
+bit = min(bit, float(np.array_equal(gs, z(s1)[:, smine])))
+tr1.release()
+t = torch.tensor([e_inv, e_dir, e_nrm, e_dist, e_gath, 1.0 - bit], device=dev, dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("dist errors inv %.2e dir %.2e norm %.2e" % tuple(t.cpu().tolist()), tr.timings())
-    ok = bool((t < 1e-12).all())
+    print("dist errors inv %.2e dir %.2e norm %.2e dist %.2e gath %.2e not-bit-identical %g" % tuple(t.cpu().tolist()), tim)
+    ok = bool((t[:3] < 1e-12).all()) and float(t[3]) == 0.0 and float(t[4]) < 1e-12 and float(t[5]) == 0.0
     print("DIST_CHECK_OK" if ok else "DIST_CHECK_FAIL")
 tr.release()
 dist.destroy_process_group()

@@ -36,6 +36,11 @@ def main():
     ap.add_argument("--uvders", action="store_true")
     ap.add_argument("--norms", action="store_true")
     ap.add_argument("--check", type=int, default=0, metavar="NCHECK")
+    ap.add_argument("--dump-checksums", default=None, metavar="FILE",
+                    help="running 64-bit checksum of every gathered field after each direct transform, in the layout of "
+                         "the reference's dump_checksums (ectrans-benchmark.F90:1455-1638; the reference's crc64 comes from "
+                         "fiat, which is not available here: the value is zlib crc32 | adler32 << 32, good for comparing "
+                         "runs of this backend across decompositions, not against reference dumps)")
     ap.add_argument("--no-pinning", action="store_true")
     ap.add_argument("--device-resident", action="store_true")
     ap.add_argument("--precision", default="dp", choices=["dp", "sp"])
@@ -80,6 +85,22 @@ def main():
         if a.device_resident:
             tr.synchronize()
 
+    def dump_checksums(jstep):
+        import zlib
+        host = lambda x: x.cpu().numpy() if a.device_resident else np.asarray(x)
+        lines = ["====================", f"iteration {jstep}", "===================="]
+        for name, arr, gath in (("zgp", host(gp), tr.gath_grid), ("zspvor", host(spvor), tr.gath_spec),
+                                ("zspdiv", host(spdiv), tr.gath_spec), ("zspscalar", host(spsc), tr.gath_spec)):
+            icrc = 0
+            nf = arr.shape[1]
+            for jf in range(nf):
+                g = gath(np.ascontiguousarray(arr[:, jf:jf + 1]), nproma=a.nproma) if name == "zgp" else gath(np.ascontiguousarray(arr[:, jf:jf + 1]))
+                buf = np.ascontiguousarray(g).tobytes()
+                icrc = zlib.crc32(buf, icrc & 0xffffffff) | (zlib.adler32(buf, (icrc >> 32) or 1) << 32)
+                lines.append(f"{name} ({jf + 1}) = {icrc:016X}")
+        with open(a.dump_checksums, "a" if jstep > 1 else "w") as fh:
+            fh.write("\n".join(lines) + "\n")
+
     print("======= Start of spectral transforms  =======\n")
     print(f"Running for {a.niter} iterations with {a.niter_warmup} extra warm-up iterations\n")
     t_inv, t_dir, t_step = [], [], []
@@ -105,6 +126,8 @@ def main():
         if jstep > a.niter_warmup:
             t_inv.append(t2 - t1); t_dir.append(t4 - t3); t_step.append((t2 - t1) + (t4 - t3))
         line = f"time step {jstep:6d} took{(t2 - t1) + (t4 - t3):8.4f}"
+        if a.dump_checksums:
+            dump_checksums(jstep)
         if a.norms:
             errs = [float(np.abs(tr.specnorm(x) / n - 1).max()) for x, n in zip((spvor, spdiv, spsc), n0)]
             line += f" | zspvor max err={errs[0]:10.3e} | zspdiv max err={errs[1]:10.3e} | zspscalar max err={errs[2]:10.3e}"
