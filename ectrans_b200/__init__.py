@@ -84,7 +84,7 @@ EXPORTED_SYMBOLS = [
     "ect_setup", "ect_inquire", "ect_inquire_array", "ect_inv_trans", "ect_dir_trans", "ect_specnorm",
     "ect_get_timings", "ect_synchronize", "ect_release", "ect_finalize", "ect_strerror", "ect_last_error",
     "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
-    "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec",
+    "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec", "ect_inv_transad", "ect_dir_transad",
 ]
 
 
@@ -103,6 +103,8 @@ def lib():
         L.ect_inquire_array.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong]
         L.ect_inv_trans.argtypes = [C.c_int, C.POINTER(_InvArgs)]
         L.ect_dir_trans.argtypes = [C.c_int, C.POINTER(_DirArgs)]
+        L.ect_inv_transad.argtypes = [C.c_int, C.POINTER(_InvArgs)]
+        L.ect_dir_transad.argtypes = [C.c_int, C.POINTER(_DirArgs)]
         L.ect_specnorm.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ect_get_timings.argtypes = [C.c_int, C.POINTER(Timings)]
         L.ect_debug_get_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
@@ -318,6 +320,56 @@ class Transform:
         self._keep = (gp, out)
         _check(lib().ect_dir_trans(self.handle, C.byref(a)), "ect_dir_trans")
         return spvor, spdiv, spsc
+
+    def inv_transad(self, gp, nuv=0, nscalar=0, nproma=0, out=None):
+        """INV_TRANSAD: adjoint of ``inv_trans`` (no derivative options) for the inner products of the reference's adjoint
+        tests.  gp ``(ngpblks, 2*nuv+nscalar, nproma)`` ordered u, v, scalars; the results are ADDED to ``out`` =
+        (spvor, spdiv, spscalar) (zero arrays are created when ``out`` is None)."""
+        dev = _is_torch(gp)
+        nproma, nblk = self._blocks(nproma)
+        assert tuple(gp.shape) == (nblk, 2 * nuv + nscalar, nproma)
+        if dev:
+            import torch
+            mk = lambda n: torch.zeros((self.nspec2, n), dtype=self._tdtype(), device=gp.device) if n else None
+        else:
+            gp = np.ascontiguousarray(gp, dtype=self.dtype)
+            mk = lambda n: np.zeros((self.nspec2, n), dtype=self.dtype) if n else None
+        if out is None:
+            out = (mk(nuv), mk(nuv), mk(nscalar))
+        spvor, spdiv, spsc = out
+        a = _InvArgs()
+        a.memspace = ECT_MEM_DEVICE if dev else ECT_MEM_HOST
+        a.nproma, a.nuv, a.nscalar = nproma, nuv, nscalar
+        a.gp = _ptr(gp)
+        a.spvor, a.spdiv, a.spscalar = _ptr(spvor), _ptr(spdiv), _ptr(spsc)
+        self._keep = (gp, out)
+        _check(lib().ect_inv_transad(self.handle, C.byref(a)), "ect_inv_transad")
+        return spvor, spdiv, spsc
+
+    def dir_transad(self, spvor=None, spdiv=None, spscalar=None, nproma=0, out=None):
+        """DIR_TRANSAD: adjoint of ``dir_trans``.  Returns gp ``(ngpblks, 2*nuv+nscalar, nproma)`` ordered u, v, scalars."""
+        dev = _is_torch(spvor) or _is_torch(spscalar)
+        nuv = 0 if spvor is None else int(spvor.shape[1])
+        nsc = 0 if spscalar is None else int(spscalar.shape[1])
+        nproma, nblk = self._blocks(nproma)
+        if out is None:
+            if dev:
+                import torch
+                ref = spvor if spvor is not None else spscalar
+                out = torch.empty((nblk, 2 * nuv + nsc, nproma), dtype=self._tdtype(), device=ref.device)
+            else:
+                out = np.empty((nblk, 2 * nuv + nsc, nproma), dtype=self.dtype)
+        if not dev:
+            spvor, spdiv, spscalar = (None if a is None else np.ascontiguousarray(a, dtype=self.dtype)
+                                      for a in (spvor, spdiv, spscalar))
+        a = _DirArgs()
+        a.memspace = ECT_MEM_DEVICE if dev else ECT_MEM_HOST
+        a.nproma, a.nuv, a.nscalar = nproma, nuv, nsc
+        a.gp = _ptr(out)
+        a.spvor, a.spdiv, a.spscalar = _ptr(spvor), _ptr(spdiv), _ptr(spscalar)
+        self._keep = (spvor, spdiv, spscalar, out)
+        _check(lib().ect_dir_transad(self.handle, C.byref(a)), "ect_dir_transad")
+        return out
 
     def inv_trans_raw(self, **kw):
         """Direct access to every ect_inv_args member (call mode 2 arrays etc.)."""

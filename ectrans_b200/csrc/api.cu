@@ -481,8 +481,8 @@ static std::vector<int2> make_pairs(const std::vector<int>& groups) {
 // ---------------------------------------------------------------------------------------
 // sub-call view: the chunk's spectral fields live inside larger staged arrays (row pitch in fields)
 struct SubView { int uv_stride, sc_stride; };
-static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view);
-static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view);
+static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view, int adj);
+static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view, int adj);
 struct HostChunk { int j0, nj; int seg, s0, ns; };   // uv levels [j0, j0+nj), scalars [s0, s0+ns) (flattened index) of segment seg
 // one caller array slice: fields [start, start+count) contiguous with pitch = count; arr = which caller array,
 // dev = the slice inside the staged copy of that array
@@ -627,7 +627,7 @@ static int layout_sp_stage(EctDevice* d, SpStage& st, int es) {
 
 template <typename Fill>
 static int inv_trans_chunked(int handle, EctHandle* h, const ect_inv_args* a, const EctFieldCfg& f, bool mode2_sp,
-                             int nsc2, int n3a, int n3b, int nproma, int ngpblks, Fill& fill_gp_table) {
+                             int nsc2, int n3a, int n3b, int nproma, int ngpblks, Fill& fill_gp_table, int adj) {
     EctDevice* d = h->d;
     const EctHostPlan& P = h->hp;
     const int es = f.fp32 ? 4 : 8;
@@ -691,7 +691,7 @@ static int inv_trans_chunked(int handle, EctHandle* h, const ect_inv_args* a, co
         }
         sub.gp = out;
         trace.mark("cmp_start", (int)ic, d->stream);
-        if ((rc = inv_trans_impl(handle, &sub, &view))) return rc;
+        if ((rc = inv_trans_impl(handle, &sub, &view, adj))) return rc;
         launches += d->launches;
         ECT_CUDA(cudaEventRecord(d->ev_cmp_done[slot], d->stream));
         trace.mark("cmp_done", (int)ic, d->stream);
@@ -722,7 +722,7 @@ static int inv_trans_chunked(int handle, EctHandle* h, const ect_inv_args* a, co
 
 template <typename Fill>
 static int dir_trans_chunked(int handle, EctHandle* h, const ect_dir_args* a, const EctFieldCfg& f, bool mode2,
-                             int nsc2, int n3a, int n3b, int nproma, int ngpblks, Fill& fill_gp_table) {
+                             int nsc2, int n3a, int n3b, int nproma, int ngpblks, Fill& fill_gp_table, int adj) {
     EctDevice* d = h->d;
     const EctHostPlan& P = h->hp;
     const int es = f.fp32 ? 4 : 8;
@@ -753,6 +753,10 @@ static int dir_trans_chunked(int handle, EctHandle* h, const ect_dir_args* a, co
     ECT_CUDA(cudaStreamWaitEvent(d->cin, d->ev_c0, 0));
     ECT_CUDA(cudaStreamWaitEvent(d->cout, d->ev_c0, 0));
     ChunkTrace trace(d->ev_c0);
+    if (adj) {     // INV_TRANSAD adds to the spectral arrays: bring their present contents first
+        for (int i = 0; i < 5; ++i)
+            if (st.elems[i]) ECT_CUDA(cudaMemcpyAsync(st.dev[i], st.host[i], (size_t)st.elems[i] * es, cudaMemcpyHostToDevice, d->cin));
+    }
     i64 launches = 0;
     for (size_t ic = 0; ic < chunks.size(); ++ic) {
         const HostChunk& c = chunks[ic];
@@ -777,7 +781,7 @@ static int dir_trans_chunked(int handle, EctHandle* h, const ect_dir_args* a, co
         if (c.nj) { sub.spvor = adv(st.dev[0], c.j0, es); sub.spdiv = adv(st.dev[1], c.j0, es); }
         if (c.ns) { const ScSeg& sg = segs[c.seg]; sub.spscalar = adv(sg.dev, c.s0 - sg.start, es); view.sc_stride = sg.count; }
         trace.mark("cmp_start", (int)ic, d->stream);
-        if ((rc = dir_trans_impl(handle, &sub, &view))) return rc;
+        if ((rc = dir_trans_impl(handle, &sub, &view, adj))) return rc;
         launches += d->launches;
         ECT_CUDA(cudaEventRecord(d->ev_cmp_done[slot], d->stream));
         trace.mark("cmp_done", (int)ic, d->stream);
@@ -802,10 +806,48 @@ static int dir_trans_chunked(int handle, EctHandle* h, const ect_dir_args* a, co
     return ECT_SUCCESS;
 }
 
-extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) { return inv_trans_impl(handle, a, nullptr); }
-extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) { return dir_trans_impl(handle, a, nullptr); }
+extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) { return inv_trans_impl(handle, a, nullptr, 0); }
+extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) { return dir_trans_impl(handle, a, nullptr, 0); }
 
-static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view) {
+// INV_TRANSAD / DIR_TRANSAD (reference cpu/external/inv_transad.F90, dir_transad.F90 and the *ad_mod
+// files of cpu/internal).  With the inner products of the reference's adjoint tests (grid: plain sum; spectral:
+// weight 2 for m > 0, 1 for the real parts of m = 0; tests/trans/test_invtrans_adjoint.F90:242-311)
+//   INV_TRANSAD = M^-1 INV_TRANS^T = the direct pipeline without the 1/N of the FFT and without Gaussian weights,
+//                 whose (U, V) -> (vor, div) step VDTUV^T equals diag(-RLAPIN(n)) . UVTVD; results are ADDED to the
+//                 spectral arrays (prfi1bad_mod.F90:91-108);
+//   DIR_TRANSAD = DIR_TRANS^T M = the inverse pipeline with every latitude row scaled by w / N, whose
+//                 (vor, div) -> (U, V) step UVTVD^T equals VDTUV . diag(-1 / RLAPIN(n)).
+// The derivative / vorticity-divergence grid-point options of INV_TRANSAD are not provided.
+extern "C" int ect_inv_transad(int handle, const ect_inv_args* a) {
+    if (!a) return ECT_ERR_MISSING;
+    if (a->scders || a->vorgp || a->divgp || a->uvder) {
+        ect_set_error("ect_inv_transad: scders / vorgp / divgp / uvder are not implemented for the adjoint");
+        return ECT_ERR_NOTIMPL;
+    }
+    ect_dir_args d;
+    memset(&d, 0, sizeof(d));
+    d.memspace = a->memspace; d.nproma = a->nproma; d.nuv = a->nuv;
+    d.gp = a->gp; d.gpuv = a->gpuv; d.gp2 = a->gp2; d.gp3a = a->gp3a; d.gp3b = a->gp3b;
+    d.nsc2 = a->nsc2; d.nsc3a_lev = a->nsc3a_lev; d.nsc3a_fld = a->nsc3a_fld; d.nsc3b_lev = a->nsc3b_lev; d.nsc3b_fld = a->nsc3b_fld;
+    d.nscalar = a->spscalar ? a->nscalar : (a->spsc2 ? a->nsc2 : 0) + (a->spsc3a ? a->nsc3a_lev * a->nsc3a_fld : 0) +
+                                           (a->spsc3b ? a->nsc3b_lev * a->nsc3b_fld : 0);
+    d.spvor = (double*)a->spvor; d.spdiv = (double*)a->spdiv; d.spscalar = (double*)a->spscalar;
+    d.spsc2 = (double*)a->spsc2; d.spsc3a = (double*)a->spsc3a; d.spsc3b = (double*)a->spsc3b;
+    return dir_trans_impl(handle, &d, nullptr, 1);
+}
+extern "C" int ect_dir_transad(int handle, const ect_dir_args* a) {
+    if (!a) return ECT_ERR_MISSING;
+    ect_inv_args v;
+    memset(&v, 0, sizeof(v));
+    v.memspace = a->memspace; v.nproma = a->nproma; v.nuv = a->nuv;
+    v.spvor = a->spvor; v.spdiv = a->spdiv; v.spscalar = a->spscalar; v.nscalar = a->nscalar;
+    v.spsc2 = a->spsc2; v.nsc2 = a->nsc2; v.spsc3a = a->spsc3a; v.nsc3a_lev = a->nsc3a_lev; v.nsc3a_fld = a->nsc3a_fld;
+    v.spsc3b = a->spsc3b; v.nsc3b_lev = a->nsc3b_lev; v.nsc3b_fld = a->nsc3b_fld;
+    v.gp = (double*)a->gp; v.gpuv = (double*)a->gpuv; v.gp2 = (double*)a->gp2; v.gp3a = (double*)a->gp3a; v.gp3b = (double*)a->gp3b;
+    return inv_trans_impl(handle, &v, nullptr, 1);
+}
+
+static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view, int adj) {
     EctHandle* h = get_handle(handle);
     if (!h) { ect_set_error("ect_inv_trans: invalid handle %d", handle); return ECT_ERR_HANDLE; }
     if (!a) return ECT_ERR_MISSING;
@@ -845,6 +887,7 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     if (f.nfs == 0) return ECT_SUCCESS;
     f.cp = round_up(2 * f.nleg, ECT_CPAD);
     f.fp32 = (h->precision == ECT_PREC_SP);
+    f.adj = adj;
     const int es = f.fp32 ? 4 : 8;
     const int nproma = (a->nproma > 0 && a->nproma < P.ngptot) ? a->nproma : std::max(P.ngptot, 1);
     const int ngpblks = (P.ngptot + nproma - 1) / nproma;
@@ -885,7 +928,7 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     };
     if (host) {
         const int nch = host_chunk_count(h, f.nleg);
-        if (nch > 1) return inv_trans_chunked(handle, h, a, f, mode2_sp, nsc2, n3a, n3b, nproma, ngpblks, fill_gp_table);
+        if (nch > 1) return inv_trans_chunked(handle, h, a, f, mode2_sp, nsc2, n3a, n3b, nproma, ngpblks, fill_gp_table, adj);
     }
     if ((rc = ensure_work(h, f))) return rc;
     d->launches = 0;
@@ -1019,7 +1062,7 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     return ECT_SUCCESS;
 }
 
-static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view) {
+static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view, int adj) {
     EctHandle* h = get_handle(handle);
     if (!h) { ect_set_error("ect_dir_trans: invalid handle %d", handle); return ECT_ERR_HANDLE; }
     if (!a) return ECT_ERR_MISSING;
@@ -1050,6 +1093,7 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     if (f.nfs == 0) return ECT_SUCCESS;
     f.cp = round_up(2 * f.nleg, ECT_CPAD);
     f.fp32 = (h->precision == ECT_PREC_SP);
+    f.adj = adj;
     const int es = f.fp32 ? 4 : 8;
     const int nproma = (a->nproma > 0 && a->nproma < P.ngptot) ? a->nproma : std::max(P.ngptot, 1);
     const int ngpblks = (P.ngptot + nproma - 1) / nproma;
@@ -1076,7 +1120,7 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     };
     if (host) {
         const int nch = host_chunk_count(h, f.nleg);
-        if (nch > 1) return dir_trans_chunked(handle, h, a, f, mode2, nsc2, n3a, n3b, nproma, ngpblks, fill_gp_table);
+        if (nch > 1) return dir_trans_chunked(handle, h, a, f, mode2, nsc2, n3a, n3b, nproma, ngpblks, fill_gp_table, adj);
     }
     if ((rc = ensure_work(h, f))) return rc;
     d->launches = 0;
@@ -1112,6 +1156,15 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
         dvor = p; p = adv(p, kf_uv * nsp, es); ddiv = p; p = adv(p, kf_uv * nsp, es);
         if (!mode2) { dsc = p; }
         else { dsc2 = p; p = adv(p, nsc2 * nsp, es); dsc3a = p; p = adv(p, n3a * nsp, es); dsc3b = p; }
+        if (adj) {     // INV_TRANSAD adds to the spectral arrays: bring their present contents first
+            auto pre = [&](double* dst, const double* src, i64 n) -> int {
+                if (src && n) ECT_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * es, cudaMemcpyHostToDevice, d->stream));
+                return ECT_SUCCESS;
+            };
+            if ((rc = pre(dvor, a->spvor, kf_uv * nsp)) || (rc = pre(ddiv, a->spdiv, kf_uv * nsp))) return rc;
+            if (!mode2) { if ((rc = pre(dsc, a->spscalar, kf_sc * nsp))) return rc; }
+            else if ((rc = pre(dsc2, a->spsc2, nsc2 * nsp)) || (rc = pre(dsc3a, a->spsc3a, n3a * nsp)) || (rc = pre(dsc3b, a->spsc3b, n3b * nsp))) return rc;
+        }
     }
     const size_t n_spec = (size_t)(2 * kf_uv + kf_sc);
     std::vector<int> groups;

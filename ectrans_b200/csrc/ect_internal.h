@@ -75,6 +75,7 @@ struct EctFieldCfg {       // field bookkeeping of one call (INV_TRANS inv_trans
     int cp = 0;            // record pitch in doubles = roundup(2*nleg, ECT_CPAD)
     int npairs = 0;        // field pairs of the Fourier stage
     int fp32 = 0;          // caller arrays are float
+    int adj = 0;           // adjoint call (INV_TRANSAD runs the direct pipeline, DIR_TRANSAD the inverse one, with other scalings)
 };
 
 struct EctDevice {

@@ -36,6 +36,7 @@ struct FtArgs {
     const double* rw_loc;         // Gaussian weight per local latitude (direct: folded into the stored records)
     int n_uv_fields;              // direct: fields < n_uv_fields are u, v (also scaled by 1/(a cos theta), LDFOU2)
     int fp32;                     // sp handle: grid-point arrays are float and the FFT arithmetic is float
+    int adj;                      // adjoint call: direct pipeline without 1/N and Gaussian weight (INV_TRANSAD), inverse with them (DIR_TRANSAD)
     int nostage;                  // this launch's rows do not fit with a staging area: inputs are read straight from HBM
     int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum
 };
@@ -187,8 +188,10 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
             if (hasb) sfb = a.fsf[fb2]; else { sfb.src_c = -1; sfb.pw = 0; sfb.deriv = 0; }
             if (!blue) { for (int k = km + 1 + tid; k < N - km; k += nthr) data[ECT_PAD((int)perm[k])] = c_make<C>(0, 0); }
             else { for (int u = 2 * km + 1 + tid; u < lp.m; u += nthr) data[ECT_PAD(u)] = c_make<C>(0, 0); }
-            const R_ sa_ = sfa.pw == 0 ? (R_)1 : (sfa.pw == 1 ? s1 : s2);
-            const R_ sb_ = sfb.pw == 0 ? (R_)1 : (sfb.pw == 1 ? s1 : s2);
+            // DIR_TRANSAD: (DIR_TRANS)^T M = diag(w / N) . INV_TRANS, the row factor rides on the load scaling
+            const R_ rs_ = a.adj ? (R_)(a.rw_loc[l] / (double)N) : (R_)1;
+            const R_ sa_ = (sfa.pw == 0 ? (R_)1 : (sfa.pw == 1 ? s1 : s2)) * rs_;
+            const R_ sb_ = (sfb.pw == 0 ? (R_)1 : (sfb.pw == 1 ? s1 : s2)) * rs_;
             for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
                 C ch[NB]; int pk[NB], pn[NB]; double2 ra[NB], rb[NB];
 #pragma unroll
@@ -338,9 +341,10 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
             // 1/N + FOURIER_OUT (same arithmetic as fourier_phases.h ftdir_store)
             // 1/N (tpm_fftw.F90:317-321), Gaussian weight (ledir_mod.F90:122) and, for u and v, 1/(a cos theta)
             // (ldfou2_mod.F90:90-96) in one factor, so that the Legendre loader only forms N +- S
-            const double wl = a.rw_loc[l];
-            const R_ sca = (R_)(0.5 / (double)N * wl * (fa < a.n_uv_fields ? racthe : 1.0));
-            const R_ scb = (R_)(0.5 / (double)N * wl * (fb2 >= 0 && fb2 < a.n_uv_fields ? racthe : 1.0));
+            // INV_TRANSAD: M^-1 (INV_TRANS)^T is the direct pipeline without 1/N and without the Gaussian weight
+            const double wl = a.adj ? 1.0 : a.rw_loc[l] / (double)N;
+            const R_ sca = (R_)(0.5 * wl * (fa < a.n_uv_fields ? racthe : 1.0));
+            const R_ scb = (R_)(0.5 * wl * (fb2 >= 0 && fb2 < a.n_uv_fields ? racthe : 1.0));
             const int ca = 2 * fa, cb = hasb ? 2 * fb2 : -1;
             for (int k0 = tid; k0 <= km; k0 += NB * nthr) {
                 C zk[NB], zn[NB], ch[NB]; double* rb[NB];
@@ -384,7 +388,7 @@ static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     a.nfs = f.nfs; a.npairs = f.npairs;
     a.nchunks = (a.npairs + FT_PAIRS_PER_CTA - 1) / FT_PAIRS_PER_CTA;
     a.ngptot = h->hp.ngptot;
-    a.fp32 = f.fp32;
+    a.fp32 = f.fp32; a.adj = f.adj;
     a.rw_loc = d->rw_loc; a.n_uv_fields = 2 * f.kf_uv;
     static const char* dbg = getenv("ECT_FFT_DBG");
     a.dbg = dbg ? atoi(dbg) : 0;

@@ -61,6 +61,7 @@ struct ProArgs {
     const EctSpecField* vor; const EctSpecField* div; const EctSpecField* sc;
     double* x; int cp; int nsmax;
     int kf_uv, kf_sc, scders, vorgp, divgp, fp32;
+    int adj;      // DIR_TRANSAD: UVTVD^T = VDTUV . diag(n (n + 1) / a^2), the inputs are scaled on load
 };
 
 __device__ __forceinline__ double d_eps(int m, int n) {     // pre_suleg_mod.F90:46-65
@@ -101,6 +102,9 @@ __global__ void k_ltinv_prologue(ProArgs a) {
     }
     __syncthreads();
     const double zl = cst[0], c1 = cst[1], c2 = cst[2], e1 = cst[3], e2 = cst[4];
+    // adjoint of UVTVD: -1 / RLAPIN(n') = n' (n' + 1) / a^2 for the rows n, n - 1, n + 1 read below
+    auto ilap = [](int k) { return k >= 1 ? (double)k * (double)(k + 1) / (ECT_RA * ECT_RA) : 0.0; };
+    const double g0 = ilap(n), gm = ilap(n - 1), gp = ilap(n + 1);
     const int base = a.nasm0[blockIdx.y];
     const int idx = base + 2 * r;
     const bool m0 = (m == 0);
@@ -112,8 +116,13 @@ __global__ void k_ltinv_prologue(ProArgs a) {
     for (int j = threadIdx.x; j < a.kf_uv + a.kf_sc; j += blockDim.x) {
         if (j < a.kf_uv) {
             const EctSpecField fv = a.vor[j], fd = a.div[j];
-            const double2 z0 = ld_spec<FP32>(fv, idx, v0, m0), zm = ld_spec<FP32>(fv, idx - 2, vm, m0), zp = ld_spec<FP32>(fv, idx + 2, vp, m0);
-            const double2 d0 = ld_spec<FP32>(fd, idx, v0, m0), dm = ld_spec<FP32>(fd, idx - 2, vm, m0), dp = ld_spec<FP32>(fd, idx + 2, vp, m0);
+            double2 z0 = ld_spec<FP32>(fv, idx, v0, m0), zm = ld_spec<FP32>(fv, idx - 2, vm, m0), zp = ld_spec<FP32>(fv, idx + 2, vp, m0);
+            double2 d0 = ld_spec<FP32>(fd, idx, v0, m0), dm = ld_spec<FP32>(fd, idx - 2, vm, m0), dp = ld_spec<FP32>(fd, idx + 2, vp, m0);
+            if (a.adj) {
+                z0.x *= g0; z0.y *= g0; d0.x *= g0; d0.y *= g0;
+                zm.x *= gm; zm.y *= gm; dm.x *= gm; dm.y *= gm;
+                zp.x *= gp; zp.y *= gp; dp.x *= gp; dp.y *= gp;
+            }
             // vdtuv_mod.F90:121-139
             double2 u, v;
             u.x = -zl * d0.y + c1 * zm.x - c2 * zp.x;
@@ -147,6 +156,7 @@ void ect_launch_ltinv_prologue(EctHandle* h, const EctFieldCfg& f, const void* d
     a.vor = (const EctSpecField*)d_vor; a.div = (const EctSpecField*)d_div; a.sc = (const EctSpecField*)d_sc;
     a.x = d->xwork; a.cp = f.cp; a.nsmax = h->hp.nsmax;
     a.kf_uv = f.kf_uv; a.kf_sc = f.kf_sc; a.scders = f.scders; a.vorgp = f.vorgp; a.divgp = f.divgp;
+    a.adj = f.adj;
     if (h->hp.nump == 0) return;
     dim3 grid(h->hp.nsmax + 2, h->hp.nump);
     int items = f.kf_uv + f.kf_sc;
@@ -165,16 +175,19 @@ struct EpiArgs {
     EctSpecField* vor; EctSpecField* div; EctSpecField* sc;    // bases are written through
     const double* x; int cp; int nsmax;
     int kf_uv, kf_sc;
+    int adj;      // INV_TRANSAD: VDTUV^T = diag(-RLAPIN(n)) . UVTVD, and the results are added to the caller's arrays
 };
 
 template <bool FP32>
-__device__ __forceinline__ void st_spec(const EctSpecField f, int idx, double re, double im) {
+__device__ __forceinline__ void st_spec(const EctSpecField f, int idx, double re, double im, bool accumulate = false) {
     if (FP32) {
         float* b = reinterpret_cast<float*>(const_cast<double*>(f.base));
+        if (accumulate) { re += (double)b[(long long)idx * f.stride]; im += (double)b[(long long)(idx + 1) * f.stride]; }
         b[(long long)idx * f.stride] = (float)re;
         b[(long long)(idx + 1) * f.stride] = (float)im;
     } else {
         double* b = const_cast<double*>(f.base);
+        if (accumulate) { re += b[(long long)idx * f.stride]; im += b[(long long)(idx + 1) * f.stride]; }
         b[(long long)idx * f.stride] = re;
         b[(long long)(idx + 1) * f.stride] = im;
     }
@@ -218,13 +231,14 @@ __global__ void k_ltdir_epilogue(EpiArgs a) {
             div.x = -zkm * u0.y + c1 * vp.x - c2 * vm.x;
             div.y = zkm * u0.x + c1 * vp.y - c2 * vm.y;
             if (m0) { vor.y = 0.0; div.y = 0.0; if (n == 0) { vor.x = 0.0; div.x = 0.0; } }
-            st_spec<FP32>(a.vor[j], idx, vor.x, vor.y);
-            st_spec<FP32>(a.div[j], idx, div.x, div.y);
+            if (a.adj) { const double sl = -d_lap(n); vor.x *= sl; vor.y *= sl; div.x *= sl; div.y *= sl; }
+            st_spec<FP32>(a.vor[j], idx, vor.x, vor.y, a.adj != 0);
+            st_spec<FP32>(a.div[j], idx, div.x, div.y, a.adj != 0);
         } else {
             const int s = j - a.kf_uv;
             double2 f0 = *reinterpret_cast<const double2*>(row + 2 * (o_sc + s));
             if (m0) f0.y = 0.0;
-            st_spec<FP32>(a.sc[s], idx, f0.x, f0.y);
+            st_spec<FP32>(a.sc[s], idx, f0.x, f0.y, a.adj != 0);
         }
     }
 }
@@ -235,7 +249,7 @@ void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, 
     a.legm = d->legm; a.nasm0 = d->nasm0;
     a.vor = (EctSpecField*)d_vor; a.div = (EctSpecField*)d_div; a.sc = (EctSpecField*)d_sc;
     a.x = d->xwork; a.cp = f.cp; a.nsmax = h->hp.nsmax;
-    a.kf_uv = f.kf_uv; a.kf_sc = f.kf_sc;
+    a.kf_uv = f.kf_uv; a.kf_sc = f.kf_sc; a.adj = f.adj;
     if (h->hp.nump == 0) return;
     dim3 grid(h->hp.nsmax + 1, h->hp.nump);
     int items = f.kf_uv + f.kf_sc;

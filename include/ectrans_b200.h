@@ -169,6 +169,15 @@ int ect_inv_trans(int handle, const ect_inv_args* args);
 int ect_dir_trans(int handle, const ect_dir_args* args);
 int ect_specnorm(int handle, const double* spec, int nfld, int memspace, double* norms /* host, nfld */);
 int ect_get_timings(int handle, ect_timings* t);
+/* INV_TRANSAD / DIR_TRANSAD: adjoints for the inner products of the reference's adjoint tests (grid: plain sum;
+ * spectral: weight 2 for m > 0, 1 for the real parts of m = 0).  Replace src/trans/include/ectrans/inv_transad.h,
+ * dir_transad.h.  Same argument structs as the forward calls with the roles of the arrays exchanged:
+ *   ect_inv_transad: gp* arrays are INPUT (u, v, scalars; no scders / vorgp / divgp / uvder -> ECT_ERR_NOTIMPL),
+ *                    the results are ADDED to the spectral arrays (as the reference does);
+ *   ect_dir_transad: spectral arrays are INPUT (left untouched; the reference zeroes them), gp* arrays OUTPUT. */
+int ect_inv_transad(int handle, const ect_inv_args* args);
+int ect_dir_transad(int handle, const ect_dir_args* args);
+
 /* GATH_GRID / DIST_GRID / GATH_SPEC / DIST_SPEC: host arrays, every rank of the handle calls (collective).
  * Replaces src/trans/include/ectrans/gath_grid.h:12-60, dist_grid.h:12-68, gath_spec.h:12-70, dist_spec.h:12-71.
  *   gp_local  PGP(nproma, nfld, ngpblks)       gp_global PGPG(ngptotg, nfld_owned)

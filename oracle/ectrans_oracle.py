@@ -715,3 +715,91 @@ def benchmark_spectral(s: Setup, nfld: int) -> np.ndarray:
     if s.nsmax >= 19:
         sp[:, int(s.nasm0[4]) + 2 * (19 - 4)] = 1.0
     return sp
+
+
+# ---------------------------------------------------------------------------------------------
+# Adjoints (INV_TRANSAD / DIR_TRANSAD).  The reference hand-codes them (cpu/internal/*ad_mod.F90); what pins them
+# is the adjoint identity of its tests (tests/trans/test_invtrans_adjoint.F90:192-222, test_dirtrans_adjoint.F90)
+# with the inner products <a, b>_gp = sum_j a_j b_j and <x, y>_sp = sum mfact (Re Re + Im Im), mfact = 2 for m > 0
+# and 1 for the real parts of m = 0 (SCALPRODSP :276-311).  The oracle therefore builds the matrix of the forward
+# transform column by column and transposes it -- exact by construction, affordable only at small truncations.
+# ---------------------------------------------------------------------------------------------
+def spectral_weights(s: Setup) -> np.ndarray:
+    """mfact per local spectral index; 0 for the (ignored) imaginary parts of m = 0."""
+    w = np.zeros(s.nspec2)
+    for m in range(s.nsmax + 1):
+        n = 2 * (s.nsmax - m + 1)
+        a = s.nasm0[m]
+        if m == 0:
+            w[a:a + n:2] = 1.0
+        else:
+            w[a:a + n] = 2.0
+    return w
+
+
+def _forward_matrices(s: Setup, uv: bool):
+    """F (grid x spectral) of INV_TRANS and D (spectral x grid) of DIR_TRANS for one scalar field (uv False) or for
+    one (vor, div) -> (u, v) level (uv True; vectors are [vor; div] and [u; v])."""
+    key = ("_adj_uv" if uv else "_adj_sc")
+    if key in s.__dict__:
+        return s.__dict__[key]
+    ns, ng = s.nspec2, s.ngptot
+    if not uv:
+        F = np.zeros((ng, ns)); D = np.zeros((ns, ng))
+        for i in range(ns):
+            e = np.zeros((1, ns)); e[0, i] = 1.0
+            F[:, i] = inv_trans(s, spscalar=e)[0]
+        for j in range(ng):
+            e = np.zeros((1, ng)); e[0, j] = 1.0
+            D[:, j] = dir_trans(s, e, 0, 1)[2][0]
+    else:
+        F = np.zeros((2 * ng, 2 * ns)); D = np.zeros((2 * ns, 2 * ng))
+        z = np.zeros((1, ns))
+        for i in range(ns):
+            e = np.zeros((1, ns)); e[0, i] = 1.0
+            g = inv_trans(s, e, z, None); F[:, i] = np.concatenate([g[0], g[1]])
+            g = inv_trans(s, z, e, None); F[:, ns + i] = np.concatenate([g[0], g[1]])
+        zg = np.zeros(ng)
+        for j in range(ng):
+            e = np.zeros(ng); e[j] = 1.0
+            v, d, _ = dir_trans(s, np.stack([e, zg]), 1, 0); D[:, j] = np.concatenate([v[0], d[0]])
+            v, d, _ = dir_trans(s, np.stack([zg, e]), 1, 0); D[:, ng + j] = np.concatenate([v[0], d[0]])
+    s.__dict__[key] = (F, D)
+    return F, D
+
+
+def inv_transad(s: Setup, gp: np.ndarray, kf_uv: int = 0, kf_sc: int = 0):
+    """M^-1 F^T gp; gp (2 kf_uv + kf_sc, ngptot) ordered u, v, scalars -> (vor_ad, div_ad, sc_ad)."""
+    w = spectral_weights(s)
+    winv = np.where(w > 0, 1.0 / np.maximum(w, 1e-300), 0.0)
+    ns = s.nspec2
+    vor = np.zeros((kf_uv, ns)); div = np.zeros((kf_uv, ns)); sc = np.zeros((kf_sc, ns))
+    if kf_uv:
+        F, _ = _forward_matrices(s, True)
+        for j in range(kf_uv):
+            r = F.T @ np.concatenate([gp[j], gp[kf_uv + j]])
+            vor[j], div[j] = winv * r[:ns], winv * r[ns:]
+    if kf_sc:
+        F, _ = _forward_matrices(s, False)
+        for j in range(kf_sc):
+            sc[j] = winv * (F.T @ gp[2 * kf_uv + j])
+    return vor, div, sc
+
+
+def dir_transad(s: Setup, spvor=None, spdiv=None, spscalar=None) -> np.ndarray:
+    """D^T M psi -> gp (2 kf_uv + kf_sc, ngptot) ordered u, v, scalars."""
+    w = spectral_weights(s)
+    kf_uv = 0 if spvor is None else spvor.shape[0]
+    kf_sc = 0 if spscalar is None else spscalar.shape[0]
+    ng = s.ngptot
+    out = np.zeros((2 * kf_uv + kf_sc, ng))
+    if kf_uv:
+        _, D = _forward_matrices(s, True)
+        for j in range(kf_uv):
+            r = D.T @ np.concatenate([w * spvor[j], w * spdiv[j]])
+            out[j], out[kf_uv + j] = r[:ng], r[ng:]
+    if kf_sc:
+        _, D = _forward_matrices(s, False)
+        for j in range(kf_sc):
+            out[2 * kf_uv + j] = D.T @ (w * spscalar[j])
+    return out

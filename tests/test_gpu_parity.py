@@ -221,6 +221,75 @@ def test_host_chunked_pipeline(eb, forced_chunks, nproma):
     tr.release()
 
 
+def test_adjoints_against_matrix_oracle(eb):
+    """INV_TRANSAD / DIR_TRANSAD against the oracle's transposed forward matrices (small truncation), the
+    accumulate semantics of INV_TRANSAD (prfi1bad_mod.F90:91-108) and the not-implemented options."""
+    T, N, nuv, nsc = 10, 12, 2, 3
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen)
+    rng = np.random.default_rng(5)
+    y = rng.uniform(-1, 1, (2 * nuv + nsc, s.ngptot))
+    rv, rd, rs = eo.inv_transad(s, y, nuv, nsc)
+    ov, od, os_ = tr.inv_transad(y[None], nuv, nsc)
+    assert rel(ov.T, rv) < TOL and rel(od.T, rd) < TOL and rel(os_.T, rs) < TOL
+    assert np.all(ov[1:2 * (T + 1):2] == 0) and np.all(os_[1:2 * (T + 1):2] == 0)      # Im(m = 0)
+    pre = (np.ones_like(ov), np.full_like(od, 2.0), np.full_like(os_, -1.0))
+    tr.inv_transad(y[None], nuv, nsc, out=pre)
+    assert rel(pre[0] - 1.0, ov) < 1e-13 and rel(pre[1] - 2.0, od) < 1e-13 and rel(pre[2] + 1.0, os_) < 1e-13
+    vor = eo.random_spectral(s, nuv, 1, zero00=True); div = eo.random_spectral(s, nuv, 2, zero00=True)
+    sc = eo.random_spectral(s, nsc, 3)
+    ref = eo.dir_transad(s, vor, div, sc)
+    g = tr.dir_transad(T_(vor), T_(div), T_(sc))
+    for i in range(ref.shape[0]):
+        assert rel(g[0, i], ref[i]) < TOL, i
+    with pytest.raises(eb.EctError, match="not implemented"):
+        a = eb._InvArgs(); a.scders = 1; a.nscalar = 1
+        eb._check(eb.lib().ect_inv_transad(tr.handle, eb.C.byref(a)), "ect_inv_transad")
+    tr.release()
+
+
+@pytest.mark.parametrize("chunked", [False, True])
+def test_adjoint_identity_reference_test(eb, monkeypatch, chunked):
+    """The reference's own adjoint tests (tests/trans/test_invtrans_adjoint.F90:152-222, test_dirtrans_adjoint.F90):
+    T159, seeded random data, <F x, y> = <x, F* y> to 20000 eps with its inner products; host arrays (also through the
+    pipelined chunk path) and device arrays."""
+    import torch
+    if chunked:
+        monkeypatch.setenv("ECT_HOST_CHUNK_FIELDS", "3")
+        monkeypatch.setenv("ECT_HOST_CHUNK_MIN_BYTES", "0")
+    T, N, nuv, nsc = 159, 160, 4, 5
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    rng = np.random.default_rng(9)
+    mk = lambda n: 0.1 * (1 - 2 * rng.random((tr.nspec2, n)))
+    vor, div, sc = mk(nuv), mk(nuv), mk(nsc)
+    w = np.zeros(tr.nspec2)
+    for m in range(T + 1):
+        a0, n = int(tr.nasm0[m]), 2 * (T - m + 1)
+        if m == 0:
+            w[a0:a0 + n:2] = 1.0
+        else:
+            w[a0:a0 + n] = 2.0
+    w = w[:, None]
+    y = 1 - 2 * rng.random((1, 2 * nuv + nsc, tr.ngptot))
+    tol = 20000 * np.finfo(float).eps
+    fx = tr.inv_trans(vor, div, sc)
+    va, da, sa = tr.inv_transad(y, nuv, nsc)
+    lhs, rhs = np.sum(fx * y), np.sum(w * vor * va) + np.sum(w * div * da) + np.sum(w * sc * sa)
+    assert abs(lhs - rhs) <= tol * abs(lhs)
+    dv, dd, ds = tr.dir_trans(y, nuv, nsc)
+    ga = tr.dir_transad(vor, div, sc)
+    lhs, rhs = np.sum(w * dv * vor) + np.sum(w * dd * div) + np.sum(w * ds * sc), np.sum(y * ga)
+    assert abs(lhs - rhs) <= tol * abs(lhs)
+    if not chunked:      # device arrays give the same bits as host arrays
+        vd, dd2, sd = tr.inv_transad(torch.from_numpy(y).cuda(), nuv, nsc)
+        assert np.array_equal(vd.cpu().numpy(), va) and np.array_equal(sd.cpu().numpy(), sa)
+        gd = tr.dir_transad(torch.from_numpy(vor).cuda(), torch.from_numpy(div).cuda(), torch.from_numpy(sc).cuda())
+        assert np.array_equal(gd.cpu().numpy(), ga)
+    tr.release()
+
+
 def test_device_memspace_matches_host(eb):
     import torch
     T, N = 79, 80

@@ -124,3 +124,27 @@ def test_adjoint_identity():
     wt[:2 * (T + 1)] = 1.0
     rhs = float(np.sum(x[0] * sy[0] * wt))
     assert abs(lhs - rhs) <= 20000 * np.finfo(float).eps * max(abs(lhs), 1.0)
+
+
+def test_oracle_adjoints_satisfy_reference_identity():
+    """The adjoint identity of tests/trans/test_invtrans_adjoint.F90:192-222 and test_dirtrans_adjoint.F90 with the
+    reference's inner products, tolerance 20000 eps, for the oracle's matrix-transpose adjoints."""
+    T, N = 10, 12
+    nloen = eo.octahedral_nloen(N)
+    s = eo.setup(T, 2 * N, nloen)
+    rng = np.random.default_rng(1)
+    nuv, nsc = 2, 2
+    vor = eo.random_spectral(s, nuv, 1, zero00=True); div = eo.random_spectral(s, nuv, 2, zero00=True)
+    sc = eo.random_spectral(s, nsc, 3)
+    w = eo.spectral_weights(s)
+    y = rng.uniform(-1, 1, (2 * nuv + nsc, s.ngptot))
+    fx = eo.inv_trans(s, vor, div, sc)
+    va, da, sa = eo.inv_transad(s, y, nuv, nsc)
+    lhs = np.sum(fx * y)
+    rhs = np.sum(w * vor * va) + np.sum(w * div * da) + np.sum(w * sc * sa)
+    assert abs(lhs - rhs) <= 20000 * np.finfo(float).eps * abs(lhs)
+    dv, dd, ds = eo.dir_trans(s, y, nuv, nsc)
+    ga = eo.dir_transad(s, vor, div, sc)
+    lhs = np.sum(w * dv * vor) + np.sum(w * dd * div) + np.sum(w * ds * sc)
+    rhs = np.sum(y * ga)
+    assert abs(lhs - rhs) <= 20000 * np.finfo(float).eps * abs(lhs)
