@@ -284,8 +284,10 @@ def test_adjoint_identity_reference_test(eb, monkeypatch, chunked):
     assert abs(lhs - rhs) <= tol * abs(lhs)
     if not chunked:      # device arrays give the same bits as host arrays
         vd, dd2, sd = tr.inv_transad(torch.from_numpy(y).cuda(), nuv, nsc)
+        tr.synchronize()               # device-pointer calls are asynchronous on the handle's stream
         assert np.array_equal(vd.cpu().numpy(), va) and np.array_equal(sd.cpu().numpy(), sa)
         gd = tr.dir_transad(torch.from_numpy(vor).cuda(), torch.from_numpy(div).cuda(), torch.from_numpy(sc).cuda())
+        tr.synchronize()
         assert np.array_equal(gd.cpu().numpy(), ga)
     tr.release()
 
