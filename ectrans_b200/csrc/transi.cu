@@ -208,6 +208,100 @@ int trans_dirtrans(struct DirTrans_t* a) {
     return ect_dir_trans(a->trans->handle, &e);
 }
 
+struct DirTransAdj_t new_dirtrans_adj(struct Trans_t* t) {
+    struct DirTransAdj_t a;
+    memset(&a, 0, sizeof(a));
+    a.nproma = t ? t->ngptot : 0; a.ngpblks = 1; a.trans = t;
+    return a;
+}
+int trans_dirtrans_adj(struct DirTransAdj_t* a) {
+    if (!a || !a->trans) return TRANS_MISSING_ARG;
+    if (a->count > 0) return TRANS_STALE_ARG;
+    a->count++;
+    if (a->rmeanu || a->rmeanv) return TRANS_NOTIMPL;
+    if (!a->rgp) return TRANS_MISSING_ARG;
+    if (a->nscalar > 0 && !a->rspscalar) return TRANS_MISSING_ARG;
+    if (a->nvordiv > 0 && (!a->rspvor || !a->rspdiv)) return TRANS_MISSING_ARG;
+    if (a->lglobal && a->trans->nproc != 1) return TRANS_NOTIMPL;
+    ect_dir_args e;
+    memset(&e, 0, sizeof(e));
+    e.memspace = ECT_MEM_HOST;
+    e.nproma = a->lglobal ? a->trans->ngptot : a->nproma;
+    e.nuv = a->nvordiv; e.nscalar = a->nscalar;
+    e.gp = a->rgp;
+    e.spvor = (double*)a->rspvor; e.spdiv = (double*)a->rspdiv; e.spscalar = (double*)a->rspscalar;
+    return ect_dir_transad(a->trans->handle, &e);
+}
+
+struct InvTransAdj_t new_invtrans_adj(struct Trans_t* t) {
+    struct InvTransAdj_t a;
+    memset(&a, 0, sizeof(a));
+    a.nproma = t ? t->ngptot : 0; a.ngpblks = 1; a.trans = t;
+    return a;
+}
+int trans_invtrans_adj(struct InvTransAdj_t* a) {
+    if (!a || !a->trans) return TRANS_MISSING_ARG;
+    if (a->count > 0) return TRANS_STALE_ARG;
+    a->count++;
+    if (a->rmeanu || a->rmeanv) return TRANS_NOTIMPL;
+    if (a->lscalarders || a->luvder_EW || a->lvordivgp) return TRANS_NOTIMPL;
+    if (!a->rgp) return TRANS_MISSING_ARG;
+    if (a->nscalar > 0 && !a->rspscalar) return TRANS_MISSING_ARG;
+    if (a->nvordiv > 0 && (!a->rspvor || !a->rspdiv)) return TRANS_MISSING_ARG;
+    if (a->lglobal && a->trans->nproc != 1) return TRANS_NOTIMPL;
+    ect_inv_args e;
+    memset(&e, 0, sizeof(e));
+    e.memspace = ECT_MEM_HOST;
+    e.nproma = a->lglobal ? a->trans->ngptot : a->nproma;
+    e.nuv = a->nvordiv; e.nscalar = a->nscalar;
+    e.gp = (double*)a->rgp;
+    e.spvor = a->rspvor; e.spdiv = a->rspdiv; e.spscalar = a->rspscalar;
+    return ect_inv_transad(a->trans->handle, &e);
+}
+
+// owners: the reference counts tasks from 1
+static int owners0(const int* own1, int nfld, int nproc, std::vector<int>& out) {
+    if (nfld > 0 && !own1) return TRANS_MISSING_ARG;
+    out.resize(nfld > 0 ? nfld : 0);
+    for (int f = 0; f < nfld; ++f) {
+        if (own1[f] < 1 || own1[f] > nproc) return TRANS_ERROR;
+        out[f] = own1[f] - 1;
+    }
+    return TRANS_SUCCESS;
+}
+struct DistGrid_t new_distgrid(struct Trans_t* t) { struct DistGrid_t a; memset(&a, 0, sizeof(a)); a.nproma = t ? t->ngptot : 0; a.ngpblks = 1; a.trans = t; return a; }
+struct GathGrid_t new_gathgrid(struct Trans_t* t) { struct GathGrid_t a; memset(&a, 0, sizeof(a)); a.nproma = t ? t->ngptot : 0; a.ngpblks = 1; a.trans = t; return a; }
+struct DistSpec_t new_distspec(struct Trans_t* t) { struct DistSpec_t a; memset(&a, 0, sizeof(a)); a.trans = t; return a; }
+struct GathSpec_t new_gathspec(struct Trans_t* t) { struct GathSpec_t a; memset(&a, 0, sizeof(a)); a.trans = t; return a; }
+int trans_distgrid(struct DistGrid_t* a) {
+    if (!a || !a->trans || !a->rgp) return TRANS_MISSING_ARG;
+    if (a->count > 0) return TRANS_STALE_ARG;
+    a->count++;
+    std::vector<int> own; int rc = owners0(a->nfrom, a->nfld, a->trans->nproc, own);
+    return rc ? rc : ect_dist_grid(a->trans->handle, a->rgpg, a->nfld, a->nproma, own.data(), a->rgp);
+}
+int trans_gathgrid(struct GathGrid_t* a) {
+    if (!a || !a->trans || !a->rgp) return TRANS_MISSING_ARG;
+    if (a->count > 0) return TRANS_STALE_ARG;
+    a->count++;
+    std::vector<int> own; int rc = owners0(a->nto, a->nfld, a->trans->nproc, own);
+    return rc ? rc : ect_gath_grid(a->trans->handle, a->rgp, a->nfld, a->nproma, own.data(), a->rgpg);
+}
+int trans_distspec(struct DistSpec_t* a) {
+    if (!a || !a->trans || !a->rspec) return TRANS_MISSING_ARG;
+    if (a->count > 0) return TRANS_STALE_ARG;
+    a->count++;
+    std::vector<int> own; int rc = owners0(a->nfrom, a->nfld, a->trans->nproc, own);
+    return rc ? rc : ect_dist_spec(a->trans->handle, a->rspecg, a->nfld, own.data(), a->rspec);
+}
+int trans_gathspec(struct GathSpec_t* a) {
+    if (!a || !a->trans || !a->rspec) return TRANS_MISSING_ARG;
+    if (a->count > 0) return TRANS_STALE_ARG;
+    a->count++;
+    std::vector<int> own; int rc = owners0(a->nto, a->nfld, a->trans->nproc, own);
+    return rc ? rc : ect_gath_spec(a->trans->handle, a->rspec, a->nfld, own.data(), a->rspecg);
+}
+
 int trans_specnorm(struct SpecNorm_t* a) {
     if (!a || !a->trans || !a->rspec || !a->rnorm || a->nfld <= 0) return TRANS_MISSING_ARG;
     if (a->count > 0) return TRANS_STALE_ARG;

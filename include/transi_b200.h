@@ -6,7 +6,8 @@
  * (rspscalar[nspec2][nscalar], rgp[ngpblks][nfld][nproma], lglobal: rgp[nfld][ngptotg]) and the same
  * return codes (TRANS_SUCCESS 0, -1 error, -2 not implemented, -3 missing arg, -4 unrecognised arg,
  * -5 stale arg; transi.c:33-58).  Argument structs are single use (count guard,
- * transi_module.F90:1949-1954).  Out of scope: adjoints, dist/gath, vordiv_to_UV, LAM, I/O cache.
+ * transi_module.F90:1949-1954).  Also trans_dirtrans_adj / trans_invtrans_adj (transi.h:354, 491) and
+ * trans_distgrid / gathgrid / distspec / gathspec (transi.h:520-616).  Out of scope: vordiv_to_UV, LAM, I/O cache.
  * A caller of the reference includes this header instead of "ectrans/transi.h" and links
  * libectrans_b200.so instead of libtransi_dp.so.
  */
@@ -73,6 +74,29 @@ struct DirTrans_t {
   int count;
 };
 
+struct DirTransAdj_t {    /* transi.h:945-972: rgp is the OUTPUT of the adjoint, the spectral arrays its input */
+  double* rgp;
+  const double* rspscalar; const double* rspvor; const double* rspdiv;
+  const double* rmeanu; const double* rmeanv;
+  int nproma, nscalar, nvordiv, ngpblks, lglobal;
+  struct Trans_t* trans;
+  int count;
+};
+
+struct InvTransAdj_t {    /* transi.h:1032-1066: rgp is the INPUT, results are added to the spectral arrays */
+  double* rspscalar; double* rspvor; double* rspdiv;
+  const double* rmeanu; const double* rmeanv;
+  const double* rgp;
+  int nproma, nscalar, nvordiv, lscalarders, luvder_EW, lvordivgp, ngpblks, lglobal;
+  struct Trans_t* trans;
+  int count;
+};
+
+struct DistGrid_t { const double* rgpg; double* rgp; const int* nfrom; int nproma, nfld, ngpblks; struct Trans_t* trans; int count; };
+struct GathGrid_t { double* rgpg; const double* rgp; const int* nto; int nproma, nfld, ngpblks; struct Trans_t* trans; int count; };
+struct DistSpec_t { const double* rspecg; double* rspec; const int* nfrom; int nfld; struct Trans_t* trans; int count; };
+struct GathSpec_t { double* rspecg; const double* rspec; const int* nto; int nfld; struct Trans_t* trans; int count; };
+
 struct SpecNorm_t {
   const double* rspec;   /* [nspec2][nfld] */
   int nmaster;
@@ -95,6 +119,19 @@ struct InvTrans_t new_invtrans(struct Trans_t*);
 int trans_invtrans(struct InvTrans_t*);
 struct DirTrans_t new_dirtrans(struct Trans_t*);
 int trans_dirtrans(struct DirTrans_t*);
+struct DirTransAdj_t new_dirtrans_adj(struct Trans_t*);
+int trans_dirtrans_adj(struct DirTransAdj_t*);
+struct InvTransAdj_t new_invtrans_adj(struct Trans_t*);
+int trans_invtrans_adj(struct InvTransAdj_t*);
+/* nfrom / nto: 1-based tasks as in the reference */
+struct DistGrid_t new_distgrid(struct Trans_t*);
+int trans_distgrid(struct DistGrid_t*);
+struct GathGrid_t new_gathgrid(struct Trans_t*);
+int trans_gathgrid(struct GathGrid_t*);
+struct DistSpec_t new_distspec(struct Trans_t*);
+int trans_distspec(struct DistSpec_t*);
+struct GathSpec_t new_gathspec(struct Trans_t*);
+int trans_gathspec(struct GathSpec_t*);
 struct SpecNorm_t new_specnorm(struct Trans_t*);
 int trans_specnorm(struct SpecNorm_t*);
 int trans_delete(struct Trans_t*);

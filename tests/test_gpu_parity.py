@@ -427,6 +427,61 @@ def test_transi_face(eb):
     i2.nscalar = 1
     assert L.trans_invtrans(C.byref(i2)) == -3           # missing rspscalar
     assert b"missing" in L.trans_error_msg(-3)
+
+    # adjoints (transi.h:354, 491) and gather / distribute (transi.h:520-616)
+    class InvAdj(C.Structure):
+        _fields_ = [("rspscalar", C.c_void_p), ("rspvor", C.c_void_p), ("rspdiv", C.c_void_p), ("rmeanu", C.c_void_p),
+                    ("rmeanv", C.c_void_p), ("rgp", C.c_void_p), ("nproma", C.c_int), ("nscalar", C.c_int),
+                    ("nvordiv", C.c_int), ("lscalarders", C.c_int), ("luvder_EW", C.c_int), ("lvordivgp", C.c_int),
+                    ("ngpblks", C.c_int), ("lglobal", C.c_int), ("trans", C.POINTER(Trans)), ("count", C.c_int)]
+
+    class Gath(C.Structure):
+        _fields_ = [("rgpg", C.c_void_p), ("rgp", C.c_void_p), ("nto", C.c_void_p), ("nproma", C.c_int), ("nfld", C.c_int),
+                    ("ngpblks", C.c_int), ("trans", C.POINTER(Trans)), ("count", C.c_int)]
+
+    class GathSp(C.Structure):
+        _fields_ = [("rspecg", C.c_void_p), ("rspec", C.c_void_p), ("nto", C.c_void_p), ("nfld", C.c_int),
+                    ("trans", C.POINTER(Trans)), ("count", C.c_int)]
+
+    for fn, ty in (("new_invtrans_adj", InvAdj), ("new_dirtrans_adj", Dir), ("new_gathgrid", Gath), ("new_distgrid", Gath),
+                   ("new_gathspec", GathSp), ("new_distspec", GathSp)):
+        getattr(L, fn).restype = ty
+        getattr(L, fn).argtypes = [C.POINTER(Trans)]
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (t.nspec2, nscalar)); x[1:48:2] = 0
+    y = rng.uniform(-1, 1, (nscalar, t.ngptot))
+    fx = np.zeros_like(y)
+    i3 = L.new_invtrans(C.byref(t)); i3.nscalar = nscalar; i3.rspscalar = x.ctypes.data; i3.rgp = fx.ctypes.data
+    assert L.trans_invtrans(C.byref(i3)) == 0
+    ya = np.zeros_like(x)
+    ia = L.new_invtrans_adj(C.byref(t)); ia.nscalar = nscalar; ia.rspscalar = ya.ctypes.data; ia.rgp = y.ctypes.data
+    assert L.trans_invtrans_adj(C.byref(ia)) == 0
+    w = np.full((t.nspec2, 1), 2.0); w[0:48:2] = 1.0; w[1:48:2] = 0.0
+    assert abs(np.sum(fx * y) - np.sum(w * x * ya)) <= 20000 * np.finfo(float).eps * abs(np.sum(fx * y))
+    dy = np.zeros_like(x)
+    d2 = L.new_dirtrans(C.byref(t)); d2.nscalar = nscalar; d2.rgp = y.ctypes.data; d2.rspscalar = dy.ctypes.data
+    assert L.trans_dirtrans(C.byref(d2)) == 0
+    xa = np.zeros_like(y)
+    da = L.new_dirtrans_adj(C.byref(t)); da.nscalar = nscalar; da.rspscalar = x.ctypes.data; da.rgp = xa.ctypes.data
+    assert L.trans_dirtrans_adj(C.byref(da)) == 0
+    assert abs(np.sum(w * dy * x) - np.sum(y * xa)) <= 20000 * np.finfo(float).eps * abs(np.sum(y * xa))
+    ia2 = L.new_invtrans_adj(C.byref(t)); ia2.nscalar = 1; ia2.lscalarders = 1; ia2.rspscalar = ya.ctypes.data; ia2.rgp = y.ctypes.data
+    assert L.trans_invtrans_adj(C.byref(ia2)) == -2       # derivative options of the adjoint: not implemented
+    nto = np.ones(nscalar, dtype=np.int32)
+    gg = np.zeros_like(y)
+    g = L.new_gathgrid(C.byref(t)); g.rgp = y.ctypes.data; g.rgpg = gg.ctypes.data; g.nto = nto.ctypes.data; g.nfld = nscalar
+    assert L.trans_gathgrid(C.byref(g)) == 0 and np.array_equal(gg, y)
+    xs = rng.uniform(-1, 1, (t.nspec2, nscalar)); sg = np.zeros_like(xs)
+    gs = L.new_gathspec(C.byref(t)); gs.rspec = xs.ctypes.data; gs.rspecg = sg.ctypes.data; gs.nto = nto.ctypes.data; gs.nfld = nscalar
+    assert L.trans_gathspec(C.byref(gs)) == 0
+    xz = xs.copy(); xz[1:48:2] = 0
+    assert np.array_equal(sg, xz)
+    back = np.zeros_like(xs)
+    ds = L.new_distspec(C.byref(t)); ds.rspecg = sg.ctypes.data; ds.rspec = back.ctypes.data; ds.nfrom = nto.ctypes.data; ds.nfld = nscalar
+    assert L.trans_distspec(C.byref(ds)) == 0 and np.array_equal(back, xz)
+    bad = np.full(nscalar, 2, dtype=np.int32)
+    g2 = L.new_gathgrid(C.byref(t)); g2.rgp = y.ctypes.data; g2.rgpg = gg.ctypes.data; g2.nto = bad.ctypes.data; g2.nfld = nscalar
+    assert L.trans_gathgrid(C.byref(g2)) == -1            # task 2 of 1
     assert L.trans_delete(C.byref(t)) == 0
 
 
