@@ -29,6 +29,24 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool va
     const int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(s), "l"(gmem), "r"(sz));
 }
+// ---- bulk asynchronous copies (TMA engine, 1-D form: no tensor map) completing on an mbarrier ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes),
+                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
@@ -314,23 +332,36 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
     const double* pa = a.ptab + lm.pa_off + i0;
     const double* xb = a.x + lm.xrow0 * (long long)a.cp + c0;
 
-    auto load_chunk = [&](int chunk, int buf) {
-        double* As = smem + (size_t)buf * INV_STAGE_DOUBLES;
-        double* Aa = As + INV_KC * LEG_LD;
-        double* Bs = Aa + INV_KC * LEG_LD;
-        double* Ba = Bs + INV_KC * LEG_LD;
-        const int k0 = chunk * INV_KC;
+    // Operand tiles arrive by bulk asynchronous copies (TMA engine): a stage is 4 tiles (P sym, P antisym, X sym,
+    // X antisym) x INV_KC rows of 64 doubles = 32 row copies of 512 bytes, one per lane of warp 0, completing on
+    // the stage's mbarrier.  Rows past the end of a parity are not copied: their polynomial row is zeroed instead.
+    __shared__ __align__(8) unsigned long long s_full[INV_STAGES];
+    if (tid == 0) {
 #pragma unroll
-        for (int e = 0; e < INV_KC / 4; ++e) {   // INV_KC rows x 64 columns = INV_KC * 32 16-byte pieces per tile
-            const int idx = tid + e * LEG_THREADS;
-            const int row = idx >> 5, c2 = (idx & 31) * 2;
-            const int k = k0 + row;
-            const bool vs = k < lm.ils, va = k < lm.ila;
-            cp_async16(As + row * LEG_LD + c2, ps + (long long)(vs ? k : 0) * lm.ldp + c2, vs);
-            cp_async16(Aa + row * LEG_LD + c2, pa + (long long)(va ? k : 0) * lm.ldp + c2, va);
-            const bool cv = (c0 + c2) < a.cp;
-            cp_async16(Bs + row * LEG_LD + c2, xb + (long long)(vs ? 2 * k : 0) * a.cp + (cv ? c2 : 0), vs && cv);
-            cp_async16(Ba + row * LEG_LD + c2, xb + (long long)(va ? 2 * k + 1 : 0) * a.cp + (cv ? c2 : 0), va && cv);
+        for (int s = 0; s < INV_STAGES; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned rowb = (unsigned)(min(LEG_BN, a.cp - c0) * (int)sizeof(double));      // X row bytes inside this field tile
+    auto load_chunk = [&](int chunk, int buf) {         // called by warp 0 only
+        double* As = smem + (size_t)buf * INV_STAGE_DOUBLES;
+        const int k0 = chunk * INV_KC;
+        const int nvs = min(INV_KC, lm.ils - k0), nva = max(0, min(INV_KC, lm.ila - k0));
+        if (lane == 0) mbar_expect_tx(&s_full[buf], (unsigned)(nvs + nva) * (LEG_BM * (unsigned)sizeof(double) + rowb));
+        __syncwarp();
+        static_assert(4 * INV_KC == 32, "one (tile, row) per lane");
+        const int tile4 = lane / INV_KC, row = lane % INV_KC;
+        const int k = k0 + row;
+        const bool anti = tile4 & 1, isx = tile4 >= 2;
+        const bool valid = k < (anti ? lm.ila : lm.ils);
+        double* dst = As + (size_t)tile4 * INV_KC * LEG_LD + row * LEG_LD;      // tile order in a stage: As, Aa, Bs, Ba
+        if (valid) {
+            const double* src = !isx ? (anti ? pa : ps) + (long long)k * lm.ldp
+                                     : xb + (long long)(2 * k + (anti ? 1 : 0)) * a.cp;
+            bulk_g2s(dst, src, isx ? rowb : (unsigned)(LEG_BM * sizeof(double)), &s_full[buf]);
+        } else {       // (last chunk only) zero row: the stale contents of a never-filled stage could be NaN patterns
+#pragma unroll 8
+            for (int c = 0; c < LEG_BM; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(0.0, 0.0);
         }
     };
 
@@ -340,18 +371,20 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acs[i][j][0] = acs[i][j][1] = 0.0; aca[i][j][0] = aca[i][j][1] = 0.0; }
 
+    if (warp == 0) {
 #pragma unroll
-    for (int s = 0; s < INV_STAGES - 1; ++s) {
-        if (s < nchunks) load_chunk(s, s);
-        cp_async_commit();
+        for (int s = 0; s < INV_STAGES - 1; ++s)
+            if (s < nchunks) load_chunk(s, s);
     }
     for (int ch = 0; ch < nchunks; ++ch) {
-        cp_async_wait<INV_STAGES - 2>();
-        __syncthreads();
-        {
+        mbar_wait(&s_full[ch % INV_STAGES], (unsigned)((ch / INV_STAGES) & 1));
+        __syncthreads();           // everybody is done with chunk ch - 1: its stage can be refilled
+        if (warp == 0) {
             const int nx = ch + INV_STAGES - 1;
-            if (nx < nchunks) load_chunk(nx, nx % INV_STAGES);
-            cp_async_commit();
+            if (nx < nchunks) {
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                load_chunk(nx, nx % INV_STAGES);
+            }
         }
         const double* As = smem + (size_t)(ch % INV_STAGES) * INV_STAGE_DOUBLES;
         const double* Aa = As + INV_KC * LEG_LD;
@@ -376,7 +409,6 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
                 }
         }
     }
-    cp_async_wait<0>();
     // epilogue: north = S + A, south = S - A  (asre1b_mod.F90:99-100)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
