@@ -1365,6 +1365,57 @@ __global__ void k_peak_dfma(double* out, int iters) {
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mixed: even warps issue DMMA, odd warps DFMA -- do the two share one pipe?  (aggregate flops reported)
+__global__ void k_peak_mixed(double* out, int iters) {
+    double c[16];
+    for (int i = 0; i < 16; ++i) c[i] = i * 1e-3;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    if ((threadIdx.x >> 5) & 1) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[2 * i]), "+d"(c[2 * i + 1]) : "d"(a), "d"(b));
+        }
+    }
+    double s = 0.0;
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// legacy tensor path, TF32 m16n8k8 with fp32 accumulators (sp contraction: 3 x TF32 split products)
+__global__ void k_peak_tf32(double* out, int iters) {
+    float c[8][4];
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+    const unsigned a0 = __float_as_uint(1.0f + threadIdx.x * 1e-3f), b0 = __float_as_uint(1.0f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(a0), "r"(a0), "r"(a0), "r"(a0), "r"(b0), "r"(b0));
+    }
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) s += c[i][j];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_peak_ffma(double* out, int iters) {
+    float c[16];
+    for (int i = 0; i < 16; ++i) c[i] = i * 1e-3f;
+    const float a = 1.0f + threadIdx.x * 1e-9f, b = 1e-9f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fmaf(c[i], a, b);
+    }
+    float s = 0.f;
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 extern "C" int ect_measure_fp64_peak(int which, double* tflops) {
     if (!tflops) return ECT_ERR_MISSING;
     int dev = 0, sms = 0;
@@ -1380,6 +1431,9 @@ extern "C" int ect_measure_fp64_peak(int which, double* tflops) {
     for (int rep = 0; rep < 5; ++rep) {
         ECT_CUDA(cudaEventRecord(e0));
         if (which == 0) k_peak_dmma<<<blocks, threads>>>(out, iters);
+        else if (which == 2) k_peak_mixed<<<blocks, threads>>>(out, iters);
+        else if (which == 3) k_peak_tf32<<<blocks, threads>>>(out, iters);
+        else if (which == 4) k_peak_ffma<<<blocks, threads>>>(out, iters);
         else k_peak_dfma<<<blocks, threads>>>(out, iters);
         ECT_CUDA(cudaEventRecord(e1));
         ECT_CUDA(cudaEventSynchronize(e1));
@@ -1387,6 +1441,8 @@ extern "C" int ect_measure_fp64_peak(int which, double* tflops) {
         ECT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         double flops;
         if (which == 0) flops = (double)blocks * (threads / 32) * (double)iters * 8.0 * (2.0 * 8 * 8 * 4);
+        else if (which == 2) flops = (double)blocks * (threads / 64) * (double)iters * (8.0 * (2.0 * 8 * 8 * 4) + 32 * 16.0 * 2.0);
+        else if (which == 3) flops = (double)blocks * (threads / 32) * (double)iters * 8.0 * (2.0 * 16 * 8 * 8);
         else flops = (double)blocks * threads * (double)iters * 16.0 * 2.0;
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }

@@ -109,7 +109,7 @@ struct EctDevice {
     int* fft_rec = nullptr;
     std::vector<int> h_lat_plan;
     // per smem-class work lists (latitudes sorted by cost)
-    struct Bucket { int smem; int threads; int maxr; int nostage = 0; std::vector<int> lats; int* d_lats = nullptr; };
+    struct Bucket { int smem; int threads; int threads_inv = 0; int maxr; int nostage = 0; std::vector<int> lats; int* d_lats = nullptr; };
     std::vector<Bucket> buckets;
     // workspaces (grow only)
     double* xwork = nullptr; i64 xwork_elems = 0;       // X (inverse input) / POA (direct output)

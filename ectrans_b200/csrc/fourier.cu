@@ -422,13 +422,15 @@ static void launch_fourier(EctHandle* h, FtArgs& a) {
         cudaStream_t st = d->stream;
         if (fork) { const int k = slot % (EctDevice::kSide + 1); st = k == 0 ? d->stream : d->side[k - 1]; }
         ++slot;
+        const int thr = INVERSE ? b.threads_inv : b.threads;
         if (a.fp32) {
-            if (b.maxr <= 7 && b.threads == 512) k_fourier<INVERSE, 7, 512, true><<<grid, b.threads, b.smem, st>>>(a);
-            else if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, true><<<grid, b.threads, b.smem, st>>>(a);
-            else k_fourier<INVERSE, ECT_MAX_RADIX, 256, true><<<grid, b.threads, b.smem, st>>>(a);
-        } else if (b.maxr <= 7 && b.threads == 512) k_fourier<INVERSE, 7, 512, false><<<grid, b.threads, b.smem, st>>>(a);
-        else if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, false><<<grid, b.threads, b.smem, st>>>(a);
-        else k_fourier<INVERSE, ECT_MAX_RADIX, 256, false><<<grid, b.threads, b.smem, st>>>(a);
+            if (b.maxr <= 7 && thr == 512) k_fourier<INVERSE, 7, 512, true><<<grid, thr, b.smem, st>>>(a);
+            else if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, true><<<grid, thr, b.smem, st>>>(a);
+            else k_fourier<INVERSE, ECT_MAX_RADIX, 256, true><<<grid, thr, b.smem, st>>>(a);
+        } else if (b.maxr <= 7 && thr == 384) k_fourier<INVERSE, 7, 384, false><<<grid, thr, b.smem, st>>>(a);
+        else if (b.maxr <= 7 && thr == 512) k_fourier<INVERSE, 7, 512, false><<<grid, thr, b.smem, st>>>(a);
+        else if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, false><<<grid, thr, b.smem, st>>>(a);
+        else k_fourier<INVERSE, ECT_MAX_RADIX, 256, false><<<grid, thr, b.smem, st>>>(a);
         d->launches++;
     }
     if (fork)
@@ -519,6 +521,11 @@ int ect_fourier_setup(EctHandle* h) {
             static const char* t512 = getenv("ECT_FFT_T512");
             if (!v && i >= 4 && t512 && atoi(t512)) b.threads = 512;
             if (sp && !v && i >= 5) b.threads = 512;      // float work arrays: 128 registers/thread, 16 warps fit
+            b.threads_inv = b.threads;
+            // dp, big classes, radices <= 7 (the chirp-z rows): the inverse kernel fits 12 warps at 168 registers
+            // (49.3 against 52.7 ms at TCo1279); the direct one does not gain (59.2 against 57.1) and keeps 8 warps
+            static const char* t384 = getenv("ECT_FFT_T384");
+            if (!sp && !v && i >= 5 && !(t384 && !atoi(t384))) b.threads_inv = 384;
             b.maxr = v ? ECT_MAX_RADIX : 7;
             b.nostage = i == 6;        // last class: rows too long for a staging area next to the work array
             d->buckets.push_back(b);
@@ -558,6 +565,7 @@ int ect_fourier_setup(EctHandle* h) {
     }
 #define FT_ATTR(...) ECT_CUDA(cudaFuncSetAttribute(k_fourier<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024))
     FT_ATTR(true, 7, 512, false); FT_ATTR(false, 7, 512, false);
+    FT_ATTR(true, 7, 384, false);
     FT_ATTR(true, 7, 256, false); FT_ATTR(false, 7, 256, false);
     FT_ATTR(true, ECT_MAX_RADIX, 256, false); FT_ATTR(false, ECT_MAX_RADIX, 256, false);
     FT_ATTR(true, 7, 256, true); FT_ATTR(false, 7, 256, true);

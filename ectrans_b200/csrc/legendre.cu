@@ -318,7 +318,11 @@ struct LegArgs {
     double* const* peer; const int* dst_rank_n; const int* dst_rank_s; const int* dst_rec_n; const int* dst_rec_s;
 };
 
-__global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
+// Variant with the operand tiles staged by the TMA engine (cp.async.bulk + mbarrier), selected by ECT_LEINV_TMA=1.
+// Measured on B200 at TCo1279 L137: 70.9 ms against 48.4 ms for the cp.async loader of k_leinv below -- a stage is
+// 32 row copies of 512 bytes into the padded (conflict-free) pitch, and two CTAs per SM issue 64 such copies per
+// ~1000 clocks, which the bulk-copy path does not sustain at this granularity.  Kept for comparison only.
+__global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv_tma(LegArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int tile = blockIdx.x / a.nct, ct = blockIdx.x - tile * a.nct;
     const int2 td = a.tiles[tile];
@@ -429,6 +433,107 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
     }
 }
 
+// Inverse contraction (default): 16-byte cp.async pieces issued by all threads into a 5-stage ring.
+__global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv(LegArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int tile = blockIdx.x / a.nct, ct = blockIdx.x - tile * a.nct;
+    const int2 td = a.tiles[tile];
+    const EctLegM lm = a.legm[td.x];
+    const int i0 = td.y * LEG_BM, c0 = ct * LEG_BN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int nchunks = (lm.ils + INV_KC - 1) / INV_KC;
+    const double* ps = a.ptab + lm.ps_off + i0;
+    const double* pa = a.ptab + lm.pa_off + i0;
+    const double* xb = a.x + lm.xrow0 * (long long)a.cp + c0;
+    const int ni = min(4, (lm.ndglu - (i0 + wm * 32) + 7) >> 3);
+
+    auto load_chunk = [&](int chunk, int buf) {
+        double* As = smem + (size_t)buf * INV_STAGE_DOUBLES;
+        double* Aa = As + INV_KC * LEG_LD;
+        double* Bs = Aa + INV_KC * LEG_LD;
+        double* Ba = Bs + INV_KC * LEG_LD;
+        const int k0 = chunk * INV_KC;
+#pragma unroll
+        for (int e = 0; e < INV_KC / 4; ++e) {   // INV_KC rows x 64 columns = INV_KC * 32 16-byte pieces per tile
+            const int idx = tid + e * LEG_THREADS;
+            const int row = idx >> 5, c2 = (idx & 31) * 2;
+            const int k = k0 + row;
+            const bool vs = k < lm.ils, va = k < lm.ila;
+            cp_async16(As + row * LEG_LD + c2, ps + (long long)(vs ? k : 0) * lm.ldp + c2, vs);
+            cp_async16(Aa + row * LEG_LD + c2, pa + (long long)(va ? k : 0) * lm.ldp + c2, va);
+            const bool cv = (c0 + c2) < a.cp;
+            cp_async16(Bs + row * LEG_LD + c2, xb + (long long)(vs ? 2 * k : 0) * a.cp + (cv ? c2 : 0), vs && cv);
+            cp_async16(Ba + row * LEG_LD + c2, xb + (long long)(va ? 2 * k + 1 : 0) * a.cp + (cv ? c2 : 0), va && cv);
+        }
+    };
+
+    double acs[4][4][2], aca[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acs[i][j][0] = acs[i][j][1] = 0.0; aca[i][j][0] = aca[i][j][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < INV_STAGES - 1; ++s) {
+        if (s < nchunks) load_chunk(s, s);
+        cp_async_commit();
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        cp_async_wait<INV_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = ch + INV_STAGES - 1;
+            if (nx < nchunks) load_chunk(nx, nx % INV_STAGES);
+            cp_async_commit();
+        }
+        const double* As = smem + (size_t)(ch % INV_STAGES) * INV_STAGE_DOUBLES;
+        const double* Aa = As + INV_KC * LEG_LD;
+        const double* Bs = Aa + INV_KC * LEG_LD;
+        const double* Ba = Bs + INV_KC * LEG_LD;
+#pragma unroll
+        for (int kk = 0; kk < INV_KC; kk += 4) {
+            double fs[4], fa[4], bs[4], ba[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                fs[i] = As[(kk + t) * LEG_LD + wm * 32 + i * 8 + g];
+                fa[i] = Aa[(kk + t) * LEG_LD + wm * 32 + i * 8 + g];
+                bs[i] = Bs[(kk + t) * LEG_LD + wn * 32 + i * 8 + g];
+                ba[i] = Ba[(kk + t) * LEG_LD + wn * 32 + i * 8 + g];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i >= ni) continue;          // 8-latitude blocks past NDGLU(m) (warp-uniform)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma884(acs[i][j][0], acs[i][j][1], fs[i], bs[j]);
+                    dmma884(aca[i][j][0], aca[i][j][1], fa[i], ba[j]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    // epilogue: north = S + A, south = S - A  (asre1b_mod.F90:99-100)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int li = i0 + wm * 32 + i * 8 + g;
+        if (li >= lm.ndglu) continue;
+        // TRMTOL fused: the record goes straight into the buffer of the rank that owns the latitude
+        double* pn = a.peer[a.dst_rank_n[lm.rec0 + li]] + (long long)a.dst_rec_n[lm.rec0 + li] * a.cp;
+        double* psth = a.peer[a.dst_rank_s[lm.rec0 + li]] + (long long)a.dst_rec_s[lm.rec0 + li] * a.cp;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + wn * 32 + j * 8 + 2 * t;
+            if (c >= a.cp) continue;
+            *reinterpret_cast<double2*>(pn + c) =
+                make_double2(acs[i][j][0] + aca[i][j][0], acs[i][j][1] + aca[i][j][1]);
+            *reinterpret_cast<double2*>(psth + c) =
+                make_double2(acs[i][j][0] - aca[i][j][0], acs[i][j][1] - aca[i][j][1]);
+        }
+    }
+}
+
 // Direct: Psi[k][c] = sum_lat P[k][lat] * (w (N +- S))[lat][c].  North / south records arrive already scaled by
 // the Gaussian weight (and 1/(a cos theta) for u, v) from the Fourier stage's store; they are staged with
 // cp.async and only the N +- S combination (prfi2b_mod.F90:91-92) is formed when the B fragments are read.
@@ -444,7 +549,20 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
     const int nchunks = (lm.ndglu + LEG_KC - 1) / LEG_KC;
     const double* ps = a.ptab + lm.ps_off;
     const double* pa = a.ptab + lm.pa_off;
+    const int ni = min(4, (lm.ils - (kr0 + wm * 32) + 7) >> 3);      // 8-row blocks of this warp that hold an n (ila <= ils)
 
+    // record numbers of the north / south rows a thread stages: fetched one chunk ahead of the cp.async that
+    // uses them, so that the dependent index load is never waited for in front of the tensor work
+    int rn[2], rs[2];
+    auto load_idx = [&](int chunk) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int li = chunk * LEG_KC + ((tid + e * LEG_THREADS) >> 5);
+            const bool v = li < lm.ndglu;
+            rn[e] = v ? a.rec_n[lm.rec0 + li] : -1;
+            rs[e] = v ? a.rec_s[lm.rec0 + li] : -1;
+        }
+    };
     auto load_chunk = [&](int chunk, int buf) {
         double* As = smem + (size_t)buf * DIR_STAGE_DOUBLES;
         double* Aa = As + LEG_BM * DIR_LDA;
@@ -468,10 +586,9 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
             }
             {   // north / south records: 8 latitudes x 64 columns = 256 pieces per hemisphere
                 const int lr = idx >> 5, c2 = (idx & 31) * 2;
-                const int li = l0 + lr;
-                const bool v = li < lm.ndglu && (c0 + c2) < a.cp;
-                const long long on = v ? (long long)a.rec_n[lm.rec0 + li] * a.cp + c0 + c2 : 0;
-                const long long os = v ? (long long)a.rec_s[lm.rec0 + li] * a.cp + c0 + c2 : 0;
+                const bool v = rn[e] >= 0 && (c0 + c2) < a.cp;
+                const long long on = v ? (long long)rn[e] * a.cp + c0 + c2 : 0;
+                const long long os = v ? (long long)rs[e] * a.cp + c0 + c2 : 0;
                 cp_async16(Bn + lr * LEG_LD + c2, a.fb + on, v);
                 cp_async16(Bs + lr * LEG_LD + c2, a.fb + os, v);
             }
@@ -486,9 +603,10 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
 
 #pragma unroll
     for (int s = 0; s < LEG_STAGES - 1; ++s) {
-        if (s < nchunks) load_chunk(s, s);
+        if (s < nchunks) { load_idx(s); load_chunk(s, s); }
         cp_async_commit();
     }
+    load_idx(LEG_STAGES - 1);
     for (int ch = 0; ch < nchunks; ++ch) {
         cp_async_wait<LEG_STAGES - 2>();
         __syncthreads();
@@ -496,6 +614,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
             const int nx = ch + LEG_STAGES - 1;
             if (nx < nchunks) load_chunk(nx, nx % LEG_STAGES);
             cp_async_commit();
+            load_idx(nx + 1);
         }
         const double* As = smem + (size_t)(ch % LEG_STAGES) * DIR_STAGE_DOUBLES;
         const double* Aa = As + LEG_BM * DIR_LDA;
@@ -515,12 +634,14 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
                 ba[i] = vn - vs;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) {
+                if (i >= ni) continue;          // 8-row blocks past the last n of this m: nothing to accumulate (warp-uniform)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     dmma884(acs[i][j][0], acs[i][j][1], fs[i], bs[j]);
                     dmma884(aca[i][j][0], aca[i][j][1], fa[i], ba[j]);
                 }
+            }
         }
     }
     cp_async_wait<0>();
@@ -547,6 +668,8 @@ static void leg_set_attrs() {
     if (g_leg_attr_set) return;
     cudaFuncSetAttribute(k_leinv, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          INV_STAGES * INV_STAGE_DOUBLES * (int)sizeof(double));
+    cudaFuncSetAttribute(k_leinv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(INV_STAGES * INV_STAGE_DOUBLES * sizeof(double)));
     cudaFuncSetAttribute(k_ledir, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          LEG_STAGES * DIR_STAGE_DOUBLES * (int)sizeof(double));
     g_leg_attr_set = true;
@@ -564,7 +687,9 @@ void ect_launch_leinv(EctHandle* h, const EctFieldCfg& f) {
     a.peer = d->peer_fft; a.dst_rank_n = d->leg_dst_rank_n; a.dst_rank_s = d->leg_dst_rank_s;
     a.dst_rec_n = d->leg_dst_rec_n; a.dst_rec_s = d->leg_dst_rec_s;
     const size_t smem = INV_STAGES * INV_STAGE_DOUBLES * sizeof(double);
-    k_leinv<<<(unsigned)((long long)d->n_inv_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
+    static const char* tma = getenv("ECT_LEINV_TMA");      // bulk-copy loader: measured slower (70.9 vs 48.4 ms at TCo1279), opt-in
+    if (tma && atoi(tma)) k_leinv_tma<<<(unsigned)((long long)d->n_inv_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
+    else k_leinv<<<(unsigned)((long long)d->n_inv_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
     d->launches++;
 }
 

@@ -210,7 +210,7 @@ int ect_host_free(void* ptr);
 int ect_debug_get_table(int handle, int ml, int par, double* out, long long capacity_elems);
 
 /* FP64 peak microbenchmarks used for the roofline denominators (not part of the reference API) */
-int ect_measure_fp64_peak(int which /*0 DMMA m8n8k4, 1 DFMA*/, double* tflops);
+int ect_measure_fp64_peak(int which /*0 DMMA m8n8k4, 1 DFMA, 2 DMMA and DFMA warps mixed, 3 mma.sync TF32 m16n8k8, 4 FFMA*/, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -477,7 +477,7 @@ def test_transi_face(eb):
     xz = xs.copy(); xz[1:48:2] = 0
     assert np.array_equal(sg, xz)
     back = np.zeros_like(xs)
-    ds = L.new_distspec(C.byref(t)); ds.rspecg = sg.ctypes.data; ds.rspec = back.ctypes.data; ds.nfrom = nto.ctypes.data; ds.nfld = nscalar
+    ds = L.new_distspec(C.byref(t)); ds.rspecg = sg.ctypes.data; ds.rspec = back.ctypes.data; ds.nto = nto.ctypes.data; ds.nfld = nscalar   # nto: the slot of DistSpec_t.nfrom
     assert L.trans_distspec(C.byref(ds)) == 0 and np.array_equal(back, xz)
     bad = np.full(nscalar, 2, dtype=np.int32)
     g2 = L.new_gathgrid(C.byref(t)); g2.rgp = y.ctypes.data; g2.rgpg = gg.ctypes.data; g2.nto = bad.ctypes.data; g2.nfld = nscalar

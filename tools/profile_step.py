@@ -20,8 +20,14 @@ mk = lambda n: (torch.rand((tr.nspec2, n), generator=g, device=dev, dtype=torch.
 v, d, s = mk(nuv), mk(nuv), mk(nsc)
 gp = torch.empty((1, 2 * nuv + nsc, tr.ngptot), dtype=torch.float64, device=dev)
 out = (torch.empty_like(v), torch.empty_like(d), torch.empty_like(s))
+hist = {"inv": [], "dir": []}
 for i in range(a.warmup + a.steps):
     tr.inv_trans(v, d, s, out=gp)
+    torch.cuda.synchronize(); hist["inv"].append(tr.timings())
     tr.dir_trans(gp, nuv, nsc, out=out)
-torch.cuda.synchronize()
-print("timings(dir)", tr.timings())
+    torch.cuda.synchronize(); hist["dir"].append(tr.timings())
+for k in ("inv", "dir"):
+    h = hist[k][a.warmup:]
+    print("timings(%s) min over %d steps:" % (k, len(h)),
+          {n: round(min(t[n] for t in h), 3) for n in ("prologue", "legendre", "fourier", "epilogue", "total")},
+          "max total %.3f" % max(t["total"] for t in h))
