@@ -85,6 +85,7 @@ EXPORTED_SYMBOLS = [
     "ect_get_timings", "ect_synchronize", "ect_release", "ect_finalize", "ect_strerror", "ect_last_error",
     "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
     "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec", "ect_inv_transad", "ect_dir_transad",
+    "ect_gpnorm_trans", "ect_vordiv_to_uv", "ect_inquire_rpnm", "ect_trans_pnm",
 ]
 
 
@@ -116,6 +117,10 @@ def lib():
         L.ect_dist_grid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ect_gath_spec.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ect_dist_spec.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ect_gpnorm_trans.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ect_vordiv_to_uv.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ect_inquire_rpnm.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.POINTER(C.c_int), C.c_void_p]
+        L.ect_trans_pnm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -136,6 +141,18 @@ def measure_fp64_peak(which: int) -> float:
     v = C.c_double(0.0)
     _check(lib().ect_measure_fp64_peak(which, C.byref(v)), "ect_measure_fp64_peak")
     return v.value
+
+
+def vordiv_to_uv(nsmax: int, spvor, spdiv):
+    """VORDIV_TO_UV without a resolution handle (the reference sets up a temporary spectral-only one): one task,
+    double precision, arrays (nspec2g, nfld) with nspec2g = (nsmax+1)(nsmax+2).  Runs on the current CUDA device."""
+    spvor = np.ascontiguousarray(spvor, dtype=np.float64); spdiv = np.ascontiguousarray(spdiv, dtype=np.float64)
+    if spvor.shape[0] != (nsmax + 1) * (nsmax + 2) or spdiv.shape != spvor.shape:
+        raise EctError("vordiv_to_uv: arrays must be (nspec2g, nfld)")
+    u, v = np.zeros_like(spvor), np.zeros_like(spvor)
+    _check(lib().ect_vordiv_to_uv(0, nsmax, spvor.ctypes.data, spdiv.ctypes.data, u.ctypes.data, v.ctypes.data,
+                                  int(spvor.shape[1]), ECT_MEM_HOST), "ect_vordiv_to_uv")
+    return u, v
 
 
 def octahedral_nloen(n: int) -> np.ndarray:
@@ -405,6 +422,48 @@ class Transform:
         out = np.zeros(nf)
         _check(lib().ect_specnorm(self.handle, _ptr(spec), nf, ECT_MEM_DEVICE if dev else ECT_MEM_HOST,
                                   out.ctypes.data), "ect_specnorm")
+        return out
+
+    def gpnorm_trans(self, gp, nproma=0, ave_only=False, pmin=None, pmax=None):
+        """GPNORM_TRANS: (average, minimum, maximum) per field of gp (ngpblks, nfld, nproma); global over ranks.
+        ave_only: pmin / pmax carry the local extrema in (LDAVE_ONLY)."""
+        dev = _is_torch(gp)
+        if not dev:
+            gp = np.ascontiguousarray(gp, dtype=self.dtype)
+        nf = int(gp.shape[1])
+        ave = np.zeros(nf)
+        mn = np.zeros(nf) if pmin is None else np.ascontiguousarray(pmin, dtype=np.float64).copy()
+        mx = np.zeros(nf) if pmax is None else np.ascontiguousarray(pmax, dtype=np.float64).copy()
+        _check(lib().ect_gpnorm_trans(self.handle, _ptr(gp), nf, nproma, ECT_MEM_DEVICE if dev else ECT_MEM_HOST,
+                                      ave.ctypes.data, mn.ctypes.data, mx.ctypes.data, int(bool(ave_only))), "ect_gpnorm_trans")
+        return ave, mn, mx
+
+    def vordiv_to_uv(self, spvor, spdiv):
+        """VORDIV_TO_UV on this handle's wavenumbers: (nspec2, nfld) vor, div -> U cos(theta), V cos(theta)."""
+        dev = _is_torch(spvor)
+        if dev:
+            import torch
+            u, v = torch.empty_like(spvor), torch.empty_like(spvor)
+        else:
+            spvor = np.ascontiguousarray(spvor, dtype=self.dtype); spdiv = np.ascontiguousarray(spdiv, dtype=self.dtype)
+            u, v = np.zeros_like(spvor), np.zeros_like(spvor)
+        _check(lib().ect_vordiv_to_uv(self.handle, self.nsmax, _ptr(spvor), _ptr(spdiv), _ptr(u), _ptr(v), int(spvor.shape[1]),
+                                      ECT_MEM_DEVICE if dev else ECT_MEM_HOST), "ect_vordiv_to_uv")
+        return u, v
+
+    def legendre_polynomials(self):
+        """TRANS_INQ(PRPNM, KPMS): (rpnm (nspolegl, ndgnh) = PRPNM(ndgnh, nspolegl) column major, npms (nsmax+1))."""
+        n = C.c_int(0)
+        npms = np.zeros(self.nsmax + 1, dtype=np.int32)
+        _check(lib().ect_inquire_rpnm(self.handle, None, 0, C.byref(n), npms.ctypes.data), "ect_inquire_rpnm")
+        out = np.zeros((n.value, self.ndgl // 2))
+        _check(lib().ect_inquire_rpnm(self.handle, out.ctypes.data, out.size, None, None), "ect_inquire_rpnm")
+        return out, npms
+
+    def trans_pnm(self, m):
+        """TRANS_PNM: polynomials of one wavenumber, (nsmax - m + 3, ndgnh) = PRPNM(ndgnh, nsmax - m + 3) column major."""
+        out = np.zeros((self.nsmax - m + 3, self.ndgl // 2))
+        _check(lib().ect_trans_pnm(self.handle, m, out.ctypes.data, self.ndgl // 2, self.nsmax - m + 3), "ect_trans_pnm")
         return out
 
     # ---- GATH_GRID / DIST_GRID / GATH_SPEC / DIST_SPEC (host arrays; collective over the ranks of the handle) ----

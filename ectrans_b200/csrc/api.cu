@@ -1617,3 +1617,211 @@ extern "C" int ect_gath_spec(int handle, const void* sp_local, int nfld, const i
 extern "C" int ect_dist_spec(int handle, const void* sp_global, int nfld, const int* kfrom, void* sp_local) {
     return gath_dist(handle, false, false, sp_local, (void*)sp_global, nfld, 0, kfrom);
 }
+
+// ---------------------------------------------------------------------------------------
+// GPNORM_TRANS: cpu/external/gpnorm_trans.F90, cpu/internal/gpnorm_trans_ctl_mod.F90:170-215 (per-latitude sums,
+// weight RW(lat) / NLOEN(lat)), :422-428 (latitudes added in global order, which makes the average independent
+// of the decomposition).  One CTA per (local latitude, field); the order of the additions inside a latitude
+// depends only on its length.
+// ---------------------------------------------------------------------------------------
+template <bool FP32>
+__global__ void k_gpnorm_lat(const void* __restrict__ gp, int nfld, int nproma, const int* __restrict__ gpoff,
+                             const int* __restrict__ nloen_loc, const double* __restrict__ rw_loc, int lat0, int ndgl,
+                             double* __restrict__ aveg, double* __restrict__ mn, double* __restrict__ mx) {
+    const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int n = nloen_loc[l], g0 = gpoff[l];
+    double s = 0.0, lo = INFINITY, hi = -INFINITY;
+    for (int j = tid; j < n; j += blockDim.x) {
+        const int g = g0 + j, blk = g / nproma;
+        const long long idx = ((long long)blk * nfld + f) * nproma + (g - blk * nproma);
+        const double v = FP32 ? (double)reinterpret_cast<const float*>(gp)[idx] : reinterpret_cast<const double*>(gp)[idx];
+        s += v; lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+    __shared__ double ss[256], sl[256], sh[256];
+    ss[tid] = s; sl[tid] = lo; sh[tid] = hi;
+    __syncthreads();
+    for (int w = blockDim.x >> 1; w > 0; w >>= 1) {
+        if (tid < w) { ss[tid] += ss[tid + w]; sl[tid] = fmin(sl[tid], sl[tid + w]); sh[tid] = fmax(sh[tid], sh[tid + w]); }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        aveg[(long long)f * ndgl + lat0 + l] = ss[0] * rw_loc[l] / (double)n;
+        mn[(long long)f * gridDim.x + l] = sl[0];
+        mx[(long long)f * gridDim.x + l] = sh[0];
+    }
+}
+// per field: min / max over the local latitudes, then (all ranks hold aveg after the all-reduce) the sum over latitudes
+__global__ void k_gpnorm_fold(int nfld, int nlat, const double* __restrict__ mn, const double* __restrict__ mx, double* __restrict__ out /* [2][nfld] */) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfld) return;
+    double lo = INFINITY, hi = -INFINITY;
+    for (int l = 0; l < nlat; ++l) { lo = fmin(lo, mn[(long long)f * nlat + l]); hi = fmax(hi, mx[(long long)f * nlat + l]); }
+    out[f] = lo; out[nfld + f] = hi;
+}
+
+extern "C" int ect_gpnorm_trans(int handle, const void* gp, int nfld, int nproma, int memspace, double* ave, double* pmin,
+                                double* pmax, int ave_only) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) { ect_set_error("ect_gpnorm_trans: invalid handle"); return ECT_ERR_HANDLE; }
+    if (!gp || !ave || !pmin || !pmax || nfld <= 0) return ECT_ERR_MISSING;
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    ECT_CUDA(cudaSetDevice(d->dev));
+    if (nproma <= 0) nproma = std::max(P.ngptot, 1);
+    const int ngpblks = (P.ngptot + nproma - 1) / nproma;
+    const int es = h->precision == ECT_PREC_SP ? 4 : 8;
+    const void* dgp = gp;
+    int rc;
+    if (memspace == ECT_MEM_HOST) {
+        const i64 elems = (i64)ngpblks * nfld * nproma;
+        if ((rc = ensure(d->stage_gp, d->stage_gp_elems, elems, d->stream, false))) return rc;
+        ECT_CUDA(cudaMemcpyAsync(d->stage_gp, gp, (size_t)elems * es, cudaMemcpyHostToDevice, d->stream));
+        dgp = d->stage_gp;
+    }
+    const i64 nwork = (i64)nfld * P.ndgl + 2 * (i64)nfld * std::max(P.nlat, 1) + 2 * (i64)nfld;
+    double* w = nullptr;
+    ECT_CUDA(cudaMalloc(&w, (size_t)nwork * sizeof(double)));
+    double* aveg = w; double* mn = aveg + (i64)nfld * P.ndgl; double* mx = mn + (i64)nfld * std::max(P.nlat, 1);
+    double* fold = mx + (i64)nfld * std::max(P.nlat, 1);
+    ECT_CUDA(cudaMemsetAsync(aveg, 0, (size_t)nfld * P.ndgl * sizeof(double), d->stream));
+    if (P.nlat > 0) {
+        dim3 grid(P.nlat, nfld);
+        if (es == 4) k_gpnorm_lat<true><<<grid, 256, 0, d->stream>>>(dgp, nfld, nproma, d->gpoff, d->nloen, d->rw_loc, P.lat0, P.ndgl, aveg, mn, mx);
+        else k_gpnorm_lat<false><<<grid, 256, 0, d->stream>>>(dgp, nfld, nproma, d->gpoff, d->nloen, d->rw_loc, P.lat0, P.ndgl, aveg, mn, mx);
+    }
+    k_gpnorm_fold<<<(nfld + 127) / 128, 128, 0, d->stream>>>(nfld, P.nlat, mn, mx, fold);
+    if (ave_only) {      // LDAVE_ONLY: PMIN / PMAX already hold the local extrema (gpnorm_trans_ctl_mod.F90:243-245)
+        std::vector<double> loc(2 * (size_t)nfld);
+        for (int f = 0; f < nfld; ++f) { loc[f] = pmin[f]; loc[nfld + f] = pmax[f]; }
+        ECT_CUDA(cudaMemcpyAsync(fold, loc.data(), loc.size() * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        ECT_CUDA(cudaStreamSynchronize(d->stream));
+    }
+    if (P.nranks > 1) {
+        // every (latitude, field) sum lives on exactly one rank: adding zeros is exact
+        ECT_NCCL(ncclAllReduce(aveg, aveg, (size_t)nfld * P.ndgl, ncclDouble, ncclSum, (ncclComm_t)d->comm, d->stream));
+        ECT_NCCL(ncclAllReduce(fold, fold, nfld, ncclDouble, ncclMin, (ncclComm_t)d->comm, d->stream));
+        ECT_NCCL(ncclAllReduce(fold + nfld, fold + nfld, nfld, ncclDouble, ncclMax, (ncclComm_t)d->comm, d->stream));
+    }
+    std::vector<double> hav((size_t)nfld * P.ndgl), hf(2 * (size_t)nfld);
+    ECT_CUDA(cudaMemcpyAsync(hav.data(), aveg, hav.size() * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    ECT_CUDA(cudaMemcpyAsync(hf.data(), fold, hf.size() * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    ECT_CUDA(cudaFree(w));
+    for (int f = 0; f < nfld; ++f) {
+        double s = 0.0;
+        for (int g = 0; g < P.ndgl; ++g) s += hav[(size_t)f * P.ndgl + g];     // PAVE(:) = PAVE(:) + ZAVEG(JGL,:), JGL = 1..NDGL
+        ave[f] = s; pmin[f] = hf[f]; pmax[f] = hf[nfld + f];
+    }
+    d->launches += 2;
+    return ECT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------
+// VORDIV_TO_UV: cpu/external/vordiv_to_uv.F90, cpu/internal/vd2uv_mod.F90:86-112.  handle > 0: the wavenumbers of
+// that handle's task, its precision and stream; handle == 0: one task holding every m of truncation nsmax in
+// double precision (the reference builds a temporary LDSPSETUPONLY resolution for exactly this).
+// ---------------------------------------------------------------------------------------
+int ect_launch_vd2uv(const void* vor, const void* div, void* u, void* v, int nfld, int nsmax, int nump,
+                     const EctLegM* legm, const int* nasm0, bool fp32, cudaStream_t st);
+
+extern "C" int ect_vordiv_to_uv(int handle, int nsmax, const void* spvor, const void* spdiv, void* spu, void* spv,
+                                int nfld, int memspace) {
+    if (!spvor || !spdiv || !spu || !spv) return ECT_ERR_MISSING;
+    if (nfld <= 0) return ECT_SUCCESS;
+    EctHandle* h = nullptr;
+    if (handle != 0) {
+        h = get_handle(handle);
+        if (!h || !h->d) { ect_set_error("ect_vordiv_to_uv: invalid handle"); return ECT_ERR_HANDLE; }
+        if (nsmax != h->hp.nsmax) { ect_set_error("ect_vordiv_to_uv: nsmax %d differs from the handle's %d", nsmax, h->hp.nsmax); return ECT_ERR_BADARG; }
+        ECT_CUDA(cudaSetDevice(h->d->dev));
+    } else {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { ect_set_error("ect_vordiv_to_uv: no CUDA device (there is no CPU fallback)"); return ECT_ERR_CUDA; }
+        if (nsmax < 0) return ECT_ERR_BADARG;
+    }
+    const bool fp32 = h && h->precision == ECT_PREC_SP;
+    const int es = fp32 ? 4 : 8;
+    const i64 nspec2 = h ? h->hp.nspec2 : (i64)(nsmax + 1) * (nsmax + 2);
+    const int nump = h ? h->hp.nump : nsmax + 1;
+    cudaStream_t st = h ? h->d->stream : (cudaStream_t)0;
+    const size_t bytes = (size_t)nspec2 * nfld * es;
+    const void *dv = spvor, *dd = spdiv; void *du = spu, *dvv = spv;
+    char* tmp = nullptr;
+    if (memspace == ECT_MEM_HOST) {
+        ECT_CUDA(cudaMalloc(&tmp, 4 * bytes + 64));
+        ECT_CUDA(cudaMemcpyAsync(tmp, spvor, bytes, cudaMemcpyHostToDevice, st));
+        ECT_CUDA(cudaMemcpyAsync(tmp + bytes, spdiv, bytes, cudaMemcpyHostToDevice, st));
+        dv = tmp; dd = tmp + bytes; du = tmp + 2 * bytes; dvv = tmp + 3 * bytes;
+    }
+    int rc = ECT_SUCCESS;
+    if (nump > 0) rc = ect_launch_vd2uv(dv, dd, du, dvv, nfld, nsmax, nump, h ? h->d->legm : nullptr, h ? h->d->nasm0 : nullptr, fp32, st);
+    if (h) h->d->launches++;
+    if (memspace == ECT_MEM_HOST) {
+        if (!rc) {
+            ECT_CUDA(cudaMemcpyAsync(spu, du, bytes, cudaMemcpyDeviceToHost, st));
+            ECT_CUDA(cudaMemcpyAsync(spv, dvv, bytes, cudaMemcpyDeviceToHost, st));
+        }
+        ECT_CUDA(cudaStreamSynchronize(st));
+        ECT_CUDA(cudaFree(tmp));
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Legendre polynomials in the reference's own layout.
+//   ect_inquire_rpnm <- TRANS_INQ(PRPNM=...) cpu/external/trans_inq.F90:426-466: PRPNM(NDGNH, NSPOLEGL), column
+//       NPMS(m) + p (p = 1 .. T+2-m) holds n = T+2-p, rows ISL .. NDGNH (ISL = NDGNH-NDGLU(m)+1), the others zero;
+//       NPMS runs over this task's wavenumbers in MYMS order (sump_trans_preleg_mod.F90:124-131).
+//   ect_trans_pnm    <- TRANS_PNM cpu/external/trans_pnm.F90:127-177, one wavenumber: PRPNM(ld, T-m+3)
+// Both are read back from the table SETUP_TRANS left in HBM (the same values the transforms use).
+// ---------------------------------------------------------------------------------------
+static int rpnm_of_m(EctHandle* h, int ml, double* out, i64 ld, i64 col0) {
+    const EctLegM& lm = h->d->h_legm[ml];
+    const int T = h->hp.nsmax, m = lm.m, ndgnh = h->hp.ndgnh;
+    std::vector<double> tab;
+    for (int par = 0; par < 2; ++par) {
+        const int k = par ? lm.ila : lm.ils;
+        if (k == 0 || lm.ndglu == 0) continue;
+        tab.resize((size_t)k * lm.ndglu);
+        int rc = ect_legendre_get_table(h, ml, par, tab.data(), (long long)tab.size());
+        if (rc) return rc;
+        for (int kk = 0; kk < k; ++kk) {
+            const int n = m + par + 2 * kk, p = T + 2 - n;          // 1-based column inside the block of m
+            double* col = out + (col0 + p - 1) * ld;
+            for (int i = 0; i < lm.ndglu; ++i) col[ndgnh - lm.ndglu + i] = tab[(size_t)kk * lm.ndglu + i];
+        }
+    }
+    return ECT_SUCCESS;
+}
+extern "C" int ect_inquire_rpnm(int handle, double* rpnm, long long capacity_elems, int* nspolegl, int* npms /* nsmax+1, -1 = not local */) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) { ect_set_error("ect_inquire_rpnm: invalid handle"); return ECT_ERR_HANDLE; }
+    const EctHostPlan& P = h->hp;
+    i64 ncol = 0;
+    std::vector<i64> off(P.nump);
+    for (int ml = 0; ml < P.nump; ++ml) { off[ml] = ncol; ncol += P.nsmax + 2 - P.myms[ml]; }
+    if (nspolegl) *nspolegl = (int)ncol;
+    if (npms) {
+        for (int m = 0; m <= P.nsmax; ++m) npms[m] = -1;
+        for (int ml = 0; ml < P.nump; ++ml) npms[P.myms[ml]] = (int)off[ml];
+    }
+    if (!rpnm) return ECT_SUCCESS;
+    if ((i64)P.ndgnh * ncol > capacity_elems) { ect_set_error("ect_inquire_rpnm: array too small (%lld < %lld)", capacity_elems, (long long)P.ndgnh * ncol); return ECT_ERR_BADARG; }
+    ECT_CUDA(cudaSetDevice(h->d->dev));
+    memset(rpnm, 0, (size_t)P.ndgnh * ncol * sizeof(double));
+    for (int ml = 0; ml < P.nump; ++ml) { int rc = rpnm_of_m(h, ml, rpnm, P.ndgnh, off[ml]); if (rc) return rc; }
+    return ECT_SUCCESS;
+}
+extern "C" int ect_trans_pnm(int handle, int m, double* rpnm, int ld, int ncols) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) { ect_set_error("ect_trans_pnm: invalid handle"); return ECT_ERR_HANDLE; }
+    const EctHostPlan& P = h->hp;
+    if (!rpnm) return ECT_ERR_MISSING;
+    if (m < 0 || m > P.nsmax || ld < P.ndgnh || ncols < P.nsmax - m + 2) { ect_set_error("ect_trans_pnm: m, ld or ncols out of range"); return ECT_ERR_BADARG; }
+    int ml = -1;
+    for (int i = 0; i < P.nump; ++i) if (P.myms[i] == m) ml = i;
+    if (ml < 0) { ect_set_error("ect_trans_pnm: wavenumber %d is not held by this task", m); return ECT_ERR_NOTIMPL; }
+    ECT_CUDA(cudaSetDevice(h->d->dev));
+    for (i64 c = 0; c < ncols; ++c) memset(rpnm + c * ld, 0, (size_t)ld * sizeof(double));
+    return rpnm_of_m(h, ml, rpnm, ld, 0);
+}

@@ -103,23 +103,19 @@ __device__ __forceinline__ double2 ld_spec(const EctSpecField f, int idx, bool v
     return make_double2(re, im);
 }
 
+#define PRO_ROWS 4
 template <bool FP32>
 __global__ void k_ltinv_prologue(ProArgs a) {
     const EctLegM lm = a.legm[blockIdx.y];
     const int m = lm.m, T = a.nsmax;
-    const int r = blockIdx.x;
-    if (r > T - m + 1) return;
+    // a CTA walks PRO_ROWS consecutive rows n of one m (one CTA per row made the launch rate, not HBM, the limit)
+    for (int r = blockIdx.x * PRO_ROWS; r < min((int)(blockIdx.x + 1) * PRO_ROWS, T - m + 2); ++r) {
     const int n = m + r;
-    __shared__ double cst[5];
-    if (threadIdx.x == 0) {
-        cst[0] = (double)m * d_lap(n);                                    // zkm * lapin(n)
-        cst[1] = ((double)(n - 1) * d_eps(m, n)) * d_lap(n - 1);           // c1
-        cst[2] = ((double)(n + 2) * d_eps(m, n + 1)) * d_lap(n + 1);       // c2
-        cst[3] = (double)(n - 1) * d_eps(m, n);                            // spnsde
-        cst[4] = (double)(n + 2) * d_eps(m, n + 1);
-    }
-    __syncthreads();
-    const double zl = cst[0], c1 = cst[1], c2 = cst[2], e1 = cst[3], e2 = cst[4];
+    const double zl = (double)m * d_lap(n);                                       // zkm * lapin(n)
+    const double c1 = ((double)(n - 1) * d_eps(m, n)) * d_lap(n - 1);
+    const double c2 = ((double)(n + 2) * d_eps(m, n + 1)) * d_lap(n + 1);
+    const double e1 = (double)(n - 1) * d_eps(m, n);                              // spnsde
+    const double e2 = (double)(n + 2) * d_eps(m, n + 1);
     // adjoint of UVTVD: -1 / RLAPIN(n') = n' (n' + 1) / a^2 for the rows n, n - 1, n + 1 read below
     auto ilap = [](int k) { return k >= 1 ? (double)k * (double)(k + 1) / (ECT_RA * ECT_RA) : 0.0; };
     const double g0 = ilap(n), gm = ilap(n - 1), gp = ilap(n + 1);
@@ -164,6 +160,7 @@ __global__ void k_ltinv_prologue(ProArgs a) {
             }
         }
     }
+    }
 }
 
 void ect_launch_ltinv_prologue(EctHandle* h, const EctFieldCfg& f, const void* d_vor, const void* d_div,
@@ -176,7 +173,7 @@ void ect_launch_ltinv_prologue(EctHandle* h, const EctFieldCfg& f, const void* d
     a.kf_uv = f.kf_uv; a.kf_sc = f.kf_sc; a.scders = f.scders; a.vorgp = f.vorgp; a.divgp = f.divgp;
     a.adj = f.adj;
     if (h->hp.nump == 0) return;
-    dim3 grid(h->hp.nsmax + 2, h->hp.nump);
+    dim3 grid((h->hp.nsmax + 2 + PRO_ROWS - 1) / PRO_ROWS, h->hp.nump);
     int items = f.kf_uv + f.kf_sc;
     int threads = items >= 192 ? 256 : (items >= 96 ? 128 : 64);
     a.fp32 = f.fp32;
@@ -215,16 +212,11 @@ template <bool FP32>
 __global__ void k_ltdir_epilogue(EpiArgs a) {
     const EctLegM lm = a.legm[blockIdx.y];
     const int m = lm.m, T = a.nsmax;
-    const int r = blockIdx.x;
-    if (r > T - m) return;
+    for (int r = blockIdx.x * PRO_ROWS; r < min((int)(blockIdx.x + 1) * PRO_ROWS, T - m + 1); ++r) {
     const int n = m + r;
-    __shared__ double cst[2];
-    if (threadIdx.x == 0) {
-        cst[0] = (double)n * d_eps(m, n + 1);          // ZN(JN)*PEPSNM(JN+1)
-        cst[1] = (double)(n + 1) * d_eps(m, n);        // ZN(JN+1)*PEPSNM(JN)
-    }
-    __syncthreads();
-    const double c1 = cst[0], c2 = cst[1], zkm = (double)m;
+    const double c1 = (double)n * d_eps(m, n + 1);          // ZN(JN)*PEPSNM(JN+1)
+    const double c2 = (double)(n + 1) * d_eps(m, n);        // ZN(JN+1)*PEPSNM(JN)
+    const double zkm = (double)m;
     const int idx = a.nasm0[blockIdx.y] + 2 * r;
     const bool m0 = (m == 0);
     const double* row = a.x + (lm.xrow0 + r) * (long long)a.cp;
@@ -259,6 +251,7 @@ __global__ void k_ltdir_epilogue(EpiArgs a) {
             st_spec<FP32>(a.sc[s], idx, f0.x, f0.y, a.adj != 0);
         }
     }
+    }
 }
 
 void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, void* d_div, void* d_sc) {
@@ -269,12 +262,59 @@ void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, 
     a.x = d->xwork; a.cp = f.cp; a.nsmax = h->hp.nsmax;
     a.kf_uv = f.kf_uv; a.kf_sc = f.kf_sc; a.adj = f.adj;
     if (h->hp.nump == 0) return;
-    dim3 grid(h->hp.nsmax + 1, h->hp.nump);
+    dim3 grid((h->hp.nsmax + 1 + PRO_ROWS - 1) / PRO_ROWS, h->hp.nump);
     int items = f.kf_uv + f.kf_sc;
     int threads = items >= 192 ? 256 : (items >= 96 ? 128 : 64);
     if (f.fp32) k_ltdir_epilogue<true><<<grid, threads, 0, d->stream>>>(a);
     else k_ltdir_epilogue<false><<<grid, threads, 0, d->stream>>>(a);
     d->launches++;
+}
+
+// ------------------------------------------------------------------------------------------
+// VORDIV_TO_UV (vd2uv_mod.F90:86-112): spectral (vor, div) -> spectral (U, V) cos(theta) / a for n <= T, arrays
+// (nfld, nspec2).  legm == nullptr: one task holding every m, m-major (NASM0(m) = m (2T + 3 - m)).
+// ------------------------------------------------------------------------------------------
+template <bool FP32>
+__global__ void k_vd2uv(const void* vor, const void* div, void* u, void* v, int nfld, int T, const EctLegM* legm,
+                        const int* nasm0) {
+    const int m = legm ? legm[blockIdx.y].m : (int)blockIdx.y;
+    const int base = legm ? nasm0[blockIdx.y] : m * (2 * T + 3 - m);
+    const bool m0 = (m == 0);
+    const double ra_r = 1.0 / ECT_RA;
+    for (int r = blockIdx.x * PRO_ROWS; r < min((int)(blockIdx.x + 1) * PRO_ROWS, T - m + 1); ++r) {
+        const int n = m + r, idx = base + 2 * r;
+        const double zl = (double)m * d_lap(n);
+        const double c1 = ((double)(n - 1) * d_eps(m, n)) * d_lap(n - 1);
+        const double c2 = ((double)(n + 2) * d_eps(m, n + 1)) * d_lap(n + 1);
+        const bool vm = (n - 1 >= m), vp = (n + 1 <= T);
+        for (int j = threadIdx.x; j < nfld; j += blockDim.x) {
+            const EctSpecField fv{reinterpret_cast<const double*>(FP32 ? (const void*)(reinterpret_cast<const float*>(vor) + j) : (const void*)(reinterpret_cast<const double*>(vor) + j)), nfld};
+            const EctSpecField fd{reinterpret_cast<const double*>(FP32 ? (const void*)(reinterpret_cast<const float*>(div) + j) : (const void*)(reinterpret_cast<const double*>(div) + j)), nfld};
+            const double2 z0 = ld_spec<FP32>(fv, idx, true, m0), zm = ld_spec<FP32>(fv, idx - 2, vm, m0), zp = ld_spec<FP32>(fv, idx + 2, vp, m0);
+            const double2 d0 = ld_spec<FP32>(fd, idx, true, m0), dm = ld_spec<FP32>(fd, idx - 2, vm, m0), dp = ld_spec<FP32>(fd, idx + 2, vp, m0);
+            // vdtuv_mod.F90:121-139
+            double2 uu, vv;
+            uu.x = -zl * d0.y + c1 * zm.x - c2 * zp.x;
+            uu.y = zl * d0.x + c1 * zm.y - c2 * zp.y;
+            vv.x = -zl * z0.y - c1 * dm.x + c2 * dp.x;
+            vv.y = zl * z0.x - c1 * dm.y + c2 * dp.y;
+            if (m0) { uu.y = 0.0; vv.y = 0.0; }
+            const EctSpecField fu{reinterpret_cast<const double*>(FP32 ? (void*)(reinterpret_cast<float*>(u) + j) : (void*)(reinterpret_cast<double*>(u) + j)), nfld};
+            const EctSpecField fw{reinterpret_cast<const double*>(FP32 ? (void*)(reinterpret_cast<float*>(v) + j) : (void*)(reinterpret_cast<double*>(v) + j)), nfld};
+            st_spec<FP32>(fu, idx, uu.x * ra_r, uu.y * ra_r);
+            st_spec<FP32>(fw, idx, vv.x * ra_r, vv.y * ra_r);
+        }
+    }
+}
+
+int ect_launch_vd2uv(const void* vor, const void* div, void* u, void* v, int nfld, int nsmax, int nump,
+                     const EctLegM* legm, const int* nasm0, bool fp32, cudaStream_t st) {
+    dim3 grid((nsmax + 1 + PRO_ROWS - 1) / PRO_ROWS, nump);
+    const int threads = nfld >= 192 ? 256 : (nfld >= 96 ? 128 : 64);
+    if (fp32) k_vd2uv<true><<<grid, threads, 0, st>>>(vor, div, u, v, nfld, nsmax, legm, nasm0);
+    else k_vd2uv<false><<<grid, threads, 0, st>>>(vor, div, u, v, nfld, nsmax, legm, nasm0);
+    ECT_CUDA(cudaGetLastError());
+    return ECT_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------------

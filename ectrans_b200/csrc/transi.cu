@@ -302,6 +302,19 @@ int trans_gathspec(struct GathSpec_t* a) {
     return rc ? rc : ect_gath_spec(a->trans->handle, a->rspec, a->nfld, own.data(), a->rspecg);
 }
 
+struct VorDivToUV_t new_vordiv_to_UV(void) { struct VorDivToUV_t a; memset(&a, 0, sizeof(a)); return a; }
+// transi_module.F90:2663-2743
+int trans_vordiv_to_UV(struct VorDivToUV_t* a) {
+    if (!a) return TRANS_MISSING_ARG;
+    if (a->count > 0) return TRANS_STALE_ARG;
+    a->count = 1;
+    if (a->ncoeff == 0 || a->nsmax == 0) return TRANS_MISSING_ARG;
+    if (!a->rspvor || !a->rspdiv || !a->rspu || !a->rspv) return TRANS_MISSING_ARG;
+    if (a->ncoeff != (a->nsmax + 1) * (a->nsmax + 2)) return TRANS_ERROR;      // distributed ncoeff needs a Trans_t: use ect_vordiv_to_uv
+    const int rc = ect_vordiv_to_uv(0, a->nsmax, a->rspvor, a->rspdiv, a->rspu, a->rspv, a->nfld, ECT_MEM_HOST);
+    return rc == ECT_SUCCESS ? TRANS_SUCCESS : (rc >= -5 ? rc : TRANS_ERROR);
+}
+
 int trans_specnorm(struct SpecNorm_t* a) {
     if (!a || !a->trans || !a->rspec || !a->rnorm || a->nfld <= 0) return TRANS_MISSING_ARG;
     if (a->count > 0) return TRANS_STALE_ARG;

@@ -64,17 +64,7 @@ def get_legendre_assets(KSIZEJ, KTRUNC, KSLOEN, KSPOLEGL, KLOEN, KNUMMAXRESOL):
     (per m, n descending from T+1 to m, setup_dims_mod.F90:28-38); entries of latitudes that do not
     carry m on the reduced grid (not resident in HBM) are returned as 0."""
     t = _get(KTRUNC, KSIZEJ, KLOEN, KNUMMAXRESOL)
-    T = t.nsmax
-    ndgnh = t.ndgl // 2
-    rpnm = np.zeros((ndgnh, int(KSPOLEGL)))
-    col = 0
-    for ml, m in enumerate(t.myms):
-        nd = int(t.ndglu[m])
-        ps, pa = t.legendre_table(ml, 0), t.legendre_table(ml, 1)       # [k, i]
-        for n in range(T + 1, m - 1, -1):
-            k, par = divmod(n - m, 2)
-            src = pa if par else ps
-            if k < src.shape[0] and nd:
-                rpnm[ndgnh - nd:, col] = src[k]
-            col += 1
-    return t.nmen.astype(np.int64), t.rgw.copy(), rpnm
+    rpnm, _ = t.legendre_polynomials()                    # TRANS_INQ(PRPNM): (nspolegl, ndgnh)
+    if rpnm.shape[0] != int(KSPOLEGL):
+        raise RuntimeError("get_legendre_assets: KSPOLEGL must be sum(T + 2 - m), m = 0 .. T")
+    return t.nmen.astype(np.int64), t.rgw.copy(), np.ascontiguousarray(rpnm.T)

@@ -190,6 +190,26 @@ int ect_dist_grid(int handle, const void* gp_global, int nfld, int nproma, const
 int ect_gath_spec(int handle, const void* sp_local, int nfld, const int* kto, void* sp_global);
 int ect_dist_spec(int handle, const void* sp_global, int nfld, const int* kfrom, void* sp_local);
 
+/* GPNORM_TRANS (src/trans/include/ectrans/gpnorm_trans.h:12-47): global average (Gaussian weight / points of the
+ * latitude, latitudes added in global order), minimum and maximum of nfld grid-point fields PGP(nproma, nfld,
+ * ngpblks).  ave_only != 0 (LDAVE_ONLY): pmin / pmax hold the task-local extrema on entry.  Collective; the results
+ * arrive on every rank (the reference defines them on the first task only).  ave, pmin, pmax: host, double[nfld]. */
+int ect_gpnorm_trans(int handle, const void* gp, int nfld, int nproma, int memspace, double* ave, double* pmin,
+                     double* pmax, int ave_only);
+/* VORDIV_TO_UV (src/trans/include/ectrans/vordiv_to_uv.h; transi trans_vordiv_to_UV, transi.h:1193-1217): spectral
+ * vorticity / divergence (nfld, nspec2) -> spectral U cos(theta), V cos(theta), rows n <= nsmax.  handle > 0: that
+ * handle's wavenumbers, precision and stream; handle == 0: one task holding every m (nspec2 = (nsmax+1)(nsmax+2)),
+ * double precision -- the reference builds a temporary spectral-only resolution for this call. */
+int ect_vordiv_to_uv(int handle, int nsmax, const void* spvor, const void* spdiv, void* spu, void* spv, int nfld,
+                     int memspace);
+/* Legendre polynomials in the reference's layouts, read back from the table in HBM.
+ *   ect_inquire_rpnm <- TRANS_INQ(PRPNM, KSPOLEGL, KPMS) src/trans/include/ectrans/trans_inq.h:93-101: rpnm is
+ *       PRPNM(ndgnh, nspolegl) column major (may be NULL to query the sizes), npms[m] = NPMS(m) or -1;
+ *   ect_trans_pnm    <- TRANS_PNM src/trans/include/ectrans/trans_pnm.h: one wavenumber, PRPNM(ld, ncols),
+ *       ld >= ndgnh, ncols >= nsmax - m + 2; column p (1-based) holds n = nsmax + 2 - p. */
+int ect_inquire_rpnm(int handle, double* rpnm, long long capacity_elems, int* nspolegl, int* npms);
+int ect_trans_pnm(int handle, int m, double* rpnm, int ld, int ncols);
+
 int ect_synchronize(int handle);   /* wait for asynchronous ECT_MEM_DEVICE calls on this handle */
 int ect_release(int handle);
 int ect_finalize(void);

@@ -97,6 +97,18 @@ struct GathGrid_t { double* rgpg; const double* rgp; const int* nto; int nproma,
 struct DistSpec_t { const double* rspecg; double* rspec; const int* nfrom; int nfld; struct Trans_t* trans; int count; };
 struct GathSpec_t { double* rspecg; const double* rspec; const int* nto; int nfld; struct Trans_t* trans; int count; };
 
+/* transi.h:1193-1217; handle-free: a spectral-only resolution of truncation nsmax, ncoeff = (nsmax+1)(nsmax+2) */
+struct VorDivToUV_t {
+  const double* rspvor;  /* [ncoeff][nfld] */
+  const double* rspdiv;
+  double* rspu;          /* U cos(theta)   */
+  double* rspv;
+  int nfld;
+  int nsmax;
+  int ncoeff;
+  int count;
+};
+
 struct SpecNorm_t {
   const double* rspec;   /* [nspec2][nfld] */
   int nmaster;
@@ -132,6 +144,8 @@ struct DistSpec_t new_distspec(struct Trans_t*);
 int trans_distspec(struct DistSpec_t*);
 struct GathSpec_t new_gathspec(struct Trans_t*);
 int trans_gathspec(struct GathSpec_t*);
+struct VorDivToUV_t new_vordiv_to_UV(void);
+int trans_vordiv_to_UV(struct VorDivToUV_t*);
 struct SpecNorm_t new_specnorm(struct Trans_t*);
 int trans_specnorm(struct SpecNorm_t*);
 int trans_delete(struct Trans_t*);

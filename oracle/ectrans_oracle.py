@@ -803,3 +803,53 @@ def dir_transad(s: Setup, spvor=None, spdiv=None, spscalar=None) -> np.ndarray:
         for j in range(kf_sc):
             out[2 * kf_uv + j] = D.T @ (w * spscalar[j])
     return out
+
+
+# --------------------------------------------------------------------------
+#  GPNORM_TRANS, VORDIV_TO_UV, TRANS_INQ(PRPNM)
+# --------------------------------------------------------------------------
+def gpnorm_trans(s: Setup, gp: np.ndarray):
+    """(ave, min, max) per field of gp[nfld, ngptotg]: per-latitude sums weighted by RW(lat)/NLOEN(lat), added in
+    latitude order.  cpu/internal/gpnorm_trans_ctl_mod.F90:170-215, :422-428."""
+    nf = gp.shape[0]
+    ave = np.zeros(nf)
+    off = 0
+    for j in range(s.ndgl):
+        n = int(s.nloen[j])
+        row = gp[:, off:off + n]
+        ave = ave + row.sum(axis=1) * s.rw[j] / n
+        off += n
+    return ave, gp.min(axis=1), gp.max(axis=1)
+
+
+def vordiv_to_uv(s: Setup, spvor: np.ndarray, spdiv: np.ndarray):
+    """Spectral (vor, div)[nfld, nspec2] -> spectral (U, V) cos(theta) [nfld, nspec2], rows n <= T, scaled by 1/a.
+    cpu/internal/vd2uv_mod.F90:86-112 (VDTUV as in the inverse transform, the n = T+1 row dropped)."""
+    u = np.zeros_like(spvor)
+    v = np.zeros_like(spvor)
+    for m in range(s.nsmax + 1):
+        um, vm = _vdtuv(s, m, spec_m(s, spvor, m) if m else spec_m(s, spvor, m).real + 0j,
+                        spec_m(s, spdiv, m) if m else spec_m(s, spdiv, m).real + 0j)
+        o = int(s.nasm0[m])
+        cnt = s.nsmax - m + 1
+        for dst, src in ((u, um), (v, vm)):
+            dst[:, o:o + 2 * cnt:2] = src[:, :cnt].real / RA
+            dst[:, o + 1:o + 2 * cnt:2] = 0.0 if m == 0 else src[:, :cnt].imag / RA
+    return u, v
+
+
+def rpnm_reference_layout(s: Setup) -> np.ndarray:
+    """PRPNM(NDGNH, NSPOLEGL) as TRANS_INQ returns it (cpu/external/trans_inq.F90:444-464): the block of wavenumber m
+    starts at NPMS(m) = sum_{m' < m} (T + 2 - m'), its column p = 1 .. T+2-m holds n = T + 2 - p; rows above
+    ISL = NDGNH - NDGLU(m) + 1 stay zero."""
+    T, ndgnh = s.nsmax, s.ndgl // 2
+    ncol = sum(T + 2 - m for m in range(T + 1))
+    out = np.zeros((ndgnh, ncol))
+    c0 = 0
+    for m in range(T + 1):
+        nl = int(s.ndglu[m])
+        for n in range(m, T + 2):
+            col = s.ps[m][:, (n - m) // 2] if (n - m) % 2 == 0 else s.pa[m][:, (n - m - 1) // 2]
+            out[ndgnh - nl:, c0 + (T + 2 - n) - 1] = col
+        c0 += T + 2 - m
+    return out

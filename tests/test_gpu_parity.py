@@ -484,6 +484,24 @@ def test_transi_face(eb):
     assert L.trans_gathgrid(C.byref(g2)) == -1            # task 2 of 1
     assert L.trans_delete(C.byref(t)) == 0
 
+    class VdUv(C.Structure):
+        _fields_ = [("rspvor", C.c_void_p), ("rspdiv", C.c_void_p), ("rspu", C.c_void_p), ("rspv", C.c_void_p),
+                    ("nfld", C.c_int), ("nsmax", C.c_int), ("ncoeff", C.c_int), ("count", C.c_int)]
+    L.new_vordiv_to_UV.restype = VdUv
+    Tn = 21
+    so = eo.setup(Tn, 32, eo.octahedral_nloen(16), tables=False)
+    vo = eo.random_spectral(so, 2, 7, zero00=True); di = eo.random_spectral(so, 2, 8, zero00=True)
+    ur, vr = eo.vordiv_to_uv(so, vo, di)
+    vo_t, di_t = np.ascontiguousarray(vo.T), np.ascontiguousarray(di.T)
+    uo, vv = np.zeros_like(vo_t), np.zeros_like(vo_t)
+    a = L.new_vordiv_to_UV(); a.rspvor = vo_t.ctypes.data; a.rspdiv = di_t.ctypes.data; a.rspu = uo.ctypes.data; a.rspv = vv.ctypes.data
+    a.nfld = 2; a.nsmax = Tn; a.ncoeff = so.nspec2
+    assert L.trans_vordiv_to_UV(C.byref(a)) == 0
+    assert rel(uo.T, ur) < TOL and rel(vv.T, vr) < TOL
+    assert L.trans_vordiv_to_UV(C.byref(a)) == -5          # stale
+    b = L.new_vordiv_to_UV(); b.nsmax = Tn
+    assert L.trans_vordiv_to_UV(C.byref(b)) == -3          # ncoeff missing
+
 
 @pytest.mark.parametrize("T,N,nuv,nsc,opts", [(79, 80, 3, 4, dict(scders=True, uvder=True)), (159, 160, 2, 5, {})])
 def test_single_precision_face(eb, T, N, nuv, nsc, opts):
@@ -639,3 +657,90 @@ def test_benchmark_checksums_reproducible(built, tmp_path):
         dumps.append(f.read_text())
     assert dumps[0].count("zgp (") == 2 * (2 * 3 + 3 * 2 + 1) and "zspscalar (7)" in dumps[0]
     assert dumps[0] == dumps[1] == dumps[2]
+
+
+# ---------------------------------------------------------------------------------------------
+# GPNORM_TRANS, VORDIV_TO_UV, TRANS_INQ(PRPNM) / TRANS_PNM
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nproma", [0, 333])
+def test_gpnorm_trans(eb, nproma):
+    """gpnorm_trans_ctl_mod.F90: weighted per-latitude sums added in latitude order; min / max exact."""
+    T, N = 63, 64
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen, tables=False)
+    rng = np.random.default_rng(11)
+    flat = rng.normal(size=(5, tr.ngptot)) + np.arange(5)[:, None]
+    ave, mn, mx = eo.gpnorm_trans(s, flat)
+    gp = block(flat, nproma) if nproma else flat[None]
+    a, lo, hi = tr.gpnorm_trans(gp, nproma=nproma)
+    np.testing.assert_allclose(a, ave, rtol=1e-13, atol=1e-14)
+    np.testing.assert_array_equal(lo, mn)
+    np.testing.assert_array_equal(hi, mx)
+    # a constant field: average = the constant (sum of weights = 1)
+    a, lo, hi = tr.gpnorm_trans(np.full((1, 2, tr.ngptot), 3.25))
+    np.testing.assert_allclose(a, 3.25, rtol=1e-14)
+    assert (lo == 3.25).all() and (hi == 3.25).all()
+    # LDAVE_ONLY: the extrema come from the caller
+    a2, lo2, hi2 = tr.gpnorm_trans(gp, nproma=nproma, ave_only=True, pmin=mn - 1.0, pmax=mx + 2.0)
+    np.testing.assert_allclose(a2, ave, rtol=1e-13, atol=1e-14)
+    np.testing.assert_array_equal(lo2, mn - 1.0)
+    np.testing.assert_array_equal(hi2, mx + 2.0)
+    # device pointers
+    import torch
+    a3, lo3, hi3 = tr.gpnorm_trans(torch.from_numpy(np.ascontiguousarray(gp)).cuda(), nproma=nproma)
+    np.testing.assert_array_equal(a3, a2)
+    tr.release()
+
+
+def test_vordiv_to_uv(eb):
+    """vd2uv_mod.F90: against the oracle, with and without a resolution handle, and through the transform:
+    with no vorticity / divergence at n = T the synthesis of (U, V) cos(theta) as scalars is u, v times cos(theta)."""
+    T, N = 79, 80
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen)
+    vor = eo.random_spectral(s, 3, 5, zero00=True); div = eo.random_spectral(s, 3, 6, zero00=True)
+    for m in range(T + 1):      # drop n = T so that the discarded n = T+1 row of U, V is zero
+        o = int(s.nasm0[m]) + 2 * (T - m)
+        vor[:, o:o + 2] = 0.0; div[:, o:o + 2] = 0.0
+    ur, vr = eo.vordiv_to_uv(s, vor, div)
+    u, v = tr.vordiv_to_uv(T_(vor), T_(div))
+    assert rel(u.T, ur) < TOL and rel(v.T, vr) < TOL
+    u0, v0 = eb.vordiv_to_uv(T, T_(vor), T_(div))
+    np.testing.assert_array_equal(u0, u); np.testing.assert_array_equal(v0, v)
+    gp = tr.inv_trans(T_(vor), T_(div))[0]                  # u, v
+    gs = tr.inv_trans(spscalar=np.ascontiguousarray(np.concatenate([u, v], axis=1)))[0]
+    cos = np.repeat(np.sqrt(s.r1mu2), nloen)
+    assert rel(gs, gp * cos) < 1e-11
+    import torch
+    ud, vd = tr.vordiv_to_uv(torch.from_numpy(T_(vor)).cuda(), torch.from_numpy(T_(div)).cuda())
+    tr.synchronize()
+    np.testing.assert_array_equal(ud.cpu().numpy(), u)
+    assert eb.lib().ect_vordiv_to_uv(tr.handle, T + 1, 1, 1, 1, 1, 1, 0) == -4     # truncation differs from the handle's
+    tr.release()
+
+
+def test_legendre_polynomials_reference_layout(eb):
+    """TRANS_INQ(PRPNM) (trans_inq.F90:444-464) and TRANS_PNM (trans_pnm.F90:127-177) layouts, values = the table
+    of the transforms (bit for bit the oracle's SUPOLF restatement up to its last-digit differences)."""
+    T, N = 47, 48
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, 2 * N, nloen)
+    ref = eo.rpnm_reference_layout(s)                       # (ndgnh, nspolegl)
+    rpnm, npms = tr.legendre_polynomials()
+    assert rpnm.shape == (ref.shape[1], ref.shape[0])
+    np.testing.assert_array_equal(npms, np.concatenate([[0], np.cumsum([T + 2 - m for m in range(T)])]))
+    np.testing.assert_allclose(rpnm.T, ref, rtol=0, atol=5e-14)
+    for m in (0, 1, 17, T):
+        pm = tr.trans_pnm(m)                                # (T-m+3, ndgnh)
+        np.testing.assert_array_equal(pm[:T + 2 - m], rpnm[npms[m]:npms[m] + T + 2 - m])
+        assert not pm[T + 2 - m:].any()
+    # ectrans4py.get_legendre_assets: KNMENG, PGW, PRPNM
+    from ectrans_b200 import ectrans4py as e4
+    nmeng, gw, prpnm = e4.get_legendre_assets(2 * N, T, 2 * N, ref.shape[1], nloen, 10)
+    np.testing.assert_array_equal(nmeng, s.nmen)
+    np.testing.assert_allclose(gw, s.rw, rtol=1e-14)
+    np.testing.assert_array_equal(prpnm, rpnm.T)
+    tr.release()

@@ -148,3 +148,28 @@ def test_oracle_adjoints_satisfy_reference_identity():
     lhs = np.sum(w * dv * vor) + np.sum(w * dd * div) + np.sum(w * ds * sc)
     rhs = np.sum(y * ga)
     assert abs(lhs - rhs) <= 20000 * np.finfo(float).eps * abs(lhs)
+
+
+def test_oracle_gpnorm_vordiv_rpnm_known_answers():
+    """Known answers for the restatements of GPNORM_TRANS, VORDIV_TO_UV and the TRANS_INQ(PRPNM) layout: a constant
+    field averages to itself (sum of Gaussian weights = 1, test_ectrans4py.py:119-121); (U, V) cos(theta) synthesised
+    as scalars equal u, v cos(theta) of the vor/div inverse transform when nothing sits at n = T; column NPMS(m) + p
+    of PRPNM is n = T + 2 - p (trans_inq.F90:450-462), e.g. the last column of the m = 0 block is P_0^0 = 1."""
+    T, N = 31, 32
+    nloen = eo.octahedral_nloen(N)
+    s = eo.setup(T, 2 * N, nloen)
+    ave, mn, mx = eo.gpnorm_trans(s, np.full((2, s.ngptot), 1.75))
+    assert np.allclose(ave, 1.75, rtol=1e-14) and (mn == 1.75).all() and (mx == 1.75).all()
+    vor = eo.random_spectral(s, 2, 1, zero00=True); div = eo.random_spectral(s, 2, 2, zero00=True)
+    for m in range(T + 1):
+        o = int(s.nasm0[m]) + 2 * (T - m)
+        vor[:, o:o + 2] = 0.0; div[:, o:o + 2] = 0.0
+    u, v = eo.vordiv_to_uv(s, vor, div)
+    guv = eo.inv_trans(s, vor, div, None)
+    gs = eo.inv_trans(s, None, None, np.concatenate([u, v]))
+    cos = np.repeat(np.sqrt(s.r1mu2), nloen)
+    assert np.linalg.norm(gs - guv * cos) / np.linalg.norm(gs) < 1e-12
+    r = eo.rpnm_reference_layout(s)
+    assert r.shape == (N, sum(T + 2 - m for m in range(T + 1)))
+    assert np.allclose(r[:, T + 1], 1.0, rtol=1e-13)                  # m = 0, p = T + 2: n = 0
+    assert np.allclose(r[:, T], np.sqrt(3.0) * s.rmu[:N], rtol=1e-13)  # n = 1: sqrt(3) mu
