@@ -25,6 +25,7 @@ _lib = None
 ECT_MEM_HOST, ECT_MEM_DEVICE = 0, 1
 ECT_SETUP_HOST_ONLY = 1
 ECT_SETUP_STREAM_GIVEN = 2
+ECT_SETUP_LEGPOL_DEFER = 4
 ECT_NCCL_UID_BYTES = 128
 ECT_PREC_DP, ECT_PREC_SP = 0, 1
 (ARR_NLOEN, ARR_NMEN, ARR_NDGLU, ARR_MYMS, ARR_NASM0, ARR_NPROCM, ARR_RMU, ARR_RGW, ARR_LATFIRST,
@@ -85,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "ect_get_timings", "ect_synchronize", "ect_release", "ect_finalize", "ect_strerror", "ect_last_error",
     "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
     "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec", "ect_inv_transad", "ect_dir_transad",
-    "ect_gpnorm_trans", "ect_vordiv_to_uv", "ect_inquire_rpnm", "ect_trans_pnm",
+    "ect_gpnorm_trans", "ect_vordiv_to_uv", "ect_inquire_rpnm", "ect_trans_pnm", "ect_write_legpol", "ect_read_legpol",
 ]
 
 
@@ -121,6 +122,8 @@ def lib():
         L.ect_vordiv_to_uv.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ect_inquire_rpnm.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.POINTER(C.c_int), C.c_void_p]
         L.ect_trans_pnm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.ect_write_legpol.argtypes = [C.c_int, C.c_char_p]
+        L.ect_read_legpol.argtypes = [C.c_int, C.c_char_p]
         _lib = L
     return _lib
 
@@ -203,20 +206,31 @@ class Transform:
     """
 
     def __init__(self, nsmax, nloen, nranks=1, rank=0, device=-1, stream=None, nccl_uid=None, host_only=False,
-                 precision="dp"):
+                 precision="dp", legpol_read=None, legpol_write=None):
+        """legpol_read / legpol_write: SETUP_TRANS's CDIO_LEGPOL='readf' / 'writef' with CDLEGPOLFNAME (the reference's
+        Legendre-polynomial cache file format); with legpol_read the table is not computed."""
         L = lib()
         self.precision = precision
         self.dtype = np.float64 if precision == "dp" else np.float32
         nl = np.ascontiguousarray(nloen, dtype=np.int32)
         self._uid = C.create_string_buffer(nccl_uid, ECT_NCCL_UID_BYTES) if nccl_uid else None
         o = _SetupOpts(int(nsmax), int(nl.size), nl.ctypes.data_as(C.POINTER(C.c_int)), int(nranks), int(rank),
-                       (ECT_SETUP_HOST_ONLY if host_only else 0) | (ECT_SETUP_STREAM_GIVEN if stream is not None else 0),
+                       (ECT_SETUP_HOST_ONLY if host_only else 0) | (ECT_SETUP_STREAM_GIVEN if stream is not None else 0)
+                       | (ECT_SETUP_LEGPOL_DEFER if legpol_read else 0),
                        int(device), C.c_void_p(stream) if stream else None,
                        C.cast(self._uid, C.c_void_p) if self._uid else None,
                        ECT_PREC_DP if precision == "dp" else ECT_PREC_SP)
         h = C.c_int(0)
         _check(L.ect_setup(C.byref(o), C.byref(h)), "ect_setup")
         self.handle = h.value
+        if legpol_read:
+            rc = L.ect_read_legpol(self.handle, os.fsencode(legpol_read))
+            if rc:
+                msg = (L.ect_last_error() or b"").decode()
+                L.ect_release(self.handle); self.handle = 0
+                raise EctError(f"ect_read_legpol failed ({rc}): {msg}")
+        if legpol_write:
+            _check(L.ect_write_legpol(self.handle, os.fsencode(legpol_write)), "ect_write_legpol")
         self.info = Info()
         _check(L.ect_inquire(self.handle, C.byref(self.info)), "ect_inquire")
         i = self.info

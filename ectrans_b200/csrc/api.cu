@@ -208,6 +208,7 @@ extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
     if (rc) { delete h; return rc; }
     if (o->precision != ECT_PREC_DP && o->precision != ECT_PREC_SP) { delete h; ect_set_error("ect_setup: unknown precision %d", o->precision); return ECT_ERR_BADARG; }
     h->precision = o->precision;
+    h->defer_table = (o->flags & ECT_SETUP_LEGPOL_DEFER) != 0;
     if (!(o->flags & ECT_SETUP_HOST_ONLY)) {
         rc = ect_device_setup(h, (cudaStream_t)o->stream, (o->flags & ECT_SETUP_STREAM_GIVEN) != 0, o->device, o->nccl_uid);
         if (rc) { ect_device_free(h); delete h; return rc; }
@@ -1824,4 +1825,88 @@ extern "C" int ect_trans_pnm(int handle, int m, double* rpnm, int ld, int ncols)
     ECT_CUDA(cudaSetDevice(h->d->dev));
     for (i64 c = 0; c < ncols; ++c) memset(rpnm + c * ld, 0, (size_t)ld * sizeof(double));
     return rpnm_of_m(h, ml, rpnm, ld, 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// Legendre polynomial cache files in the reference's format (SETUP_TRANS CDIO_LEGPOL = 'writef' / 'readf',
+// cpu/internal/write_legpol_mod.F90:57-170, read_legpol_mod.F90:60-150; plain matrices only -- no FLT butterfly
+// structs, no lat-lon section):
+//   int32[4]           'LEGP' 'OL  ' NSMAX NDGNH
+//   int32[2 NDGNH]     NLOEN(j), NMEN(j) of the northern latitudes, interleaved
+//   per local m (MYMS order): real64 RPNMA(IDGLU, ILA) then RPNMS(IDGLU, ILS), column major, column J holding
+//                      n = m + 2 (ILA - J) + 1 resp. n = m + 2 (ILS - J)   (n descending)
+//   int32[4]           'LEGPOL---EOF-EOF'
+// ---------------------------------------------------------------------------------------
+extern "C" int ect_write_legpol(int handle, const char* path) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) { ect_set_error("ect_write_legpol: invalid handle"); return ECT_ERR_HANDLE; }
+    if (!path) return ECT_ERR_MISSING;
+    const EctHostPlan& P = h->hp;
+    ECT_CUDA(cudaSetDevice(h->d->dev));
+    FILE* f = fopen(path, "wb");
+    if (!f) { ect_set_error("ect_write_legpol: cannot open %s", path); return ECT_ERR_GENERIC; }
+    int32_t hdr[4]; memcpy(hdr, "LEGPOL  ", 8); hdr[2] = P.nsmax; hdr[3] = P.ndgnh;
+    bool ok = fwrite(hdr, 4, 4, f) == 4;
+    std::vector<int32_t> geo(2 * (size_t)P.ndgnh);
+    for (int j = 0; j < P.ndgnh; ++j) { geo[2 * j] = P.nloen[j]; geo[2 * j + 1] = P.nmen[j]; }
+    ok = ok && fwrite(geo.data(), 4, geo.size(), f) == geo.size();
+    std::vector<double> tab, out;
+    for (int ml = 0; ml < P.nump && ok; ++ml) {
+        const EctLegM& lm = h->d->h_legm[ml];
+        for (int par = 1; par >= 0 && ok; --par) {          // antisymmetric first
+            const int k = par ? lm.ila : lm.ils;
+            if (k == 0 || lm.ndglu == 0) continue;
+            tab.resize((size_t)k * lm.ndglu); out.resize(tab.size());
+            int rc = ect_legendre_get_table(h, ml, par, tab.data(), (long long)tab.size());
+            if (rc) { fclose(f); return rc; }
+            for (int kk = 0; kk < k; ++kk)                   // mine: n ascending; file: column J = k - kk (n descending)
+                memcpy(out.data() + (size_t)(k - 1 - kk) * lm.ndglu, tab.data() + (size_t)kk * lm.ndglu, lm.ndglu * sizeof(double));
+            ok = fwrite(out.data(), 8, out.size(), f) == out.size();
+        }
+    }
+    ok = ok && fwrite("LEGPOL---EOF-EOF", 1, 16, f) == 16;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { ect_set_error("ect_write_legpol: write to %s failed", path); return ECT_ERR_GENERIC; }
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_read_legpol(int handle, const char* path) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) { ect_set_error("ect_read_legpol: invalid handle"); return ECT_ERR_HANDLE; }
+    if (!path) return ECT_ERR_MISSING;
+    const EctHostPlan& P = h->hp;
+    ECT_CUDA(cudaSetDevice(h->d->dev));
+    FILE* f = fopen(path, "rb");
+    if (!f) { ect_set_error("ect_read_legpol: cannot open %s", path); return ECT_ERR_GENERIC; }
+    auto fail = [&](const char* msg) { ect_set_error("READ_LEGPOL: %s (%s)", msg, path); fclose(f); return ECT_ERR_BADARG; };
+    int32_t hdr[4];
+    if (fread(hdr, 4, 4, f) != 4) return fail("SHORT FILE");
+    if (memcmp(hdr, "LEGPOL  ", 8) != 0) return fail("WRONG LABEL");
+    if (hdr[2] != P.nsmax) return fail("WRONG SPECTRAL TRUNCATION");
+    if (hdr[3] != P.ndgnh) return fail("WRONG NO OF GAUSSIAN LATITUDES");
+    std::vector<int32_t> geo(2 * (size_t)P.ndgnh);
+    if (fread(geo.data(), 4, geo.size(), f) != geo.size()) return fail("SHORT FILE");
+    for (int j = 0; j < P.ndgnh; ++j) {
+        if (geo[2 * j] != P.nloen[j]) return fail("WRONG NLOEN");
+        if (geo[2 * j + 1] != P.nmen[j]) return fail("WRONG NMEN");
+    }
+    std::vector<double> in, tab;
+    for (int ml = 0; ml < P.nump; ++ml) {
+        const EctLegM& lm = h->d->h_legm[ml];
+        for (int par = 1; par >= 0; --par) {
+            const int k = par ? lm.ila : lm.ils;
+            if (k == 0 || lm.ndglu == 0) continue;
+            in.resize((size_t)k * lm.ndglu); tab.resize(in.size());
+            if (fread(in.data(), 8, in.size(), f) != in.size()) return fail("SHORT FILE");
+            for (int kk = 0; kk < k; ++kk)
+                memcpy(tab.data() + (size_t)kk * lm.ndglu, in.data() + (size_t)(k - 1 - kk) * lm.ndglu, lm.ndglu * sizeof(double));
+            int rc = ect_legendre_set_table(h, ml, par, tab.data());
+            if (rc) { fclose(f); return rc; }
+        }
+    }
+    char eof[16];
+    if (fread(eof, 1, 16, f) != 16 || memcmp(eof, "LEGPOL---EOF-EOF", 16) != 0) return fail("WRONG END LABEL");
+    fclose(f);
+    h->defer_table = false;
+    return ECT_SUCCESS;
 }

@@ -154,6 +154,7 @@ struct EctHandle {
     EctHostPlan hp;
     EctDevice* d = nullptr;
     int precision = 0;
+    bool defer_table = false;     // ECT_SETUP_LEGPOL_DEFER: the table is allocated but filled by ect_read_legpol
 };
 
 // setup (device)
@@ -174,6 +175,7 @@ void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, 
 int ect_legendre_setup(EctHandle* h);
 int ect_fourier_setup(EctHandle* h);
 int ect_legendre_get_table(EctHandle* h, int ml, int par, double* out, long long cap);
+int ect_legendre_set_table(EctHandle* h, int ml, int par, const double* in);      // [k][ndglu], host
 int ect_transpose(EctHandle* h, const EctFieldCfg& f, int to_fft);   // TRMTOL (1) / TRLTOM (0)
 
 const char* ect_cuda_err(cudaError_t e);

@@ -790,7 +790,7 @@ int ect_legendre_setup(EctHandle* h) {
     ECT_CUDA(cudaMemcpyAsync(d_rmu, P.rmu.data(), P.ndgl * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     int maxdglu = 0;
     for (auto& lm : d->h_legm) maxdglu = std::max(maxdglu, lm.ndglu);
-    if (maxdglu > 0) {
+    if (maxdglu > 0 && !h->defer_table) {
         dim3 grid((maxdglu + 127) / 128, P.nump, 2);
         k_supolf_table<<<grid, 128, 0, d->stream>>>(d->legm, d_cm, d_rmu, d->ptab, T);
     }
@@ -838,5 +838,16 @@ int ect_legendre_get_table(EctHandle* h, int ml, int par, double* out, long long
     if (k == 0 || lm.ndglu == 0) return ECT_SUCCESS;
     ECT_CUDA(cudaMemcpy2D(out, lm.ndglu * sizeof(double), d->ptab + (par ? lm.pa_off : lm.ps_off),
                           lm.ldp * sizeof(double), lm.ndglu * sizeof(double), k, cudaMemcpyDeviceToHost));
+    return ECT_SUCCESS;
+}
+
+int ect_legendre_set_table(EctHandle* h, int ml, int par, const double* in) {
+    EctDevice* d = h->d;
+    if (ml < 0 || ml >= (int)d->h_legm.size()) return ECT_ERR_BADARG;
+    const EctLegM& lm = d->h_legm[ml];
+    const int k = par ? lm.ila : lm.ils;
+    if (k == 0 || lm.ndglu == 0) return ECT_SUCCESS;
+    ECT_CUDA(cudaMemcpy2D(d->ptab + (par ? lm.pa_off : lm.ps_off), lm.ldp * sizeof(double), in,
+                          lm.ndglu * sizeof(double), lm.ndglu * sizeof(double), k, cudaMemcpyHostToDevice));
     return ECT_SUCCESS;
 }

@@ -53,6 +53,7 @@ extern "C" {
 
 #define ECT_SETUP_HOST_ONLY 1   /* build geometry + decomposition only, no CUDA (inquire works) */
 #define ECT_SETUP_STREAM_GIVEN 2 /* opts.stream is valid even if it is 0 (the legacy default stream) */
+#define ECT_SETUP_LEGPOL_DEFER 4 /* do not compute the Legendre table: ect_read_legpol() fills it (CDIO_LEGPOL='readf') */
 
 #define ECT_NCCL_UID_BYTES 128
 
@@ -209,6 +210,13 @@ int ect_vordiv_to_uv(int handle, int nsmax, const void* spvor, const void* spdiv
  *       ld >= ndgnh, ncols >= nsmax - m + 2; column p (1-based) holds n = nsmax + 2 - p. */
 int ect_inquire_rpnm(int handle, double* rpnm, long long capacity_elems, int* nspolegl, int* npms);
 int ect_trans_pnm(int handle, int m, double* rpnm, int ld, int ncols);
+
+/* Legendre polynomial cache in the reference's file format (SETUP_TRANS CDIO_LEGPOL='writef' / 'readf' with
+ * CDLEGPOLFNAME, src/trans/include/ectrans/setup_trans.h:60-66; write_legpol_mod.F90, read_legpol_mod.F90).  The
+ * reader checks label, truncation, latitude count, NLOEN and NMEN like the reference and fails with ECT_ERR_BADARG
+ * ("READ_LEGPOL: WRONG ..." in ect_last_error()).  One file per task: it holds the task's wavenumbers (MYMS). */
+int ect_write_legpol(int handle, const char* path);
+int ect_read_legpol(int handle, const char* path);
 
 int ect_synchronize(int handle);   /* wait for asynchronous ECT_MEM_DEVICE calls on this handle */
 int ect_release(int handle);
