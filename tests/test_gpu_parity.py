@@ -111,6 +111,43 @@ def test_inv_dir_against_oracle(eb, T, N, nuv, nsc, opts, nproma):
     tr.release()
 
 
+def _grid(kind, golden):
+    if kind == "F24":                   # full (regular) Gaussian grid
+        return np.full(48, 96, dtype=np.int32)
+    if kind == "golden150":             # the irregular reduced grid of the reference's ectrans4py test data
+        return np.asarray(golden["nloen"], dtype=np.int32)
+    return None
+
+
+# NMEN rules of setup_geom_mod.F90:44-78 other than the cubic octahedral one: linear (T >= NDGL-1), quadratic
+# (T >= 2 NDGL / 3 - 1), a full grid, an irregular reduced grid; vor/div + scalars with derivatives each
+GRID_CASES = [("O48", 95), ("O48", 63), ("F24", 47), ("F24", 30), ("golden150", 99), ("golden150", 60)]
+
+
+@pytest.mark.parametrize("kind,T", GRID_CASES)
+def test_other_grids_and_truncation_rules(eb, golden, kind, T):
+    import ectrans_b200
+    nloen = ectrans_b200.octahedral_nloen(48) if kind == "O48" else _grid(kind, golden)
+    ndgl = int(nloen.size)
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, ndgl, nloen)
+    np.testing.assert_array_equal(tr.nmen, s.nmen)
+    np.testing.assert_array_equal(tr.ndglu, s.ndglu)
+    vor = eo.random_spectral(s, 2, 1, zero00=True); div = eo.random_spectral(s, 2, 2, zero00=True)
+    sc = eo.random_spectral(s, 3, 3)
+    opts = dict(scders=True, uvder=True, vorgp=True, divgp=True)
+    ref = eo.inv_trans(s, vor, div, sc, **opts)
+    got = unblock(tr.inv_trans(T_(vor), T_(div), T_(sc), **opts), tr.ngptot)
+    for i in range(ref.shape[0]):
+        assert rel(got[i], ref[i]) < TOL, (i, rel(got[i], ref[i]))
+    gin = ref[4:4 + 4 + 3]
+    rv, rd, rs = eo.dir_trans(s, gin, 2, 3)
+    ov, od, os_ = tr.dir_trans(gin[None], 2, 3)
+    for a, b in ((ov, rv), (od, rd), (os_, rs)):
+        assert rel(a.T, b) < TOL
+    tr.release()
+
+
 def test_benchmark_input_roundtrip(eb):
     """ectrans-benchmark's own check: Re psi(4,19) = 1 everywhere, inverse + direct, norm error <= 100 eps."""
     T, N, nlev = 159, 160, 9

@@ -51,6 +51,19 @@ def test_geometry_matches_oracle(eb, T, N):
     t.release()
 
 
+@pytest.mark.parametrize("kind,T", [("O48", 95), ("O48", 63), ("F24", 47), ("F24", 30), ("golden150", 99), ("golden150", 60)])
+def test_geometry_other_grids(eb, golden, kind, T):
+    """NMEN rules of setup_geom_mod.F90:44-78: linear, quadratic and cubic branches, full and irregular reduced grids."""
+    nloen = {"O48": eb.octahedral_nloen(48), "F24": np.full(48, 96, dtype=np.int32),
+             "golden150": np.asarray(golden["nloen"], dtype=np.int32)}[kind]
+    t = eb.Transform(T, nloen, host_only=True)
+    s = eo.setup(T, int(nloen.size), nloen, tables=False)
+    np.testing.assert_array_equal(t.nmen, s.nmen)
+    np.testing.assert_array_equal(t.ndglu, s.ndglu)
+    assert (t.nspec2, t.ngptot) == (s.nspec2, s.ngptot)
+    t.release()
+
+
 def test_golden_grid_inquire(eb, golden):
     # tests/test_ectrans4py/test_ectrans4py.py:123-131
     t = eb.Transform(148, golden["nloen"], host_only=True)

@@ -13,11 +13,13 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-buf = torch.zeros(eb.ECT_NCCL_UID_BYTES, dtype=torch.uint8, device=dev)
-if rank == 0:
-    buf.copy_(torch.frombuffer(bytearray(eb.nccl_unique_id()), dtype=torch.uint8))
-dist.broadcast(buf, 0)
-uid = bytes(buf.cpu().numpy().tobytes())
+def fresh_uid():                      # one NCCL id per communicator (= per distributed handle)
+    buf = torch.zeros(eb.ECT_NCCL_UID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(eb.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().numpy().tobytes())
+uid = fresh_uid()
 T, N, nuv, nsc = 79, 80, 3, 4
 nloen = eb.octahedral_nloen(N)
 tr = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=uid)
@@ -64,6 +66,24 @@ if rank == 0:
     bit = min(bit, float(np.array_equal(gv, z(v1))), float(np.array_equal(gd, z(d1))))
 smine = [f for f in range(nsc) if f % world == rank]
 bit = min(bit, float(np.array_equal(gs, z(s1)[:, smine])))
+# ---- GPNORM_TRANS (bit identical across decompositions: latitudes are added in global order), VORDIV_TO_UV on the
+# task's wavenumbers, Legendre cache file per task ----
+a_n, lo_n, hi_n = tr.gpnorm_trans(gp)
+a_1, lo_1, hi_1 = tr1.gpnorm_trans(g1)
+bit = min(bit, float(np.array_equal(a_n, a_1) and np.array_equal(lo_n, lo_1) and np.array_equal(hi_n, hi_1)))
+un, vn = tr.vordiv_to_uv(loc(vor), loc(div))
+u1, v1_ = tr1.vordiv_to_uv(T_(vor), T_(div))
+if tr.nump:
+    bit = min(bit, float(np.array_equal(un, u1[idx]) and np.array_equal(vn, v1_[idx])))
+import tempfile
+path = os.path.join(tempfile.gettempdir(), "legpol_%d_of_%d.bin" % (rank, world))
+tr.release()
+trw = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=fresh_uid(), legpol_write=path)
+trw.release()
+tr = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=fresh_uid(), legpol_read=path)
+gp2 = tr.inv_trans(loc(vor), loc(div), loc(sc), scders=True)
+bit = min(bit, float(np.array_equal(gp2, gp)))
+os.remove(path)
 tr1.release()
 t = torch.tensor([e_inv, e_dir, e_nrm, e_dist, e_gath, 1.0 - bit], device=dev, dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
