@@ -316,6 +316,7 @@ def run_ours(args):
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if tj.get("workload") == args.config and world == 1:
             traffic = {"k_leinv_dram_bytes_per_launch": tj["dram_bytes_per_launch"],
+                       "k_ledir_dram_bytes_per_launch": tj.get("k_ledir_dram_bytes_per_launch"),
                        "algorithmic_bytes_per_launch": int(tr.info.table_bytes + 8 * (nf * 2) * (sum(T - m + 2 for m in range(T + 1)) + 2 * sum(int(x) for x in tr.ndglu))),
                        "source": tj["source"]}
     except Exception:
