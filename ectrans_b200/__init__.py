@@ -87,6 +87,7 @@ EXPORTED_SYMBOLS = [
     "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
     "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec", "ect_inv_transad", "ect_dir_transad",
     "ect_gpnorm_trans", "ect_vordiv_to_uv", "ect_inquire_rpnm", "ect_trans_pnm", "ect_write_legpol", "ect_read_legpol",
+    "ect_gridpoint_partition",
 ]
 
 
@@ -124,6 +125,8 @@ def lib():
         L.ect_trans_pnm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.ect_write_legpol.argtypes = [C.c_int, C.c_char_p]
         L.ect_read_legpol.argtypes = [C.c_int, C.c_char_p]
+        L.ect_gridpoint_partition.argtypes = [C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
 
@@ -144,6 +147,21 @@ def measure_fp64_peak(which: int) -> float:
     v = C.c_double(0.0)
     _check(lib().ect_measure_fp64_peak(which, C.byref(v)), "ect_measure_fp64_peak")
     return v.value
+
+
+def gridpoint_partition(nloen, nproc: int):
+    """The reference's default grid-point decomposition (LDEQ_REGIONS=T, LDSPLIT=T) for nproc tasks: (regions per
+    band, [per task: array (npieces, 3) of (latitude, first point, count), 0-based, in local point order])."""
+    nl = np.ascontiguousarray(nloen, dtype=np.int32)
+    nb, ns = C.c_int(0), C.c_longlong(0)
+    reg = np.zeros(nproc, dtype=np.int32)
+    seg0 = np.zeros(nproc + 1, dtype=np.int32)
+    _check(lib().ect_gridpoint_partition(nl.size, nl.ctypes.data, nproc, C.byref(nb), reg.ctypes.data, seg0.ctypes.data,
+                                         None, 0, C.byref(ns)), "ect_gridpoint_partition")
+    segs = np.zeros((ns.value, 3), dtype=np.int32)
+    _check(lib().ect_gridpoint_partition(nl.size, nl.ctypes.data, nproc, None, None, None, segs.ctypes.data, ns.value,
+                                         None), "ect_gridpoint_partition")
+    return reg[:nb.value].copy(), [segs[seg0[p]:seg0[p + 1]] for p in range(nproc)]
 
 
 def vordiv_to_uv(nsmax: int, spvor, spdiv):

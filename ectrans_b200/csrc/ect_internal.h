@@ -50,6 +50,18 @@ struct EctHostPlan {
 };
 
 int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank);
+
+// Grid-point decomposition LDEQ_REGIONS=T, LDSPLIT=T (gp_partition.cu)
+struct EctGpSeg { int lat, first, count; };       // 0-based latitude, first point on it, number of points
+struct EctGpPartition {
+    std::vector<int> regions;                     // N_REGIONS(band)
+    std::vector<int> band_first, band_last;       // NFRSTLAT / NLSTLAT (0-based; a split latitude belongs to both bands)
+    std::vector<long long> band_points;           // KPROCAGP
+    std::vector<int> seg0;                        // task -> first entry of segs (size ntasks + 1)
+    std::vector<EctGpSeg> segs;                   // per task, in its local point order (latitude, then longitude)
+};
+int ect_eq_regions(int n, std::vector<int>& regions);
+int ect_gp_partition(const std::vector<int>& nloen, int nproc, EctGpPartition& G);
 void ect_gauss_latitudes(int ndgl, std::vector<double>& mu, std::vector<double>& w);
 
 // ---------------------------------------------------------------------------------------

@@ -218,6 +218,14 @@ int ect_trans_pnm(int handle, int m, double* rpnm, int ld, int ncols);
 int ect_write_legpol(int handle, const char* path);
 int ect_read_legpol(int handle, const char* path);
 
+/* The reference's default grid-point decomposition (SETUP_TRANS0 LDEQ_REGIONS=T, SETUP_TRANS LDSPLIT=T:
+ * eq_regions_mod.F90, sumplatbeq_mod.F90, sumplat_mod.F90, sustaonl_mod.F90, pe2set_mod.F90) for nproc tasks; host only,
+ * no handle.  regions: int[nproc], the first *nbands entries are N_REGIONS(band); task (0-based) = regions of the bands
+ * before + region.  seg0: int[nproc + 1]; segs: int[3 * capacity_segs] = (latitude, first point = NSTA - 1, NONL) of
+ * the pieces of every task in its local point order; *nsegs = number of pieces (call with segs = NULL to size). */
+int ect_gridpoint_partition(int ndgl, const int* nloen, int nproc, int* nbands, int* regions, int* seg0, int* segs,
+                            long long capacity_segs, long long* nsegs);
+
 int ect_synchronize(int handle);   /* wait for asynchronous ECT_MEM_DEVICE calls on this handle */
 int ect_release(int handle);
 int ect_finalize(void);

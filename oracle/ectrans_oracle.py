@@ -853,3 +853,146 @@ def rpnm_reference_layout(s: Setup) -> np.ndarray:
             out[ndgnh - nl:, c0 + (T + 2 - n) - 1] = col
         c0 += T + 2 - m
     return out
+
+
+# --------------------------------------------------------------------------
+#  Grid-point decomposition: eq_regions + SUMPLAT (LDSPLIT=T) + SUSTAONL
+#  (the default of ectrans-benchmark: LDEQ_REGIONS=T, LDSPLIT=T, ectrans-benchmark.F90:385)
+# --------------------------------------------------------------------------
+def _eq_gamma(x: float) -> float:
+    """The reference's own gamma function (eq_regions_mod.F90:282-330), used for the area of the sphere."""
+    p = [0.999999999999999990e+00, -0.422784335098466784e+00, -0.233093736421782878e+00, 0.191091101387638410e+00,
+         -0.024552490005641278e+00, -0.017645244547851414e+00, 0.008023273027855346e+00, -0.000804329819255744e+00,
+         -0.000360837876648255e+00, 0.000145596568617526e+00, -0.000017545539395205e+00, -0.000002591225267689e+00,
+         0.000001337767384067e+00, -0.000000199542863674e+00]
+    n = int(round(x - 2))
+    w = x - (n + 2)
+    y = 0.0
+    for c in reversed(p):
+        y = y * w + c
+    if n > 0:
+        w = x - 1
+        for k in range(2, n + 1):
+            w = w * (x - k)
+    else:
+        w = 1.0
+        for k in range(0, -n):
+            y = y * (x + k)
+    return w / y
+
+
+def _nint(x: float) -> int:
+    """Fortran NINT: half away from zero."""
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def eq_regions(n: int):
+    """Number of regions per latitude band of the equal-area partition of the sphere into n regions (Leopardi's
+    recursive zonal partition as coded in common/internal/eq_regions_mod.F90:76-230)."""
+    if n == 1:
+        return [1]
+    pi = 2.0 * math.asin(1.0)
+    area = (2.0 * pi ** 1.5 / _eq_gamma(1.5)) / n                     # area_of_ideal_region
+    cap = lambda s: 4.0 * pi * math.sin(s / 2.0) ** 2                  # area_of_cap
+    c_polar = pi / 2.0 if n == 2 else 2.0 * math.asin(math.sqrt(area / pi) / 2.0)
+    a_ideal = area ** 0.5
+    n_collars = max(1, _nint((pi - 2.0 * c_polar) / a_ideal)) if (n > 2 and a_ideal > 0) else 0
+    r = [1.0]
+    if n_collars > 0:
+        a_fit = (pi - 2.0 * c_polar) / n_collars
+        for c in range(1, n_collars + 1):
+            r.append((cap(c_polar + c * a_fit) - cap(c_polar + (c - 1) * a_fit)) / area)
+    r.append(1.0)
+    out, disc = [], 0.0
+    for v in r:                                                        # round_to_naturals
+        k = _nint(v + disc)
+        disc += v - k
+        out.append(k)
+    assert sum(out) == n
+    return out
+
+
+def sumplat_eq_split(nloen, nproc: int, n_regions):
+    """SUMPLATBEQ (LDSPLIT=T, unweighted; sumplatbeq_mod.F90:84-150) + SUMPLAT (sumplat_mod.F90:138-150): for every
+    A-set (band) its number of points and first / last latitude (0-based, a split latitude belongs to both)."""
+    nloen = [int(x) for x in nloen]
+    ndgl = len(nloen)
+    total = sum(nloen)
+    mediap = total // nproc
+    restm = total - mediap * nproc
+    if restm > 0:
+        mediap += 1
+    nprocagp, last, indic = [], [], []
+    rest, ilast, ipe = 0, -1, 0
+    for ja, nb in enumerate(n_regions):
+        comp = 0
+        for _ in range(nb):
+            ipe += 1
+            comp += mediap if (ipe <= restm or restm == 0) else mediap - 1
+        nprocagp.append(comp)
+        itot = rest
+        for jgl in range(ilast + 1, ndgl):
+            ilast = jgl
+            if itot + nloen[jgl] < comp:
+                itot += nloen[jgl]
+            elif itot + nloen[jgl] == comp:
+                rest = 0
+                last.append(jgl); indic.append(-1)
+                break
+            else:
+                rest = nloen[jgl] - (comp - itot)
+                last.append(jgl); indic.append(jgl)
+                break
+    na = len(n_regions)
+    frst, lst = [0] * na, [0] * na
+    lst[na - 1] = ndgl - 1
+    for ja in range(na - 1):
+        if indic[ja] < 0:
+            frst[ja + 1] = last[ja] + 1
+            lst[ja] = last[ja]
+        else:
+            frst[ja + 1] = indic[ja]
+            lst[ja] = indic[ja]
+    return nprocagp, frst, lst
+
+
+def gridpoint_partition(nloen, nproc: int):
+    """Grid-point decomposition of the reference for LDEQ_REGIONS=T, LDSPLIT=T (SUSTAONL, sustaonl_mod.F90:118-196):
+    inside a band the points go to the B-sets one at a time, always from the latitude whose next point lies furthest
+    west (angle in 1/1000 degree, NINT; ties -> the northernmost latitude).  Returns (n_regions, segs) with
+    segs[pe] = [(lat, first point, count), ...] (0-based) in the task's local point order; pe = sum(n_regions[:a]) + b."""
+    nloen = [int(x) for x in nloen]
+    nreg = eq_regions(nproc)
+    if nproc == 1:
+        return nreg, [[(j, 0, nloen[j]) for j in range(len(nloen))]]
+    agp, frst, lst = sumplat_eq_split(nloen, nproc, nreg)
+    segs = []
+    gpta = 0
+    for ja, nb in enumerate(nreg):
+        lats = list(range(frst[ja], lst[ja] + 1))
+        gptprsets = sum(nloen[:frst[ja]])
+        gpts = agp[ja]
+        ix = [1] * len(lats)                       # IXPTLAT (1-based next point)
+        ilst = [nloen[j] for j in lats]            # ILSTPTLAT
+        ix[0] = gpta - gptprsets + 1
+        nplat = nloen[lats[0]] - ix[0] + 1 + sum(nloen[j] for j in lats[1:])
+        ilst[-1] = nloen[lats[-1]] - nplat + gpts
+        div = [360000.0 / nloen[j] for j in lats]
+        gptsp, irest = gpts // nb, gpts - nb * (gpts // nb)
+        for jb in range(nb):
+            npts = gptsp + 1 if jb < irest else gptsp
+            sta = [0] * len(lats); onl = [0] * len(lats)
+            for _ in range(npts):
+                best, inx = 360000, -1
+                for k in range(len(lats)):
+                    if ix[k] <= ilst[k]:
+                        a = _nint((ix[k] - 1) * div[k])
+                        if a < best:
+                            best, inx = a, k
+                if sta[inx] == 0:
+                    sta[inx] = ix[inx]
+                onl[inx] += 1
+                ix[inx] += 1
+            segs.append([(lats[k], sta[k] - 1, onl[k]) for k in range(len(lats)) if onl[k] > 0])
+        gpta += gpts
+    return nreg, segs

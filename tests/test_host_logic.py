@@ -179,3 +179,37 @@ def test_gath_dist_single_rank(built):
     with pytest.raises(eb.EctError):
         tr.gath_spec(sp, kto=[0, 1, 0])              # rank 1 does not exist
     tr.release()
+
+
+@pytest.mark.parametrize("kind", ["O16", "O48", "F24", "golden150"])
+def test_eq_regions_gridpoint_partition(eb, golden, kind):
+    """The reference's default grid-point decomposition (LDEQ_REGIONS=T, LDSPLIT=T): the C++ host code (heap ordered)
+    against the oracle's restatement of eq_regions / SUMPLATBEQ / SUSTAONL (point-by-point scan), plus the invariants
+    SUSTAONL itself asserts (sustaonl_mod.F90:330-372: every point assigned exactly once) and the balance SUMPLATBEQ
+    aims for (tasks differ by at most one point)."""
+    nloen = {"O16": eb.octahedral_nloen(16), "O48": eb.octahedral_nloen(48), "F24": np.full(48, 96, dtype=np.int32),
+             "golden150": np.asarray(golden["nloen"], dtype=np.int32)}[kind]
+    for nproc in (1, 2, 3, 4, 5, 8, 12, 16, 32, 61):
+        nreg, segs = eo.gridpoint_partition(nloen, nproc)
+        reg, mine = eb.gridpoint_partition(nloen, nproc)
+        assert list(reg) == list(nreg) and int(reg.sum()) == nproc
+        cover = [np.zeros(int(n), dtype=np.int32) for n in nloen]
+        for a, b in zip(segs, mine):
+            np.testing.assert_array_equal(np.asarray(a, dtype=np.int32).reshape(-1, 3), b)
+            assert (np.diff(b[:, 0]) > 0).all()                     # local order: latitude ascending, one piece per latitude
+            for lat, first, cnt in b:
+                cover[lat][first:first + cnt] += 1
+        assert all((c == 1).all() for c in cover)
+        npts = np.array([int(b[:, 2].sum()) for b in mine])
+        assert npts.max() - npts.min() <= 1 and npts.sum() == int(np.sum(nloen))
+
+
+def test_eq_regions_known_partitions():
+    """Leopardi's recursive zonal equal-area partition of the sphere (what eq_regions_mod.F90 codes): polar caps are
+    single regions, the collars are symmetric about the equator."""
+    assert eo.eq_regions(1) == [1] and eo.eq_regions(2) == [1, 1] and eo.eq_regions(3) == [1, 1, 1]
+    assert eo.eq_regions(4) == [1, 2, 1] and eo.eq_regions(8) == [1, 6, 1] and eo.eq_regions(10) == [1, 4, 4, 1]
+    assert eo.eq_regions(32) == [1, 6, 9, 9, 6, 1] and eo.eq_regions(100) == [1, 6, 11, 15, 17, 17, 15, 11, 6, 1]
+    for n in range(1, 300):
+        r = eo.eq_regions(n)
+        assert sum(r) == n and r == r[::-1] and (n < 3 or (r[0] == 1 and r[-1] == 1))
