@@ -26,6 +26,7 @@ ECT_MEM_HOST, ECT_MEM_DEVICE = 0, 1
 ECT_SETUP_HOST_ONLY = 1
 ECT_SETUP_STREAM_GIVEN = 2
 ECT_SETUP_LEGPOL_DEFER = 4
+ECT_SETUP_GP_EQ_REGIONS = 8
 ECT_NCCL_UID_BYTES = 128
 ECT_PREC_DP, ECT_PREC_SP = 0, 1
 (ARR_NLOEN, ARR_NMEN, ARR_NDGLU, ARR_MYMS, ARR_NASM0, ARR_NPROCM, ARR_RMU, ARR_RGW, ARR_LATFIRST,
@@ -224,9 +225,14 @@ class Transform:
     """
 
     def __init__(self, nsmax, nloen, nranks=1, rank=0, device=-1, stream=None, nccl_uid=None, host_only=False,
-                 precision="dp", legpol_read=None, legpol_write=None):
+                 precision="dp", legpol_read=None, legpol_write=None, gp_partition="latbands"):
         """legpol_read / legpol_write: SETUP_TRANS's CDIO_LEGPOL='readf' / 'writef' with CDLEGPOLFNAME (the reference's
-        Legendre-polynomial cache file format); with legpol_read the table is not computed."""
+        Legendre-polynomial cache file format); with legpol_read the table is not computed.
+        gp_partition: "latbands" (native: the caller's grid points are the task's Fourier latitude band, TRLTOG / TRGTOL
+        are local) or "eq_regions" (the reference's default LDEQ_REGIONS=T, LDSPLIT=T decomposition; TRLTOG / TRGTOL are
+        NCCL all-to-alls)."""
+        if gp_partition not in ("latbands", "eq_regions"):
+            raise EctError("gp_partition must be 'latbands' or 'eq_regions'")
         L = lib()
         self.precision = precision
         self.dtype = np.float64 if precision == "dp" else np.float32
@@ -234,7 +240,8 @@ class Transform:
         self._uid = C.create_string_buffer(nccl_uid, ECT_NCCL_UID_BYTES) if nccl_uid else None
         o = _SetupOpts(int(nsmax), int(nl.size), nl.ctypes.data_as(C.POINTER(C.c_int)), int(nranks), int(rank),
                        (ECT_SETUP_HOST_ONLY if host_only else 0) | (ECT_SETUP_STREAM_GIVEN if stream is not None else 0)
-                       | (ECT_SETUP_LEGPOL_DEFER if legpol_read else 0),
+                       | (ECT_SETUP_LEGPOL_DEFER if legpol_read else 0)
+                       | (ECT_SETUP_GP_EQ_REGIONS if gp_partition == "eq_regions" else 0),
                        int(device), C.c_void_p(stream) if stream else None,
                        C.cast(self._uid, C.c_void_p) if self._uid else None,
                        ECT_PREC_DP if precision == "dp" else ECT_PREC_SP)
@@ -270,6 +277,9 @@ class Transform:
         self.recv_cnt = self._arr(ARR_RECVCNT, np.int64, i.nranks)
         self.send_off = self._arr(ARR_SENDOFF, np.int64, i.nranks)
         self.recv_off = self._arr(ARR_RECVOFF, np.int64, i.nranks)
+        nseg = int(self._arr(28, np.int32, 1)[0])
+        self.gp_segs = self._arr(27, np.int32, 3 * nseg).reshape(nseg, 3)      # (latitude, first point, count) of my grid points
+        self.n_regions = self._arr(29, np.int32, i.nranks)
 
     def record_tables(self):
         """Fourier-buffer record tables of this rank (test / diagnostic access)."""

@@ -181,7 +181,8 @@ void ect_device_free(EctHandle* h) {
                     d->nasm0, d->inv_tiles, d->dir_tiles, d->plans, d->latplans, d->perm_pool, d->tw_pool,
                     d->cz_pool, d->cz_pool_f, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->xwork, d->fbuf_leg,
                     d->stage_sp, d->stage_gp, d->normbuf, d->leg_dst_rank_n, d->leg_dst_rank_s, d->leg_dst_rec_n,
-                    d->leg_dst_rec_s, d->fft_dst_rank, d->fft_dst_rec, d->peer_fft, d->peer_leg, d->barrier_buf};
+                    d->leg_dst_rec_s, d->fft_dst_rank, d->fft_dst_rec, d->peer_fft, d->peer_leg, d->barrier_buf,
+                    d->gpband, d->gpsend, d->gprecv, d->xb_idx, d->xb_off, d->xg_off};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < EctDevice::kSlots; ++i) {
         if (d->ring_d[i]) cudaFree(d->ring_d[i]);
@@ -204,7 +205,8 @@ void ect_device_free(EctHandle* h) {
 extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
     if (!o || !handle) { ect_set_error("ect_setup: null argument"); return ECT_ERR_MISSING; }
     EctHandle* h = new EctHandle();
-    int rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, o->nranks < 1 ? 1 : o->nranks, o->rank);
+    int rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, o->nranks < 1 ? 1 : o->nranks, o->rank,
+                                 (o->flags & ECT_SETUP_GP_EQ_REGIONS) != 0);
     if (rc) { delete h; return rc; }
     if (o->precision != ECT_PREC_DP && o->precision != ECT_PREC_SP) { delete h; ect_set_error("ect_setup: unknown precision %d", o->precision); return ECT_ERR_BADARG; }
     h->precision = o->precision;
@@ -297,6 +299,21 @@ extern "C" int ect_inquire_array(int handle, int which, void* out, long long cap
         case ECT_ARR_LEGDSTRECS: return copy_out<int>(out, cap, P.leg_dst_rec_s);
         case ECT_ARR_FFTDSTRANK: return copy_out<int>(out, cap, P.fft_dst_rank);
         case ECT_ARR_FFTDSTREC: return copy_out<int>(out, cap, P.fft_dst_rec);
+        case ECT_ARR_GPSEGS: case ECT_ARR_NGPSEGS: {
+            std::vector<int> v;
+            if (P.gp_eq) for (const EctGpSeg& sg : P.gp_segs) { v.push_back(sg.lat); v.push_back(sg.first); v.push_back(sg.count); }
+            else for (int l = 0; l < P.nlat; ++l) { v.push_back(P.lat0 + l); v.push_back(0); v.push_back(P.nloen[P.lat0 + l]); }
+            if (which == ECT_ARR_NGPSEGS) return copy_out<int>(out, cap, std::vector<int>(1, (int)v.size() / 3));
+            return copy_out<int>(out, cap, v);
+        }
+        case ECT_ARR_XBIDX: return copy_out<int>(out, cap, P.xb_idx);
+        case ECT_ARR_XBOFF: return copy_out<long long>(out, cap, P.xb_off);
+        case ECT_ARR_XGOFF: return copy_out<long long>(out, cap, P.xg_off);
+        case ECT_ARR_NREGIONS: {
+            std::vector<int> v(P.nranks, 0);
+            for (size_t i = 0; i < P.gp_regions.size(); ++i) v[i] = P.gp_regions[i];
+            return copy_out<int>(out, cap, v);
+        }
         default: ect_set_error("ect_inquire_array: unknown array id %d", which); return ECT_ERR_BADARG;
     }
 }
@@ -442,6 +459,97 @@ int ect_transpose(EctHandle* h, const EctFieldCfg& f, int to_fft) {
         }
     }
     ECT_NCCL(ncclGroupEnd());
+    return ECT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------
+// TRLTOG / TRGTOL for the eq_regions grid-point partition (cpu/internal/trltog_mod.F90:213-271, trgtol_mod.F90): an
+// all-to-all between the owners of the Fourier latitude bands and the grid-point tasks.  The Fourier stage works on a
+// band buffer B(point of the band, field); messages are [field][points of the pair (band owner, task)], points in
+// the task's local order, so both ends address them with one offset table each:
+//   band owner:  message to task p   = points xb_idx[xb_off[p] .. xb_off[p+1]) of B
+//   task:        message from owner r = local points [xg_off[r], xg_off[r+1])  of the caller's PGP arrays
+// ---------------------------------------------------------------------------------------
+template <typename T, bool TO_MSG>
+__global__ void k_gp_band_msg(T* __restrict__ band, T* __restrict__ msg, const int* __restrict__ idx,
+                              const i64* __restrict__ off, int nranks, int nband, int nf) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nband) return;
+    int lo = 0, hi = nranks;                       // task p with off[p] <= k < off[p+1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= k) lo = mid; else hi = mid; }
+    const i64 o = off[lo], cnt = off[lo + 1] - o;
+    const int src = idx[k];
+    for (int f = blockIdx.y; f < nf; f += gridDim.y) {
+        T* m = msg + o * nf + (i64)f * cnt + (k - o);
+        T* b = band + (i64)f * nband + src;
+        if (TO_MSG) *m = *b; else *b = *m;
+    }
+}
+template <typename T, bool TO_MSG>
+__global__ void k_gp_user_msg(double* const* __restrict__ base, const i64* __restrict__ blkstride, T* __restrict__ msg,
+                              const i64* __restrict__ off, int nranks, int ngptot, int nproma, int nf) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngptot) return;
+    int lo = 0, hi = nranks;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= g) lo = mid; else hi = mid; }
+    const i64 o = off[lo], cnt = off[lo + 1] - o;
+    const int blk = g / nproma, in = g - blk * nproma;
+    for (int f = blockIdx.y; f < nf; f += gridDim.y) {
+        T* m = msg + o * nf + (i64)f * cnt + (g - o);
+        T* u = reinterpret_cast<T*>(base[f]) + (i64)blk * blkstride[f] + in;
+        if (TO_MSG) *m = *u; else *u = *m;
+    }
+}
+
+static int gp_exchange_setup(EctHandle* h, int nf) {
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    int rc;
+    if (!d->xb_idx) {
+        ECT_CUDA(cudaMalloc(&d->xb_idx, std::max<size_t>(P.xb_idx.size(), 1) * sizeof(int)));
+        ECT_CUDA(cudaMalloc(&d->xb_off, (P.nranks + 1) * sizeof(i64)));
+        ECT_CUDA(cudaMalloc(&d->xg_off, (P.nranks + 1) * sizeof(i64)));
+        ECT_CUDA(cudaMemcpy(d->xb_idx, P.xb_idx.data(), P.xb_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        ECT_CUDA(cudaMemcpy(d->xb_off, P.xb_off.data(), (P.nranks + 1) * sizeof(i64), cudaMemcpyHostToDevice));
+        ECT_CUDA(cudaMemcpy(d->xg_off, P.xg_off.data(), (P.nranks + 1) * sizeof(i64), cudaMemcpyHostToDevice));
+    }
+    const i64 nb = (i64)std::max(P.ngpband, 1) * nf, ng = (i64)std::max(P.ngptot, 1) * nf;
+    if ((rc = ensure(d->gpband, d->gpband_elems, nb, d->stream, false))) return rc;
+    if ((rc = ensure(d->gpsend, d->gpsend_elems, std::max(nb, ng), d->stream, false))) return rc;
+    if ((rc = ensure(d->gprecv, d->gprecv_elems, std::max(nb, ng), d->stream, false))) return rc;
+    return ECT_SUCCESS;
+}
+
+// to_grid = 1: TRLTOG (band buffer -> caller's arrays), 0: TRGTOL.  d_gpb / d_gps: the caller-array field table on the device.
+static int gp_exchange(EctHandle* h, int nf, int es, int to_grid, double* const* d_gpb, const i64* d_gps, int nproma) {
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    ncclComm_t comm = (ncclComm_t)d->comm;
+    const int fy = std::min(nf, 64);
+    const dim3 gb((P.ngpband + 255) / 256, fy), gu((P.ngptot + 255) / 256, fy);
+#define ECT_GPX(T) do { \
+        if (to_grid) { if (P.ngpband) k_gp_band_msg<T, true><<<gb, 256, 0, d->stream>>>((T*)d->gpband, (T*)d->gpsend, d->xb_idx, d->xb_off, P.nranks, P.ngpband, nf); } \
+        else if (P.ngptot) k_gp_user_msg<T, true><<<gu, 256, 0, d->stream>>>(d_gpb, d_gps, (T*)d->gpsend, d->xg_off, P.nranks, P.ngptot, nproma, nf); \
+    } while (0)
+    if (es == 4) ECT_GPX(float); else ECT_GPX(double);
+#undef ECT_GPX
+    const std::vector<i64>& soff = to_grid ? P.xb_off : P.xg_off;
+    const std::vector<i64>& roff = to_grid ? P.xg_off : P.xb_off;
+    ECT_NCCL(ncclGroupStart());
+    for (int p = 0; p < P.nranks; ++p) {
+        const size_t ns = (size_t)(soff[p + 1] - soff[p]) * nf * es, nr = (size_t)(roff[p + 1] - roff[p]) * nf * es;
+        if (ns) ECT_NCCL(ncclSend((char*)d->gpsend + (size_t)soff[p] * nf * es, ns, ncclChar, p, comm, d->stream));
+        if (nr) ECT_NCCL(ncclRecv((char*)d->gprecv + (size_t)roff[p] * nf * es, nr, ncclChar, p, comm, d->stream));
+    }
+    ECT_NCCL(ncclGroupEnd());
+#define ECT_GPX(T) do { \
+        if (to_grid) { if (P.ngptot) k_gp_user_msg<T, false><<<gu, 256, 0, d->stream>>>(d_gpb, d_gps, (T*)d->gprecv, d->xg_off, P.nranks, P.ngptot, nproma, nf); } \
+        else if (P.ngpband) k_gp_band_msg<T, false><<<gb, 256, 0, d->stream>>>((T*)d->gpband, (T*)d->gprecv, d->xb_idx, d->xb_off, P.nranks, P.ngpband, nf); \
+    } while (0)
+    if (es == 4) ECT_GPX(float); else ECT_GPX(double);
+#undef ECT_GPX
+    ECT_CUDA(cudaGetLastError());
+    d->launches += 2;
     return ECT_SUCCESS;
 }
 
@@ -991,7 +1099,9 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     }
     std::vector<int2> pairs = make_pairs(groups);
     f.npairs = (int)pairs.size();
-    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (sizeof(double*) + sizeof(i64) + sizeof(EctFsField)) +
+    const bool gpx = P.gp_eq;       // TRLTOG is an exchange: the Fourier stage writes the band buffer, not the caller's arrays
+    if (gpx && (rc = gp_exchange_setup(h, f.nfs))) return rc;
+    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (2 * (sizeof(double*) + sizeof(i64)) + sizeof(EctFsField)) +
                          pairs.size() * sizeof(int2) + 64;
     if ((rc = ensure_callbuf(d, bytes))) return rc;
     char* hb = (char*)d->h_callbuf;
@@ -1000,9 +1110,12 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     EctSpecFieldH* t_sc = t_div + kf_uv;
     double** t_gpb = (double**)(t_sc + kf_sc);
     i64* t_gps = (i64*)(t_gpb + f.nfs);
-    int2* t_pairs = (int2*)(t_gps + f.nfs);
+    double** t_bandb = (double**)(t_gps + f.nfs);       // gp_eq: field table of the band buffer
+    i64* t_bands = (i64*)(t_bandb + f.nfs);
+    int2* t_pairs = (int2*)(t_bands + f.nfs);
     EctFsField* t_fs = (EctFsField*)(t_pairs + pairs.size());
     memcpy(t_pairs, pairs.data(), pairs.size() * sizeof(int2));
+    for (int i = 0; i < f.nfs; ++i) { t_bandb[i] = gpx ? adv(d->gpband, (i64)i * P.ngpband, es) : nullptr; t_bands[i] = (i64)f.nfs * P.ngpband; }
     const int st_uv = view ? view->uv_stride : kf_uv, st_sc = view ? view->sc_stride : kf_sc;
     for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {adv(dvor, j, es), st_uv}; t_div[j] = {adv(ddiv, j, es), st_uv}; }
     if (!mode2_sp) for (int s = 0; s < kf_sc; ++s) t_sc[s] = {adv(dsc, s, es), st_sc};
@@ -1043,8 +1156,16 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
     if ((rc = ect_transpose(h, f, 1))) return rc;
     ECT_CUDA(cudaEventRecord(d->ev[4], d->stream));
-    ect_launch_ftinv(h, f, d_gpb, d_gps, d_fs, d_pairs, nproma);
-    ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
+    if (gpx) {
+        double* const* d_bandb = (double* const*)(db + ((char*)t_bandb - hb));
+        const i64* d_bands = (const i64*)(db + ((char*)t_bands - hb));
+        ect_launch_ftinv(h, f, d_bandb, d_bands, d_fs, d_pairs, std::max(P.ngpband, 1));
+        ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
+        if ((rc = gp_exchange(h, f.nfs, es, 1, d_gpb, d_gps, nproma))) return rc;      // TRLTOG (timed with the d2h interval)
+    } else {
+        ect_launch_ftinv(h, f, d_gpb, d_gps, d_fs, d_pairs, nproma);
+        ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
+    }
     ECT_CUDA(cudaGetLastError());
     if ((rc = release_callbuf(d))) return rc;
     if (host) {
@@ -1178,7 +1299,9 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     }
     std::vector<int2> pairs = make_pairs(groups);
     f.npairs = (int)pairs.size();
-    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (sizeof(double*) + sizeof(i64)) +
+    const bool gpx = P.gp_eq;       // TRGTOL is an exchange: the caller's points travel to the band buffer first
+    if (gpx && (rc = gp_exchange_setup(h, f.nfs))) return rc;
+    const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * 2 * (sizeof(double*) + sizeof(i64)) +
                          pairs.size() * sizeof(int2) + 64;
     if ((rc = ensure_callbuf(d, bytes))) return rc;
     char* hb = (char*)d->h_callbuf;
@@ -1187,8 +1310,11 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     EctSpecFieldH* t_sc = t_div + kf_uv;
     double** t_gpb = (double**)(t_sc + kf_sc);
     i64* t_gps = (i64*)(t_gpb + f.nfs);
-    int2* t_pairs = (int2*)(t_gps + f.nfs);
+    double** t_bandb = (double**)(t_gps + f.nfs);
+    i64* t_bands = (i64*)(t_bandb + f.nfs);
+    int2* t_pairs = (int2*)(t_bands + f.nfs);
     memcpy(t_pairs, pairs.data(), pairs.size() * sizeof(int2));
+    for (int i = 0; i < f.nfs; ++i) { t_bandb[i] = gpx ? adv(d->gpband, (i64)i * P.ngpband, es) : nullptr; t_bands[i] = (i64)f.nfs * P.ngpband; }
     const int st_uv = view ? view->uv_stride : kf_uv, st_sc = view ? view->sc_stride : kf_sc;
     for (int j = 0; j < kf_uv; ++j) { t_vor[j] = {adv(dvor, j, es), st_uv}; t_div[j] = {adv(ddiv, j, es), st_uv}; }
     if (!mode2) {
@@ -1210,7 +1336,13 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     double* const* d_gpb = (double* const*)(db + ((char*)t_gpb - hb));
     const i64* d_gps = (const i64*)(db + ((char*)t_gps - hb));
     const void* d_pairs = db + ((char*)t_pairs - hb);
-    ect_launch_ftdir(h, f, d_gpb, d_gps, d_pairs, nproma);
+    if (gpx) {
+        double* const* d_bandb = (double* const*)(db + ((char*)t_bandb - hb));
+        const i64* d_bands = (const i64*)(db + ((char*)t_bands - hb));
+        if ((rc = gp_exchange(h, f.nfs, es, 0, d_gpb, d_gps, nproma))) return rc;      // TRGTOL (timed with the Fourier interval)
+        ect_launch_ftdir(h, f, d_bandb, d_bands, d_pairs, std::max(P.ngpband, 1));
+    } else
+        ect_launch_ftdir(h, f, d_gpb, d_gps, d_pairs, nproma);
     ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
     if ((rc = ect_transpose(h, f, 0))) return rc;
     ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
@@ -1471,7 +1603,8 @@ static PieceMap grid_pieces(const EctHostPlan& P) {
     i64 pos = 0;
     for (int r = 0; r < P.nranks; ++r) {
         i64 n = 0;
-        for (int j = 0; j < P.lat_count[r]; ++j) n += P.nloen[P.lat_first[r] + j];
+        if (P.gp_eq) for (int i = P.gp_all_seg0[r]; i < P.gp_all_seg0[r + 1]; ++i) n += P.gp_all_segs[i].count;   // scattered: see gpos
+        else for (int j = 0; j < P.lat_count[r]; ++j) n += P.nloen[P.lat_first[r] + j];
         g.off[r] = pos; g.cnt[r] = n; pos += n;
     }
     return g;
@@ -1585,8 +1718,19 @@ static int gath_dist(int handle, bool grid, bool gather, void* v_local, void* v_
             for (int m : P.ms_of[s]) for (int i = 0; i < 2 * (P.nsmax - m + 1); ++i) gpos.push_back(iasm0g[m] + i);
         }
         gpos0[P.nranks] = (i64)gpos.size();
+    } else if (P.gp_eq) {       // eq_regions partition: a task's points are pieces of latitudes, scattered in the global order
+        gpos.reserve((size_t)nglob);
+        std::vector<i64> latoff(P.ndgl + 1, 0);
+        for (int j = 0; j < P.ndgl; ++j) latoff[j + 1] = latoff[j] + P.nloen[j];
+        for (int s = 0; s < P.nranks; ++s) {
+            gpos0[s] = (i64)gpos.size();
+            for (int i = P.gp_all_seg0[s]; i < P.gp_all_seg0[s + 1]; ++i)
+                for (int j = 0; j < P.gp_all_segs[i].count; ++j) gpos.push_back(latoff[P.gp_all_segs[i].lat] + P.gp_all_segs[i].first + j);
+        }
+        gpos0[P.nranks] = (i64)gpos.size();
     }
     auto gcaller = [&](int q, int s, i64 i) -> char* {
+        if (grid && P.gp_eq) return glob + ((i64)q * nglob + gpos[gpos0[s] + i]) * es;
         if (grid) return glob + ((i64)q * nglob + pm.off[s] + i) * es;   // PGPG(ngptotg, nfld)
         return glob + (gpos[gpos0[s] + i] * mine + q) * es;              // PSPECG(nfld, nspec2g)
     };
@@ -1667,6 +1811,7 @@ extern "C" int ect_gpnorm_trans(int handle, const void* gp, int nfld, int nproma
     if (!gp || !ave || !pmin || !pmax || nfld <= 0) return ECT_ERR_MISSING;
     const EctHostPlan& P = h->hp;
     EctDevice* d = h->d;
+    if (P.gp_eq) { ect_set_error("ect_gpnorm_trans: not implemented for the eq_regions grid-point partition"); return ECT_ERR_NOTIMPL; }
     ECT_CUDA(cudaSetDevice(d->dev));
     if (nproma <= 0) nproma = std::max(P.ngptot, 1);
     const int ngpblks = (P.ngptot + nproma - 1) / nproma;

@@ -18,6 +18,8 @@ typedef long long i64;
 // reference's R/G/D/F module globals (common/internal/tpm_dim.F90, tpm_geometry.F90,
 // tpm_distr.F90, tpm_fields.F90).
 // ---------------------------------------------------------------------------------------
+struct EctGpSeg { int lat, first, count; };       // piece of a latitude: 0-based latitude, first point on it, number of points
+
 struct EctHostPlan {
     int nsmax = 0, ndgl = 0, ndgnh = 0;
     int nranks = 1, rank = 0;
@@ -46,13 +48,24 @@ struct EctHostPlan {
     std::vector<int> leg_dst_rank_n, leg_dst_rank_s, leg_dst_rec_n, leg_dst_rec_s;   // per (local m, northern lat i)
     std::vector<int> fft_dst_rank, fft_dst_rec;                                      // per (local lat, m)
     i64 nrec_leg = 0, nrec_fft = 0;
+    // Grid-point partition of the caller's arrays.  Default: the Fourier latitude bands themselves (TRLTOG / TRGTOL
+    // are local).  gp_eq: the reference's eq_regions / LDSPLIT decomposition; then the caller's ngptot points are the
+    // pieces gp_segs and TRLTOG / TRGTOL become an all-to-all between band owners and grid-point tasks.
+    bool gp_eq = false;
+    int ngpband = 0;                         // points of this rank's latitude band (what the Fourier stage works on)
+    std::vector<int> gp_regions;             // N_REGIONS(band)
+    std::vector<EctGpSeg> gp_segs;           // my pieces, local point order
+    std::vector<EctGpSeg> gp_all_segs; std::vector<int> gp_all_seg0;    // every task's pieces (GATH_GRID / DIST_GRID)
+    // band owner side: my band points ordered by (grid-point task, its local order); xb_off[p] .. xb_off[p+1] go to task p
+    std::vector<int> xb_idx; std::vector<i64> xb_off;
+    // grid-point task side: my local points [xg_off[r], xg_off[r+1]) lie on latitudes of band owner r
+    std::vector<i64> xg_off;
     std::string err;
 };
 
-int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank);
+int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank, bool gp_eq = false);
 
 // Grid-point decomposition LDEQ_REGIONS=T, LDSPLIT=T (gp_partition.cu)
-struct EctGpSeg { int lat, first, count; };       // 0-based latitude, first point on it, number of points
 struct EctGpPartition {
     std::vector<int> regions;                     // N_REGIONS(band)
     std::vector<int> band_first, band_last;       // NFRSTLAT / NLSTLAT (0-based; a split latitude belongs to both bands)
@@ -130,6 +143,11 @@ struct EctDevice {
     // staging for host-pointer calls
     double* stage_sp = nullptr; i64 stage_sp_elems = 0;
     double* stage_gp = nullptr; i64 stage_gp_elems = 0;
+    // gp_eq: band buffer the Fourier stage works on, send / receive buffers of TRLTOG / TRGTOL, exchange tables
+    double* gpband = nullptr; i64 gpband_elems = 0;
+    double* gpsend = nullptr; i64 gpsend_elems = 0;
+    double* gprecv = nullptr; i64 gprecv_elems = 0;
+    int* xb_idx = nullptr; i64* xb_off = nullptr; i64* xg_off = nullptr;
     // chunked host path: copy streams and per-slot events
     cudaStream_t cin = nullptr, cout = nullptr;
     cudaEvent_t ev_in_ready[2] = {}, ev_cmp_done[2] = {}, ev_out_done[2] = {}, ev_sp[4] = {}, ev_c0 = nullptr, ev_c1 = nullptr;

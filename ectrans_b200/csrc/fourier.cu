@@ -387,7 +387,7 @@ static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     a.peer = d->peer_leg; a.dst_rank = d->fft_dst_rank; a.dst_rec = d->fft_dst_rec;
     a.nfs = f.nfs; a.npairs = f.npairs;
     a.nchunks = (a.npairs + FT_PAIRS_PER_CTA - 1) / FT_PAIRS_PER_CTA;
-    a.ngptot = h->hp.ngptot;
+    a.ngptot = h->hp.ngpband;      // the Fourier stage addresses the latitude band (== ngptot unless gp_eq)
     a.fp32 = f.fp32; a.adj = f.adj;
     a.rw_loc = d->rw_loc; a.n_uv_fields = 2 * f.kf_uv;
     static const char* dbg = getenv("ECT_FFT_DBG");

@@ -151,7 +151,7 @@ static void lat_bands(const std::vector<int>& nloen, int nproca, std::vector<int
     }
 }
 
-int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank) {
+int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank, bool gp_eq) {
     if (nsmax < 0 || ndgl < 2 || (ndgl & 1) || !nloen || nranks < 1 || rank < 0 || rank >= nranks) {
         ect_set_error("ect_setup: bad arguments (nsmax=%d ndgl=%d nranks=%d rank=%d)", nsmax, ndgl, nranks, rank);
         return ECT_ERR_BADARG;
@@ -306,6 +306,36 @@ int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, i
                     }
                     ++q;
                 }
+    }
+    // ---- grid-point partition of the caller's arrays ----
+    P.ngpband = P.ngptot;
+    P.gp_eq = gp_eq && nranks > 1;
+    if (P.gp_eq) {
+        EctGpPartition G;
+        int rc = ect_gp_partition(P.nloen, nranks, G);
+        if (rc) return rc;
+        P.gp_regions = G.regions;
+        P.gp_all_segs = G.segs; P.gp_all_seg0 = G.seg0;
+        P.gp_segs.assign(G.segs.begin() + G.seg0[rank], G.segs.begin() + G.seg0[rank + 1]);
+        P.ngptot = 0;
+        for (const EctGpSeg& sg : P.gp_segs) P.ngptot += sg.count;
+        // band owner side (TRLTOG sends / TRGTOL receives): the pieces of every task that lie in my band
+        P.xb_off.assign(nranks + 1, 0);
+        P.xb_idx.clear(); P.xb_idx.reserve(P.ngpband);
+        for (int p = 0; p < nranks; ++p) {
+            for (int i = G.seg0[p]; i < G.seg0[p + 1]; ++i) {
+                const EctGpSeg& sg = G.segs[i];
+                if (sg.lat < P.lat0 || sg.lat >= P.lat0 + P.nlat) continue;
+                const int b0 = P.gpoff[sg.lat - P.lat0] + sg.first;
+                for (int j = 0; j < sg.count; ++j) P.xb_idx.push_back(b0 + j);
+            }
+            P.xb_off[p + 1] = (i64)P.xb_idx.size();
+        }
+        if ((int)P.xb_idx.size() != P.ngpband) { ect_set_error("ect_setup: grid-point partition does not cover the latitude band"); return ECT_ERR_GENERIC; }
+        // grid-point task side: my pieces are ordered by latitude, the band owners hold ascending latitude ranges
+        P.xg_off.assign(nranks + 1, 0);
+        for (const EctGpSeg& sg : P.gp_segs) P.xg_off[rank_of_lat[sg.lat] + 1] += sg.count;
+        for (int r = 0; r < nranks; ++r) P.xg_off[r + 1] += P.xg_off[r];
     }
     if (P.nrec_leg >= (1LL << 24) || P.nrec_fft >= (1LL << 24) || nranks > 127) {
         ect_set_error("ect_setup: record count overflows the packed (rank, record) table (2^24 records per rank)");

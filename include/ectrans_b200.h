@@ -53,6 +53,9 @@ extern "C" {
 
 #define ECT_SETUP_HOST_ONLY 1   /* build geometry + decomposition only, no CUDA (inquire works) */
 #define ECT_SETUP_STREAM_GIVEN 2 /* opts.stream is valid even if it is 0 (the legacy default stream) */
+#define ECT_SETUP_GP_EQ_REGIONS 8 /* grid-point arrays follow the reference's default decomposition (LDEQ_REGIONS=T, LDSPLIT=T:
+                                     eq_regions bands x regions, split latitudes) instead of this library's native one (= the
+                                     Fourier latitude bands, TRLTOG / TRGTOL local); TRLTOG / TRGTOL then are NCCL all-to-alls */
 #define ECT_SETUP_LEGPOL_DEFER 4 /* do not compute the Legendre table: ect_read_legpol() fills it (CDIO_LEGPOL='readf') */
 
 #define ECT_NCCL_UID_BYTES 128
@@ -116,6 +119,16 @@ typedef struct ect_info {
 #define ECT_ARR_LEGDSTRECS  24
 #define ECT_ARR_FFTDSTRANK  25 /* int[latrow0[nlat]] rank owning m                                      */
 #define ECT_ARR_FFTDSTREC   26 /* int[latrow0[nlat]] record in that rank's Legendre-side buffer         */
+/* grid-point partition of the caller's arrays (TRANS_INQ KSTA / KONL / N_REGIONS; 0-based) */
+#define ECT_ARR_GPSEGS      27 /* int[3 * npieces]: (latitude, first point, count) of this task's pieces, local order;
+                                  call with capacity 0 ... the count is ect_inquire_array(..., ECT_ARR_NGPSEGS) */
+#define ECT_ARR_NGPSEGS     28 /* int[1]  number of pieces                                            */
+/* TRLTOG / TRGTOL message tables of the eq_regions partition (test access): the message between band owner r and
+   task p carries the band points XBIDX[XBOFF[p] .. XBOFF[p+1]) of r = the local points [XGOFF[r], XGOFF[r+1]) of p */
+#define ECT_ARR_XBIDX       30 /* int[points of the latitude band]  */
+#define ECT_ARR_XBOFF       31 /* long long[nranks + 1]             */
+#define ECT_ARR_XGOFF       32 /* long long[nranks + 1]             */
+#define ECT_ARR_NREGIONS    29 /* int[nranks] N_REGIONS(band), zero padded (ECT_SETUP_GP_EQ_REGIONS only) */
 
 typedef struct ect_inv_args {
     int memspace;                 /* ECT_MEM_HOST / ECT_MEM_DEVICE                          */

@@ -18,15 +18,16 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("world,no_p2p", [(2, 0), (2, 1), (4, 0)])
-def test_distributed_equals_single(built, world, no_p2p):
+@pytest.mark.parametrize("world,no_p2p,gp", [(2, 0, "latbands"), (2, 1, "latbands"), (4, 0, "latbands"),
+                                             (2, 0, "eq_regions"), (4, 0, "eq_regions"), (8, 0, "eq_regions")])
+def test_distributed_equals_single(built, world, no_p2p, gp):
     """no_p2p = 0: GEMM / FFT epilogues write records into the consumer rank's buffer over NVLink (CUDA IPC),
     the transposition is only a barrier; no_p2p = 1: NCCL grouped send/recv all-to-all-v."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    env = dict(os.environ, ECT_NO_P2P=str(no_p2p))
+    env = dict(os.environ, ECT_NO_P2P=str(no_p2p), ECT_DIST_GP=gp)      # eq_regions: TRLTOG / TRGTOL as NCCL all-to-alls
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world + 10 * no_p2p), os.path.join(ROOT, "tools", "dist_check.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world + 10 * no_p2p + (20 if gp == "eq_regions" else 0)), os.path.join(ROOT, "tools", "dist_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DIST_CHECK_OK" in out.stdout

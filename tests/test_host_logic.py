@@ -213,3 +213,33 @@ def test_eq_regions_known_partitions():
     for n in range(1, 300):
         r = eo.eq_regions(n)
         assert sum(r) == n and (n % 2 == 1 or r == r[::-1]) and (n < 3 or (r[0] == 1 and r[-1] == 1))
+
+
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+def test_trltog_tables_eq_regions(eb, world):
+    """TRLTOG / TRGTOL with the reference's grid-point decomposition, host logic only: the message a band owner packs
+    for a task (band points XBIDX[XBOFF[p] ..]) must be, point for point, what the task expects from that owner
+    (its local points [XGOFF[r], XGOFF[r+1])); every band point travels exactly once."""
+    T, N = 47, 48
+    nloen = eb.octahedral_nloen(N)
+    trs = [eb.Transform(T, nloen, nranks=world, rank=r, host_only=True, gp_partition="eq_regions") for r in range(world)]
+    reg, segs = eb.gridpoint_partition(nloen, world)
+    latoff = np.concatenate([[0], np.cumsum(nloen)])
+    assert sum(t.ngptot for t in trs) == int(nloen.sum())
+    local_global = []          # task -> global index of its local points
+    for p, t in enumerate(trs):
+        np.testing.assert_array_equal(t.gp_segs, segs[p])
+        np.testing.assert_array_equal(t.n_regions[:len(reg)], reg)
+        local_global.append(np.concatenate([latoff[l] + f + np.arange(c) for l, f, c in t.gp_segs]) if len(t.gp_segs) else np.zeros(0, int))
+        assert t.ngptot == local_global[-1].size
+    for r, t in enumerate(trs):
+        band0 = latoff[t.info.lat0]
+        nband = int(latoff[t.info.lat0 + t.info.nlat] - band0)
+        xb_idx = t._arr(30, np.int32, nband); xb_off = t._arr(31, np.int64, world + 1)
+        assert sorted(xb_idx.tolist()) == list(range(nband))
+        for p, tp in enumerate(trs):
+            xg_off = tp._arr(32, np.int64, world + 1)
+            sent = band0 + xb_idx[xb_off[p]:xb_off[p + 1]]
+            np.testing.assert_array_equal(sent, local_global[p][xg_off[r]:xg_off[r + 1]])
+    for t in trs:
+        t.release()

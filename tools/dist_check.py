@@ -22,7 +22,8 @@ def fresh_uid():                      # one NCCL id per communicator (= per dist
 uid = fresh_uid()
 T, N, nuv, nsc = 79, 80, 3, 4
 nloen = eb.octahedral_nloen(N)
-tr = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=uid)
+GP = os.environ.get("ECT_DIST_GP", "latbands")     # "eq_regions": the reference's grid-point decomposition, TRLTOG / TRGTOL as all-to-alls
+tr = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=uid, gp_partition=GP)
 s = eo.setup(T, 2 * N, nloen)
 vor = eo.random_spectral(s, nuv, 1, zero00=True); div = eo.random_spectral(s, nuv, 2, zero00=True); sc = eo.random_spectral(s, nsc, 3)
 ref = eo.inv_trans(s, vor, div, sc, scders=True)
@@ -30,8 +31,9 @@ ref = eo.inv_trans(s, vor, div, sc, scders=True)
 idx = np.concatenate([np.arange(s.nasm0[m], s.nasm0[m] + 2 * (T - m + 1)) for m in tr.myms]) if tr.nump else np.zeros(0, int)
 loc = lambda a: np.ascontiguousarray(a[:, idx].T)
 gp = tr.inv_trans(loc(vor), loc(div), loc(sc), scders=True)
-g0 = int(s.latoff[tr.info.lat0]) if tr.info.nlat else 0
-refloc = ref[:, g0:g0 + tr.ngptot]
+gidx = np.concatenate([s.latoff[l] + f + np.arange(c) for l, f, c in tr.gp_segs]) if len(tr.gp_segs) else np.zeros(0, int)
+assert gidx.size == tr.ngptot
+refloc = ref[:, gidx]                                # this task's grid points (pieces of latitudes)
 rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 e_inv = rel(gp[0], refloc)
 ov, od, os_ = tr.dir_trans(np.ascontiguousarray(gp[:, :2 * nuv + nsc]), nuv, nsc)
@@ -68,9 +70,10 @@ smine = [f for f in range(nsc) if f % world == rank]
 bit = min(bit, float(np.array_equal(gs, z(s1)[:, smine])))
 # ---- GPNORM_TRANS (bit identical across decompositions: latitudes are added in global order), VORDIV_TO_UV on the
 # task's wavenumbers, Legendre cache file per task ----
-a_n, lo_n, hi_n = tr.gpnorm_trans(gp)
-a_1, lo_1, hi_1 = tr1.gpnorm_trans(g1)
-bit = min(bit, float(np.array_equal(a_n, a_1) and np.array_equal(lo_n, lo_1) and np.array_equal(hi_n, hi_1)))
+if GP == "latbands":
+    a_n, lo_n, hi_n = tr.gpnorm_trans(gp)
+    a_1, lo_1, hi_1 = tr1.gpnorm_trans(g1)
+    bit = min(bit, float(np.array_equal(a_n, a_1) and np.array_equal(lo_n, lo_1) and np.array_equal(hi_n, hi_1)))
 un, vn = tr.vordiv_to_uv(loc(vor), loc(div))
 u1, v1_ = tr1.vordiv_to_uv(T_(vor), T_(div))
 if tr.nump:
@@ -78,9 +81,9 @@ if tr.nump:
 import tempfile
 path = os.path.join(tempfile.gettempdir(), "legpol_%d_of_%d.bin" % (rank, world))
 tr.release()
-trw = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=fresh_uid(), legpol_write=path)
+trw = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=fresh_uid(), legpol_write=path, gp_partition=GP)
 trw.release()
-tr = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=fresh_uid(), legpol_read=path)
+tr = eb.Transform(T, nloen, nranks=world, rank=rank, device=local, nccl_uid=fresh_uid(), legpol_read=path, gp_partition=GP)
 gp2 = tr.inv_trans(loc(vor), loc(div), loc(sc), scders=True)
 bit = min(bit, float(np.array_equal(gp2, gp)))
 os.remove(path)
