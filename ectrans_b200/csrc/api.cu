@@ -1811,7 +1811,6 @@ extern "C" int ect_gpnorm_trans(int handle, const void* gp, int nfld, int nproma
     if (!gp || !ave || !pmin || !pmax || nfld <= 0) return ECT_ERR_MISSING;
     const EctHostPlan& P = h->hp;
     EctDevice* d = h->d;
-    if (P.gp_eq) { ect_set_error("ect_gpnorm_trans: not implemented for the eq_regions grid-point partition"); return ECT_ERR_NOTIMPL; }
     ECT_CUDA(cudaSetDevice(d->dev));
     if (nproma <= 0) nproma = std::max(P.ngptot, 1);
     const int ngpblks = (P.ngptot + nproma - 1) / nproma;
@@ -1824,6 +1823,22 @@ extern "C" int ect_gpnorm_trans(int handle, const void* gp, int nfld, int nproma
         ECT_CUDA(cudaMemcpyAsync(d->stage_gp, gp, (size_t)elems * es, cudaMemcpyHostToDevice, d->stream));
         dgp = d->stage_gp;
     }
+    int nproma_k = nproma;
+    if (P.gp_eq) {
+        // like the reference (gpnorm_trans_ctl_mod.F90:166-168): TRGTOL first, then whole latitudes are summed by their band owner
+        if ((rc = gp_exchange_setup(h, nfld))) return rc;
+        std::vector<double*> hb(nfld); std::vector<i64> hs(nfld, (i64)nfld * nproma);
+        for (int f = 0; f < nfld; ++f) hb[f] = (double*)((char*)dgp + (size_t)f * nproma * es);
+        char* tab = nullptr;
+        ECT_CUDA(cudaMalloc(&tab, nfld * (sizeof(double*) + sizeof(i64))));
+        ECT_CUDA(cudaMemcpyAsync(tab, hb.data(), nfld * sizeof(double*), cudaMemcpyHostToDevice, d->stream));
+        ECT_CUDA(cudaMemcpyAsync(tab + nfld * sizeof(double*), hs.data(), nfld * sizeof(i64), cudaMemcpyHostToDevice, d->stream));
+        rc = gp_exchange(h, nfld, es, 0, (double* const*)tab, (const i64*)(tab + nfld * sizeof(double*)), nproma);
+        ECT_CUDA(cudaStreamSynchronize(d->stream));
+        ECT_CUDA(cudaFree(tab));
+        if (rc) return rc;
+        dgp = d->gpband; nproma_k = std::max(P.ngpband, 1);
+    }
     const i64 nwork = (i64)nfld * P.ndgl + 2 * (i64)nfld * std::max(P.nlat, 1) + 2 * (i64)nfld;
     double* w = nullptr;
     ECT_CUDA(cudaMalloc(&w, (size_t)nwork * sizeof(double)));
@@ -1832,8 +1847,8 @@ extern "C" int ect_gpnorm_trans(int handle, const void* gp, int nfld, int nproma
     ECT_CUDA(cudaMemsetAsync(aveg, 0, (size_t)nfld * P.ndgl * sizeof(double), d->stream));
     if (P.nlat > 0) {
         dim3 grid(P.nlat, nfld);
-        if (es == 4) k_gpnorm_lat<true><<<grid, 256, 0, d->stream>>>(dgp, nfld, nproma, d->gpoff, d->nloen, d->rw_loc, P.lat0, P.ndgl, aveg, mn, mx);
-        else k_gpnorm_lat<false><<<grid, 256, 0, d->stream>>>(dgp, nfld, nproma, d->gpoff, d->nloen, d->rw_loc, P.lat0, P.ndgl, aveg, mn, mx);
+        if (es == 4) k_gpnorm_lat<true><<<grid, 256, 0, d->stream>>>(dgp, nfld, nproma_k, d->gpoff, d->nloen, d->rw_loc, P.lat0, P.ndgl, aveg, mn, mx);
+        else k_gpnorm_lat<false><<<grid, 256, 0, d->stream>>>(dgp, nfld, nproma_k, d->gpoff, d->nloen, d->rw_loc, P.lat0, P.ndgl, aveg, mn, mx);
     }
     k_gpnorm_fold<<<(nfld + 127) / 128, 128, 0, d->stream>>>(nfld, P.nlat, mn, mx, fold);
     if (ave_only) {      // LDAVE_ONLY: PMIN / PMAX already hold the local extrema (gpnorm_trans_ctl_mod.F90:243-245)

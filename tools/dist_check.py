@@ -70,10 +70,9 @@ smine = [f for f in range(nsc) if f % world == rank]
 bit = min(bit, float(np.array_equal(gs, z(s1)[:, smine])))
 # ---- GPNORM_TRANS (bit identical across decompositions: latitudes are added in global order), VORDIV_TO_UV on the
 # task's wavenumbers, Legendre cache file per task ----
-if GP == "latbands":
-    a_n, lo_n, hi_n = tr.gpnorm_trans(gp)
-    a_1, lo_1, hi_1 = tr1.gpnorm_trans(g1)
-    bit = min(bit, float(np.array_equal(a_n, a_1) and np.array_equal(lo_n, lo_1) and np.array_equal(hi_n, hi_1)))
+a_n, lo_n, hi_n = tr.gpnorm_trans(gp)
+a_1, lo_1, hi_1 = tr1.gpnorm_trans(g1)
+bit = min(bit, float(np.array_equal(a_n, a_1) and np.array_equal(lo_n, lo_1) and np.array_equal(hi_n, hi_1)))
 un, vn = tr.vordiv_to_uv(loc(vor), loc(div))
 u1, v1_ = tr1.vordiv_to_uv(T_(vor), T_(div))
 if tr.nump:
