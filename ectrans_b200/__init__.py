@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "lib", "libectrans_b200.so")
+_LIBPATH = os.environ.get("ECTRANS_B200_LIB") or os.path.join(_HERE, "lib", "libectrans_b200.so")    # override: A/B builds
 _lib = None
 
 ECT_MEM_HOST, ECT_MEM_DEVICE = 0, 1

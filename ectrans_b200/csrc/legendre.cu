@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_leinv_tma(LegArgs a) {
         const int nvs = min(INV_KC, lm.ils - k0), nva = max(0, min(INV_KC, lm.ila - k0));
         if (lane == 0) mbar_expect_tx(&s_full[buf], (unsigned)(nvs + nva) * (LEG_BM * (unsigned)sizeof(double) + rowb));
         __syncwarp();
-        static_assert(4 * INV_KC == 32, "one (tile, row) per lane");
+        if (4 * INV_KC != 32) __trap();      // one (tile, row) per lane: this variant exists for INV_KC = 8 only
         const int tile4 = lane / INV_KC, row = lane % INV_KC;
         const int k = k0 + row;
         const bool anti = tile4 & 1, isx = tile4 >= 2;
