@@ -171,7 +171,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ms per INV_TRANS+DIR_TRANS step", "value": v, "unit": "ms",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64" if prec == "dp" else "f32 at the boundary and in the Fourier stage, f64 DMMA contraction", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.config, "fields": 2 * nuv + nsc},
             "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample, "detail": detail},
             "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

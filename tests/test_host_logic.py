@@ -243,3 +243,16 @@ def test_trltog_tables_eq_regions(eb, world):
             np.testing.assert_array_equal(sent, local_global[p][xg_off[r]:xg_off[r + 1]])
     for t in trs:
         t.release()
+
+
+def test_bench_reference_arm_runs_without_gpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) must work on a box without a GPU and
+    print one JSON line carrying the contract's keys."""
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "T79_O80_L10",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "ms" and line["higher_is_better"] is False
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
