@@ -821,3 +821,23 @@ def test_legendre_cache_file_reference_format(eb, tmp_path):
     bad = str(tmp_path / "bad.bin"); open(bad, "wb").write(b"LEGPOLBF" + raw[8:])
     with pytest.raises(eb.EctError, match="WRONG LABEL"):
         eb.Transform(T, nloen, legpol_read=bad)
+
+
+def test_gpnorm_vordiv_single_precision(eb):
+    """sp handles: float arrays at the boundary of GPNORM_TRANS / VORDIV_TO_UV (tolerance 1e-5, north_star)."""
+    T, N = 63, 64
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen, precision="sp")
+    s = eo.setup(T, 2 * N, nloen, tables=False)
+    rng = np.random.default_rng(5)
+    flat = (rng.normal(size=(3, tr.ngptot)) + 2.0).astype(np.float32)
+    ave, mn, mx = eo.gpnorm_trans(s, flat.astype(np.float64))
+    a, lo, hi = tr.gpnorm_trans(flat[None])
+    np.testing.assert_allclose(a, ave, rtol=1e-12)          # sums run in fp64 on the float data
+    np.testing.assert_array_equal(lo, mn); np.testing.assert_array_equal(hi, mx)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)
+    vor = f32(eo.random_spectral(s, 2, 1, zero00=True)); div = f32(eo.random_spectral(s, 2, 2, zero00=True))
+    ur, vr = eo.vordiv_to_uv(s, vor, div)
+    u, v = tr.vordiv_to_uv(T_(vor).astype(np.float32), T_(div).astype(np.float32))
+    assert u.dtype == np.float32 and rel(u.T, ur) < 1e-6 and rel(v.T, vr) < 1e-6
+    tr.release()

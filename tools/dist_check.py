@@ -36,7 +36,14 @@ assert gidx.size == tr.ngptot
 refloc = ref[:, gidx]                                # this task's grid points (pieces of latitudes)
 rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 e_inv = rel(gp[0], refloc)
+# NPROMA-blocked arrays (ragged last block) must carry the same numbers
+npr = 37
+gpb = tr.inv_trans(loc(vor), loc(div), loc(sc), scders=True, nproma=npr)
+unb = gpb.transpose(1, 0, 2).reshape(gpb.shape[1], -1)[:, :tr.ngptot]
+blocked_same = float(np.array_equal(unb, gp[0]))
 ov, od, os_ = tr.dir_trans(np.ascontiguousarray(gp[:, :2 * nuv + nsc]), nuv, nsc)
+obv, obd, obs = tr.dir_trans(np.ascontiguousarray(gpb[:, :2 * nuv + nsc]), nuv, nsc, nproma=npr)
+blocked_same = min(blocked_same, float(np.array_equal(obv, ov) and np.array_equal(obd, od) and np.array_equal(obs, os_)))
 rv, rd, rs = eo.dir_trans(s, ref[:2 * nuv + nsc], nuv, nsc)
 e_dir = max(rel(ov.T, rv[:, idx]), rel(od.T, rd[:, idx]), rel(os_.T, rs[:, idx])) if tr.nump else 0.0
 nrm = tr.specnorm(loc(sc))
@@ -54,7 +61,7 @@ dv = tr.dist_spec(T_(vor) if rank == 0 else None, nuv, kfrom=0)
 e_dist = float(np.abs(dv - loc(vor)).max()) if tr.nump else 0.0
 dg = tr.dist_grid(ref[:nfg] if rank == 0 else None, nfg, kfrom=0)
 e_dist = max(e_dist, float(np.abs(dg[0] - refloc[:nfg]).max()))
-bit = 1.0
+bit = blocked_same
 tr1 = eb.Transform(T, nloen, device=local)                          # the same transform on one rank
 g1 = tr1.inv_trans(T_(vor), T_(div), T_(sc), scders=True)
 mine = [f for f in range(nfg) if kto[f] == rank]
