@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
     "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec", "ect_inv_transad", "ect_dir_transad",
     "ect_gpnorm_trans", "ect_vordiv_to_uv", "ect_inquire_rpnm", "ect_trans_pnm", "ect_write_legpol", "ect_read_legpol",
-    "ect_gridpoint_partition",
+    "ect_gridpoint_partition", "ect_specnorm_met",
 ]
 
 
@@ -110,6 +110,7 @@ def lib():
         L.ect_inv_transad.argtypes = [C.c_int, C.POINTER(_InvArgs)]
         L.ect_dir_transad.argtypes = [C.c_int, C.POINTER(_DirArgs)]
         L.ect_specnorm.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ect_specnorm_met.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ect_get_timings.argtypes = [C.c_int, C.POINTER(Timings)]
         L.ect_debug_get_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
         L.ect_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -455,15 +456,18 @@ class Transform:
         self._keep = keep
         _check(lib().ect_dir_trans(self.handle, C.byref(a)), "ect_dir_trans")
 
-    def specnorm(self, spec):
-        """SPECNORM: spectral L2 norm per field (global over ranks)."""
+    def specnorm(self, spec, pmet=None):
+        """SPECNORM: spectral L2 norm per field (global over ranks); pmet: optional metric (0:nsmax)."""
         dev = _is_torch(spec)
         nf = int(spec.shape[1])
         if not dev:
             spec = np.ascontiguousarray(spec, dtype=self.dtype)
         out = np.zeros(nf)
-        _check(lib().ect_specnorm(self.handle, _ptr(spec), nf, ECT_MEM_DEVICE if dev else ECT_MEM_HOST,
-                                  out.ctypes.data), "ect_specnorm")
+        met = None if pmet is None else np.ascontiguousarray(pmet, dtype=np.float64)
+        if met is not None and met.size != self.nsmax + 1:
+            raise EctError("specnorm: pmet must have nsmax + 1 entries")
+        _check(lib().ect_specnorm_met(self.handle, _ptr(spec), nf, ECT_MEM_DEVICE if dev else ECT_MEM_HOST,
+                                      None if met is None else met.ctypes.data, out.ctypes.data), "ect_specnorm")
         return out
 
     def gpnorm_trans(self, gp, nproma=0, ave_only=False, pmin=None, pmax=None):

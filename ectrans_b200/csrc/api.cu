@@ -1409,23 +1409,29 @@ extern "C" int ect_get_timings(int handle, ect_timings* t) {
 // ---------------------------------------------------------------------------------------
 // SPECNORM: cpu/internal/spnormd_mod.F90:36-51, spnorm_ctl_mod.F90:56-57
 // ---------------------------------------------------------------------------------------
+// one thread per (local wavenumber, field): the n-sum in the reference's order (spnormd_mod.F90:36-51); the sums over m
+// are added on the host in ascending m (spnorm_ctl_mod.F90:56-57), so the norm does not depend on the decomposition
 template <bool FP32>
-__global__ void k_specnorm(const double* __restrict__ sp, int nfld, int nspec2, int z0, int z1, int chunk,
-                           double* __restrict__ acc) {
+__global__ void k_specnorm(const double* __restrict__ sp, int nfld, int T, const EctLegM* __restrict__ legm,
+                           const int* __restrict__ nasm0, const double* __restrict__ pmet, double* __restrict__ zgm) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nfld) return;
-    const int i0 = blockIdx.y * chunk, i1 = min(i0 + chunk, nspec2);
+    const int m = legm[blockIdx.y].m, base = nasm0[blockIdx.y];
     double s = 0.0;
-    for (int i = i0; i < i1; ++i) {
-        const double v = FP32 ? (double)reinterpret_cast<const float*>(sp)[(long long)i * nfld + f] : sp[(long long)i * nfld + f];
-        const bool zonal = (i >= z0 && i < z1);
-        if (zonal) { if (((i - z0) & 1) == 0) s += v * v; }
-        else s += 2.0 * v * v;
+    for (int n = m; n <= T; ++n) {
+        const long long i = base + 2 * (n - m);
+        const double re = FP32 ? (double)reinterpret_cast<const float*>(sp)[i * nfld + f] : sp[i * nfld + f];
+        const double w = pmet ? pmet[n] : 1.0;
+        if (m == 0) s += w * re * re;
+        else {
+            const double im = FP32 ? (double)reinterpret_cast<const float*>(sp)[(i + 1) * nfld + f] : sp[(i + 1) * nfld + f];
+            s += 2.0 * w * (re * re + im * im);
+        }
     }
-    atomicAdd(acc + f, s);
+    zgm[(long long)f * (T + 1) + m] = s;
 }
 
-extern "C" int ect_specnorm(int handle, const double* spec, int nfld, int memspace, double* norms) {
+extern "C" int ect_specnorm_met(int handle, const double* spec, int nfld, int memspace, const double* pmet, double* norms) {
     EctHandle* h = get_handle(handle);
     if (!h || !h->d) { ect_set_error("ect_specnorm: invalid handle"); return ECT_ERR_HANDLE; }
     if (!spec || !norms || nfld <= 0) return ECT_ERR_MISSING;
@@ -1439,24 +1445,38 @@ extern "C" int ect_specnorm(int handle, const double* spec, int nfld, int memspa
         ECT_CUDA(cudaMemcpyAsync(d->stage_sp, spec, (size_t)nfld * P.nspec2 * (h->precision == ECT_PREC_SP ? 4 : 8), cudaMemcpyHostToDevice, d->stream));
         dsp = d->stage_sp;
     }
-    if (d->normbuf_n < nfld) {
+    const int nm = P.nsmax + 1;
+    const int need = nfld * nm + nm;
+    if (d->normbuf_n < need) {
         if (d->normbuf) cudaFree(d->normbuf);
-        ECT_CUDA(cudaMalloc(&d->normbuf, nfld * sizeof(double)));
-        d->normbuf_n = nfld;
+        ECT_CUDA(cudaMalloc(&d->normbuf, (size_t)need * sizeof(double)));
+        d->normbuf_n = need;
     }
-    ECT_CUDA(cudaMemsetAsync(d->normbuf, 0, nfld * sizeof(double), d->stream));
-    const int z0 = P.nasm0[0] >= 0 ? P.nasm0[0] : -1, z1 = z0 >= 0 ? z0 + 2 * (P.nsmax + 1) : -1;
-    if (P.nspec2 > 0) {
-        const int chunk = 2048;
-        dim3 grid((nfld + 127) / 128, (P.nspec2 + chunk - 1) / chunk);
-        if (h->precision == ECT_PREC_SP) k_specnorm<true><<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nspec2, z0, z1, chunk, d->normbuf);
-        else k_specnorm<false><<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nspec2, z0, z1, chunk, d->normbuf);
+    double* zgm = d->normbuf; double* dmet = nullptr;
+    ECT_CUDA(cudaMemsetAsync(zgm, 0, (size_t)nfld * nm * sizeof(double), d->stream));
+    if (pmet) {
+        dmet = d->normbuf + (size_t)nfld * nm;
+        ECT_CUDA(cudaMemcpyAsync(dmet, pmet, nm * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     }
-    if (P.nranks > 1) ECT_NCCL(ncclAllReduce(d->normbuf, d->normbuf, nfld, ncclDouble, ncclSum, (ncclComm_t)d->comm, d->stream));
-    ECT_CUDA(cudaMemcpyAsync(norms, d->normbuf, nfld * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    if (P.nump > 0) {
+        dim3 grid((nfld + 127) / 128, P.nump);
+        if (h->precision == ECT_PREC_SP) k_specnorm<true><<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nsmax, d->legm, d->nasm0, dmet, zgm);
+        else k_specnorm<false><<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nsmax, d->legm, d->nasm0, dmet, zgm);
+    }
+    // every (m, field) sum lives on exactly one rank: adding zeros is exact
+    if (P.nranks > 1) ECT_NCCL(ncclAllReduce(zgm, zgm, (size_t)nfld * nm, ncclDouble, ncclSum, (ncclComm_t)d->comm, d->stream));
+    std::vector<double> hz((size_t)nfld * nm);
+    ECT_CUDA(cudaMemcpyAsync(hz.data(), zgm, hz.size() * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
     ECT_CUDA(cudaStreamSynchronize(d->stream));
-    for (int i = 0; i < nfld; ++i) norms[i] = sqrt(norms[i]);
+    for (int f = 0; f < nfld; ++f) {
+        double t = 0.0;
+        for (int m = 0; m < nm; ++m) t += hz[(size_t)f * nm + m];       // PNORM = SUM(ZGM, DIM=2)
+        norms[f] = sqrt(t);
+    }
     return ECT_SUCCESS;
+}
+extern "C" int ect_specnorm(int handle, const double* spec, int nfld, int memspace, double* norms) {
+    return ect_specnorm_met(handle, spec, nfld, memspace, nullptr, norms);
 }
 
 // ---------------------------------------------------------------------------------------

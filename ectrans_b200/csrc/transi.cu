@@ -319,8 +319,7 @@ int trans_specnorm(struct SpecNorm_t* a) {
     if (!a || !a->trans || !a->rspec || !a->rnorm || a->nfld <= 0) return TRANS_MISSING_ARG;
     if (a->count > 0) return TRANS_STALE_ARG;
     a->count++;
-    if (a->rmet) return TRANS_NOTIMPL;
-    return ect_specnorm(a->trans->handle, a->rspec, a->nfld, ECT_MEM_HOST, a->rnorm);
+    return ect_specnorm_met(a->trans->handle, a->rspec, a->nfld, ECT_MEM_HOST, a->rmet, a->rnorm);
 }
 
 int trans_delete(struct Trans_t* t) {

@@ -182,6 +182,10 @@ int ect_inquire_array(int handle, int which, void* out, long long capacity_elems
 int ect_inv_trans(int handle, const ect_inv_args* args);
 int ect_dir_trans(int handle, const ect_dir_args* args);
 int ect_specnorm(int handle, const double* spec, int nfld, int memspace, double* norms /* host, nfld */);
+/* SPECNORM with the optional metric PMET(0:NSMAX) (host, may be NULL).  The n-sums of every wavenumber and then the
+ * wavenumbers are added in the reference's order (spnormd_mod.F90:36-51, spnorm_ctl_mod.F90:56-57): the norms are bit
+ * identical across decompositions. */
+int ect_specnorm_met(int handle, const double* spec, int nfld, int memspace, const double* pmet, double* norms);
 int ect_get_timings(int handle, ect_timings* t);
 /* INV_TRANSAD / DIR_TRANSAD: adjoints for the inner products of the reference's adjoint tests (grid: plain sum;
  * spectral: weight 2 for m > 0, 1 for the real parts of m = 0).  Replace src/trans/include/ectrans/inv_transad.h,

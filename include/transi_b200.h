@@ -112,7 +112,7 @@ struct VorDivToUV_t {
 struct SpecNorm_t {
   const double* rspec;   /* [nspec2][nfld] */
   int nmaster;
-  const int* rmet;       /* must be NULL   */
+  const double* rmet;    /* metric (0:nsmax), optional */
   double* rnorm;         /* [nfld]         */
   int nfld;
   struct Trans_t* trans;

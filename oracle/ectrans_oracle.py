@@ -441,15 +441,16 @@ def spec_m(s: Setup, sp: np.ndarray, m: int) -> np.ndarray:
     return blk[:, 0::2] + 1j * blk[:, 1::2]
 
 
-def specnorm(s: Setup, sp: np.ndarray) -> np.ndarray:
-    """cpu/internal/spnormd_mod.F90:36-51 + spnorm_ctl_mod.F90:56-57."""
+def specnorm(s: Setup, sp: np.ndarray, pmet=None) -> np.ndarray:
+    """cpu/internal/spnormd_mod.F90:36-51 + spnorm_ctl_mod.F90:56-57; pmet: optional metric (0:nsmax)."""
     out = np.zeros(sp.shape[0])
     for m in range(s.nsmax + 1):
         c = spec_m(s, sp, m)
+        w = np.ones(s.nsmax + 1 - m) if pmet is None else np.asarray(pmet, dtype=np.float64)[m:]
         if m == 0:
-            out += np.sum(c.real ** 2, axis=1)
+            out += np.sum(w * c.real ** 2, axis=1)
         else:
-            out += 2.0 * np.sum(np.abs(c) ** 2, axis=1)
+            out += 2.0 * np.sum(w * np.abs(c) ** 2, axis=1)
     return np.sqrt(out)
 
 

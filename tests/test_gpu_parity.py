@@ -108,6 +108,8 @@ def test_inv_dir_against_oracle(eb, T, N, nuv, nsc, opts, nproma):
         assert np.all(ov[0] == 0.0) and np.all(od[0] == 0.0)
     if nsc:
         assert rel(tr.specnorm(T_(sc)), eo.specnorm(s, sc)) < 1e-13
+        pmet = 1.0 / (1.0 + np.arange(T + 1.0)) ** 2         # SPECNORM's optional metric PMET(0:NSMAX)
+        assert rel(tr.specnorm(T_(sc), pmet=pmet), eo.specnorm(s, sc, pmet)) < 1e-13
     tr.release()
 
 

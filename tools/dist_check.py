@@ -77,6 +77,7 @@ smine = [f for f in range(nsc) if f % world == rank]
 bit = min(bit, float(np.array_equal(gs, z(s1)[:, smine])))
 # ---- GPNORM_TRANS (bit identical across decompositions: latitudes are added in global order), VORDIV_TO_UV on the
 # task's wavenumbers, Legendre cache file per task ----
+bit = min(bit, float(np.array_equal(tr.specnorm(os_), tr1.specnorm(s1))))        # SPECNORM: m sums added in order
 a_n, lo_n, hi_n = tr.gpnorm_trans(gp)
 a_1, lo_1, hi_1 = tr1.gpnorm_trans(g1)
 bit = min(bit, float(np.array_equal(a_n, a_1) and np.array_equal(lo_n, lo_1) and np.array_equal(hi_n, hi_1)))
