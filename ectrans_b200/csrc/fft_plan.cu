@@ -143,10 +143,15 @@ int EctFftTables::get_latplan(int nlon, int km) {
         lp.ctw_off = (int)cz_pool.size();
         for (int a = 0; a < ECT_TW1_LEN(2 * N); ++a) cz_pool.push_back(expi2pi((128LL * a) % (2LL * N), 2LL * N));
         for (int b = 0; b < ECT_TW2_LEN; ++b) cz_pool.push_back(expi2pi(b % (2LL * N), 2LL * N));
-        auto chirp = [&](long long d) -> double2 {   // c[d] for any integer d (even N: period N, even symmetry)
-            long long j = std::llabs(d) % N;
-            if (j > N / 2) j = N - j;
-            return cz_pool[lp.chirp_off + (int)j];
+        // c[d] for any integer d from the stored c[0 .. N/2]: c is even, c[j + N] = (-1)^N c[j] and hence
+        // c[N - j] = (-1)^N c[j] -- for odd row lengths (classic reduced grids) the reflections flip the sign
+        auto chirp = [&](long long d) -> double2 {
+            long long j = std::llabs(d) % (2LL * N);
+            double sg = 1.0;
+            if (j >= N) { j -= N; if (N & 1) sg = -sg; }
+            if (j > N / 2) { j = N - j; if (N & 1) sg = -sg; }
+            const double2 c = cz_pool[lp.chirp_off + (int)j];
+            return make_double2(sg * c.x, sg * c.y);
         };
         const EctFftPlan& pm = plans[lp.plan];
         for (int dir = 0; dir < 2; ++dir) {

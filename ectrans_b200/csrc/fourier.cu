@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
     const int len = plan_n;
     const int N = lp.nlon, km = lp.km;
     const bool staged = !a.nostage;
+    const bool oddrefl = (N & 1) != 0;     // odd row length (chirp-z always): c[N - j] = -c[j]
     const FtLayout lay = ft_layout(INVERSE, blue, len, N, km, NROOTS, (int)sizeof(C), FP32 ? 4 : 8, !staged);
     C* data = reinterpret_cast<C*>(smraw);
     double2* stage = reinterpret_cast<double2*>(smraw + lay.stage);
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
                     const int j = j0 + i * nthr;
                     ch[i] = c_make<C>(1, 0); pj[i] = 0; xa[i] = xb[i] = 0;
                     if (j < N) {
-                        if (blue) ch[i] = g_chirp[j > N / 2 ? N - j : j];
+                        if (blue) { ch[i] = g_chirp[j > N / 2 ? N - j : j]; if (oddrefl && j > N / 2) ch[i] = c_make<C>(-ch[i].x, -ch[i].y); }
                         else pj[i] = perm[j];
                         if (!staged) {
                             const int g = g0 + j;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
                     const int j = j0 + i * nthr;
                     if (j < N) {
                         x[i] = data[ECT_PAD(j)];
-                        if (blue) ch[i] = chirp_tab[j > N / 2 ? N - j : j];
+                        if (blue) { ch[i] = chirp_tab[j > N / 2 ? N - j : j]; if (oddrefl && j > N / 2) ch[i] = c_make<C>(-ch[i].x, -ch[i].y); }
                     }
                 }
 #pragma unroll

@@ -81,8 +81,10 @@ ECT_HD void ftinv_load(double2* data, const double* __restrict__ fb, const EctPa
 ECT_HD double2 ftinv_out(const double2* data, const EctPairCtx& c, int j) {
     if (!c.bluestein) return data[ECT_PAD(j)];
     long long jj = j;
-    if (jj > c.nlon / 2) jj = c.nlon - jj;
-    return c_mul(c.chirp[jj], data[ECT_PAD(j)]);   // t = k - o0 with o0 = 0
+    double sg = 1.0;        // c[N - j] = (-1)^N c[j]
+    if (jj > c.nlon / 2) { jj = c.nlon - jj; if (c.nlon & 1) sg = -1.0; }
+    const double2 ch = c.chirp[jj];
+    return c_mul(make_double2(sg * ch.x, sg * ch.y), data[ECT_PAD(j)]);   // t = k - o0 with o0 = 0
 }
 
 // ---- direct, phase 1: load two real rows (swapped: sign - transform on the sign + core) ----
@@ -91,8 +93,9 @@ ECT_HD void ftdir_put(double2* data, const EctPairCtx& c, int j, double va, doub
         data[ECT_PAD((int)c.perm[j])] = make_double2(vb, va);
     } else {
         long long jj = j;
-        if (jj > c.nlon / 2) jj = c.nlon - jj;
-        const double2 a = c_mul(make_double2(vb, va), c.chirp[jj]);
+        double sg = 1.0;
+        if (jj > c.nlon / 2) { jj = c.nlon - jj; if (c.nlon & 1) sg = -1.0; }
+        const double2 a = c_mul(make_double2(sg * vb, sg * va), c.chirp[jj]);
         data[ECT_PAD(j)] = make_double2(a.y, a.x);
     }
 }

@@ -160,9 +160,9 @@ int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, i
     P.nranks = nranks; P.rank = rank;
     P.nloen.assign(nloen, nloen + ndgl);
     for (int j = 0; j < ndgl; ++j) {
-        if (P.nloen[j] < 2 || P.nloen[j] % 2 != 0) {
-            ect_set_error("ect_setup: nloen(%d)=%d; this backend requires an even number of longitudes", j + 1, P.nloen[j]);
-            return ECT_ERR_NOTIMPL;
+        if (P.nloen[j] < 2) {
+            ect_set_error("ect_setup: nloen(%d)=%d", j + 1, P.nloen[j]);
+            return ECT_ERR_BADARG;
         }
         if (P.nloen[j] != P.nloen[ndgl - 1 - j]) {
             ect_set_error("ect_setup: grid not symmetric about the equator");

@@ -90,6 +90,16 @@ def test_pair_transforms(emu, nlon, km):
     assert e1 < 5e-15 and e2 < 5e-15, (blue, e1, e2)
 
 
+@pytest.mark.parametrize("nlon,km", [(25, 12), (27, 13), (45, 20), (75, 37), (81, 40), (125, 62), (135, 40), (243, 121),
+                                     (375, 100), (1125, 562), (3, 1), (5, 2)])
+def test_pair_transforms_odd_lengths(emu, nlon, km):
+    """Odd row lengths (classic reduced Gaussian grids: 25, 27, 45, 75, 81, 125, ...) always go through chirp-z; the
+    reflected chirp entries change sign there (c[N - j] = (-1)^N c[j])."""
+    rng = np.random.default_rng(nlon)
+    blue, e1, e2 = _pair(emu, nlon, km, 0, 7, rng)
+    assert blue == 1 and e1 < 5e-15 and e2 < 5e-15, (blue, e1, e2)
+
+
 @pytest.mark.parametrize("nlon,km", [(20, 8), (24, 11), (18, 8), (300, 148), (336, 79)])
 def test_pair_transforms_forced_chirpz(emu, nlon, km):
     rng = np.random.default_rng(nlon + 1)

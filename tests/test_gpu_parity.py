@@ -118,12 +118,19 @@ def _grid(kind, golden):
         return np.full(48, 96, dtype=np.int32)
     if kind == "golden150":             # the irregular reduced grid of the reference's ectrans4py test data
         return np.asarray(golden["nloen"], dtype=np.int32)
+    if kind == "N32classic":            # classic reduced Gaussian grid: odd row lengths (27, 45, 75) -> chirp-z with sign-flipped reflections
+        return np.asarray(N32_CLASSIC + N32_CLASSIC[::-1], dtype=np.int32)
     return None
+
+
+N32_CLASSIC = [20, 27, 36, 40, 45, 50, 60, 64, 72, 75, 80, 90, 90, 96, 100, 108, 108, 120, 120, 120, 128, 128, 128, 128,
+               128, 128, 128, 128, 128, 128, 128, 128]
 
 
 # NMEN rules of setup_geom_mod.F90:44-78 other than the cubic octahedral one: linear (T >= NDGL-1), quadratic
 # (T >= 2 NDGL / 3 - 1), a full grid, an irregular reduced grid; vor/div + scalars with derivatives each
-GRID_CASES = [("O48", 95), ("O48", 63), ("F24", 47), ("F24", 30), ("golden150", 99), ("golden150", 60)]
+GRID_CASES = [("O48", 95), ("O48", 63), ("F24", 47), ("F24", 30), ("golden150", 99), ("golden150", 60),
+              ("N32classic", 63), ("N32classic", 42), ("N32classic", 21)]
 
 
 @pytest.mark.parametrize("kind,T", GRID_CASES)

@@ -51,11 +51,17 @@ def test_geometry_matches_oracle(eb, T, N):
     t.release()
 
 
-@pytest.mark.parametrize("kind,T", [("O48", 95), ("O48", 63), ("F24", 47), ("F24", 30), ("golden150", 99), ("golden150", 60)])
+N32_CLASSIC = [20, 27, 36, 40, 45, 50, 60, 64, 72, 75, 80, 90, 90, 96, 100, 108, 108, 120, 120, 120, 128, 128, 128, 128,
+               128, 128, 128, 128, 128, 128, 128, 128]       # classic reduced grid, odd row lengths
+
+
+@pytest.mark.parametrize("kind,T", [("O48", 95), ("O48", 63), ("F24", 47), ("F24", 30), ("golden150", 99), ("golden150", 60),
+                                    ("N32classic", 63), ("N32classic", 42), ("N32classic", 21)])
 def test_geometry_other_grids(eb, golden, kind, T):
     """NMEN rules of setup_geom_mod.F90:44-78: linear, quadratic and cubic branches, full and irregular reduced grids."""
     nloen = {"O48": eb.octahedral_nloen(48), "F24": np.full(48, 96, dtype=np.int32),
-             "golden150": np.asarray(golden["nloen"], dtype=np.int32)}[kind]
+             "golden150": np.asarray(golden["nloen"], dtype=np.int32),
+             "N32classic": np.asarray(N32_CLASSIC + N32_CLASSIC[::-1], dtype=np.int32)}[kind]
     t = eb.Transform(T, nloen, host_only=True)
     s = eo.setup(T, int(nloen.size), nloen, tables=False)
     np.testing.assert_array_equal(t.nmen, s.nmen)
@@ -138,9 +144,12 @@ def test_error_codes(eb):
     assert L.ect_inquire(12345, ctypes.byref(eb.Info())) == -8          # invalid handle
     assert L.ect_release(12345) == -8
     assert L.ect_strerror(-2) == b"not implemented"
-    odd = nl.copy(); odd[0] = odd[-1] = 21
+    odd = nl.copy(); odd[0] = odd[-1] = 21                              # odd row lengths are fine (classic reduced grids)
     o = eb._SetupOpts(7, 16, odd.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 1, 0, 1, -1, None, None)
-    assert L.ect_setup(ctypes.byref(o), ctypes.byref(h)) == -2          # odd nlon not implemented
+    assert L.ect_setup(ctypes.byref(o), ctypes.byref(h)) == 0 and L.ect_release(h.value) == 0
+    skew = nl.copy(); skew[0] = 24
+    o = eb._SetupOpts(7, 16, skew.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 1, 0, 1, -1, None, None)
+    assert L.ect_setup(ctypes.byref(o), ctypes.byref(h)) == -4          # grid not symmetric about the equator
     t = eb.Transform(7, nl, host_only=True)
     a = eb._InvArgs()
     assert L.ect_inv_trans(t.handle, ctypes.byref(a)) == -6             # host-only handle has no device state
