@@ -73,6 +73,12 @@ class _DirArgs(C.Structure):
                 ("spsc2", C.c_void_p), ("spsc3a", C.c_void_p), ("spsc3b", C.c_void_p)]
 
 
+class _VsetArgs(C.Structure):
+    _fields_ = [("kvsetuv", C.c_void_p), ("nuv_g", C.c_int), ("kvsetsc", C.c_void_p), ("nscalar_g", C.c_int),
+                ("kvsetsc2", C.c_void_p), ("nsc2_g", C.c_int), ("kvsetsc3a", C.c_void_p), ("nsc3a_lev_g", C.c_int),
+                ("kvsetsc3b", C.c_void_p), ("nsc3b_lev_g", C.c_int)]
+
+
 class Timings(C.Structure):
     _fields_ = [("h2d", C.c_float), ("prologue", C.c_float), ("legendre", C.c_float), ("transpose", C.c_float),
                 ("fourier", C.c_float), ("epilogue", C.c_float), ("d2h", C.c_float), ("total", C.c_float),
@@ -88,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
     "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec", "ect_inv_transad", "ect_dir_transad",
     "ect_gpnorm_trans", "ect_vordiv_to_uv", "ect_inquire_rpnm", "ect_trans_pnm", "ect_write_legpol", "ect_read_legpol",
-    "ect_gridpoint_partition", "ect_specnorm_met",
+    "ect_gridpoint_partition", "ect_specnorm_met", "ect_inv_trans_vset", "ect_dir_trans_vset",
 ]
 
 
@@ -111,6 +117,8 @@ def lib():
         L.ect_dir_transad.argtypes = [C.c_int, C.POINTER(_DirArgs)]
         L.ect_specnorm.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ect_specnorm_met.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ect_inv_trans_vset.argtypes = [C.c_int, C.POINTER(_InvArgs), C.POINTER(_VsetArgs)]
+        L.ect_dir_trans_vset.argtypes = [C.c_int, C.POINTER(_DirArgs), C.POINTER(_VsetArgs)]
         L.ect_get_timings.argtypes = [C.c_int, C.POINTER(Timings)]
         L.ect_debug_get_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
         L.ect_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -226,12 +234,15 @@ class Transform:
     """
 
     def __init__(self, nsmax, nloen, nranks=1, rank=0, device=-1, stream=None, nccl_uid=None, host_only=False,
-                 precision="dp", legpol_read=None, legpol_write=None, gp_partition="latbands"):
+                 precision="dp", legpol_read=None, legpol_write=None, gp_partition="latbands", nprtrv=1):
         """legpol_read / legpol_write: SETUP_TRANS's CDIO_LEGPOL='readf' / 'writef' with CDLEGPOLFNAME (the reference's
         Legendre-polynomial cache file format); with legpol_read the table is not computed.
         gp_partition: "latbands" (native: the caller's grid points are the task's Fourier latitude band, TRLTOG / TRGTOL
         are local) or "eq_regions" (the reference's default LDEQ_REGIONS=T, LDSPLIT=T decomposition; TRLTOG / TRGTOL are
-        NCCL all-to-alls)."""
+        NCCL all-to-alls).
+        nprtrv: NPRTRV; > 1: nranks is NPROC = NPRTRW * NPRTRV, rank pe is W-set pe // nprtrv, V-set pe % nprtrv, the
+        grid-point arrays follow eq_regions over all tasks and carry every field (use inv_trans_vset / dir_trans_vset)."""
+        self.nprtrv = int(nprtrv)
         if gp_partition not in ("latbands", "eq_regions"):
             raise EctError("gp_partition must be 'latbands' or 'eq_regions'")
         L = lib()
@@ -242,13 +253,15 @@ class Transform:
         o = _SetupOpts(int(nsmax), int(nl.size), nl.ctypes.data_as(C.POINTER(C.c_int)), int(nranks), int(rank),
                        (ECT_SETUP_HOST_ONLY if host_only else 0) | (ECT_SETUP_STREAM_GIVEN if stream is not None else 0)
                        | (ECT_SETUP_LEGPOL_DEFER if legpol_read else 0)
-                       | (ECT_SETUP_GP_EQ_REGIONS if gp_partition == "eq_regions" else 0),
+                       | (ECT_SETUP_GP_EQ_REGIONS if gp_partition == "eq_regions" else 0)
+                       | ((int(nprtrv) & 0xff) << 8 if int(nprtrv) > 1 else 0),
                        int(device), C.c_void_p(stream) if stream else None,
                        C.cast(self._uid, C.c_void_p) if self._uid else None,
                        ECT_PREC_DP if precision == "dp" else ECT_PREC_SP)
         h = C.c_int(0)
         _check(L.ect_setup(C.byref(o), C.byref(h)), "ect_setup")
         self.handle = h.value
+        self.rank_world = int(rank)
         if legpol_read:
             rc = L.ect_read_legpol(self.handle, os.fsencode(legpol_read))
             if rc:
@@ -469,6 +482,55 @@ class Transform:
         _check(lib().ect_specnorm_met(self.handle, _ptr(spec), nf, ECT_MEM_DEVICE if dev else ECT_MEM_HOST,
                                       None if met is None else met.ctypes.data, out.ctypes.data), "ect_specnorm")
         return out
+
+    # ---- V-sets (NPRTRV > 1): call mode 1, host arrays ----
+    def _vset(self, kvsetuv, kvsetsc):
+        ku = np.ascontiguousarray(kvsetuv if kvsetuv is not None else [], dtype=np.int32)
+        ks = np.ascontiguousarray(kvsetsc if kvsetsc is not None else [], dtype=np.int32)
+        va = _VsetArgs(ku.ctypes.data if ku.size else None, int(ku.size), ks.ctypes.data if ks.size else None, int(ks.size),
+                       None, 0, None, 0, None, 0)
+        return va, (ku, ks)
+
+    def inv_trans_vset(self, spvor, spdiv, spscalar, kvsetuv, kvsetsc, nproma=0, **flags):
+        """INV_TRANS with KVSETUV / KVSETSC (1-based V-set per global level / scalar): spvor, spdiv, spscalar hold this
+        task's levels (nspec2, local); returns gp (ngpblks, all fields, nproma) on the task's eq_regions points."""
+        va, keep = self._vset(kvsetuv, kvsetsc)
+        nuv_g, nsc_g = keep[0].size, keep[1].size
+        scd = bool(flags.get("scders")) and nsc_g > 0
+        nfg = ((nuv_g if flags.get("vorgp") else 0) + (nuv_g if flags.get("divgp") else 0) + 2 * nuv_g + nsc_g
+               + (nsc_g if scd else 0) + (2 * nuv_g if flags.get("uvder") else 0) + (nsc_g if scd else 0))
+        npr, nblk = self._blocks(nproma)
+        gp = np.zeros((nblk, nfg, npr), dtype=self.dtype)
+        cv = lambda x: None if x is None or x.shape[1] == 0 else np.ascontiguousarray(x, dtype=self.dtype)
+        spvor, spdiv, spscalar = cv(spvor), cv(spdiv), cv(spscalar)
+        a = _InvArgs()
+        a.memspace = ECT_MEM_HOST; a.nproma = nproma
+        a.scders, a.vorgp, a.divgp, a.uvder = (int(bool(flags.get(k))) for k in ("scders", "vorgp", "divgp", "uvder"))
+        if spvor is not None:
+            a.spvor, a.spdiv, a.nuv = spvor.ctypes.data, spdiv.ctypes.data, spvor.shape[1]
+        if spscalar is not None:
+            a.spscalar, a.nscalar = spscalar.ctypes.data, spscalar.shape[1]
+        a.gp = gp.ctypes.data
+        _check(lib().ect_inv_trans_vset(self.handle, C.byref(a), C.byref(va)), "ect_inv_trans_vset")
+        return gp
+
+    def dir_trans_vset(self, gp, kvsetuv, kvsetsc, nproma=0):
+        """DIR_TRANS with V-sets: gp (ngpblks, 2 nuv_g + nsc_g, nproma) -> (spvor, spdiv, spscalar) of this task's levels."""
+        va, keep = self._vset(kvsetuv, kvsetsc)
+        me = self.rank_world % self.nprtrv + 1
+        nuv_l, nsc_l = int((keep[0] == me).sum()), int((keep[1] == me).sum())
+        gp = np.ascontiguousarray(gp, dtype=self.dtype)
+        ov, od = np.zeros((self.nspec2, nuv_l), dtype=self.dtype), np.zeros((self.nspec2, nuv_l), dtype=self.dtype)
+        os_ = np.zeros((self.nspec2, nsc_l), dtype=self.dtype)
+        a = _DirArgs()
+        a.memspace = ECT_MEM_HOST; a.nproma = nproma; a.nuv = nuv_l; a.nscalar = nsc_l
+        a.gp = gp.ctypes.data
+        if nuv_l:
+            a.spvor, a.spdiv = ov.ctypes.data, od.ctypes.data
+        if nsc_l:
+            a.spscalar = os_.ctypes.data
+        _check(lib().ect_dir_trans_vset(self.handle, C.byref(a), C.byref(va)), "ect_dir_trans_vset")
+        return ov, od, os_
 
     def gpnorm_trans(self, gp, nproma=0, ave_only=False, pmin=None, pmax=None):
         """GPNORM_TRANS: (average, minimum, maximum) per field of gp (ngpblks, nfld, nproma); global over ranks.

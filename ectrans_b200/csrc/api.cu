@@ -50,6 +50,7 @@ struct EctNccl {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;     // optional (NCCL >= 2.18): V-sets only
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -71,6 +72,7 @@ static int nccl_load() {
     ECT_SYM(GroupStart, "ncclGroupStart"); ECT_SYM(GroupEnd, "ncclGroupEnd"); ECT_SYM(Send, "ncclSend"); ECT_SYM(Recv, "ncclRecv");
     ECT_SYM(AllReduce, "ncclAllReduce"); ECT_SYM(AllGather, "ncclAllGather"); ECT_SYM(GetErrorString, "ncclGetErrorString");
 #undef ECT_SYM
+    *(void**)(&g_nccl.CommSplit) = dlsym(L, "ncclCommSplit");
     g_nccl.lib = L;
     return ECT_SUCCESS;
 }
@@ -135,14 +137,31 @@ int ect_device_setup(EctHandle* h, cudaStream_t stream, bool use_given_stream, i
     int rc;
     if ((rc = ect_legendre_setup(h))) return rc;
     if ((rc = ect_fourier_setup(h))) return rc;
-    if (P.nranks > 1) {
+    if (h->vs.V > 1) {       // V-sets: one communicator over all tasks, split into the W-groups (same v)
         if (!uid) { ect_set_error("ect_setup: nranks > 1 needs nccl_uid"); return ECT_ERR_MISSING; }
         if ((rc = nccl_load())) return rc;
         ncclUniqueId id;
         memcpy(&id, uid, sizeof(id));
-        ncclComm_t comm;
-        ECT_NCCL(ncclCommInitRank(&comm, P.nranks, id, P.rank));
-        d->comm = comm;
+        ncclComm_t world;
+        ECT_NCCL(ncclCommInitRank(&world, h->vs.world, id, h->vs.wrank));
+        d->comm_world = world;
+        if (P.nranks > 1) {
+            if (!g_nccl.CommSplit) { ect_set_error("ect_setup: NPRTRV > 1 needs ncclCommSplit (NCCL >= 2.18)"); return ECT_ERR_NCCL; }
+            ncclComm_t sub;
+            ECT_NCCL(g_nccl.CommSplit(world, h->vs.v, P.rank, &sub, nullptr));
+            d->comm = sub;
+        }
+    }
+    if (P.nranks > 1) {
+        if (h->vs.V == 1) {
+            if (!uid) { ect_set_error("ect_setup: nranks > 1 needs nccl_uid"); return ECT_ERR_MISSING; }
+            if ((rc = nccl_load())) return rc;
+            ncclUniqueId id;
+            memcpy(&id, uid, sizeof(id));
+            ncclComm_t comm;
+            ECT_NCCL(ncclCommInitRank(&comm, P.nranks, id, P.rank));
+            d->comm = comm;
+        }
         const char* nop2p = getenv("ECT_NO_P2P");
         d->p2p = !(nop2p && atoi(nop2p) != 0);
         ECT_CUDA(cudaMalloc(&d->barrier_buf, 64));
@@ -177,6 +196,7 @@ void ect_device_free(EctHandle* h) {
     cudaStreamSynchronize(d->stream);
     for (void* m : d->ipc_open) cudaIpcCloseMemHandle(m);
     if (d->comm) ncclCommDestroy((ncclComm_t)d->comm);
+    if (d->comm_world) ncclCommDestroy((ncclComm_t)d->comm_world);
     void* ptrs[] = {d->rw, d->racthe, d->racthe_loc, d->rw_loc, d->nloen, d->gpoff, d->ptab, d->legm, d->leg_rec_n, d->leg_rec_s,
                     d->nasm0, d->inv_tiles, d->dir_tiles, d->plans, d->latplans, d->perm_pool, d->tw_pool,
                     d->cz_pool, d->cz_pool_f, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->xwork, d->fbuf_leg,
@@ -205,8 +225,39 @@ void ect_device_free(EctHandle* h) {
 extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
     if (!o || !handle) { ect_set_error("ect_setup: null argument"); return ECT_ERR_MISSING; }
     EctHandle* h = new EctHandle();
-    int rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, o->nranks < 1 ? 1 : o->nranks, o->rank,
-                                 (o->flags & ECT_SETUP_GP_EQ_REGIONS) != 0);
+    const int world = o->nranks < 1 ? 1 : o->nranks, V = std::max(1, (o->flags >> 8) & 0xff);
+    int rc;
+    if (V > 1) {
+        // NPRTRV > 1: W = world / V groups of wavenumbers / latitude bands, fields spread over the V tasks of a group
+        if (world % V != 0 || o->rank < 0 || o->rank >= world) { delete h; ect_set_error("ect_setup: NPROC = %d inconsistent with NPRTRV = %d", world, V); return ECT_ERR_BADARG; }
+        h->vs.V = V; h->vs.world = world; h->vs.wrank = o->rank; h->vs.v = o->rank % V;
+        rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, world / V, o->rank / V, false);
+        if (!rc) {
+            EctHostPlan& P = h->hp;
+            EctGpPartition G;
+            rc = ect_gp_partition(P.nloen, world, G);
+            if (!rc) {
+                P.gp_regions = G.regions;
+                P.gp_segs.assign(G.segs.begin() + G.seg0[o->rank], G.segs.begin() + G.seg0[o->rank + 1]);
+                for (const EctGpSeg& sg : P.gp_segs) h->vs.ngptot += sg.count;
+                P.xb_off.assign(world + 1, 0);
+                for (int p = 0; p < world; ++p) {
+                    for (int i = G.seg0[p]; i < G.seg0[p + 1]; ++i) {
+                        const EctGpSeg& sg = G.segs[i];
+                        if (sg.lat < P.lat0 || sg.lat >= P.lat0 + P.nlat) continue;
+                        for (int j = 0; j < sg.count; ++j) P.xb_idx.push_back(P.gpoff[sg.lat - P.lat0] + sg.first + j);
+                    }
+                    P.xb_off[p + 1] = (i64)P.xb_idx.size();
+                }
+                P.xg_off.assign(P.nranks + 1, 0);
+                for (const EctGpSeg& sg : P.gp_segs)
+                    for (int r = 0; r < P.nranks; ++r)
+                        if (sg.lat >= P.lat_first[r] && sg.lat < P.lat_first[r] + P.lat_count[r]) P.xg_off[r + 1] += sg.count;
+                for (int r = 0; r < P.nranks; ++r) P.xg_off[r + 1] += P.xg_off[r];
+            }
+        }
+    } else
+        rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, world, o->rank, (o->flags & ECT_SETUP_GP_EQ_REGIONS) != 0);
     if (rc) { delete h; return rc; }
     if (o->precision != ECT_PREC_DP && o->precision != ECT_PREC_SP) { delete h; ect_set_error("ect_setup: unknown precision %d", o->precision); return ECT_ERR_BADARG; }
     h->precision = o->precision;
@@ -253,7 +304,7 @@ extern "C" int ect_inquire(int handle, ect_info* info) {
     info->nsmax = P.nsmax; info->ndgl = P.ndgl; info->ndgnh = P.ndgnh;
     info->nranks = P.nranks; info->rank = P.rank;
     info->nspec2 = P.nspec2; info->nspec2g = P.nspec2_g;
-    info->ngptot = P.ngptot; info->ngptotg = P.ngptotg;
+    info->ngptot = h->vs.V > 1 ? h->vs.ngptot : P.ngptot; info->ngptotg = P.ngptotg;
     info->nump = P.nump; info->lat0 = P.lat0; info->nlat = P.nlat;
     info->table_bytes = h->d ? h->d->ptab_elems * (long long)sizeof(double) : 0;
     return ECT_SUCCESS;
@@ -301,7 +352,7 @@ extern "C" int ect_inquire_array(int handle, int which, void* out, long long cap
         case ECT_ARR_FFTDSTREC: return copy_out<int>(out, cap, P.fft_dst_rec);
         case ECT_ARR_GPSEGS: case ECT_ARR_NGPSEGS: {
             std::vector<int> v;
-            if (P.gp_eq) for (const EctGpSeg& sg : P.gp_segs) { v.push_back(sg.lat); v.push_back(sg.first); v.push_back(sg.count); }
+            if (P.gp_eq || h->vs.V > 1) for (const EctGpSeg& sg : P.gp_segs) { v.push_back(sg.lat); v.push_back(sg.first); v.push_back(sg.count); }
             else for (int l = 0; l < P.nlat; ++l) { v.push_back(P.lat0 + l); v.push_back(0); v.push_back(P.nloen[P.lat0 + l]); }
             if (which == ECT_ARR_NGPSEGS) return copy_out<int>(out, cap, std::vector<int>(1, (int)v.size() / 3));
             return copy_out<int>(out, cap, v);
@@ -501,50 +552,73 @@ __global__ void k_gp_user_msg(double* const* __restrict__ base, const i64* __res
     }
 }
 
-static int gp_exchange_setup(EctHandle* h, int nf) {
+// nf_band: fields of the band buffer (this task's V-set); nf_user: fields of the caller's arrays (all V-sets)
+static int gp_exchange_setup(EctHandle* h, int nf_band, int nf_user) {
     const EctHostPlan& P = h->hp;
     EctDevice* d = h->d;
+    const int ntasks = h->vs.V > 1 ? h->vs.world : P.nranks;
+    const int ngp_user = h->vs.V > 1 ? h->vs.ngptot : P.ngptot;
     int rc;
     if (!d->xb_idx) {
         ECT_CUDA(cudaMalloc(&d->xb_idx, std::max<size_t>(P.xb_idx.size(), 1) * sizeof(int)));
-        ECT_CUDA(cudaMalloc(&d->xb_off, (P.nranks + 1) * sizeof(i64)));
+        ECT_CUDA(cudaMalloc(&d->xb_off, (ntasks + 1) * sizeof(i64)));
         ECT_CUDA(cudaMalloc(&d->xg_off, (P.nranks + 1) * sizeof(i64)));
         ECT_CUDA(cudaMemcpy(d->xb_idx, P.xb_idx.data(), P.xb_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
-        ECT_CUDA(cudaMemcpy(d->xb_off, P.xb_off.data(), (P.nranks + 1) * sizeof(i64), cudaMemcpyHostToDevice));
+        ECT_CUDA(cudaMemcpy(d->xb_off, P.xb_off.data(), (ntasks + 1) * sizeof(i64), cudaMemcpyHostToDevice));
         ECT_CUDA(cudaMemcpy(d->xg_off, P.xg_off.data(), (P.nranks + 1) * sizeof(i64), cudaMemcpyHostToDevice));
     }
-    const i64 nb = (i64)std::max(P.ngpband, 1) * nf, ng = (i64)std::max(P.ngptot, 1) * nf;
+    const i64 nb = (i64)std::max(P.ngpband, 1) * std::max(nf_band, 1), ng = (i64)std::max(ngp_user, 1) * std::max(nf_user, 1);
     if ((rc = ensure(d->gpband, d->gpband_elems, nb, d->stream, false))) return rc;
     if ((rc = ensure(d->gpsend, d->gpsend_elems, std::max(nb, ng), d->stream, false))) return rc;
     if ((rc = ensure(d->gprecv, d->gprecv_elems, std::max(nb, ng), d->stream, false))) return rc;
     return ECT_SUCCESS;
 }
 
-// to_grid = 1: TRLTOG (band buffer -> caller's arrays), 0: TRGTOL.  d_gpb / d_gps: the caller-array field table on the device.
-static int gp_exchange(EctHandle* h, int nf, int es, int to_grid, double* const* d_gpb, const i64* d_gps, int nproma) {
+// to_grid = 1: TRLTOG (band buffer -> caller's arrays), 0: TRGTOL.  d_gpb / d_gps: the caller-array field table on the
+// device, in MESSAGE order: the fields of V-set 0 first, then V-set 1, ... (nfl[v] of them; one V-set: all fields).
+static int gp_exchange(EctHandle* h, int nf_band, int nf_user, const std::vector<int>& nfl, int es, int to_grid,
+                       double* const* d_gpb, const i64* d_gps, int nproma) {
     const EctHostPlan& P = h->hp;
     EctDevice* d = h->d;
-    ncclComm_t comm = (ncclComm_t)d->comm;
-    const int fy = std::min(nf, 64);
-    const dim3 gb((P.ngpband + 255) / 256, fy), gu((P.ngptot + 255) / 256, fy);
+    const int V = h->vs.V, W = P.nranks;
+    const int ntasks = V > 1 ? h->vs.world : P.nranks;
+    const int ngp_user = V > 1 ? h->vs.ngptot : P.ngptot;
+    ncclComm_t comm = (ncclComm_t)(V > 1 ? d->comm_world : d->comm);
+    const dim3 gb((P.ngpband + 255) / 256, std::max(1, std::min(nf_band, 64))), gu((ngp_user + 255) / 256, std::max(1, std::min(nf_user, 64)));
 #define ECT_GPX(T) do { \
-        if (to_grid) { if (P.ngpband) k_gp_band_msg<T, true><<<gb, 256, 0, d->stream>>>((T*)d->gpband, (T*)d->gpsend, d->xb_idx, d->xb_off, P.nranks, P.ngpband, nf); } \
-        else if (P.ngptot) k_gp_user_msg<T, true><<<gu, 256, 0, d->stream>>>(d_gpb, d_gps, (T*)d->gpsend, d->xg_off, P.nranks, P.ngptot, nproma, nf); \
+        if (to_grid) { if (P.ngpband && nf_band) k_gp_band_msg<T, true><<<gb, 256, 0, d->stream>>>((T*)d->gpband, (T*)d->gpsend, d->xb_idx, d->xb_off, ntasks, P.ngpband, nf_band); } \
+        else if (ngp_user && nf_user) k_gp_user_msg<T, true><<<gu, 256, 0, d->stream>>>(d_gpb, d_gps, (T*)d->gpsend, d->xg_off, W, ngp_user, nproma, nf_user); \
     } while (0)
     if (es == 4) ECT_GPX(float); else ECT_GPX(double);
 #undef ECT_GPX
-    const std::vector<i64>& soff = to_grid ? P.xb_off : P.xg_off;
-    const std::vector<i64>& roff = to_grid ? P.xg_off : P.xb_off;
+    // band side: one message per task p, nf_band fields; task side: one message per (band owner w, V-set v), nfl[v] fields,
+    // stored inside the block of w ([field slot][points of w]) behind the fields of the V-sets before v
+    char* bandbuf = (char*)(to_grid ? d->gpsend : d->gprecv);
+    char* userbuf = (char*)(to_grid ? d->gprecv : d->gpsend);
     ECT_NCCL(ncclGroupStart());
-    for (int p = 0; p < P.nranks; ++p) {
-        const size_t ns = (size_t)(soff[p + 1] - soff[p]) * nf * es, nr = (size_t)(roff[p + 1] - roff[p]) * nf * es;
-        if (ns) ECT_NCCL(ncclSend((char*)d->gpsend + (size_t)soff[p] * nf * es, ns, ncclChar, p, comm, d->stream));
-        if (nr) ECT_NCCL(ncclRecv((char*)d->gprecv + (size_t)roff[p] * nf * es, nr, ncclChar, p, comm, d->stream));
+    for (int p = 0; p < ntasks; ++p) {
+        const size_t nb = (size_t)(P.xb_off[p + 1] - P.xb_off[p]) * nf_band * es;
+        if (!nb) continue;
+        char* at = bandbuf + (size_t)P.xb_off[p] * nf_band * es;
+        if (to_grid) ECT_NCCL(ncclSend(at, nb, ncclChar, p, comm, d->stream));
+        else ECT_NCCL(ncclRecv(at, nb, ncclChar, p, comm, d->stream));
+    }
+    for (int w = 0; w < W; ++w) {
+        const size_t cnt = (size_t)(P.xg_off[w + 1] - P.xg_off[w]);
+        size_t pre = 0;
+        for (int v = 0; v < V; ++v) {
+            const size_t nu = cnt * nfl[v] * es;
+            char* at = userbuf + ((size_t)P.xg_off[w] * nf_user + cnt * pre) * es;
+            pre += nfl[v];
+            if (!nu) continue;
+            if (to_grid) ECT_NCCL(ncclRecv(at, nu, ncclChar, w * V + v, comm, d->stream));
+            else ECT_NCCL(ncclSend(at, nu, ncclChar, w * V + v, comm, d->stream));
+        }
     }
     ECT_NCCL(ncclGroupEnd());
 #define ECT_GPX(T) do { \
-        if (to_grid) { if (P.ngptot) k_gp_user_msg<T, false><<<gu, 256, 0, d->stream>>>(d_gpb, d_gps, (T*)d->gprecv, d->xg_off, P.nranks, P.ngptot, nproma, nf); } \
-        else if (P.ngpband) k_gp_band_msg<T, false><<<gb, 256, 0, d->stream>>>((T*)d->gpband, (T*)d->gprecv, d->xb_idx, d->xb_off, P.nranks, P.ngpband, nf); \
+        if (to_grid) { if (ngp_user && nf_user) k_gp_user_msg<T, false><<<gu, 256, 0, d->stream>>>(d_gpb, d_gps, (T*)d->gprecv, d->xg_off, W, ngp_user, nproma, nf_user); } \
+        else if (P.ngpband && nf_band) k_gp_band_msg<T, false><<<gb, 256, 0, d->stream>>>((T*)d->gpband, (T*)d->gprecv, d->xb_idx, d->xb_off, ntasks, P.ngpband, nf_band); \
     } while (0)
     if (es == 4) ECT_GPX(float); else ECT_GPX(double);
 #undef ECT_GPX
@@ -915,8 +989,13 @@ static int dir_trans_chunked(int handle, EctHandle* h, const ect_dir_args* a, co
     return ECT_SUCCESS;
 }
 
-extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) { return inv_trans_impl(handle, a, nullptr, 0); }
-extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) { return dir_trans_impl(handle, a, nullptr, 0); }
+static int vset_guard(int handle, const char* who) {
+    EctHandle* h = get_handle(handle);
+    if (h && h->vs.V > 1) { ect_set_error("%s: this resolution has NPRTRV = %d; use the *_vset entry points (V-set arrays needed) -- not available for this call", who, h->vs.V); return ECT_ERR_NOTIMPL; }
+    return ECT_SUCCESS;
+}
+extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) { int g = vset_guard(handle, "ect_inv_trans"); return g ? g : inv_trans_impl(handle, a, nullptr, 0); }
+extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) { int g = vset_guard(handle, "ect_dir_trans"); return g ? g : dir_trans_impl(handle, a, nullptr, 0); }
 
 // INV_TRANSAD / DIR_TRANSAD (reference cpu/external/inv_transad.F90, dir_transad.F90 and the *ad_mod
 // files of cpu/internal).  With the inner products of the reference's adjoint tests (grid: plain sum; spectral:
@@ -928,6 +1007,7 @@ extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) { return dir_tra
 //                 (vor, div) -> (U, V) step UVTVD^T equals VDTUV . diag(-1 / RLAPIN(n)).
 // The derivative / vorticity-divergence grid-point options of INV_TRANSAD are not provided.
 extern "C" int ect_inv_transad(int handle, const ect_inv_args* a) {
+    if (int g = vset_guard(handle, "ect_inv_transad")) return g;
     if (!a) return ECT_ERR_MISSING;
     if (a->scders || a->vorgp || a->divgp || a->uvder) {
         ect_set_error("ect_inv_transad: scders / vorgp / divgp / uvder are not implemented for the adjoint");
@@ -945,6 +1025,7 @@ extern "C" int ect_inv_transad(int handle, const ect_inv_args* a) {
     return dir_trans_impl(handle, &d, nullptr, 1);
 }
 extern "C" int ect_dir_transad(int handle, const ect_dir_args* a) {
+    if (int g = vset_guard(handle, "ect_dir_transad")) return g;
     if (!a) return ECT_ERR_MISSING;
     ect_inv_args v;
     memset(&v, 0, sizeof(v));
@@ -1100,7 +1181,7 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     std::vector<int2> pairs = make_pairs(groups);
     f.npairs = (int)pairs.size();
     const bool gpx = P.gp_eq;       // TRLTOG is an exchange: the Fourier stage writes the band buffer, not the caller's arrays
-    if (gpx && (rc = gp_exchange_setup(h, f.nfs))) return rc;
+    if (gpx && (rc = gp_exchange_setup(h, f.nfs, f.nfs))) return rc;
     const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * (2 * (sizeof(double*) + sizeof(i64)) + sizeof(EctFsField)) +
                          pairs.size() * sizeof(int2) + 64;
     if ((rc = ensure_callbuf(d, bytes))) return rc;
@@ -1161,7 +1242,7 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
         const i64* d_bands = (const i64*)(db + ((char*)t_bands - hb));
         ect_launch_ftinv(h, f, d_bandb, d_bands, d_fs, d_pairs, std::max(P.ngpband, 1));
         ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
-        if ((rc = gp_exchange(h, f.nfs, es, 1, d_gpb, d_gps, nproma))) return rc;      // TRLTOG (timed with the d2h interval)
+        if ((rc = gp_exchange(h, f.nfs, f.nfs, std::vector<int>(1, f.nfs), es, 1, d_gpb, d_gps, nproma))) return rc;      // TRLTOG (timed with the d2h interval)
     } else {
         ect_launch_ftinv(h, f, d_gpb, d_gps, d_fs, d_pairs, nproma);
         ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
@@ -1300,7 +1381,7 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     std::vector<int2> pairs = make_pairs(groups);
     f.npairs = (int)pairs.size();
     const bool gpx = P.gp_eq;       // TRGTOL is an exchange: the caller's points travel to the band buffer first
-    if (gpx && (rc = gp_exchange_setup(h, f.nfs))) return rc;
+    if (gpx && (rc = gp_exchange_setup(h, f.nfs, f.nfs))) return rc;
     const size_t bytes = n_spec * sizeof(EctSpecFieldH) + (size_t)f.nfs * 2 * (sizeof(double*) + sizeof(i64)) +
                          pairs.size() * sizeof(int2) + 64;
     if ((rc = ensure_callbuf(d, bytes))) return rc;
@@ -1339,7 +1420,7 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     if (gpx) {
         double* const* d_bandb = (double* const*)(db + ((char*)t_bandb - hb));
         const i64* d_bands = (const i64*)(db + ((char*)t_bands - hb));
-        if ((rc = gp_exchange(h, f.nfs, es, 0, d_gpb, d_gps, nproma))) return rc;      // TRGTOL (timed with the Fourier interval)
+        if ((rc = gp_exchange(h, f.nfs, f.nfs, std::vector<int>(1, f.nfs), es, 0, d_gpb, d_gps, nproma))) return rc;      // TRGTOL (timed with the Fourier interval)
         ect_launch_ftdir(h, f, d_bandb, d_bands, d_pairs, std::max(P.ngpband, 1));
     } else
         ect_launch_ftdir(h, f, d_gpb, d_gps, d_pairs, nproma);
@@ -1432,6 +1513,7 @@ __global__ void k_specnorm(const double* __restrict__ sp, int nfld, int T, const
 }
 
 extern "C" int ect_specnorm_met(int handle, const double* spec, int nfld, int memspace, const double* pmet, double* norms) {
+    if (int g = vset_guard(handle, "ect_specnorm")) return g;
     EctHandle* h = get_handle(handle);
     if (!h || !h->d) { ect_set_error("ect_specnorm: invalid handle"); return ECT_ERR_HANDLE; }
     if (!spec || !norms || nfld <= 0) return ECT_ERR_MISSING;
@@ -1680,6 +1762,7 @@ static int check_owner(const EctHostPlan& P, const int* own, int nfld, const cha
 // gather = true : local (blocked grid / local spectral) -> global arrays on the owners
 // gather = false: global arrays on the owners -> local
 static int gath_dist(int handle, bool grid, bool gather, void* v_local, void* v_global, int nfld, int nproma_in, const int* own) {
+    if (int g = vset_guard(handle, "gath/dist")) return g;
     EctHandle* h = get_handle(handle);
     if (!h) { ect_set_error("gath/dist: invalid handle %d", handle); return ECT_ERR_HANDLE; }
     const EctHostPlan& P = h->hp;
@@ -1826,6 +1909,7 @@ __global__ void k_gpnorm_fold(int nfld, int nlat, const double* __restrict__ mn,
 
 extern "C" int ect_gpnorm_trans(int handle, const void* gp, int nfld, int nproma, int memspace, double* ave, double* pmin,
                                 double* pmax, int ave_only) {
+    if (int g = vset_guard(handle, "ect_gpnorm_trans")) return g;
     EctHandle* h = get_handle(handle);
     if (!h || !h->d) { ect_set_error("ect_gpnorm_trans: invalid handle"); return ECT_ERR_HANDLE; }
     if (!gp || !ave || !pmin || !pmax || nfld <= 0) return ECT_ERR_MISSING;
@@ -1846,14 +1930,14 @@ extern "C" int ect_gpnorm_trans(int handle, const void* gp, int nfld, int nproma
     int nproma_k = nproma;
     if (P.gp_eq) {
         // like the reference (gpnorm_trans_ctl_mod.F90:166-168): TRGTOL first, then whole latitudes are summed by their band owner
-        if ((rc = gp_exchange_setup(h, nfld))) return rc;
+        if ((rc = gp_exchange_setup(h, nfld, nfld))) return rc;
         std::vector<double*> hb(nfld); std::vector<i64> hs(nfld, (i64)nfld * nproma);
         for (int f = 0; f < nfld; ++f) hb[f] = (double*)((char*)dgp + (size_t)f * nproma * es);
         char* tab = nullptr;
         ECT_CUDA(cudaMalloc(&tab, nfld * (sizeof(double*) + sizeof(i64))));
         ECT_CUDA(cudaMemcpyAsync(tab, hb.data(), nfld * sizeof(double*), cudaMemcpyHostToDevice, d->stream));
         ECT_CUDA(cudaMemcpyAsync(tab + nfld * sizeof(double*), hs.data(), nfld * sizeof(i64), cudaMemcpyHostToDevice, d->stream));
-        rc = gp_exchange(h, nfld, es, 0, (double* const*)tab, (const i64*)(tab + nfld * sizeof(double*)), nproma);
+        rc = gp_exchange(h, nfld, nfld, std::vector<int>(1, nfld), es, 0, (double* const*)tab, (const i64*)(tab + nfld * sizeof(double*)), nproma);
         ECT_CUDA(cudaStreamSynchronize(d->stream));
         ECT_CUDA(cudaFree(tab));
         if (rc) return rc;
@@ -2089,4 +2173,281 @@ extern "C" int ect_read_legpol(int handle, const char* path) {
     fclose(f);
     h->defer_table = false;
     return ECT_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------
+// V-sets (NPRTRV > 1): INV_TRANS / DIR_TRANS with the fields (levels) of the spectral arrays spread over the V tasks of
+// a W-group (KVSETUV / KVSETSC / KVSETSC2 / KVSETSC3A / KVSETSC3B, inv_trans.h:36-58) and grid-point arrays that carry
+// every field on the task's eq_regions points.  The W-group transforms its local fields exactly as a W-task run does,
+// into / out of the band buffer; TRLTOG / TRGTOL (trltog_mod.F90:213-271: "field -> V-set redistribution") move points
+// and fields at once.  Field order of the messages: V-set 0's fields, then V-set 1's, ... each in the Fourier order of
+// ftinv_ctl_mod.F90:144-166 restricted to its levels -- which is the order the W-group transform of that V-set uses.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct VsLists {
+    std::vector<int> uv, sc;          // V-set (0-based) of every global vor/div/u/v level and of every global scalar field
+    int nuv_g = 0, nsc2_g = 0, lev3a_g = 0, lev3b_g = 0, nsc_g = 0;
+    bool mode2_sp = false;
+};
+}
+static int vs_lists(const EctHandle* h, const ect_vset_args* vs, bool mode2, int n3a_fld, int n3b_fld, VsLists& L, const char* who) {
+    const int V = h->vs.V;
+    auto take = [&](const int* k, int n, std::vector<int>& out, const char* name) -> int {
+        if (n < 0 || (n > 0 && !k)) { ect_set_error("%s: %s missing", who, name); return ECT_ERR_MISSING; }
+        for (int i = 0; i < n; ++i) {
+            if (k[i] < 1 || k[i] > V) { ect_set_error("%s: %s TOO LONG OR CONTAINS VALUES OUTSIDE RANGE", who, name); return ECT_ERR_BADARG; }
+            out.push_back(k[i] - 1);
+        }
+        return ECT_SUCCESS;
+    };
+    int rc;
+    L.mode2_sp = mode2;
+    L.nuv_g = vs->nuv_g;
+    if ((rc = take(vs->kvsetuv, vs->nuv_g, L.uv, "KVSETUV"))) return rc;
+    if (!mode2) { if ((rc = take(vs->kvsetsc, vs->nscalar_g, L.sc, "KVSETSC"))) return rc; }
+    else {
+        L.nsc2_g = vs->nsc2_g; L.lev3a_g = n3a_fld ? vs->nsc3a_lev_g : 0; L.lev3b_g = n3b_fld ? vs->nsc3b_lev_g : 0;
+        if ((rc = take(vs->kvsetsc2, vs->nsc2_g, L.sc, "KVSETSC2"))) return rc;
+        for (int j = 0; j < n3a_fld; ++j) if ((rc = take(vs->kvsetsc3a, L.lev3a_g, L.sc, "KVSETSC3A"))) return rc;
+        for (int j = 0; j < n3b_fld; ++j) if ((rc = take(vs->kvsetsc3b, L.lev3b_g, L.sc, "KVSETSC3B"))) return rc;
+    }
+    L.nsc_g = (int)L.sc.size();
+    return ECT_SUCCESS;
+}
+static int vs_count(const std::vector<int>& v, int n, int me) { int c = 0; for (int i = 0; i < n; ++i) c += (v[i] == me); return c; }
+
+// message order of the caller's fields + device table (base, block stride) in that order
+static int vs_upload_table(EctDevice* d, const std::vector<int>& gv, int V, const std::vector<double*>& base, const std::vector<i64>& stride,
+                           std::vector<int>& nfl, char** tab) {
+    const int n = (int)gv.size();
+    nfl.assign(V, 0);
+    std::vector<double*> pb; std::vector<i64> ps;
+    for (int v = 0; v < V; ++v)
+        for (int g = 0; g < n; ++g) if (gv[g] == v) { pb.push_back(base[g]); ps.push_back(stride[g]); ++nfl[v]; }
+    ECT_CUDA(cudaMalloc(tab, std::max(n, 1) * (sizeof(double*) + sizeof(i64))));
+    if (n) {
+        ECT_CUDA(cudaMemcpyAsync(*tab, pb.data(), n * sizeof(double*), cudaMemcpyHostToDevice, d->stream));
+        ECT_CUDA(cudaMemcpyAsync(*tab + n * sizeof(double*), ps.data(), n * sizeof(i64), cudaMemcpyHostToDevice, d->stream));
+        ECT_CUDA(cudaStreamSynchronize(d->stream));     // pb / ps are about to go out of scope
+    }
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_inv_trans_vset(int handle, const ect_inv_args* a, const ect_vset_args* vs) {
+    EctHandle* h = get_handle(handle);
+    if (!h) { ect_set_error("ect_inv_trans_vset: invalid handle %d", handle); return ECT_ERR_HANDLE; }
+    if (!a || !vs) return ECT_ERR_MISSING;
+    if (h->vs.V == 1) return ect_inv_trans(handle, a);
+    if (!h->d) { ect_set_error("ect_inv_trans_vset: handle was set up host-only"); return ECT_ERR_CUDA; }
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    ECT_CUDA(cudaSetDevice(d->dev));
+    const int V = h->vs.V, me = h->vs.v, ngp = h->vs.ngptot;
+    const int es = h->precision == ECT_PREC_SP ? 4 : 8;
+    const bool mode2_sp = (a->spscalar == nullptr) && (a->spsc2 || a->spsc3a || a->spsc3b || vs->nsc2_g || vs->nsc3a_lev_g || vs->nsc3b_lev_g);
+    const int f3a = mode2_sp ? a->nsc3a_fld : 0, f3b = mode2_sp ? a->nsc3b_fld : 0;
+    VsLists L;
+    int rc;
+    if ((rc = vs_lists(h, vs, mode2_sp, f3a, f3b, L, "INV_TRANS"))) return rc;
+    // local counts must be what the V-set arrays say (inv_trans.F90:236-330)
+    const int nuv_l = vs_count(L.uv, L.nuv_g, me);
+    if (nuv_l != a->nuv) { ect_set_error("INV_TRANS: PSPVOR holds %d fields, KVSETUV gives this V-set %d", a->nuv, nuv_l); return ECT_ERR_BADARG; }
+    if (!mode2_sp && vs_count(L.sc, L.nsc_g, me) != (a->spscalar ? a->nscalar : 0)) { ect_set_error("INV_TRANS: PSPSCALAR field count differs from KVSETSC"); return ECT_ERR_BADARG; }
+    if (mode2_sp) {
+        std::vector<int> k2(L.sc.begin(), L.sc.begin() + L.nsc2_g);
+        if (vs_count(k2, L.nsc2_g, me) != (a->spsc2 ? a->nsc2 : 0)) { ect_set_error("INV_TRANS: PSPSC2 field count differs from KVSETSC2"); return ECT_ERR_BADARG; }
+        if (f3a) { std::vector<int> k(L.sc.begin() + L.nsc2_g, L.sc.begin() + L.nsc2_g + L.lev3a_g); if (vs_count(k, L.lev3a_g, me) != a->nsc3a_lev) { ect_set_error("INV_TRANS: PSPSC3A level count differs from KVSETSC3A"); return ECT_ERR_BADARG; } }
+        if (f3b) { std::vector<int> k(L.sc.end() - (size_t)f3b * L.lev3b_g, L.sc.end() - (size_t)(f3b - 1) * L.lev3b_g); if (vs_count(k, L.lev3b_g, me) != a->nsc3b_lev) { ect_set_error("INV_TRANS: PSPSC3B level count differs from KVSETSC3B"); return ECT_ERR_BADARG; } }
+    }
+    const bool scders = a->scders && L.nsc_g > 0, vorgp = a->vorgp && L.nuv_g > 0, divgp = a->divgp && L.nuv_g > 0, uvder = a->uvder && L.nuv_g > 0;
+    // global Fourier field list (V-set of every field), ftinv_ctl_mod.F90:144-166
+    std::vector<int> gv;
+    auto app = [&](const std::vector<int>& x) { gv.insert(gv.end(), x.begin(), x.end()); };
+    if (vorgp) app(L.uv);
+    if (divgp) app(L.uv);
+    if (L.nuv_g) { app(L.uv); app(L.uv); }
+    app(L.sc);
+    if (scders) app(L.sc);
+    if (uvder) { app(L.uv); app(L.uv); }
+    if (scders) app(L.sc);
+    const int nfg = (int)gv.size();
+    if (nfg == 0) return ECT_SUCCESS;
+    // the caller's grid-point arrays (all fields): base pointer / block stride per global Fourier field (trltog_mod.F90:579-731)
+    const int nproma = (a->nproma > 0 && a->nproma < ngp) ? a->nproma : std::max(ngp, 1);
+    const i64 blk = (i64)nproma * ((ngp + nproma - 1) / nproma);
+    const bool mode2_gp = (a->gp == nullptr);
+    const int nvar_uv = (vorgp ? 1 : 0) + (divgp ? 1 : 0) + 2 + (uvder ? 2 : 0), dfac = scders ? 3 : 1;
+    const int n3a_g = f3a * L.lev3a_g, n3b_g = f3b * L.lev3b_g;
+    const i64 sz_gp = (i64)nfg * blk, sz_uv = (i64)L.nuv_g * nvar_uv * blk, sz_2 = (i64)L.nsc2_g * dfac * blk, sz_3a = (i64)n3a_g * dfac * blk, sz_3b = (i64)n3b_g * dfac * blk;
+    if (mode2_gp && ((L.nuv_g && !a->gpuv) || (L.nsc2_g && !a->gp2) || (n3a_g && !a->gp3a) || (n3b_g && !a->gp3b) || (!mode2_sp && L.nsc_g))) { ect_set_error("INV_TRANS: grid-point output array missing"); return ECT_ERR_MISSING; }
+    const bool host = a->memspace == ECT_MEM_HOST;
+    double *q_gp = a->gp, *q_uv = a->gpuv, *q_2 = a->gp2, *q_3a = a->gp3a, *q_3b = a->gp3b;
+    if (host) {
+        const i64 tot = mode2_gp ? sz_uv + sz_2 + sz_3a + sz_3b : sz_gp;
+        if ((rc = ensure(d->stage_gp, d->stage_gp_elems, tot, d->stream, false))) return rc;
+        double* p = d->stage_gp;
+        if (!mode2_gp) q_gp = p;
+        else { q_uv = p; p = adv(p, sz_uv, es); q_2 = p; p = adv(p, sz_2, es); q_3a = p; p = adv(p, sz_3a, es); q_3b = p; }
+    }
+    std::vector<double*> base(nfg); std::vector<i64> stride(nfg);
+    if (!mode2_gp) for (int i = 0; i < nfg; ++i) { base[i] = adv(q_gp, (i64)i * nproma, es); stride[i] = (i64)nfg * nproma; }
+    else {
+        int fi = 0, var = 0;
+        auto uvgroup = [&](int vv) { for (int l = 0; l < L.nuv_g; ++l, ++fi) { base[fi] = adv(q_uv, ((i64)vv * L.nuv_g + l) * nproma, es); stride[fi] = (i64)nproma * L.nuv_g * nvar_uv; } };
+        auto scgroup = [&](int part) {
+            for (int j = 0; j < L.nsc2_g; ++j, ++fi) { base[fi] = adv(q_2, ((i64)part * L.nsc2_g + j) * nproma, es); stride[fi] = (i64)nproma * L.nsc2_g * dfac; }
+            for (int j3 = 0; j3 < f3a; ++j3) for (int l = 0; l < L.lev3a_g; ++l, ++fi) { base[fi] = adv(q_3a, (((i64)part * f3a + j3) * L.lev3a_g + l) * nproma, es); stride[fi] = (i64)nproma * L.lev3a_g * f3a * dfac; }
+            for (int j3 = 0; j3 < f3b; ++j3) for (int l = 0; l < L.lev3b_g; ++l, ++fi) { base[fi] = adv(q_3b, (((i64)part * f3b + j3) * L.lev3b_g + l) * nproma, es); stride[fi] = (i64)nproma * L.lev3b_g * f3b * dfac; }
+        };
+        if (vorgp) uvgroup(var++);
+        if (divgp) uvgroup(var++);
+        if (L.nuv_g) { uvgroup(var++); uvgroup(var++); }
+        scgroup(0);
+        if (scders) scgroup(1);
+        if (uvder) { uvgroup(var++); uvgroup(var++); }
+        if (scders) scgroup(2);
+    }
+    std::vector<int> nfl; char* tab = nullptr;
+    if ((rc = vs_upload_table(d, gv, V, base, stride, nfl, &tab))) return rc;
+    if ((rc = gp_exchange_setup(h, nfl[me], nfg))) { cudaFree(tab); return rc; }
+    // ---- the W-group's transform of this V-set's fields into the band buffer (PGP(band points, local fields)) ----
+    ect_inv_args la = *a;
+    la.memspace = ECT_MEM_DEVICE; la.nproma = 0;
+    la.gp = d->gpband; la.gpuv = la.gp2 = la.gp3a = la.gp3b = nullptr;
+    char* sp_tmp = nullptr;
+    if (host) {       // spectral inputs to the device
+        const i64 nsp = P.nspec2;
+        const i64 nsc_l = mode2_sp ? (i64)(a->spsc2 ? a->nsc2 : 0) + (a->spsc3a ? (i64)a->nsc3a_lev * a->nsc3a_fld : 0) + (a->spsc3b ? (i64)a->nsc3b_lev * a->nsc3b_fld : 0)
+                                   : (a->spscalar ? a->nscalar : 0);
+        ECT_CUDA(cudaMalloc(&sp_tmp, (size_t)std::max<i64>((2 * (i64)a->nuv + nsc_l) * nsp * es, 16)));
+        char* p = sp_tmp;
+        auto up = [&](const double*& ptr, i64 n) -> int {
+            if (!ptr || n == 0) return ECT_SUCCESS;
+            ECT_CUDA(cudaMemcpyAsync(p, ptr, (size_t)n * es, cudaMemcpyHostToDevice, d->stream));
+            ptr = (const double*)p; p += (size_t)n * es;
+            return ECT_SUCCESS;
+        };
+        if ((rc = up(la.spvor, a->nuv * nsp)) || (rc = up(la.spdiv, a->nuv * nsp)) || (rc = up(la.spscalar, (i64)a->nscalar * nsp)) ||
+            (rc = up(la.spsc2, (i64)a->nsc2 * nsp)) || (rc = up(la.spsc3a, (i64)a->nsc3a_lev * a->nsc3a_fld * nsp)) ||
+            (rc = up(la.spsc3b, (i64)a->nsc3b_lev * a->nsc3b_fld * nsp))) { cudaFree(tab); cudaFree(sp_tmp); return rc; }
+    }
+    rc = inv_trans_impl(handle, &la, nullptr, 0);
+    // ---- TRLTOG: points and fields to the grid-point tasks ----
+    if (!rc) rc = gp_exchange(h, nfl[me], nfg, nfl, es, 1, (double* const*)tab, (const i64*)(tab + nfg * sizeof(double*)), nproma);
+    if (!rc && host) {
+        if (!mode2_gp) ECT_CUDA(cudaMemcpyAsync(a->gp, q_gp, (size_t)sz_gp * es, cudaMemcpyDeviceToHost, d->stream));
+        else {
+            if (sz_uv) ECT_CUDA(cudaMemcpyAsync(a->gpuv, q_uv, (size_t)sz_uv * es, cudaMemcpyDeviceToHost, d->stream));
+            if (sz_2) ECT_CUDA(cudaMemcpyAsync(a->gp2, q_2, (size_t)sz_2 * es, cudaMemcpyDeviceToHost, d->stream));
+            if (sz_3a) ECT_CUDA(cudaMemcpyAsync(a->gp3a, q_3a, (size_t)sz_3a * es, cudaMemcpyDeviceToHost, d->stream));
+            if (sz_3b) ECT_CUDA(cudaMemcpyAsync(a->gp3b, q_3b, (size_t)sz_3b * es, cudaMemcpyDeviceToHost, d->stream));
+        }
+    }
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    cudaFree(tab);
+    if (sp_tmp) cudaFree(sp_tmp);
+    return rc;
+}
+
+extern "C" int ect_dir_trans_vset(int handle, const ect_dir_args* a, const ect_vset_args* vs) {
+    EctHandle* h = get_handle(handle);
+    if (!h) { ect_set_error("ect_dir_trans_vset: invalid handle %d", handle); return ECT_ERR_HANDLE; }
+    if (!a || !vs) return ECT_ERR_MISSING;
+    if (h->vs.V == 1) return ect_dir_trans(handle, a);
+    if (!h->d) { ect_set_error("ect_dir_trans_vset: handle was set up host-only"); return ECT_ERR_CUDA; }
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    ECT_CUDA(cudaSetDevice(d->dev));
+    const int V = h->vs.V, me = h->vs.v, ngp = h->vs.ngptot;
+    const int es = h->precision == ECT_PREC_SP ? 4 : 8;
+    const bool mode2 = (a->gp == nullptr);
+    const int f3a = mode2 && a->gp3a ? a->nsc3a_fld : 0, f3b = mode2 && a->gp3b ? a->nsc3b_fld : 0;
+    VsLists L;
+    int rc;
+    if ((rc = vs_lists(h, vs, mode2, f3a, f3b, L, "DIR_TRANS"))) return rc;
+    const int nuv_l = vs_count(L.uv, L.nuv_g, me), nsc_l = vs_count(L.sc, L.nsc_g, me);
+    if (nuv_l != a->nuv) { ect_set_error("DIR_TRANS: PSPVOR holds %d fields, KVSETUV gives this V-set %d", a->nuv, nuv_l); return ECT_ERR_BADARG; }
+    int nsc2_l = 0, lev3a_l = 0, lev3b_l = 0;
+    if (mode2) {
+        nsc2_l = vs_count(L.sc, L.nsc2_g, me);
+        if (f3a) { std::vector<int> k(L.sc.begin() + L.nsc2_g, L.sc.begin() + L.nsc2_g + L.lev3a_g); lev3a_l = vs_count(k, L.lev3a_g, me); }
+        if (f3b) { std::vector<int> k(L.sc.end() - (size_t)f3b * L.lev3b_g, L.sc.end() - (size_t)(f3b - 1) * L.lev3b_g); lev3b_l = vs_count(k, L.lev3b_g, me); }
+        if (nsc2_l != (a->gp2 ? a->nsc2 : 0) || (f3a && lev3a_l != a->nsc3a_lev) || (f3b && lev3b_l != a->nsc3b_lev)) { ect_set_error("DIR_TRANS: local field counts differ from KVSETSC2 / KVSETSC3A / KVSETSC3B"); return ECT_ERR_BADARG; }
+        if ((nsc2_l && !a->spsc2) || (f3a && lev3a_l && !a->spsc3a) || (f3b && lev3b_l && !a->spsc3b)) { ect_set_error("DIR_TRANS: missing spectral output for call mode 2"); return ECT_ERR_MISSING; }
+    } else if (nsc_l != a->nscalar) { ect_set_error("DIR_TRANS: PSPSCALAR field count differs from KVSETSC"); return ECT_ERR_BADARG; }
+    std::vector<int> gv;
+    if (L.nuv_g) { gv.insert(gv.end(), L.uv.begin(), L.uv.end()); gv.insert(gv.end(), L.uv.begin(), L.uv.end()); }
+    gv.insert(gv.end(), L.sc.begin(), L.sc.end());
+    const int nfg = (int)gv.size();
+    if (nfg == 0) return ECT_SUCCESS;
+    const int nproma = (a->nproma > 0 && a->nproma < ngp) ? a->nproma : std::max(ngp, 1);
+    const i64 blk = (i64)nproma * ((ngp + nproma - 1) / nproma);
+    const int n3a_g = f3a * L.lev3a_g, n3b_g = f3b * L.lev3b_g;
+    const i64 sz_gp = (i64)nfg * blk, sz_uv = (i64)L.nuv_g * 2 * blk, sz_2 = (i64)L.nsc2_g * blk, sz_3a = (i64)n3a_g * blk, sz_3b = (i64)n3b_g * blk;
+    if (mode2 && ((L.nuv_g && !a->gpuv) || (L.nsc2_g && !a->gp2))) { ect_set_error("DIR_TRANS: grid-point input array missing"); return ECT_ERR_MISSING; }
+    const bool host = a->memspace == ECT_MEM_HOST;
+    const double *q_gp = a->gp, *q_uv = a->gpuv, *q_2 = a->gp2, *q_3a = a->gp3a, *q_3b = a->gp3b;
+    if (host) {
+        const i64 tot = mode2 ? sz_uv + sz_2 + sz_3a + sz_3b : sz_gp;
+        if ((rc = ensure(d->stage_gp, d->stage_gp_elems, tot, d->stream, false))) return rc;
+        double* p = d->stage_gp;
+        auto up = [&](const double*& ptr, i64 n) -> int {
+            if (!ptr || n == 0) return ECT_SUCCESS;
+            ECT_CUDA(cudaMemcpyAsync(p, ptr, (size_t)n * es, cudaMemcpyHostToDevice, d->stream));
+            ptr = p; p = adv(p, n, es);
+            return ECT_SUCCESS;
+        };
+        if (!mode2) { if ((rc = up(q_gp, sz_gp))) return rc; }
+        else if ((rc = up(q_uv, sz_uv)) || (rc = up(q_2, sz_2)) || (rc = up(q_3a, sz_3a)) || (rc = up(q_3b, sz_3b))) return rc;
+    }
+    std::vector<double*> base(nfg); std::vector<i64> stride(nfg);
+    if (!mode2) for (int i = 0; i < nfg; ++i) { base[i] = (double*)adv(q_gp, (i64)i * nproma, es); stride[i] = (i64)nfg * nproma; }
+    else {
+        int fi = 0;
+        for (int vv = 0; vv < (L.nuv_g ? 2 : 0); ++vv) for (int l = 0; l < L.nuv_g; ++l, ++fi) { base[fi] = (double*)adv(q_uv, ((i64)vv * L.nuv_g + l) * nproma, es); stride[fi] = (i64)nproma * L.nuv_g * 2; }
+        for (int j = 0; j < L.nsc2_g; ++j, ++fi) { base[fi] = (double*)adv(q_2, (i64)j * nproma, es); stride[fi] = (i64)nproma * L.nsc2_g; }
+        for (int j3 = 0; j3 < f3a; ++j3) for (int l = 0; l < L.lev3a_g; ++l, ++fi) { base[fi] = (double*)adv(q_3a, ((i64)j3 * L.lev3a_g + l) * nproma, es); stride[fi] = (i64)nproma * L.lev3a_g * f3a; }
+        for (int j3 = 0; j3 < f3b; ++j3) for (int l = 0; l < L.lev3b_g; ++l, ++fi) { base[fi] = (double*)adv(q_3b, ((i64)j3 * L.lev3b_g + l) * nproma, es); stride[fi] = (i64)nproma * L.lev3b_g * f3b; }
+    }
+    std::vector<int> nfl; char* tab = nullptr;
+    if ((rc = vs_upload_table(d, gv, V, base, stride, nfl, &tab))) return rc;
+    if ((rc = gp_exchange_setup(h, nfl[me], nfg))) { cudaFree(tab); return rc; }
+    // ---- TRGTOL: this V-set's fields of the band's points arrive in the band buffer ----
+    rc = gp_exchange(h, nfl[me], nfg, nfl, es, 0, (double* const*)tab, (const i64*)(tab + nfg * sizeof(double*)), nproma);
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    cudaFree(tab);
+    if (rc) return rc;
+    // ---- the W-group's direct transform: call mode 1 on the band buffer, one (nsc_local, nspec2) scalar array ----
+    const i64 nsp = P.nspec2;
+    char* sp_tmp = nullptr;
+    ECT_CUDA(cudaMalloc(&sp_tmp, (size_t)std::max<i64>((2 * (i64)nuv_l + nsc_l) * nsp * es, 16)));
+    ect_dir_args la = *a;
+    la.memspace = ECT_MEM_DEVICE; la.nproma = 0; la.nuv = nuv_l; la.nscalar = nsc_l;
+    la.gp = d->gpband; la.gpuv = la.gp2 = la.gp3a = la.gp3b = nullptr;
+    la.spsc2 = la.spsc3a = la.spsc3b = nullptr;
+    double* t_vor = (double*)sp_tmp; double* t_div = adv(t_vor, nuv_l * nsp, es); double* t_sc = adv(t_div, nuv_l * nsp, es);
+    const bool direct_out = !host && !mode2;        // device pointers, call mode 1: the caller's arrays take the results as they come
+    if (!direct_out) { la.spvor = t_vor; la.spdiv = t_div; la.spscalar = t_sc; }
+    rc = dir_trans_impl(handle, &la, nullptr, 0);
+    if (!rc && !direct_out) {
+        const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        if (nuv_l) {
+            ECT_CUDA(cudaMemcpyAsync(a->spvor, t_vor, (size_t)nuv_l * nsp * es, kind, d->stream));
+            ECT_CUDA(cudaMemcpyAsync(a->spdiv, t_div, (size_t)nuv_l * nsp * es, kind, d->stream));
+        }
+        if (!mode2) { if (nsc_l) ECT_CUDA(cudaMemcpyAsync(a->spscalar, t_sc, (size_t)nsc_l * nsp * es, kind, d->stream)); }
+        else {
+            // scalars came out as one (nsc_local, nspec2) array in the order [sc2][3a fields x levels][3b ...]
+            const size_t pitch = (size_t)nsc_l * es;
+            int col = 0;
+            if (nsc2_l) { ECT_CUDA(cudaMemcpy2DAsync(a->spsc2, (size_t)nsc2_l * es, (char*)t_sc, pitch, (size_t)nsc2_l * es, nsp, kind, d->stream)); col += nsc2_l; }
+            for (int j3 = 0; j3 < f3a; ++j3, col += lev3a_l)
+                if (lev3a_l) ECT_CUDA(cudaMemcpy2DAsync((char*)a->spsc3a + (size_t)j3 * lev3a_l * nsp * es, (size_t)lev3a_l * es, (char*)t_sc + (size_t)col * es, pitch, (size_t)lev3a_l * es, nsp, kind, d->stream));
+            for (int j3 = 0; j3 < f3b; ++j3, col += lev3b_l)
+                if (lev3b_l) ECT_CUDA(cudaMemcpy2DAsync((char*)a->spsc3b + (size_t)j3 * lev3b_l * nsp * es, (size_t)lev3b_l * es, (char*)t_sc + (size_t)col * es, pitch, (size_t)lev3b_l * es, nsp, kind, d->stream));
+        }
+    }
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    cudaFree(sp_tmp);
+    return rc;
 }

@@ -162,6 +162,7 @@ struct EctDevice {
     double* normbuf = nullptr; int normbuf_n = 0;
     // NCCL + fused (peer-memory) transposition
     void* comm = nullptr;
+    void* comm_world = nullptr;           // V-sets: communicator of all W * V tasks (comm is then the W-group's)
     bool p2p = false;                     // kernels write records straight into the consumer rank's buffer
     int *leg_dst_rank_n = nullptr, *leg_dst_rank_s = nullptr, *leg_dst_rec_n = nullptr, *leg_dst_rec_s = nullptr;
     int *fft_dst_rank = nullptr, *fft_dst_rec = nullptr;
@@ -180,7 +181,18 @@ struct EctDevice {
     i64 launches = 0;
 };
 
+// V-sets (NPRTRV > 1): tasks form a W x V grid (PE2SET: w = pe / V, v = pe % V).  hp describes the W-group of this task
+// (wavenumbers, Fourier latitude band: shared by the V tasks of the group, each working on its own fields); the
+// caller's grid-point arrays follow the eq_regions decomposition over all W * V tasks and carry ALL fields, so
+// TRLTOG / TRGTOL redistribute points and fields at once.  The exchange tables live in hp (xb_* over the world tasks,
+// xg_off over the W band owners).
+struct EctVsets {
+    int V = 1, v = 0, world = 1, wrank = 0;
+    int ngptot = 0;                       // my grid points
+};
+
 struct EctHandle {
+    EctVsets vs;
     EctHostPlan hp;
     EctDevice* d = nullptr;
     int precision = 0;

@@ -243,6 +243,23 @@ int ect_read_legpol(int handle, const char* path);
 int ect_gridpoint_partition(int ndgl, const int* nloen, int nproc, int* nbands, int* regions, int* seg0, int* segs,
                             long long capacity_segs, long long* nsegs);
 
+/* V-sets (NPRTRV > 1).  ect_setup with flags |= ECT_SETUP_NPRTRV(V): opts.nranks is then the total number of tasks
+ * NPROC = NPRTRW * V and task pe (0-based) is W-set pe / V, V-set pe % V (pe2set_mod.F90:81-82).  Spectral arrays hold the
+ * levels / fields of the task's V-set, the grid-point arrays ALL of them on the task's eq_regions points (as in the
+ * reference, inv_trans.h:36-58, :100-160); the kvset* arrays (1-based V-set per GLOBAL level / field) say which is which.
+ * In ect_inv_args / ect_dir_args the spectral counts (nuv, nscalar, nsc2, nsc3a_lev, nsc3b_lev) are the LOCAL ones;
+ * nsc3a_fld / nsc3b_fld are not distributed.  Calls are synchronous. */
+#define ECT_SETUP_NPRTRV(v) (((v) & 0xff) << 8)
+typedef struct ect_vset_args {
+    const int* kvsetuv;   int nuv_g;         /* KVSETUV(:)   vor / div / u / v levels                   */
+    const int* kvsetsc;   int nscalar_g;     /* KVSETSC(:)   scalars of call mode 1                      */
+    const int* kvsetsc2;  int nsc2_g;        /* KVSETSC2(:)                                              */
+    const int* kvsetsc3a; int nsc3a_lev_g;   /* KVSETSC3A(:) levels (every 3-D field of PSPSC3A alike)   */
+    const int* kvsetsc3b; int nsc3b_lev_g;
+} ect_vset_args;
+int ect_inv_trans_vset(int handle, const ect_inv_args* args, const ect_vset_args* vs);
+int ect_dir_trans_vset(int handle, const ect_dir_args* args, const ect_vset_args* vs);
+
 int ect_synchronize(int handle);   /* wait for asynchronous ECT_MEM_DEVICE calls on this handle */
 int ect_release(int handle);
 int ect_finalize(void);

@@ -31,3 +31,17 @@ def test_distributed_equals_single(built, world, no_p2p, gp):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DIST_CHECK_OK" in out.stdout
+
+
+@pytest.mark.parametrize("world,V", [(2, 2), (4, 2), (8, 2)])
+def test_vsets_equal_single(built, world, V):
+    """NPRTRV > 1 (the reference benchmark's default 4 x 2 on 8 ranks): fields spread over V-sets, eq_regions grid-point
+    tasks, TRLTOG / TRGTOL moving points and fields; results bit identical with one rank."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, ECT_DIST_V=str(V))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29800 + world), os.path.join(ROOT, "tools", "dist_check_vsets.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "VSET_CHECK_OK" in out.stdout

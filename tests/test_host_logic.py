@@ -224,6 +224,40 @@ def test_eq_regions_known_partitions():
         assert sum(r) == n and (n % 2 == 1 or r == r[::-1]) and (n < 3 or (r[0] == 1 and r[-1] == 1))
 
 
+@pytest.mark.parametrize("world,V", [(2, 2), (4, 2), (8, 2), (6, 3)])
+def test_trltog_tables_vsets(eb, world, V):
+    """NPRTRV > 1: tasks form a W x V grid (w = pe // V, v = pe % V); the grid-point partition is eq_regions over all
+    tasks, the latitude bands belong to the W-groups.  Band-owner tables run over all tasks, task tables over the W owners."""
+    T, N = 47, 48
+    nloen = eb.octahedral_nloen(N)
+    W = world // V
+    trs = [eb.Transform(T, nloen, nranks=world, rank=r, host_only=True, nprtrv=V) for r in range(world)]
+    ref_w = [eb.Transform(T, nloen, nranks=W, rank=w, host_only=True) for w in range(W)]
+    reg, segs = eb.gridpoint_partition(nloen, world)
+    latoff = np.concatenate([[0], np.cumsum(nloen)])
+    local_global = []
+    for p, t in enumerate(trs):
+        w = p // V
+        assert t.info.nranks == W and t.info.rank == w                      # the W-group's wavenumbers and latitude band
+        np.testing.assert_array_equal(t.myms, ref_w[w].myms)
+        assert (t.info.lat0, t.info.nlat) == (ref_w[w].info.lat0, ref_w[w].info.nlat)
+        np.testing.assert_array_equal(t.gp_segs, segs[p])
+        local_global.append(np.concatenate([latoff[l] + f + np.arange(c) for l, f, c in t.gp_segs]))
+        assert t.ngptot == local_global[-1].size
+    assert sum(t.ngptot for t in trs) == int(nloen.sum())
+    for r, t in enumerate(trs):
+        w = r // V
+        band0 = latoff[t.info.lat0]
+        nband = int(latoff[t.info.lat0 + t.info.nlat] - band0)
+        xb_idx = t._arr(30, np.int32, nband); xb_off = t._arr(31, np.int64, world + 1)
+        assert sorted(xb_idx.tolist()) == list(range(nband))
+        for p, tp in enumerate(trs):
+            xg_off = tp._arr(32, np.int64, W + 1)
+            np.testing.assert_array_equal(band0 + xb_idx[xb_off[p]:xb_off[p + 1]], local_global[p][xg_off[w]:xg_off[w + 1]])
+    for t in trs + ref_w:
+        t.release()
+
+
 @pytest.mark.parametrize("world", [2, 3, 5, 8])
 def test_trltog_tables_eq_regions(eb, world):
     """TRLTOG / TRGTOL with the reference's grid-point decomposition, host logic only: the message a band owner packs
