@@ -36,7 +36,7 @@ def test_distributed_equals_single(built, world, no_p2p, gp):
 @pytest.mark.parametrize("world,V", [(2, 2), (4, 2), (8, 2)])
 def test_vsets_equal_single(built, world, V):
     """NPRTRV > 1 (the reference benchmark's default 4 x 2 on 8 ranks): fields spread over V-sets, eq_regions grid-point
-    tasks, TRLTOG / TRGTOL moving points and fields; results bit identical with one rank."""
+    tasks, TRLTOG / TRGTOL moving points and fields; results equal one rank's to rounding (field pairs of the FFT change)."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, ECT_DIST_V=str(V))

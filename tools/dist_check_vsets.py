@@ -1,5 +1,7 @@
 """Run under torchrun: INV_TRANS / DIR_TRANS with NPRTRV > 1 (fields spread over V-sets, eq_regions grid-point tasks,
-TRLTOG / TRGTOL redistributing points and fields) against the oracle and, bit for bit, against one rank.
+TRLTOG / TRGTOL redistributing points and fields) against the oracle and against one rank.  Across NPRTRV the results
+agree to rounding, not bit for bit: two real fields share one complex FFT and the V-sets change which fields pair up
+(across NPRTRW, where the pairs stay the same, tools/dist_check.py demands bit identity).
 ECT_DIST_V = NPRTRV (default 2); world must be a multiple of it."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -51,15 +53,15 @@ if tr.nump:
 tr1 = eb.Transform(T, nloen, device=local)
 T_ = lambda a: np.ascontiguousarray(a.T)
 g1 = tr1.inv_trans(T_(vor), T_(div), T_(sc), **opts)
-same = min(same, float(np.array_equal(gp[0], g1[0][:, gidx])))
+e_one = rel(gp[0], g1[0][:, gidx])
 v1, d1, s1 = tr1.dir_trans(np.ascontiguousarray(g1[:, nuv:nuv + 2 * nuv + nsc]), nuv, nsc)
 if tr.nump:
-    same = min(same, float(np.array_equal(ov, v1[idx][:, luv]) and np.array_equal(od, d1[idx][:, luv]) and np.array_equal(os_, s1[idx][:, lsc])))
+    e_one = max(e_one, rel(ov, v1[idx][:, luv]), rel(od, d1[idx][:, luv]), rel(os_, s1[idx][:, lsc]))
 tr1.release()
-t = torch.tensor([e_inv, e_dir, 1.0 - same], device=dev, dtype=torch.float64)
+t = torch.tensor([e_inv, e_dir, e_one, 1.0 - same], device=dev, dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("vset check (W=%d V=%d): inv %.2e dir %.2e not-bit-identical %g" % ((world // V, V) + tuple(t.cpu().tolist())))
-    print("VSET_CHECK_OK" if float(t[0]) < 1e-12 and float(t[1]) < 1e-12 and float(t[2]) == 0.0 else "VSET_CHECK_FAIL")
+    print("vset check (W=%d V=%d): inv %.2e dir %.2e vs-one-rank %.2e blocked-differs %g" % ((world // V, V) + tuple(t.cpu().tolist())))
+    print("VSET_CHECK_OK" if float(t[0]) < 1e-12 and float(t[1]) < 1e-12 and float(t[2]) < 1e-13 and float(t[3]) == 0.0 else "VSET_CHECK_FAIL")
 tr.release()
 dist.destroy_process_group()
