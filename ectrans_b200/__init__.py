@@ -469,6 +469,30 @@ class Transform:
         self._keep = keep
         _check(lib().ect_dir_trans(self.handle, C.byref(a)), "ect_dir_trans")
 
+    def _vset_raw(self, fn, args, kw, vsets):
+        keep = []
+        for k, v in kw.items():
+            if hasattr(v, "shape"):
+                keep.append(v); setattr(args, k, _ptr(v))
+            else:
+                setattr(args, k, v)
+        va = _VsetArgs()
+        for k, v in vsets.items():                  # kvsetuv, kvsetsc, kvsetsc2, kvsetsc3a, kvsetsc3b: 1-based V-set arrays
+            arr = np.ascontiguousarray(v, dtype=np.int32); keep.append(arr)
+            setattr(va, k, arr.ctypes.data if arr.size else None)
+            setattr(va, {"kvsetuv": "nuv_g", "kvsetsc": "nscalar_g", "kvsetsc2": "nsc2_g", "kvsetsc3a": "nsc3a_lev_g",
+                         "kvsetsc3b": "nsc3b_lev_g"}[k], int(arr.size))
+        self._keep = keep
+        _check(fn(self.handle, C.byref(args), C.byref(va)), "ect_*_trans_vset")
+
+    def inv_trans_vset_raw(self, vsets, **kw):
+        """Every ect_inv_args member + the V-set arrays (call mode 2 with NPRTRV > 1); numpy arrays = host memory
+        (set memspace=ECT_MEM_HOST), torch CUDA tensors = device pointers."""
+        self._vset_raw(lib().ect_inv_trans_vset, _InvArgs(), kw, vsets)
+
+    def dir_trans_vset_raw(self, vsets, **kw):
+        self._vset_raw(lib().ect_dir_trans_vset, _DirArgs(), kw, vsets)
+
     def specnorm(self, spec, pmet=None):
         """SPECNORM: spectral L2 norm per field (global over ranks); pmet: optional metric (0:nsmax)."""
         dev = _is_torch(spec)

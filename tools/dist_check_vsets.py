@@ -49,7 +49,58 @@ e_dir = 0.0
 if tr.nump:
     if len(luv): e_dir = max(e_dir, rel(ov.T, rv[luv][:, idx]), rel(od.T, rd[luv][:, idx]))
     if len(lsc): e_dir = max(e_dir, rel(os_.T, rs[lsc][:, idx]))
-# one rank, same input: bit identity
+# ---- call mode 2, the benchmark's shape (ectrans-benchmark.F90:473-527): PSPVOR/PSPDIV(lev_l, nspec2), PSPSC3A(lev_l, nspec2,
+# nfld), PSPSC2(1, nspec2) -> PGPUV(nproma, lev, 2 + 2 ders, blk), PGP3A(nproma, lev, 3 nfld, blk), PGP2(nproma, 3, blk); device
+# pointers for the inverse, host arrays for the direct transform ----
+nlev, nfld3 = nuv, 2
+sc3 = eo.random_spectral(s, nlev * nfld3, 7).reshape(nfld3, nlev, -1)          # [fld][lev][nspec2]
+sc2 = eo.random_spectral(s, 1, 8)
+kv3a = kvuv.copy(); kv2 = np.array([1 % V + 1])
+l3 = np.where(kv3a == v + 1)[0]; l2 = np.where(kv2 == v + 1)[0]
+ref2 = eo.inv_trans(s, vor, div, np.concatenate([sc2, sc3.reshape(nfld3 * nlev, -1)]), scders=True, uvder=True)
+npr = tr.ngptot
+dv_ = torch.from_numpy(loc(vor, luv)).to(dev); dd_ = torch.from_numpy(loc(div, luv)).to(dev)
+d3a = torch.from_numpy(np.ascontiguousarray(sc3[:, l3][:, :, idx].transpose(0, 2, 1))).to(dev)      # (fld, nspec2, lev_l) = PSPSC3A(lev_l, nspec2, fld)
+d2 = torch.from_numpy(loc(sc2, l2)).to(dev)
+guv = torch.zeros((1, 4, nlev, npr), dtype=torch.float64, device=dev)             # PGPUV(nproma, lev, 4, 1): u v du dv
+g3a = torch.zeros((1, 3 * nfld3, nlev, npr), dtype=torch.float64, device=dev)
+g2 = torch.zeros((1, 3, npr), dtype=torch.float64, device=dev)
+vsets = dict(kvsetuv=kvuv, kvsetsc2=kv2, kvsetsc3a=kv3a)
+kw = dict(memspace=eb.ECT_MEM_DEVICE, scders=1, uvder=1, nuv=len(luv), gpuv=guv, gp2=g2, gp3a=g3a, nsc3a_fld=nfld3, nsc3a_lev=len(l3), nsc2=len(l2))
+if len(luv): kw.update(spvor=dv_, spdiv=dd_)
+if len(l3): kw.update(spsc3a=d3a)
+if len(l2): kw.update(spsc2=d2)
+tr.inv_trans_vset_raw(vsets, **kw)
+torch.cuda.synchronize()
+# oracle field order: u v | sc2, 3a(fld, lev) | nsd of those | du dv | ewd of those
+nscg = 1 + nfld3 * nlev
+R = ref2[:, gidx]
+e_m2 = max(rel(guv[0, 0].cpu().numpy(), R[0:nlev]), rel(guv[0, 1].cpu().numpy(), R[nlev:2 * nlev]),
+           rel(guv[0, 2].cpu().numpy(), R[2 * nlev + 2 * nscg:3 * nlev + 2 * nscg]), rel(guv[0, 3].cpu().numpy(), R[3 * nlev + 2 * nscg:4 * nlev + 2 * nscg]))
+o_sc, o_ns, o_ew = 2 * nlev, 2 * nlev + nscg, 4 * nlev + 2 * nscg
+for part, o in enumerate((o_sc, o_ns, o_ew)):
+    e_m2 = max(e_m2, rel(g2[0, part].cpu().numpy(), R[o]))
+    for j3 in range(nfld3):
+        e_m2 = max(e_m2, rel(g3a[0, part * nfld3 + j3].cpu().numpy(), R[o + 1 + j3 * nlev:o + 1 + (j3 + 1) * nlev]))
+# direct, host arrays: PGPUV(nproma, lev, 2, 1), PGP3A(nproma, lev, nfld, 1), PGP2(nproma, 1, 1)
+huv = np.ascontiguousarray(np.stack([R[0:nlev], R[nlev:2 * nlev]])[None])
+h3a = np.ascontiguousarray(R[o_sc + 1:o_sc + 1 + nfld3 * nlev].reshape(nfld3, nlev, -1)[None])
+h2 = np.ascontiguousarray(R[o_sc:o_sc + 1][None])
+o_v = np.zeros((tr.nspec2, len(luv))); o_d = np.zeros_like(o_v)
+o_3a = np.zeros((nfld3, tr.nspec2, len(l3))); o_2 = np.zeros((tr.nspec2, len(l2)))
+kw = dict(memspace=eb.ECT_MEM_HOST, nuv=len(luv), gpuv=huv, gp2=h2, gp3a=h3a, nsc3a_fld=nfld3, nsc3a_lev=len(l3), nsc2=len(l2))
+if len(luv): kw.update(spvor=o_v, spdiv=o_d)
+if len(l3): kw.update(spsc3a=o_3a)
+if len(l2): kw.update(spsc2=o_2)
+tr.dir_trans_vset_raw(vsets, **kw)
+rv2, rd2, rs2 = eo.dir_trans(s, np.concatenate([ref2[0:2 * nlev], ref2[o_sc:o_sc + nscg]]), nlev, nscg)
+if tr.nump:
+    if len(luv): e_m2 = max(e_m2, rel(o_v.T, rv2[luv][:, idx]), rel(o_d.T, rd2[luv][:, idx]))
+    if len(l2): e_m2 = max(e_m2, rel(o_2.T, rs2[0:1][:, idx]))
+    for j3 in range(nfld3):
+        if len(l3): e_m2 = max(e_m2, rel(o_3a[j3].T, rs2[1 + j3 * nlev:1 + (j3 + 1) * nlev][l3][:, idx]))
+e_dir = max(e_dir, e_m2)
+# one rank, same input
 tr1 = eb.Transform(T, nloen, device=local)
 T_ = lambda a: np.ascontiguousarray(a.T)
 g1 = tr1.inv_trans(T_(vor), T_(div), T_(sc), **opts)
