@@ -94,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "ect_nccl_unique_id", "ect_host_alloc", "ect_host_free", "ect_debug_get_table", "ect_measure_fp64_peak",
     "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec", "ect_inv_transad", "ect_dir_transad",
     "ect_gpnorm_trans", "ect_vordiv_to_uv", "ect_inquire_rpnm", "ect_trans_pnm", "ect_write_legpol", "ect_read_legpol",
-    "ect_gridpoint_partition", "ect_specnorm_met", "ect_inv_trans_vset", "ect_dir_trans_vset",
+    "ect_gridpoint_partition", "ect_specnorm_met", "ect_inv_trans_vset", "ect_dir_trans_vset", "ect_specnorm_vset",
 ]
 
 
@@ -117,6 +117,7 @@ def lib():
         L.ect_dir_transad.argtypes = [C.c_int, C.POINTER(_DirArgs)]
         L.ect_specnorm.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ect_specnorm_met.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ect_specnorm_vset.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ect_inv_trans_vset.argtypes = [C.c_int, C.POINTER(_InvArgs), C.POINTER(_VsetArgs)]
         L.ect_dir_trans_vset.argtypes = [C.c_int, C.POINTER(_DirArgs), C.POINTER(_VsetArgs)]
         L.ect_get_timings.argtypes = [C.c_int, C.POINTER(Timings)]
@@ -492,6 +493,17 @@ class Transform:
 
     def dir_trans_vset_raw(self, vsets, **kw):
         self._vset_raw(lib().ect_dir_trans_vset, _DirArgs(), kw, vsets)
+
+    def specnorm_vset(self, spec, kvset, pmet=None):
+        """SPECNORM with KVSET: spec (nspec2, local fields of this V-set) -> norms of all len(kvset) global fields."""
+        kv = np.ascontiguousarray(kvset, dtype=np.int32)
+        spec = np.ascontiguousarray(spec, dtype=self.dtype)
+        out = np.zeros(kv.size)
+        met = None if pmet is None else np.ascontiguousarray(pmet, dtype=np.float64)
+        _check(lib().ect_specnorm_vset(self.handle, spec.ctypes.data if spec.size else None, int(spec.shape[1]), ECT_MEM_HOST,
+                                       None if met is None else met.ctypes.data, kv.ctypes.data, int(kv.size), out.ctypes.data),
+               "ect_specnorm_vset")
+        return out
 
     def specnorm(self, spec, pmet=None):
         """SPECNORM: spectral L2 norm per field (global over ranks); pmet: optional metric (0:nsmax)."""

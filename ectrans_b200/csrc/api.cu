@@ -1561,6 +1561,59 @@ extern "C" int ect_specnorm(int handle, const double* spec, int nfld, int memspa
     return ect_specnorm_met(handle, spec, nfld, memspace, nullptr, norms);
 }
 
+// SPECNORM with KVSET (specnorm.h; spnorm_ctl_mod.F90:44-57 + spnormc_mod.F90): spec holds the nfld fields of this task's
+// V-set, kvset (1-based V-set per GLOBAL field, nfld_g entries) says which global fields they are; norms: nfld_g values,
+// on every task.  Works for NPRTRV = 1 too (kvset all ones).
+extern "C" int ect_specnorm_vset(int handle, const double* spec, int nfld, int memspace, const double* pmet, const int* kvset,
+                                 int nfld_g, double* norms) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) { ect_set_error("ect_specnorm: invalid handle"); return ECT_ERR_HANDLE; }
+    if (!norms || !kvset || nfld_g <= 0 || nfld < 0 || (nfld > 0 && !spec)) return ECT_ERR_MISSING;
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    const int V = h->vs.V, me = h->vs.v + 1, nm = P.nsmax + 1;
+    std::vector<int> mine;                     // global index of my local fields, in order
+    for (int f = 0; f < nfld_g; ++f) {
+        if (kvset[f] < 1 || kvset[f] > V) { ect_set_error("SPECNORM: KVSET TOO LONG OR CONTAINS VALUES OUTSIDE RANGE"); return ECT_ERR_BADARG; }
+        if (kvset[f] == me) mine.push_back(f);
+    }
+    if ((int)mine.size() != nfld) { ect_set_error("SPECNORM: PSPEC holds %d fields, KVSET gives this V-set %d", nfld, (int)mine.size()); return ECT_ERR_BADARG; }
+    ECT_CUDA(cudaSetDevice(d->dev));
+    const int es = h->precision == ECT_PREC_SP ? 4 : 8;
+    const double* dsp = spec;
+    int rc;
+    if (memspace == ECT_MEM_HOST && nfld > 0) {
+        if ((rc = ensure(d->stage_sp, d->stage_sp_elems, (i64)nfld * P.nspec2, d->stream, false))) return rc;
+        ECT_CUDA(cudaMemcpyAsync(d->stage_sp, spec, (size_t)nfld * P.nspec2 * es, cudaMemcpyHostToDevice, d->stream));
+        dsp = d->stage_sp;
+    }
+    double* w = nullptr;        // [local sums nfld x nm][global sums nfld_g x nm][metric nm]
+    ECT_CUDA(cudaMalloc(&w, ((size_t)(nfld + nfld_g) * nm + nm) * sizeof(double)));
+    double* zl = w; double* zg = w + (size_t)nfld * nm; double* dmet = nullptr;
+    ECT_CUDA(cudaMemsetAsync(w, 0, (size_t)(nfld + nfld_g) * nm * sizeof(double), d->stream));
+    if (pmet) { dmet = zg + (size_t)nfld_g * nm; ECT_CUDA(cudaMemcpyAsync(dmet, pmet, nm * sizeof(double), cudaMemcpyHostToDevice, d->stream)); }
+    if (P.nump > 0 && nfld > 0) {
+        dim3 grid((nfld + 127) / 128, P.nump);
+        if (es == 4) k_specnorm<true><<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nsmax, d->legm, d->nasm0, dmet, zl);
+        else k_specnorm<false><<<grid, 128, 0, d->stream>>>(dsp, nfld, P.nsmax, d->legm, d->nasm0, dmet, zl);
+    }
+    for (int i = 0; i < nfld; ++i)      // local field i is global field mine[i]
+        ECT_CUDA(cudaMemcpyAsync(zg + (size_t)mine[i] * nm, zl + (size_t)i * nm, nm * sizeof(double), cudaMemcpyDeviceToDevice, d->stream));
+    // every (m, global field) sum lives on exactly one task: adding zeros is exact
+    ncclComm_t comm = (ncclComm_t)(V > 1 ? d->comm_world : d->comm);
+    if (comm) ECT_NCCL(ncclAllReduce(zg, zg, (size_t)nfld_g * nm, ncclDouble, ncclSum, comm, d->stream));
+    std::vector<double> hz((size_t)nfld_g * nm);
+    ECT_CUDA(cudaMemcpyAsync(hz.data(), zg, hz.size() * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    ECT_CUDA(cudaFree(w));
+    for (int f = 0; f < nfld_g; ++f) {
+        double t = 0.0;
+        for (int m = 0; m < nm; ++m) t += hz[(size_t)f * nm + m];
+        norms[f] = sqrt(t);
+    }
+    return ECT_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------------
 // test / debug access (not part of the reference API)
 // ---------------------------------------------------------------------------------------

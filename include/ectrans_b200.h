@@ -186,6 +186,10 @@ int ect_specnorm(int handle, const double* spec, int nfld, int memspace, double*
  * wavenumbers are added in the reference's order (spnormd_mod.F90:36-51, spnorm_ctl_mod.F90:56-57): the norms are bit
  * identical across decompositions. */
 int ect_specnorm_met(int handle, const double* spec, int nfld, int memspace, const double* pmet, double* norms);
+/* SPECNORM with KVSET (NPRTRV > 1, specnorm.h): spec holds the nfld fields of this task's V-set, kvset[nfld_g] the 1-based
+ * V-set of every global field; norms[nfld_g] arrive on every task. */
+int ect_specnorm_vset(int handle, const double* spec, int nfld, int memspace, const double* pmet, const int* kvset,
+                      int nfld_g, double* norms);
 int ect_get_timings(int handle, ect_timings* t);
 /* INV_TRANSAD / DIR_TRANSAD: adjoints for the inner products of the reference's adjoint tests (grid: plain sum;
  * spectral: weight 2 for m > 0, 1 for the real parts of m = 0).  Replace src/trans/include/ectrans/inv_transad.h,

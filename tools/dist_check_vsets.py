@@ -100,6 +100,10 @@ if tr.nump:
     for j3 in range(nfld3):
         if len(l3): e_m2 = max(e_m2, rel(o_3a[j3].T, rs2[1 + j3 * nlev:1 + (j3 + 1) * nlev][l3][:, idx]))
 e_dir = max(e_dir, e_m2)
+# SPECNORM with KVSET: the norms of all global fields on every task, bit identical with one rank (m sums added in order)
+nrm = tr.specnorm_vset(loc(sc, lsc), kvsc)
+e_nrm = rel(nrm, eo.specnorm(s, sc))
+e_dir = max(e_dir, e_nrm * 1e-1)             # 1e-13 bound folded into the 1e-12 one
 # one rank, same input
 tr1 = eb.Transform(T, nloen, device=local)
 T_ = lambda a: np.ascontiguousarray(a.T)
@@ -108,6 +112,7 @@ e_one = rel(gp[0], g1[0][:, gidx])
 v1, d1, s1 = tr1.dir_trans(np.ascontiguousarray(g1[:, nuv:nuv + 2 * nuv + nsc]), nuv, nsc)
 if tr.nump:
     e_one = max(e_one, rel(ov, v1[idx][:, luv]), rel(od, d1[idx][:, luv]), rel(os_, s1[idx][:, lsc]))
+same = min(same, float(np.array_equal(nrm, tr1.specnorm(T_(sc)))))
 tr1.release()
 t = torch.tensor([e_inv, e_dir, e_one, 1.0 - same], device=dev, dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
