@@ -2237,6 +2237,7 @@ extern "C" int ect_read_legpol(int handle, const char* path) {
 // ftinv_ctl_mod.F90:144-166 restricted to its levels -- which is the order the W-group transform of that V-set uses.
 // ---------------------------------------------------------------------------------------
 namespace {
+struct DevFree { void* p = nullptr; ~DevFree() { if (p) cudaFree(p); } };      // frees a temporary device buffer on every return path
 struct VsLists {
     std::vector<int> uv, sc;          // V-set (0-based) of every global vor/div/u/v level and of every global scalar field
     int nuv_g = 0, nsc2_g = 0, lev3a_g = 0, lev3b_g = 0, nsc_g = 0;
@@ -2361,8 +2362,10 @@ extern "C" int ect_inv_trans_vset(int handle, const ect_inv_args* a, const ect_v
         if (scders) scgroup(2);
     }
     std::vector<int> nfl; char* tab = nullptr;
+    DevFree f_tab, f_sp;
     if ((rc = vs_upload_table(d, gv, V, base, stride, nfl, &tab))) return rc;
-    if ((rc = gp_exchange_setup(h, nfl[me], nfg))) { cudaFree(tab); return rc; }
+    f_tab.p = tab;
+    if ((rc = gp_exchange_setup(h, nfl[me], nfg))) return rc;
     // ---- the W-group's transform of this V-set's fields into the band buffer (PGP(band points, local fields)) ----
     ect_inv_args la = *a;
     la.memspace = ECT_MEM_DEVICE; la.nproma = 0;
@@ -2373,6 +2376,7 @@ extern "C" int ect_inv_trans_vset(int handle, const ect_inv_args* a, const ect_v
         const i64 nsc_l = mode2_sp ? (i64)(a->spsc2 ? a->nsc2 : 0) + (a->spsc3a ? (i64)a->nsc3a_lev * a->nsc3a_fld : 0) + (a->spsc3b ? (i64)a->nsc3b_lev * a->nsc3b_fld : 0)
                                    : (a->spscalar ? a->nscalar : 0);
         ECT_CUDA(cudaMalloc(&sp_tmp, (size_t)std::max<i64>((2 * (i64)a->nuv + nsc_l) * nsp * es, 16)));
+        f_sp.p = sp_tmp;
         char* p = sp_tmp;
         auto up = [&](const double*& ptr, i64 n) -> int {
             if (!ptr || n == 0) return ECT_SUCCESS;
@@ -2382,7 +2386,7 @@ extern "C" int ect_inv_trans_vset(int handle, const ect_inv_args* a, const ect_v
         };
         if ((rc = up(la.spvor, a->nuv * nsp)) || (rc = up(la.spdiv, a->nuv * nsp)) || (rc = up(la.spscalar, (i64)a->nscalar * nsp)) ||
             (rc = up(la.spsc2, (i64)a->nsc2 * nsp)) || (rc = up(la.spsc3a, (i64)a->nsc3a_lev * a->nsc3a_fld * nsp)) ||
-            (rc = up(la.spsc3b, (i64)a->nsc3b_lev * a->nsc3b_fld * nsp))) { cudaFree(tab); cudaFree(sp_tmp); return rc; }
+            (rc = up(la.spsc3b, (i64)a->nsc3b_lev * a->nsc3b_fld * nsp))) return rc;
     }
     rc = inv_trans_impl(handle, &la, nullptr, 0);
     // ---- TRLTOG: points and fields to the grid-point tasks ----
@@ -2397,8 +2401,6 @@ extern "C" int ect_inv_trans_vset(int handle, const ect_inv_args* a, const ect_v
         }
     }
     ECT_CUDA(cudaStreamSynchronize(d->stream));
-    cudaFree(tab);
-    if (sp_tmp) cudaFree(sp_tmp);
     return rc;
 }
 
@@ -2463,17 +2465,19 @@ extern "C" int ect_dir_trans_vset(int handle, const ect_dir_args* a, const ect_v
         for (int j3 = 0; j3 < f3b; ++j3) for (int l = 0; l < L.lev3b_g; ++l, ++fi) { base[fi] = (double*)adv(q_3b, ((i64)j3 * L.lev3b_g + l) * nproma, es); stride[fi] = (i64)nproma * L.lev3b_g * f3b; }
     }
     std::vector<int> nfl; char* tab = nullptr;
+    DevFree f_tab, f_sp;
     if ((rc = vs_upload_table(d, gv, V, base, stride, nfl, &tab))) return rc;
-    if ((rc = gp_exchange_setup(h, nfl[me], nfg))) { cudaFree(tab); return rc; }
+    f_tab.p = tab;
+    if ((rc = gp_exchange_setup(h, nfl[me], nfg))) return rc;
     // ---- TRGTOL: this V-set's fields of the band's points arrive in the band buffer ----
     rc = gp_exchange(h, nfl[me], nfg, nfl, es, 0, (double* const*)tab, (const i64*)(tab + nfg * sizeof(double*)), nproma);
     ECT_CUDA(cudaStreamSynchronize(d->stream));
-    cudaFree(tab);
     if (rc) return rc;
     // ---- the W-group's direct transform: call mode 1 on the band buffer, one (nsc_local, nspec2) scalar array ----
     const i64 nsp = P.nspec2;
     char* sp_tmp = nullptr;
     ECT_CUDA(cudaMalloc(&sp_tmp, (size_t)std::max<i64>((2 * (i64)nuv_l + nsc_l) * nsp * es, 16)));
+    f_sp.p = sp_tmp;
     ect_dir_args la = *a;
     la.memspace = ECT_MEM_DEVICE; la.nproma = 0; la.nuv = nuv_l; la.nscalar = nsc_l;
     la.gp = d->gpband; la.gpuv = la.gp2 = la.gp3a = la.gp3b = nullptr;
@@ -2501,6 +2505,5 @@ extern "C" int ect_dir_trans_vset(int handle, const ect_dir_args* a, const ect_v
         }
     }
     ECT_CUDA(cudaStreamSynchronize(d->stream));
-    cudaFree(sp_tmp);
     return rc;
 }
