@@ -11,6 +11,9 @@
  *   ect_inv_trans  <- INV_TRANS                    src/trans/include/ectrans/inv_trans.h:12-161; transi trans_invtrans()
  *   ect_dir_trans  <- DIR_TRANS                    src/trans/include/ectrans/dir_trans.h:12-140; transi trans_dirtrans()
  *   ect_specnorm   <- SPECNORM                     src/trans/include/ectrans/specnorm.h
+ *   ect_inv_transad / ect_dir_transad, ect_gath_* / ect_dist_*, ect_gpnorm_trans, ect_vordiv_to_uv, ect_inquire_rpnm,
+ *   ect_trans_pnm, ect_write_legpol / ect_read_legpol, ect_gridpoint_partition, ect_*_trans_vset, ect_specnorm_vset:
+ *                  the interfaces they replace are cited at their declarations below
  *   ect_release    <- TRANS_RELEASE / trans_delete src/trans/include/ectrans/trans_release.h
  *   ect_finalize   <- TRANS_END / trans_finalize   src/trans/include/ectrans/trans_end.h
  *
@@ -71,8 +74,8 @@ typedef struct ect_setup_opts {
     int nsmax;            /* KSMAX: spectral truncation                                  */
     int ndgl;             /* KDGL : number of Gaussian latitudes (even)                  */
     const int* nloen;     /* KLOEN(ndgl): points per latitude, north -> south            */
-    int nranks;           /* number of tasks = NPRTRW (NPRTRV = 1); 1 = LDMPOFF          */
-    int rank;             /* 0-based task id (MYSETW-1)                                  */
+    int nranks;           /* number of tasks NPROC = NPRTRW * NPRTRV (NPRTRV = 1 unless ECT_SETUP_NPRTRV is in flags); 1 = LDMPOFF */
+    int rank;             /* 0-based task id (MYPROC-1); W-set = rank / NPRTRV, V-set = rank % NPRTRV */
     int flags;            /* ECT_SETUP_*                                                 */
     int device;           /* CUDA device ordinal, -1 = current                           */
     void* stream;         /* cudaStream_t to run on, NULL = library-owned stream         */
