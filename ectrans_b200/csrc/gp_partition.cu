@@ -14,15 +14,39 @@
 
 static long long f_nint(double x) { return x >= 0 ? (long long)std::floor(x + 0.5) : -(long long)std::floor(-x + 0.5); }
 
+// Gamma(x) by the polynomial the reference uses for the area of the sphere (eq_regions_mod.F90:282-330).  For odd task
+// counts the ideal collar sizes come in exact-tie pairs (r1 + r2 = integer + 1/2 with r2 = k + 1/2), so which collar gets
+// the extra region hangs on the last bits of the area: std::tgamma would flip e.g. eq_regions(31) from the reference's
+// [1 6 8 9 6 1] to [1 6 9 8 6 1].
+static double eq_gamma(double x) {
+    static const double c[14] = {0.999999999999999990e+00, -0.422784335098466784e+00, -0.233093736421782878e+00,
+                                 0.191091101387638410e+00, -0.024552490005641278e+00, -0.017645244547851414e+00,
+                                 0.008023273027855346e+00, -0.000804329819255744e+00, -0.000360837876648255e+00,
+                                 0.000145596568617526e+00, -0.000017545539395205e+00, -0.000002591225267689e+00,
+                                 0.000001337767384067e+00, -0.000000199542863674e+00};
+    const int n = (int)f_nint(x - 2.0);
+    double w = x - (double)(n + 2);
+    double y = c[13];
+    for (int i = 12; i >= 0; --i) y = y * w + c[i];
+    if (n > 0) {
+        w = x - 1.0;
+        for (int k = 2; k <= n; ++k) w *= x - (double)k;
+    } else {
+        w = 1.0;
+        for (int k = 0; k < -n; ++k) y *= x + (double)k;
+    }
+    return w / y;
+}
+
 int ect_eq_regions(int n, std::vector<int>& regions) {
     regions.clear();
     if (n < 1) return ECT_ERR_BADARG;
     if (n == 1) { regions.push_back(1); return ECT_SUCCESS; }
     const double pi = 2.0 * std::asin(1.0);
-    // area of the unit sphere as 2 pi^(3/2) / Gamma(3/2) (the reference evaluates Gamma by its own polynomial; the two
-    // agree to the last bits and only feed roundings to the nearest integer)
-    const double area = (2.0 * std::pow(pi, 1.5) / std::tgamma(1.5)) / (double)n;
-    auto cap = [&](double s) { const double h = std::sin(0.5 * s); return 4.0 * pi * h * h; };
+    const double area = (2.0 * std::pow(pi, 1.5) / eq_gamma(1.5)) / (double)n;      // area of the unit sphere / n
+    // area of a cap: (4 pi) * sin^2, associated as the reference's 4*pi*sin(s/2)**2 -- the ties described above make
+    // even this last bit matter
+    auto cap = [&](double s) { const double h = std::sin(s / 2.0); return (4.0 * pi) * (h * h); };
     const double polar = n == 2 ? 0.5 * pi : 2.0 * std::asin(0.5 * std::sqrt(area / pi));
     const double ideal = std::sqrt(area);
     int collars = 0;
@@ -77,6 +101,10 @@ int ect_gp_partition(const std::vector<int>& nloen, int nproc, EctGpPartition& G
             for (int b = 0; b < G.regions[a]; ++b) { ++task; want += (task <= extra || extra == 0) ? share : share - 1; }
             G.band_points[a] = want;
             long long have = left_over;
+            if (a > 0 && have >= want) {       // a band inside what is left of one latitude: SUMPLATBEQ cannot describe that
+                ect_set_error("SUMPLATBEQ: NPROC TOO BIG FOR THIS RESOLUTION, LDSPLIT=T (a band of %lld points inside one latitude)", want);
+                return ECT_ERR_BADARG;
+            }
             while (++lat < ndgl) {
                 if (have + nloen[lat] < want) { have += nloen[lat]; continue; }
                 last[a] = lat;
@@ -105,6 +133,10 @@ int ect_gp_partition(const std::vector<int>& nloen, int nproc, EctGpPartition& G
         long long span = nloen[l0] - next[0] + 1;
         for (int k = 1; k < nl; ++k) span += nloen[l0 + k];
         end[nl - 1] = (int)(nloen[l0 + nl - 1] - span + pts);
+        if (nl < 1 || next[0] < 1 || next[0] > nloen[l0] || end[nl - 1] < 0 || end[nl - 1] > nloen[l0 + nl - 1]) {
+            ect_set_error("SUSTAONL: inconsistent partitioning (band %d)", a);
+            return ECT_ERR_GENERIC;
+        }
         typedef std::pair<long long, int> Key;                 // (angle of the next point in 1/1000 degree, latitude)
         std::priority_queue<Key, std::vector<Key>, std::greater<Key>> heap;
         auto angle = [&](int k) { return f_nint((double)(next[k] - 1) * (360000.0 / (double)nloen[l0 + k])); };

@@ -299,3 +299,46 @@ def test_bench_reference_arm_runs_without_gpu():
     assert line["impl"] == "reference" and line["unit"] == "ms" and line["higher_is_better"] is False
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_gridpoint_partition_random_grids(eb):
+    """Random symmetric reduced grids (even and odd row lengths, plateaus) x random task counts: the heap-ordered C++
+    SUSTAONL must reproduce the oracle's point-by-point scan, ties included (equal angles -> northernmost latitude)."""
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for _ in range(40):
+        nh = int(rng.integers(4, 28))
+        half = np.sort(rng.integers(8, 200, size=nh))
+        if rng.random() < 0.5:
+            half = (half // 4) * 4 + 4                      # many equal angles between rows
+        nloen = np.concatenate([half, half[::-1]]).astype(np.int32)
+        nproc = int(rng.integers(2, 41))
+        try:
+            nreg, segs = eo.gridpoint_partition(nloen, nproc)
+        except Exception:
+            continue                                         # too many tasks for this grid: both sides refuse (below)
+        reg, mine = eb.gridpoint_partition(nloen, nproc)
+        assert list(reg) == list(nreg)
+        for a, b in zip(segs, mine):
+            np.testing.assert_array_equal(np.asarray(a, dtype=np.int32).reshape(-1, 3), b)
+        checked += 1
+    assert checked >= 25
+    # SUMPLATBEQ's "NPROC TOO BIG FOR THIS RESOLUTION" (sumplatbeq_mod.F90:94-99) is an error code here, not an abort
+    with pytest.raises(eb.EctError):
+        eb.gridpoint_partition(np.full(4, 8, dtype=np.int32), 32)
+
+
+def test_eq_regions_cxx_matches_reference_arithmetic(eb):
+    """For odd task counts the ideal collar sizes come in exact-tie pairs, so eq_regions hangs on the last bits of the
+    reference's arithmetic (its own gamma polynomial, 4*pi*sin(s/2)**2 association): the C++ must give the oracle's
+    restatement for every count, e.g. eq_regions(31) = [1 6 8 9 6 1], not [1 6 9 8 6 1]."""
+    L = eb.lib()
+    nl = np.full(8192, 16, dtype=np.int32)
+    for n in list(range(1, 300)) + [511, 777, 1001, 1023, 2047]:
+        nb, ns = ctypes.c_int(0), ctypes.c_longlong(0)
+        reg = np.zeros(n, dtype=np.int32); seg0 = np.zeros(n + 1, dtype=np.int32)
+        assert L.ect_gridpoint_partition(8192, nl.ctypes.data, n, ctypes.byref(nb), reg.ctypes.data, seg0.ctypes.data, None, 0, ctypes.byref(ns)) == 0
+        assert list(reg[:nb.value]) == eo.eq_regions(n), n
+    # a band that would fit inside what is left of one latitude cannot be described: an error code, not a crash
+    with pytest.raises(eb.EctError, match="NPROC TOO BIG"):
+        eb.gridpoint_partition(np.full(64, 4096, dtype=np.int32), 1024)
