@@ -101,7 +101,9 @@ int ect_gp_partition(const std::vector<int>& nloen, int nproc, EctGpPartition& G
             for (int b = 0; b < G.regions[a]; ++b) { ++task; want += (task <= extra || extra == 0) ? share : share - 1; }
             G.band_points[a] = want;
             long long have = left_over;
-            if (a > 0 && have >= want) {       // a band inside what is left of one latitude: SUMPLATBEQ cannot describe that
+            // a band inside what is left of one latitude cannot be described by SUMPLATBEQ -- except the last band, which
+            // may be exactly the rest of the last latitude
+            if (a > 0 && have >= want && !(a == nbands - 1 && have == want && lat == ndgl - 1)) {
                 ect_set_error("SUMPLATBEQ: NPROC TOO BIG FOR THIS RESOLUTION, LDSPLIT=T (a band of %lld points inside one latitude)", want);
                 return ECT_ERR_BADARG;
             }
