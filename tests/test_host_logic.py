@@ -342,3 +342,29 @@ def test_eq_regions_cxx_matches_reference_arithmetic(eb):
     # a band that would fit inside what is left of one latitude cannot be described: an error code, not a crash
     with pytest.raises(eb.EctError, match="NPROC TOO BIG"):
         eb.gridpoint_partition(np.full(64, 4096, dtype=np.int32), 1024)
+
+
+def test_host_plan_fuzz_against_oracle(eb):
+    """Random symmetric reduced grids (odd and even row lengths), truncations and task counts: NMEN / NDGLU / Gaussian
+    latitudes, the wavenumber distribution (SUWAVEDI) and the Fourier latitude bands (SUMPLATB) of the C++ host plan
+    against the oracle's restatements."""
+    rng = np.random.default_rng(11)
+    for it in range(120):
+        nh = int(rng.integers(2, 50))
+        half = np.sort(rng.integers(4, 400, size=nh))
+        nloen = np.concatenate([half, half[::-1]]).astype(np.int32)
+        T = int(rng.integers(1, 3 * nh))
+        W = int(rng.integers(1, min(2 * nh, 12) + 1))
+        trs = [eb.Transform(T, nloen, nranks=W, rank=r, host_only=True) for r in range(W)]
+        s = eo.setup(T, 2 * nh, nloen, tables=False)
+        t = trs[0]
+        np.testing.assert_array_equal(t.nmen, s.nmen)
+        np.testing.assert_array_equal(t.ndglu, s.ndglu)
+        assert np.abs(t.rmu - s.rmu).max() < 1e-15 and np.abs(t.rgw - s.rw).max() < 1e-15
+        first, count = eo.sumplatb_fourier(nloen, W)[:2]
+        np.testing.assert_array_equal(t.lat_first, np.asarray(first)); np.testing.assert_array_equal(t.lat_count, np.asarray(count))
+        wave = eo.suwavedi(T, W)
+        np.testing.assert_array_equal(t.nprocm, np.asarray(wave[0] if isinstance(wave, tuple) else wave))
+        assert sum(x.nspec2 for x in trs) == (T + 1) * (T + 2) and sum(x.ngptot for x in trs) == int(nloen.sum())
+        for x in trs:
+            x.release()
