@@ -134,3 +134,19 @@ def test_supolf_column_bitwise(emu, T, N, ms):
             out = np.zeros((kc, N))
             emu.emu_supolf(m, par, kc, kn, N, P(mun), P(out))
             assert np.array_equal(out, ref), (m, par)
+
+
+def test_every_row_of_o1280_and_every_small_length(emu):
+    """Every row length of the TCo1279 / O1280 benchmark grid with its own NMEN, and every length 3 .. 600 (odd and even)
+    at the largest truncation it can carry: the plan builder finds a plan (smooth or chirp-z) and the pair transforms
+    agree with pocketfft to a few ulp."""
+    rng = np.random.default_rng(3)
+    s = eo.setup(1279, 2560, eo.octahedral_nloen(1280), tables=False)
+    worst, blue = 0.0, 0
+    for i in range(1280):
+        b, e1, e2 = _pair(emu, 20 + 4 * i, max(int(s.nmen[i]), 1), 0, 5, rng)
+        worst = max(worst, e1, e2); blue += b
+    assert worst < 1e-14 and blue == 774                # 60 % of the rows (68 % of the points) go through chirp-z
+    for n in range(3, 601):
+        b, e1, e2 = _pair(emu, n, max((n - 1) // 2, 1), 0, 3, rng)
+        assert e1 < 1e-14 and e2 < 1e-14, (n, b, e1, e2)
