@@ -26,5 +26,10 @@ emu:
 	@mkdir -p tests/hostemu/_build
 	$(NVCC) -std=c++17 -O2 -shared -Xcompiler -fPIC -Wno-deprecated-gpu-targets -o tests/hostemu/_build/libemu.so tests/hostemu/emu.cu $(CSRC)/fft_plan.cu
 
+# compile check of the round-2 tcgen05 probe (tools/probes; not part of the library)
+probe:
+	@mkdir -p tools/probes/_build
+	$(NVCC) -O2 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -shared -Wno-deprecated-gpu-targets -o tools/probes/_build/libtcprobe.so tools/probes/tcgen05_tf32_probe.cu
+
 clean:
 	rm -rf $(OBJ) $(LIB) tests/hostemu/_build

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Round-2 preparation: runs tools/probes/tcgen05_tf32_probe.cu (one CTA, tcgen05.mma kind::tf32, MN-major SWIZZLE_128B
+operands, TMEM accumulator read back with tcgen05.ld) for a list of descriptor variants and compares each with a CPU
+product of the TF32-truncated inputs.  Wrap the call in `timeout 120` under gpurun: every wait in the kernel is bounded,
+but this has never run on a GPU.
+
+    timeout 120 python tools/probes/tcgen05_probe.py
+
+The variant that matches tells which (LBO, SBO, layout type, major bits) the sp Legendre kernel has to use; the expected
+one, from the vendored CUTLASS headers, is the first in the list."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libtcprobe.so")
+
+
+def build():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    src = os.path.join(HERE, "tcgen05_tf32_probe.cu")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-Xcompiler", "-fPIC", "-shared", "-Wno-deprecated-gpu-targets", "-o", SO, src])
+    return SO
+
+
+def tf32_trunc(x):
+    return (x.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def main():
+    import torch
+    L = C.CDLL(build())
+    L.tcgen05_probe_run.argtypes = [C.c_void_p] * 4 + [C.c_int] * 2 + [C.c_uint] * 7 + [C.c_int]
+    rng = np.random.default_rng(0)
+    ok_any = False
+    for n, k in ((64, 8), (64, 32), (128, 64)):
+        a = rng.standard_normal((k, 128)).astype(np.float32)          # A[k][m]
+        b = rng.standard_normal((k, n)).astype(np.float32)            # B[k][n]
+        ref = tf32_trunc(a).astype(np.float64).T @ tf32_trunc(b).astype(np.float64)
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        nb = n // 32
+        variants = [
+            ("expected: LBO = next 32 of MN (1024), SBO = next 8 of K, SW128, MN-major", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 1),
+            ("K groups adjacent (SBO = 1024), MN chunks behind them", (k // 8) * 1024, 1024, (k // 8) * 1024, 1024, 2, 1, 1, 1),
+            ("no swizzle in the fill (negative control)", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 0),
+            ("K-major bits (negative control)", 1024, 4 * 1024, 1024, nb * 1024, 2, 0, 0, 1),
+        ]
+        for name, lba, sba, lbb, sbb, lay, am, bm, swz in variants:
+            d = torch.full((128, n), float("nan"), dtype=torch.float32, device="cuda")
+            st = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+            rc = L.tcgen05_probe_run(da.data_ptr(), db.data_ptr(), d.data_ptr(), st.data_ptr(), n, k, lba, sba, lbb, sbb, lay, am, bm, swz)
+            if rc != 0:
+                print(f"N={n} K={k} {name}: launch rc {rc}"); continue
+            out = d.cpu().numpy().astype(np.float64)
+            err = float(np.nanmax(np.abs(out - ref)) / np.abs(ref).max()) if np.isfinite(out).any() else float("nan")
+            good = np.isfinite(out).all() and err < 1e-5
+            ok_any |= bool(good) and swz == 1 and am == 1
+            print(f"N={n:3d} K={k:2d} status={int(st.item())} rel.err={err:9.2e} {'MATCH' if good else '     '}  {name}")
+    print("PROBE_OK" if ok_any else "PROBE_NO_MATCH")
+    return 0 if ok_any else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
