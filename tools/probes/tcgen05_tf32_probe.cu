@@ -104,11 +104,11 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_tcgen05_tf32_probe(ProbeA
         // completion of all MMAs above -> one arrival on the mbarrier (implies tcgen05.fence::before_thread_sync)
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(&bar)) : "memory");
     }
-    // bounded wait for phase 0
+    // bounded wait for phase 0 (test_wait never blocks: 2^22 polls are a fraction of a second)
     int ok = 0;
     for (int spin = 0; spin < (1 << 22) && !ok; ++spin) {
         unsigned done;
-        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
                      : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
         ok = (int)done;
     }
