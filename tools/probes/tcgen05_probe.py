@@ -32,8 +32,36 @@ def tf32_trunc(x):
     return (x.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
+class Cuda:
+    """Minimal cudart binding (no torch: the probe starts in a second on a fresh box)."""
+    def __init__(self):
+        for name in ("libcudart.so", "/usr/local/cuda/lib64/libcudart.so", "libcudart.so.12"):
+            try:
+                self.rt = C.CDLL(name); break
+            except OSError:
+                continue
+        else:
+            raise RuntimeError("libcudart not found")
+        self.rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        self.rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        self.rt.cudaFree.argtypes = [C.c_void_p]
+
+    def to_device(self, arr):
+        p = C.c_void_p()
+        assert self.rt.cudaMalloc(C.byref(p), arr.nbytes) == 0
+        assert self.rt.cudaMemcpy(p, arr.ctypes.data, arr.nbytes, 1) == 0
+        return p
+
+    def to_host(self, p, arr):
+        assert self.rt.cudaMemcpy(arr.ctypes.data, p, arr.nbytes, 2) == 0
+        return arr
+
+    def free(self, p):
+        self.rt.cudaFree(p)
+
+
 def main():
-    import torch
+    cu = Cuda()
     L = C.CDLL(build())
     L.tcgen05_probe_run.argtypes = [C.c_void_p] * 4 + [C.c_int] * 2 + [C.c_uint] * 7 + [C.c_int]
     rng = np.random.default_rng(0)
@@ -42,7 +70,7 @@ def main():
         a = rng.standard_normal((k, 128)).astype(np.float32)          # A[k][m]
         b = rng.standard_normal((k, n)).astype(np.float32)            # B[k][n]
         ref = tf32_trunc(a).astype(np.float64).T @ tf32_trunc(b).astype(np.float64)
-        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        da, db = cu.to_device(a), cu.to_device(b)
         nb = n // 32
         variants = [
             ("expected: LBO = next 32 of MN (1024), SBO = next 8 of K, SW128, MN-major", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 1),
@@ -51,16 +79,22 @@ def main():
             ("K-major bits (negative control)", 1024, 4 * 1024, 1024, nb * 1024, 2, 0, 0, 1),
         ]
         for name, lba, sba, lbb, sbb, lay, am, bm, swz in variants:
-            d = torch.full((128, n), float("nan"), dtype=torch.float32, device="cuda")
-            st = torch.full((1,), -1, dtype=torch.int32, device="cuda")
-            rc = L.tcgen05_probe_run(da.data_ptr(), db.data_ptr(), d.data_ptr(), st.data_ptr(), n, k, lba, sba, lbb, sbb, lay, am, bm, swz)
+            out = np.full((128, n), np.nan, dtype=np.float32)
+            st = np.full(1, -1, dtype=np.int32)
+            dd, ds = cu.to_device(out), cu.to_device(st)
+            rc = L.tcgen05_probe_run(da, db, dd, ds, n, k, lba, sba, lbb, sbb, lay, am, bm, swz)
             if rc != 0:
-                print(f"N={n} K={k} {name}: launch rc {rc}"); continue
-            out = d.cpu().numpy().astype(np.float64)
-            err = float(np.nanmax(np.abs(out - ref)) / np.abs(ref).max()) if np.isfinite(out).any() else float("nan")
-            good = np.isfinite(out).all() and err < 1e-5
-            ok_any |= bool(good) and swz == 1 and am == 1
-            print(f"N={n:3d} K={k:2d} status={int(st.item())} rel.err={err:9.2e} {'MATCH' if good else '     '}  {name}")
+                print(f"N={n} K={k} {name}: launch rc {rc}", flush=True)
+                if rc == -6:
+                    print("PROBE_CUDA_ERROR"); return 2          # sticky error: nothing after this would mean anything
+                continue
+            cu.to_host(dd, out); cu.to_host(ds, st)
+            cu.free(dd); cu.free(ds)
+            o64 = out.astype(np.float64)
+            err = float(np.nanmax(np.abs(o64 - ref)) / np.abs(ref).max()) if np.isfinite(o64).any() else float("nan")
+            good = bool(np.isfinite(o64).all()) and err < 1e-5
+            ok_any |= good and swz == 1 and am == 1
+            print(f"N={n:3d} K={k:2d} status={int(st[0])} rel.err={err:9.2e} {'MATCH' if good else '     '}  {name}", flush=True)
     print("PROBE_OK" if ok_any else "PROBE_NO_MATCH")
     return 0 if ok_any else 1
 
