@@ -63,26 +63,28 @@ class Cuda:
 def main():
     cu = Cuda()
     L = C.CDLL(build())
-    L.tcgen05_probe_run.argtypes = [C.c_void_p] * 4 + [C.c_int] * 2 + [C.c_uint] * 7 + [C.c_int]
+    L.tcgen05_probe_run.argtypes = [C.c_void_p] * 4 + [C.c_int] * 2 + [C.c_uint] * 7 + [C.c_int] * 2
     rng = np.random.default_rng(0)
     ok_any = False
-    for n, k in ((64, 8), (64, 32), (128, 64)):
+    for n, k in ((64, 8), (64, 32)):
         a = rng.standard_normal((k, 128)).astype(np.float32)          # A[k][m]
         b = rng.standard_normal((k, n)).astype(np.float32)            # B[k][n]
         ref = tf32_trunc(a).astype(np.float64).T @ tf32_trunc(b).astype(np.float64)
         da, db = cu.to_device(a), cu.to_device(b)
         nb = n // 32
         variants = [
-            ("expected: LBO = next 32 of MN (1024), SBO = next 8 of K, SW128, MN-major", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 1),
-            ("K groups adjacent (SBO = 1024), MN chunks behind them", (k // 8) * 1024, 1024, (k // 8) * 1024, 1024, 2, 1, 1, 1),
-            ("no swizzle in the fill (negative control)", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 0),
-            ("K-major bits (negative control)", 1024, 4 * 1024, 1024, nb * 1024, 2, 0, 0, 1),
+            ("expected: LBO = next 32 of MN (1024), SBO = next 8 of K, SW128, MN-major", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 1, 0),
+            ("same, operands all ones (D = K whatever the layout)", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 1, 1),
+            ("same, accumulator pre-set to 7 (7 left = the MMA did not write)", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 1, 2),
+            ("ones + sentinel", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 1, 3),
+            ("K groups adjacent (SBO = 1024), MN chunks behind them", (k // 8) * 1024, 1024, (k // 8) * 1024, 1024, 2, 1, 1, 1, 0),
+            ("no swizzle in the fill (negative control)", 1024, 4 * 1024, 1024, nb * 1024, 2, 1, 1, 0, 0),
         ]
-        for name, lba, sba, lbb, sbb, lay, am, bm, swz in variants:
+        for name, lba, sba, lbb, sbb, lay, am, bm, swz, diag in variants:
             out = np.full((128, n), np.nan, dtype=np.float32)
             st = np.full(1, -1, dtype=np.int32)
             dd, ds = cu.to_device(out), cu.to_device(st)
-            rc = L.tcgen05_probe_run(da, db, dd, ds, n, k, lba, sba, lbb, sbb, lay, am, bm, swz)
+            rc = L.tcgen05_probe_run(da, db, dd, ds, n, k, lba, sba, lbb, sbb, lay, am, bm, swz, diag)
             if rc != 0:
                 print(f"N={n} K={k} {name}: launch rc {rc}", flush=True)
                 if rc == -6:
@@ -91,10 +93,14 @@ def main():
             cu.to_host(dd, out); cu.to_host(ds, st)
             cu.free(dd); cu.free(ds)
             o64 = out.astype(np.float64)
-            err = float(np.nanmax(np.abs(o64 - ref)) / np.abs(ref).max()) if np.isfinite(o64).any() else float("nan")
+            want = np.full_like(ref, float(k)) if diag & 1 else ref
+            err = float(np.nanmax(np.abs(o64 - want)) / np.abs(want).max()) if np.isfinite(o64).any() else float("nan")
             good = bool(np.isfinite(o64).all()) and err < 1e-5
-            ok_any |= good and swz == 1 and am == 1
-            print(f"N={n:3d} K={k:2d} status={int(st[0])} rel.err={err:9.2e} {'MATCH' if good else '     '}  {name}", flush=True)
+            ok_any |= good and swz == 1 and am == 1 and diag == 0
+            vals, cnts = np.unique(np.round(o64, 3), return_counts=True)
+            top = ", ".join(f"{v:g} x{c}" for v, c in sorted(zip(vals, cnts), key=lambda t: -t[1])[:3])
+            print(f"N={n:3d} K={k:2d} status={int(st[0])} rel.err={err:9.2e} {'MATCH' if good else '     '}  {name}  | row0: "
+                  f"{np.array2string(out[0, :4], precision=3)} most frequent: {top}", flush=True)
     print("PROBE_OK" if ok_any else "PROBE_NO_MATCH")
     return 0 if ok_any else 1
 

@@ -32,6 +32,8 @@ struct ProbeArgs {
     unsigned layout_type;                    // 2 = SWIZZLE_128B
     unsigned a_major, b_major;               // 1 = MN
     int swizzle_fill;                        // 1: the fill applies Swizzle<3,4,3>
+    int diag;                                // bit 0: operands are all ones (D = K whatever the layout); bit 1: the accumulator is
+                                             // pre-set to 7.0 with tcgen05.st (left untouched = the MMA did not write)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -65,11 +67,11 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_tcgen05_tf32_probe(ProbeA
     unsigned char* sb = smem + ((a_bytes + 1023u) & ~1023u);
     for (int i = tid; i < p.k * PROBE_M; i += blockDim.x) {
         const int k = i / PROBE_M, m = i - k * PROBE_M;
-        *reinterpret_cast<float*>(sa + tile_off(m, k, p.lbo_a, p.sbo_a, p.swizzle_fill)) = p.a[i];
+        *reinterpret_cast<float*>(sa + tile_off(m, k, p.lbo_a, p.sbo_a, p.swizzle_fill)) = (p.diag & 1) ? 1.0f : p.a[i];
     }
     for (int i = tid; i < p.k * p.n; i += blockDim.x) {
         const int k = i / p.n, n = i - k * p.n;
-        *reinterpret_cast<float*>(sb + tile_off(n, k, p.lbo_b, p.sbo_b, p.swizzle_fill)) = p.b[i];
+        *reinterpret_cast<float*>(sb + tile_off(n, k, p.lbo_b, p.sbo_b, p.swizzle_fill)) = (p.diag & 1) ? 1.0f : p.b[i];
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(&bar)));
@@ -89,6 +91,17 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_tcgen05_tf32_probe(ProbeA
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n");
     const unsigned taddr = tmem_base;
+    if (p.diag & 2) {      // sentinel in every accumulator element this warp can reach
+        const unsigned sv = __float_as_uint(7.0f);
+        for (int c0 = 0; c0 < p.n; c0 += 8) {
+            const unsigned addr = taddr + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};\n" :: "r"(addr), "r"(sv) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
+    }
     if (tid == 0) {
         // instruction descriptor: F32 accumulate, TF32 x TF32, majors as given, N, M = 128
         const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.a_major & 1u) << 15) | ((p.b_major & 1u) << 16) |
@@ -139,9 +152,9 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_tcgen05_tf32_probe(ProbeA
 
 // C entry for ctypes: runs one variant; all pointers are device pointers
 extern "C" int tcgen05_probe_run(const float* a, const float* b, float* d, int* status, int n, int k, unsigned lbo_a, unsigned sbo_a,
-                                 unsigned lbo_b, unsigned sbo_b, unsigned layout_type, unsigned a_major, unsigned b_major, int swizzle_fill) {
+                                 unsigned lbo_b, unsigned sbo_b, unsigned layout_type, unsigned a_major, unsigned b_major, int swizzle_fill, int diag) {
     if (n % 32 || n < 32 || n > PROBE_MAXN || k % 8 || k < 8 || k > PROBE_MAXK) return -4;
-    ProbeArgs p{a, b, d, status, n, k, lbo_a, sbo_a, lbo_b, sbo_b, layout_type, a_major, b_major, swizzle_fill};
+    ProbeArgs p{a, b, d, status, n, k, lbo_a, sbo_a, lbo_b, sbo_b, layout_type, a_major, b_major, swizzle_fill, diag};
     const unsigned a_bytes = (PROBE_M / 32) * (lbo_a > 1024u ? lbo_a : 1024u) + (k / 8) * (sbo_a > 1024u ? sbo_a : 1024u);
     const unsigned b_bytes = (n / 32) * (lbo_b > 1024u ? lbo_b : 1024u) + (k / 8) * (sbo_b > 1024u ? sbo_b : 1024u);
     const size_t smem = ((a_bytes + 1023u) & ~1023u) + b_bytes + 1024;
