@@ -66,7 +66,7 @@ def main():
     L.tcgen05_probe_run.argtypes = [C.c_void_p] * 4 + [C.c_int] * 2 + [C.c_uint] * 7 + [C.c_int] * 2
     rng = np.random.default_rng(0)
     ok_any = False
-    for n, k in ((64, 8), (64, 32)):
+    for n, k in ((64, 8),):
         a = rng.standard_normal((k, 128)).astype(np.float32)          # A[k][m]
         b = rng.standard_normal((k, n)).astype(np.float32)            # B[k][n]
         ref = tf32_trunc(a).astype(np.float64).T @ tf32_trunc(b).astype(np.float64)
@@ -82,7 +82,7 @@ def main():
         ]
         for name, lba, sba, lbb, sbb, lay, am, bm, swz, diag in variants:
             out = np.full((128, n), np.nan, dtype=np.float32)
-            st = np.full(1, -1, dtype=np.int32)
+            st = np.full(8, -1, dtype=np.int32)
             dd, ds = cu.to_device(out), cu.to_device(st)
             rc = L.tcgen05_probe_run(da, db, dd, ds, n, k, lba, sba, lbb, sbb, lay, am, bm, swz, diag)
             if rc != 0:
@@ -100,7 +100,7 @@ def main():
             vals, cnts = np.unique(np.round(o64, 3), return_counts=True)
             top = ", ".join(f"{v:g} x{c}" for v, c in sorted(zip(vals, cnts), key=lambda t: -t[1])[:3])
             print(f"N={n:3d} K={k:2d} status={int(st[0])} rel.err={err:9.2e} {'MATCH' if good else '     '}  {name}  | row0: "
-                  f"{np.array2string(out[0, :4], precision=3)} most frequent: {top}", flush=True)
+                  f"{np.array2string(out[0, :4], precision=3)} most frequent: {top} | tmem_base=0x{int(st[1]) & 0xffffffff:08x} sentinel readback={[hex(int(x) & 0xffffffff) for x in st[2:4]]}", flush=True)
     print("PROBE_OK" if ok_any else "PROBE_NO_MATCH")
     return 0 if ok_any else 1
 

@@ -79,6 +79,8 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_tcgen05_tf32_probe(ProbeA
     }
     // generic-proxy writes of the operands -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (tid == 0) tmem_base = 0xdeadbeefu;      // an allocation that does not write its address shows up in status[1]
+    __syncthreads();
     if (warp == 0) {       // TMEM: N fp32 columns x 128 lanes, power of two >= 32
         unsigned cols = 32; while ((int)cols < p.n) cols <<= 1;
         if (cols == 32) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;\n" :: "r"(smem_u32(&tmem_base)));
@@ -91,6 +93,7 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_tcgen05_tf32_probe(ProbeA
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n");
     const unsigned taddr = tmem_base;
+    if (tid == 0) p.status[1] = (int)taddr;
     if (p.diag & 2) {      // sentinel in every accumulator element this warp can reach
         const unsigned sv = __float_as_uint(7.0f);
         for (int c0 = 0; c0 < p.n; c0 += 8) {
@@ -98,6 +101,14 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_tcgen05_tf32_probe(ProbeA
             asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};\n" :: "r"(addr), "r"(sv) : "memory");
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        {   // read the sentinel straight back (status[2]: warp 0, status[3]: warp 1)
+            unsigned r[8];
+            const unsigned addr = taddr + ((unsigned)(warp * 32) << 16);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (lane == 0 && warp < 2) p.status[2 + warp] = (int)r[0];
+        }
         asm volatile("tcgen05.fence::before_thread_sync;\n");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;\n");
