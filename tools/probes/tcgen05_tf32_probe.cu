@@ -50,6 +50,12 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned saddr, unsigned
 
 // byte offset of element (mn, k) of an MN-major operand tile: chunks of 32 along MN at `lbo`, groups of 8 k rows at `sbo`
 __device__ __forceinline__ unsigned tile_off(int mn, int k, unsigned lbo, unsigned sbo, int swz) {
+    if (swz == 2) {      // SWIZZLE_128B_BASE32B (layout type 1): groups of 4 k rows, Swizzle<2,5,2>: 32-byte chunk ^= row
+        const unsigned row = (unsigned)(k & 3);
+        unsigned inrow = (unsigned)(mn & 31) * 4u;
+        inrow ^= row << 5;
+        return (unsigned)(mn >> 5) * lbo + (unsigned)(k >> 2) * sbo + row * 128u + inrow;
+    }
     const unsigned row = (unsigned)(k & 7);
     unsigned inrow = (unsigned)(mn & 31) * 4u;        // byte inside the 128-byte row
     if (swz) inrow ^= row << 4;                       // Swizzle<3,4,3>: 16-byte chunk ^= row
@@ -118,8 +124,8 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_tcgen05_tf32_probe(ProbeA
         const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((p.a_major & 1u) << 15) | ((p.b_major & 1u) << 16) |
                                ((unsigned)(p.n >> 3) << 17) | ((unsigned)(PROBE_M >> 4) << 24);
         for (int ks = 0; ks < p.k / 8; ++ks) {        // one MMA per group of 8 k rows
-            const unsigned long long da = make_desc(smem_u32(sa) + (unsigned)ks * p.sbo_a, p.lbo_a, p.sbo_a, p.layout_type);
-            const unsigned long long db = make_desc(smem_u32(sb) + (unsigned)ks * p.sbo_b, p.lbo_b, p.sbo_b, p.layout_type);
+            const unsigned long long da = make_desc(smem_u32(sa) + (unsigned)ks * p.sbo_a * (p.swizzle_fill == 2 ? 2u : 1u), p.lbo_a, p.sbo_a, p.layout_type);
+            const unsigned long long db = make_desc(smem_u32(sb) + (unsigned)ks * p.sbo_b * (p.swizzle_fill == 2 ? 2u : 1u), p.lbo_b, p.sbo_b, p.layout_type);
             const unsigned acc = ks > 0 ? 1u : 0u;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
