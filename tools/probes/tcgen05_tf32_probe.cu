@@ -1,4 +1,8 @@
-// tcgen05 TF32 probe (round-2 preparation for the sp Legendre contraction; NOT part of the library, NOT run yet).
+// tcgen05 TF32 probe (preparation for the sp Legendre contraction; NOT part of the library).
+// RESULT on B200 (round 1, last GPU seconds): MATCH (rel. error 6.5e-8) with layout type 1 = SWIZZLE_128B_BASE32B,
+// swizzle_fill = 2 (atoms of 32 floats x 4 k rows, Swizzle<2,5,2>), LBO = stride of the 32-element MN chunks, SBO = stride of
+// the 4-row K groups, two groups per K = 8 instruction; with layout type 2 (SWIZZLE_128B, the first guess described below)
+// the MMA runs and writes zeros; K-major bits on MN-major descriptors fault the launch.
 //
 // One CTA computes D[128 x N] = sum_k A[k][m] * B[k][n] with both operands MN-major in shared memory -- the layouts the
 // Legendre tables (P[k][lat], latitude contiguous) and the spectral / Fourier operands ([k][column]) have in HBM -- through
