@@ -190,14 +190,32 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     uid = None
-    if world > 1:
+
+    def fresh_uid():                      # one NCCL id per communicator (= per distributed handle)
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
         buf = torch.zeros(eb.ECT_NCCL_UID_BYTES, dtype=torch.uint8, device=dev)
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(eb.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
+        return bytes(buf.cpu().numpy().tobytes())
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    # ---- parity gate before anything is timed: reference golden vectors through the N-rank transform, N ranks ==
+    # one rank bit for bit (T159 with all derivative options), back-to-back same-direction transforms with one rank
+    # delayed, chunked host path.  No oracle involved (ectrans_b200/selfcheck.py). ----
+    parity = None
+    if not args.no_parity:
+        from ectrans_b200 import selfcheck
+        parity = selfcheck.reduce(selfcheck.run(eb, world, rank, local, fresh_uid), world, dev)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": "ms per INV_TRANS+DIR_TRANS step", "n_gpus": world, "parity": parity,
+                                  "error": "parity check failed: nothing was timed"}), flush=True)
+            sys.exit(3)
+    if world > 1:
+        uid = fresh_uid()
     T, N, nlev, nfld = CONFIGS[args.config]
     nuv, nsc = nlev, nlev * nfld + 1
     nf = 2 * nuv + nsc
@@ -343,6 +361,8 @@ def run_ours(args):
     }
     if e2e:
         line["e2e"] = e2e
+    if parity is not None:
+        line["parity"] = parity
     if world == 1 and not args.no_cpu:
         stride = args.cpu_stride or {79: 1, 159: 2, 399: 8, 1279: 32}.get(T, 16)
         v, detail = cpu_sample_step(T, N, nuv, nsc, stride)
@@ -363,6 +383,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=["dp", "sp"], help="default: the config's (TCo399, TCo2559: sp)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate that runs before the timed region")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-stride", type=int, default=0)
     ap.add_argument("--stage-timings", action="store_true", help=argparse.SUPPRESS)

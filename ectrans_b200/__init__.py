@@ -95,6 +95,7 @@ EXPORTED_SYMBOLS = [
     "ect_gath_grid", "ect_dist_grid", "ect_gath_spec", "ect_dist_spec", "ect_inv_transad", "ect_dir_transad",
     "ect_gpnorm_trans", "ect_vordiv_to_uv", "ect_inquire_rpnm", "ect_trans_pnm", "ect_write_legpol", "ect_read_legpol",
     "ect_gridpoint_partition", "ect_specnorm_met", "ect_inv_trans_vset", "ect_dir_trans_vset", "ect_specnorm_vset",
+    "ect_comm_info",
 ]
 
 
@@ -121,6 +122,7 @@ def lib():
         L.ect_inv_trans_vset.argtypes = [C.c_int, C.POINTER(_InvArgs), C.POINTER(_VsetArgs)]
         L.ect_dir_trans_vset.argtypes = [C.c_int, C.POINTER(_DirArgs), C.POINTER(_VsetArgs)]
         L.ect_get_timings.argtypes = [C.c_int, C.POINTER(Timings)]
+        L.ect_comm_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
         L.ect_debug_get_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
         L.ect_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.ect_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_longlong]
@@ -666,6 +668,12 @@ class Transform:
 
     def synchronize(self):
         _check(lib().ect_synchronize(self.handle), "ect_synchronize")
+
+    def comm_info(self):
+        """(peer-memory transposition active, consumer-done barriers issued so far) -- ect_comm_info."""
+        p2p, nb = C.c_int(0), C.c_longlong(0)
+        _check(lib().ect_comm_info(self.handle, C.byref(p2p), C.byref(nb)), "ect_comm_info")
+        return {"peer_memory": bool(p2p.value), "entry_barriers": int(nb.value)}
 
     def release(self):
         if getattr(self, "handle", 0):

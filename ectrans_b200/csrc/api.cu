@@ -5,6 +5,7 @@
 //   DIR_TRANS  cpu/external/dir_trans.F90 -> dir_trans_ctl_mod.F90
 //              (TRGTOL -> FTDIR/FOURIER_OUT -> TRLTOM -> LTDIR)
 #include "ect_internal.h"
+#include <unistd.h>
 #include "fourier_phases.h"
 #include <nccl.h>
 #include <dlfcn.h>
@@ -111,6 +112,50 @@ extern "C" int ect_host_free(void* ptr) {
     return ECT_SUCCESS;
 }
 
+// Peer-memory transposition is a collective decision taken once per handle: every pair of ranks of the W-group must
+// sit on the same host, in different processes (CUDA IPC cannot map a handle of its own process), on devices that
+// can address each other.  Anything else (several nodes, no NVLink / PCIe peer access, two ranks in one process)
+// uses the NCCL all-to-all-v -- the reference's own TRMTOL / TRLTOM structure (trmtol_mod.F90:101-141).
+struct EctPeerId { char host[64]; long long pid; char busid[32]; };
+static int p2p_capable(EctHandle* h, bool wanted, bool* out) {
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    ncclComm_t comm = (ncclComm_t)d->comm;
+    EctPeerId me;
+    memset(&me, 0, sizeof(me));
+    if (gethostname(me.host, sizeof(me.host) - 1) != 0) strcpy(me.host, "?");
+    {   // same hostname in two containers: the boot id tells hosts apart
+        FILE* fp = fopen("/proc/sys/kernel/random/boot_id", "r");
+        if (fp) { char b[40] = {0}; if (fgets(b, sizeof(b), fp)) { size_t l = strlen(me.host); strncpy(me.host + l, b, sizeof(me.host) - 1 - l); } fclose(fp); }
+    }
+    me.pid = (long long)getpid();
+    ECT_CUDA(cudaDeviceGetPCIBusId(me.busid, sizeof(me.busid), d->dev));
+    char *dsend = nullptr, *drecv = nullptr;
+    ECT_CUDA(cudaMalloc(&dsend, sizeof(me)));
+    ECT_CUDA(cudaMalloc(&drecv, sizeof(me) * P.nranks));
+    ECT_CUDA(cudaMemcpyAsync(dsend, &me, sizeof(me), cudaMemcpyHostToDevice, d->stream));
+    ECT_NCCL(ncclAllGather(dsend, drecv, sizeof(me), ncclChar, comm, d->stream));
+    std::vector<EctPeerId> all(P.nranks);
+    ECT_CUDA(cudaMemcpyAsync(all.data(), drecv, sizeof(me) * P.nranks, cudaMemcpyDeviceToHost, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    int ok = wanted ? 1 : 0;
+    for (int r = 0; r < P.nranks && ok; ++r) {
+        if (r == P.rank) continue;
+        if (memcmp(all[r].host, me.host, sizeof(me.host)) != 0 || all[r].pid == me.pid) { ok = 0; break; }
+        int pd = -1, can = 0;
+        if (cudaDeviceGetByPCIBusId(&pd, all[r].busid) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }   // not visible to this process
+        if (pd != d->dev && (cudaDeviceCanAccessPeer(&can, d->dev, pd) != cudaSuccess || !can)) { cudaGetLastError(); ok = 0; break; }
+    }
+    int* dok = (int*)dsend;
+    ECT_CUDA(cudaMemcpyAsync(dok, &ok, sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    ECT_NCCL(ncclAllReduce(dok, dok, 1, ncclInt, ncclMin, comm, d->stream));
+    ECT_CUDA(cudaMemcpyAsync(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    ECT_CUDA(cudaStreamSynchronize(d->stream));
+    cudaFree(dsend); cudaFree(drecv);
+    *out = ok != 0;
+    return ECT_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------------
 // setup / release
 // ---------------------------------------------------------------------------------------
@@ -162,10 +207,10 @@ int ect_device_setup(EctHandle* h, cudaStream_t stream, bool use_given_stream, i
             ECT_NCCL(ncclCommInitRank(&comm, P.nranks, id, P.rank));
             d->comm = comm;
         }
+        ECT_CUDA(cudaMalloc(&d->barrier_buf, 256));
+        ECT_CUDA(cudaMemset(d->barrier_buf, 0, 256));
         const char* nop2p = getenv("ECT_NO_P2P");
-        d->p2p = !(nop2p && atoi(nop2p) != 0);
-        ECT_CUDA(cudaMalloc(&d->barrier_buf, 64));
-        ECT_CUDA(cudaMemset(d->barrier_buf, 0, 64));
+        if ((rc = p2p_capable(h, !(nop2p && atoi(nop2p) != 0), &d->p2p))) return rc;
     }
     // destination tables of the transposition-fused stores.  One rank or NCCL mode: everything stays local
     // (rank 0 of a one-entry pointer table, record = local record); peer mode: consumer rank + its record.
@@ -430,7 +475,15 @@ static int ensure_work(EctHandle* h, const EctFieldCfg& f) {
     if ((rc = ensure(d->xwork, d->xwork_elems, (d->xrows + 2) * (i64)f.cp, d->stream, true))) return rc;
     // the Fourier buffers grow by record pitch only (same decision on every rank: the IPC exchange is collective)
     if (f.cp > d->cp_alloc) {
-        if (d->p2p) { for (void* m : d->ipc_open) ECT_CUDA(cudaIpcCloseMemHandle(m)); d->ipc_open.clear(); }
+        if (d->p2p) {
+            // peers hold IPC mappings of the buffers about to be freed and may still be storing into them: wait until
+            // every rank has finished all work queued so far (collective, like the exchange of the new handles below)
+            ECT_NCCL(ncclAllReduce(d->barrier_buf + 16, d->barrier_buf + 24, 1, ncclInt, ncclSum, (ncclComm_t)d->comm, d->stream));
+            ECT_CUDA(cudaStreamSynchronize(d->stream));
+            for (void* m : d->ipc_open) ECT_CUDA(cudaIpcCloseMemHandle(m));
+            d->ipc_open.clear();
+            d->p2p_last = -1;
+        }
         if ((rc = ensure(d->fbuf_leg, d->fbuf_leg_elems, (P.nrec_leg + 1) * (i64)f.cp, d->stream, true))) return rc;
         if (P.nranks > 1) {
             if ((rc = ensure(d->fbuf_fft, d->fbuf_fft_elems, (P.nrec_fft + 1) * (i64)f.cp, d->stream, true))) return rc;
@@ -479,6 +532,26 @@ static int ensure_callbuf(EctDevice* d, size_t bytes) {
 static int release_callbuf(EctDevice* d) {
     ECT_CUDA(cudaEventRecord(d->ring_ev[d->ring_cur], d->stream));
     d->ring_used[d->ring_cur] = true;
+    return ECT_SUCCESS;
+}
+
+// Peer mode, before the producing kernel of a transform: its stores land in buffers that the CONSUMER kernel of the
+// previous transform may still be reading on another rank (rank A's k_leinv of call c+1 writes rank B's Fourier-side
+// buffer while B's k_fourier<inverse> of call c reads it; the same for k_fourier<direct> -> k_ledir).  One barrier
+// per transform, after the producer, does not order that.  Alternating inverse / direct calls are ordered by the
+// other direction's barrier (different buffer pair); two transforms on the same pipeline in a row -- inv, inv or
+// dir, dir: the chunked host path, several INV_TRANS per time step -- need this second, consumer-done barrier.
+int ect_transpose_enter(EctHandle* h, int to_fft) {
+    const EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    if (P.nranks == 1 || !d->p2p) return ECT_SUCCESS;
+    static const char* mode = getenv("ECT_P2P_ENTRY_BARRIER");      // 0: never (reproduces the round-1 hazard), 2: always
+    const int m = mode ? atoi(mode) : 1;
+    if ((m == 1 && d->p2p_last == to_fft) || m == 2) {
+        ECT_NCCL(ncclAllReduce(d->barrier_buf + 16, d->barrier_buf + 24, 1, ncclInt, ncclSum, (ncclComm_t)d->comm, d->stream));
+        d->entry_barriers++;
+    }
+    d->p2p_last = to_fft;
     return ECT_SUCCESS;
 }
 
@@ -1233,6 +1306,7 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     // ---- stages ----
     ect_launch_ltinv_prologue(h, f, d_vor, d_div, d_sc);
     ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
+    if ((rc = ect_transpose_enter(h, 1))) return rc;
     ect_launch_leinv(h, f);
     ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
     if ((rc = ect_transpose(h, f, 1))) return rc;
@@ -1421,9 +1495,12 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
         double* const* d_bandb = (double* const*)(db + ((char*)t_bandb - hb));
         const i64* d_bands = (const i64*)(db + ((char*)t_bands - hb));
         if ((rc = gp_exchange(h, f.nfs, f.nfs, std::vector<int>(1, f.nfs), es, 0, d_gpb, d_gps, nproma))) return rc;      // TRGTOL (timed with the Fourier interval)
+        if ((rc = ect_transpose_enter(h, 0))) return rc;
         ect_launch_ftdir(h, f, d_bandb, d_bands, d_pairs, std::max(P.ngpband, 1));
-    } else
+    } else {
+        if ((rc = ect_transpose_enter(h, 0))) return rc;
         ect_launch_ftdir(h, f, d_gpb, d_gps, d_pairs, nproma);
+    }
     ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
     if ((rc = ect_transpose(h, f, 0))) return rc;
     ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
@@ -1452,6 +1529,14 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     d->last_dir = 1;
     d->timed = true;
     if (host) ECT_CUDA(cudaStreamSynchronize(d->stream));
+    return ECT_SUCCESS;
+}
+
+extern "C" int ect_comm_info(int handle, int* peer_memory, long long* entry_barriers) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d) return ECT_ERR_HANDLE;
+    if (peer_memory) *peer_memory = h->d->p2p ? 1 : 0;
+    if (entry_barriers) *entry_barriers = h->d->entry_barriers;
     return ECT_SUCCESS;
 }
 

@@ -171,6 +171,8 @@ struct EctDevice {
     std::vector<void*> ipc_open;          // mappings to close on reallocation / release
     int cp_alloc = 0;                     // record pitch the Fourier buffers were sized for
     int* barrier_buf = nullptr;
+    int p2p_last = -1;                    // pipeline of the previous peer-mode transform (1: inverse / TRMTOL, 0: direct / TRLTOM)
+    i64 entry_barriers = 0;               // consumer-done barriers issued (ect_transpose_enter)
     // side streams: the shared-memory classes of the Fourier stage run concurrently so that small classes fill the
     // tails of large ones
     static const int kSide = 3;
@@ -219,6 +221,7 @@ int ect_fourier_setup(EctHandle* h);
 int ect_legendre_get_table(EctHandle* h, int ml, int par, double* out, long long cap);
 int ect_legendre_set_table(EctHandle* h, int ml, int par, const double* in);      // [k][ndglu], host
 int ect_transpose(EctHandle* h, const EctFieldCfg& f, int to_fft);   // TRMTOL (1) / TRLTOM (0)
+int ect_transpose_enter(EctHandle* h, int to_fft);                   // peer mode: consumer-done barrier before the producing kernel
 
 const char* ect_cuda_err(cudaError_t e);
 #define ECT_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \

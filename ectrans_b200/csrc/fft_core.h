@@ -198,6 +198,53 @@ ECT_HD void bfly_pow2(C* v) {
     else bfly16(v);
 }
 
+// rt_all: concatenated root tables; the table of odd radix R occupies [R(R-1)/2, R(R+1)/2)
+#define ECT_ROOTS_OFF(R) ((R) * ((R) - 1) / 2)
+#define ECT_ROOTS_SIZE (ECT_MAX_RADIX * (ECT_MAX_RADIX + 1) / 2)
+
+// Composite radix R = RO * RP (RO odd in {3, 5, 7}, RP in {2, 4}: 6, 10, 12, 14) by the prime-factor map, all in
+// registers and without internal twiddles: with q = (RP a + RO b) mod R and p = CRT(p1, p2) (p1 = p mod RO,
+// p2 = p mod RP), exp(2 pi i p q / R) = exp(2 pi i p1 a / RO) exp(2 pi i p2 b / RP).  One pass of radix 14 where the
+// plain plan needs a radix-7 and a radix-2 pass over shared memory.
+template <int RO, int RP, typename C>
+ECT_HD void bfly_pfa(C* v, const C* __restrict__ rt_all) {
+    constexpr int R = RO * RP;
+    const C* rt = rt_all + ECT_ROOTS_OFF(RO);
+#pragma unroll
+    for (int b = 0; b < RP; ++b) {
+        C u[RO];
+#pragma unroll
+        for (int a = 0; a < RO; ++a) u[a] = v[(RP * a + RO * b) % R];
+        bfly_odd<RO>(u, rt, [&](int p1, C val) { v[(RP * p1 + RO * b) % R] = val; });
+    }
+#pragma unroll
+    for (int p1 = 0; p1 < RO; ++p1) {
+        if constexpr (RP == 2) {
+            const C x = v[(RP * p1) % R], y = v[(RP * p1 + RO) % R];
+            v[(RP * p1) % R] = c_add(x, y);
+            v[(RP * p1 + RO) % R] = c_sub(x, y);
+        } else {
+            bfly4(v[(RP * p1) % R], v[(RP * p1 + RO) % R], v[(RP * p1 + 2 * RO) % R], v[(RP * p1 + 3 * RO) % R]);
+        }
+    }
+    C t[R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) t[p] = v[(RP * (p % RO) + RO * (p % RP)) % R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) v[p] = t[p];
+}
+
+// register-resident butterflies: powers of two and the composite radices
+#define ECT_REG_RADIX(R) ((R) == 2 || (R) == 4 || (R) == 8 || (R) == 16 || (R) == 6 || (R) == 10 || (R) == 12 || (R) == 14)
+template <int R, typename C>
+ECT_HD void bfly_reg(C* v, const C* __restrict__ rt_all) {
+    if constexpr (R == 6) bfly_pfa<3, 2>(v, rt_all);
+    else if constexpr (R == 10) bfly_pfa<5, 2>(v, rt_all);
+    else if constexpr (R == 12) bfly_pfa<3, 4>(v, rt_all);
+    else if constexpr (R == 14) bfly_pfa<7, 2>(v, rt_all);
+    else bfly_pow2<R>(v);
+}
+
 // v[q] *= w1^q, q = 1 .. R-1.  Powers 1..7 come from a shallow product tree, the rest as
 // w1^(8c) * w1^(q mod 8), so that only eight twiddles are live at a time.
 template <int R, typename C>
@@ -234,16 +281,17 @@ ECT_HD void stage_addr(int b, int L, int lshift, int& base, int& k) {
     else { blk = b / L; k = b - blk * L; }
     base = blk * R * L + k;
 }
-// power-of-two radix: twiddles + butterfly on a register-resident column
+// power-of-two / composite radix: twiddles + butterfly on a register-resident column
 template <int R, bool DIF, typename C>
-ECT_HD void stage_math_pow2(C* v, bool tw, C w1) {
+ECT_HD void stage_math_pow2(C* v, bool tw, C w1, const C* __restrict__ rt_all) {
     if (!DIF && tw) apply_twiddles<R>(v, w1);
-    bfly_pow2<R>(v);
+    bfly_reg<R>(v, rt_all);
     if (DIF && tw) apply_twiddles<R>(v, w1);
 }
 template <int R, bool DIF, typename C>
 ECT_HD void fft_stage_r(C* data, int n, int L, int lshift, const EctTwT<C> qt,
-                        const C* __restrict__ rt, int tid, int nthr) {
+                        const C* __restrict__ rt_all, int tid, int nthr) {
+    const C* rt = rt_all + ECT_ROOTS_OFF(R < ECT_MAX_RADIX ? R : ECT_MAX_RADIX);
     const int nb = n / R;
     const int tstride = n / (R * L);   // twiddle index stride: exp(2 pi i q k / (R L))
     for (int b = tid; b < nb; b += nthr) {
@@ -255,8 +303,8 @@ ECT_HD void fft_stage_r(C* data, int n, int L, int lshift, const EctTwT<C> qt,
         C w1 = c_make<C>(1, 0);
         const bool tw = (L > 1) && (k > 0);
         if (tw) w1 = tw_get(qt, k * tstride);
-        if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
-            stage_math_pow2<R, DIF>(v, tw, w1);
+        if constexpr (ECT_REG_RADIX(R)) {
+            stage_math_pow2<R, DIF>(v, tw, w1, rt_all);
 #pragma unroll
             for (int q = 0; q < R; ++q) data[ECT_PAD(base + q * L)] = v[q];
         } else {
@@ -284,14 +332,16 @@ ECT_HD void fft_stage_r(C* data, int n, int L, int lshift, const EctTwT<C> qt,
     }
 }
 
-// rt_all: concatenated root tables; the table of odd radix R occupies [R(R-1)/2, R(R+1)/2)
-#define ECT_ROOTS_OFF(R) ((R) * ((R) - 1) / 2)
-#define ECT_ROOTS_SIZE (ECT_MAX_RADIX * (ECT_MAX_RADIX + 1) / 2)
-template <bool DIF, int MAXR = ECT_MAX_RADIX, typename C>
+// COMP: the plan may contain the composite radices 6 / 10 / 12 / 14 (chirp-z half plans)
+template <bool DIF, int MAXR = ECT_MAX_RADIX, bool COMP = true, typename C>
 ECT_HD void fft_stage(C* data, int n, int r, int L, int lshift, const EctTwT<C> qt,
                       const C* __restrict__ rt_all, int tid, int nthr) {
-    const C* rt = rt_all + ECT_ROOTS_OFF(r);
+    const C* rt = rt_all;
     switch (r) {
+        case 14: if constexpr (COMP) fft_stage_r<14, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 12: if constexpr (COMP) fft_stage_r<12, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 10: if constexpr (COMP) fft_stage_r<10, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
+        case 6:  if constexpr (COMP) fft_stage_r<6, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
         case 16: fft_stage_r<16, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
         case 8:  fft_stage_r<8, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;
         case 4:  fft_stage_r<4, DIF>(data, n, L, lshift, qt, rt, tid, nthr); break;

@@ -38,6 +38,27 @@ bool ect_fft_factorize(int n, std::vector<int>& radices, bool pow2_inner) {
     return (int)radices.size() <= ECT_MAX_STAGES;
 }
 
+// Half plans of the split chirp-z (H = r 2^k, r in {1, 3, 5, 7}): 16s innermost (the fused middle step wants a power
+// of two), then what is left of the power of two merged with r into ONE register-resident composite radix where it
+// fits (6, 10, 12, 14), so that H = 2560, 3072, 3584, 4096 are all three-stage plans 16 x 16 x {10, 12, 14, 16}.
+bool ect_fft_factorize_half(int n, std::vector<int>& radices) {
+    radices.clear();
+    if (n < 2 || n % 2 != 0) return false;
+    int rem = n, twos = 0;
+    while (rem % 2 == 0) { rem /= 2; ++twos; }
+    const int r = rem;
+    if (r != 1 && r != 3 && r != 5 && r != 7) return ect_fft_factorize(n, radices, true);
+    const int a = twos / 4, j = twos % 4;
+    if (a == 0) return ect_fft_factorize(n, radices, true);
+    for (int i = 0; i < a; ++i) radices.push_back(16);
+    if (r == 1) { if (j) radices.push_back(1 << j); }
+    else if (j == 0) radices.push_back(r);
+    else if ((r << j) <= 14) radices.push_back(r << j);
+    else if (r == 3) { radices.push_back(2); radices.push_back(12); }            // 24 = 2 x 12
+    else { radices.push_back(1 << (j - 1)); radices.push_back(2 * r); }          // 20, 40 = {2, 4} x 10; 28, 56 = {2, 4} x 14
+    return (int)radices.size() <= ECT_MAX_STAGES;
+}
+
 int ect_fft_smooth_size(int need) {          // smallest r * 2^k >= need, r in {1, 3, 5, 7}, k >= 4
     int best = 0;
     for (int r : {1, 3, 5, 7}) {
@@ -56,12 +77,12 @@ static double2 expi2pi(long long num, long long den) {   // exp(2 pi i num/den),
     return make_double2((double)cosl(a), (double)sinl(a));
 }
 
-int EctFftTables::get_plan(int n, bool pow2_inner) {
-    const int key = pow2_inner ? -n : n;
+int EctFftTables::get_plan(int n, bool pow2_inner, bool half) {
+    const int key = half ? n + (1 << 24) : (pow2_inner ? -n : n);
     auto it = plan_of_len.find(key);
     if (it != plan_of_len.end()) return it->second;
     std::vector<int> rad;
-    if (!ect_fft_factorize(n, rad, pow2_inner)) return -1;
+    if (!(half ? ect_fft_factorize_half(n, rad) : ect_fft_factorize(n, rad, pow2_inner))) return -1;
     if (roots.empty()) {
         roots.assign(ECT_ROOTS_SIZE, make_double2(0.0, 0.0));
         for (int p : kPrimes) {
@@ -125,6 +146,7 @@ int EctFftTables::get_latplan(int nlon, int km) {
         lp.bluestein = 0;
         lp.m = 0;
         lp.chirp_off = lp.bhat_inv_off = lp.bhat_dir_off = lp.ctw_off = -1;
+        lp.plan_h = -1; lp.bhat_inv_eo[0] = lp.bhat_inv_eo[1] = lp.bhat_dir_eo[0] = lp.bhat_dir_eo[1] = -1;
         lp.smem_bytes = ECT_PADDED_LEN(nlon) * (int)sizeof(double2);
     } else {
         const int N = nlon;
@@ -133,6 +155,7 @@ int EctFftTables::get_latplan(int nlon, int km) {
         lp.bluestein = 1;
         lp.m = M;
         lp.plan = get_plan(M, true);
+        lp.plan_h = get_plan(M / 2, true, true);      // before any reference into plans[] is taken
         lp.smem_bytes = ECT_PADDED_LEN(M) * (int)sizeof(double2);
         // chirp c[j] = exp(+i pi j^2 / N) = exp(2 pi i (j^2 mod 2N) / (2N)), j = 0 .. N/2
         lp.chirp_off = (int)cz_pool.size();
@@ -178,6 +201,18 @@ int EctFftTables::get_latplan(int nlon, int km) {
                 cz_pool[off + (pos % r0) * nb0 + pos / r0] = make_double2(h[n].x * inv, h[n].y * inv);
             }
             if (dir == 0) lp.bhat_inv_off = off; else lp.bhat_dir_off = off;
+            // split form: bins 2 r (even) and 2 r + 1 (odd) of the same spectrum, each permuted for the length-H plan
+            const EctFftPlan& ph = plans[lp.plan_h];
+            const int H = M / 2, rh = ph.radix[0], nbh = H / rh;
+            for (int par = 0; par < 2; ++par) {
+                const int offh = (int)cz_pool.size();
+                cz_pool.resize(offh + H);
+                for (int rr = 0; rr < H; ++rr) {
+                    const int pos = perm_pool[ph.perm_off + rr];
+                    cz_pool[offh + (pos % rh) * nbh + pos / rh] = make_double2(h[2 * rr + par].x * inv, h[2 * rr + par].y * inv);
+                }
+                if (dir == 0) lp.bhat_inv_eo[par] = offh; else lp.bhat_dir_eo[par] = offh;
+            }
         }
     }
     latplans.push_back(lp);

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
         FT_PROBE(1);
         if (blue) {
             for (int s = plan_nst - 1; s >= 1; --s) {
-                fft_stage<true, 7>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
+                fft_stage<true, 7, false>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
                 __syncthreads();
                 FT_PROBE(2 + (plan_nst - 1 - s));
             }
@@ -298,13 +298,13 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
             __syncthreads();
             FT_PROBE(10);
             for (int s = 1; s < plan_nst; ++s) {
-                fft_stage<false, 7>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
+                fft_stage<false, 7, false>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
                 __syncthreads();
                 FT_PROBE(10 + s);
             }
         } else {
             for (int s = 0; s < plan_nst; ++s) {
-                fft_stage<false, MAXR>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
+                fft_stage<false, MAXR, false>(data, len, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qt, (const C*)s_roots, tid, nthr);
                 __syncthreads();
             }
             FT_PROBE(19);

@@ -703,16 +703,21 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) k_ledir(LegArgs a) {
     }
 }
 
-static bool g_leg_attr_set = false;
+// cudaFuncSetAttribute applies to the current device only: the opt-in is taken once per device (a process may hold
+// handles on several GPUs)
+static bool g_leg_attr_set[64] = {};
 static void leg_set_attrs() {
-    if (g_leg_attr_set) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (g_leg_attr_set[dev] && dev != 63) return;
     cudaFuncSetAttribute(k_leinv, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          INV_STAGES * INV_STAGE_DOUBLES * (int)sizeof(double));
     cudaFuncSetAttribute(k_leinv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(INV_STAGES * INV_STAGE_DOUBLES * sizeof(double)));
     cudaFuncSetAttribute(k_ledir, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          LEG_STAGES * DIR_STAGE_DOUBLES * (int)sizeof(double));
-    g_leg_attr_set = true;
+    g_leg_attr_set[dev] = true;
 }
 
 void ect_launch_leinv(EctHandle* h, const EctFieldCfg& f) {

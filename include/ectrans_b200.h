@@ -268,6 +268,11 @@ int ect_inv_trans_vset(int handle, const ect_inv_args* args, const ect_vset_args
 int ect_dir_trans_vset(int handle, const ect_dir_args* args, const ect_vset_args* vs);
 
 int ect_synchronize(int handle);   /* wait for asynchronous ECT_MEM_DEVICE calls on this handle */
+/* How TRMTOL / TRLTOM (trmtol_mod.F90:101-141) run on this handle: *peer_memory = 1 when the producing kernels store
+ * straight into the consumer rank's buffer over NVLink (decided collectively at setup: one host, one process per GPU,
+ * peer access between every pair; otherwise 0 = NCCL all-to-all-v); *entry_barriers = consumer-done barriers issued so
+ * far (one before every transform that follows a transform of the same direction). */
+int ect_comm_info(int handle, int* peer_memory, long long* entry_barriers);
 int ect_release(int handle);
 int ect_finalize(void);
 const char* ect_strerror(int code);
