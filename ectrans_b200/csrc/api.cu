@@ -231,6 +231,7 @@ int ect_device_setup(EctHandle* h, cudaStream_t stream, bool use_given_stream, i
         if ((rc = up(d->fft_dst_rec, fused ? P.fft_dst_rec : P.fft_rec))) return rc;
         ECT_CUDA(cudaMalloc(&d->peer_fft, P.nranks * sizeof(double*)));
         ECT_CUDA(cudaMalloc(&d->peer_leg, P.nranks * sizeof(double*)));
+        if ((rc = ect_fourier_set_affine(h))) return rc;
     }
     return ECT_SUCCESS;
 }
@@ -244,7 +245,7 @@ void ect_device_free(EctHandle* h) {
     if (d->comm_world) ncclCommDestroy((ncclComm_t)d->comm_world);
     void* ptrs[] = {d->rw, d->racthe, d->racthe_loc, d->rw_loc, d->nloen, d->gpoff, d->ptab, d->legm, d->leg_rec_n, d->leg_rec_s,
                     d->nasm0, d->inv_tiles, d->dir_tiles, d->plans, d->latplans, d->perm_pool, d->tw_pool,
-                    d->cz_pool, d->cz_pool_f, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->xwork, d->fbuf_leg,
+                    d->cz_pool, d->cz_pool_f, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->lat_aff, d->xwork, d->fbuf_leg,
                     d->stage_sp, d->stage_gp, d->normbuf, d->leg_dst_rank_n, d->leg_dst_rank_s, d->leg_dst_rec_n,
                     d->leg_dst_rec_s, d->fft_dst_rank, d->fft_dst_rec, d->peer_fft, d->peer_leg, d->barrier_buf,
                     d->gpband, d->gpsend, d->gprecv, d->xb_idx, d->xb_off, d->xg_off};
@@ -535,6 +536,11 @@ static int release_callbuf(EctDevice* d) {
     return ECT_SUCCESS;
 }
 
+__global__ void k_debug_delay(long long cycles) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) { }
+}
+
 // Peer mode, before the producing kernel of a transform: its stores land in buffers that the CONSUMER kernel of the
 // previous transform may still be reading on another rank (rank A's k_leinv of call c+1 writes rank B's Fourier-side
 // buffer while B's k_fourier<inverse> of call c reads it; the same for k_fourier<direct> -> k_ledir).  One barrier
@@ -566,6 +572,13 @@ int ect_transpose(EctHandle* h, const EctFieldCfg& f, int to_fft) {
         // the producing kernels already wrote every record into its consumer's buffer over NVLink: all that is
         // left of TRMTOL / TRLTOM is "everybody has finished writing"
         ECT_NCCL(ncclAllReduce(d->barrier_buf, d->barrier_buf + 8, 1, ncclInt, ncclSum, comm, d->stream));
+        // test hook (tools/selfcheck_run.py): the last rank's consumer kernel starts late, so that its peers reach the
+        // producer of their next transform while it still reads -- the schedule the consumer-done barrier exists for
+        static const char* delay = getenv("ECT_DEBUG_DELAY_CONSUMER_MS");
+        if (delay && atof(delay) > 0 && P.rank == P.nranks - 1) {
+            k_debug_delay<<<1, 1, 0, d->stream>>>((long long)(atof(delay) * 1.9e6));
+            d->launches++;
+        }
         return ECT_SUCCESS;
     }
     const i64 cp = f.cp;

@@ -132,9 +132,11 @@ struct EctDevice {
     int* lat_plan = nullptr;              // local lat -> latplan id
     i64* latrow0 = nullptr;
     int* fft_rec = nullptr;
+    int* lat_aff = nullptr;               // per local latitude: record tables affine in the wavenumber (fourier.cu FtArgs::lat_aff)
     std::vector<int> h_lat_plan;
     // per smem-class work lists (latitudes sorted by cost)
-    struct Bucket { int smem; int threads; int threads_inv = 0; int maxr; int nostage = 0; std::vector<int> lats; int* d_lats = nullptr; };
+    struct Bucket { int smem; int threads; int threads_inv = 0; int maxr; int nostage = 0; int cz = 0;   // cz: chirp-z rows on CTA pairs (k_fourier_cz)
+                    std::vector<int> lats; int* d_lats = nullptr; };
     std::vector<Bucket> buckets;
     // workspaces (grow only)
     double* xwork = nullptr; i64 xwork_elems = 0;       // X (inverse input) / POA (direct output)
@@ -218,6 +220,7 @@ void ect_launch_ledir(EctHandle* h, const EctFieldCfg& f);
 void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, void* d_div, void* d_sc);
 int ect_legendre_setup(EctHandle* h);
 int ect_fourier_setup(EctHandle* h);
+int ect_fourier_set_affine(EctHandle* h);       // after the transposition mode is decided
 int ect_legendre_get_table(EctHandle* h, int ml, int par, double* out, long long cap);
 int ect_legendre_set_table(EctHandle* h, int ml, int par, const double* in);      // [k][ndglu], host
 int ect_transpose(EctHandle* h, const EctFieldCfg& f, int to_fft);   // TRMTOL (1) / TRLTOM (0)

@@ -80,12 +80,13 @@ template <typename C>
 struct EctTwT {
     const C* t1;           // exp(2 pi i 128 a / n), a <= n / 128
     const C* t2;           // exp(2 pi i b / n), b < 128
+    int sh = 0;            // index shift: a table of length n 2^sh serves transforms of length n (split chirp-z: M = 2 H)
 };
 typedef EctTwT<double2> EctTw;
 #define ECT_TW1_LEN(n) ((n) / 128 + 2)
 #define ECT_TW2_LEN 128
 template <typename C>
-ECT_HD C tw_get(const EctTwT<C>& t, int j) { return c_mul(t.t1[j >> 7], t.t2[j & 127]); }
+ECT_HD C tw_get(const EctTwT<C>& t, int j) { j <<= t.sh; return c_mul(t.t1[j >> 7], t.t2[j & 127]); }
 // fills the tables cooperatively from the per-length table qt (quarter / half wave, see tw_lookup)
 template <typename C>
 ECT_HD void tw_build(C* t1, C* t2, const double2* __restrict__ qt, int n, int tid, int nthr) {
@@ -376,6 +377,36 @@ ECT_HD void blue_middle_r(C* data, int n, const C* __restrict__ bhat, int tid, i
         bfly_pow2<R>(v);
 #pragma unroll
         for (int q = 0; q < R; ++q) data[ECT_PAD(b * R + q)] = v[q];
+    }
+}
+// The same step with the kernel spectrum fetched BEFORE the work array is read: the global-memory (L2) latency of
+// the R spectrum values then overlaps the shared-memory loads and the first butterfly (split chirp-z kernels, where
+// no staging phase hides it)
+template <int R, typename C>
+ECT_HD void blue_middle_early_r(C* data, int n, const C* __restrict__ bhat, int tid, int nthr) {
+    const int nb = n / R;
+    for (int b = tid; b < nb; b += nthr) {
+        C bh[R], v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) bh[q] = bhat[q * nb + b];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = data[ECT_PAD(b * R + q)];
+        bfly_pow2<R>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = c_mul(c_make<C>(v[q].y, v[q].x), bh[q]);
+        bfly_pow2<R>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) data[ECT_PAD(b * R + q)] = v[q];
+    }
+}
+template <typename C>
+ECT_HD void blue_middle_early(C* data, int n, int r, const C* __restrict__ bhat, int tid, int nthr) {
+    switch (r) {
+        case 16: blue_middle_early_r<16>(data, n, bhat, tid, nthr); break;
+        case 8:  blue_middle_early_r<8>(data, n, bhat, tid, nthr); break;
+        case 4:  blue_middle_early_r<4>(data, n, bhat, tid, nthr); break;
+        case 2:  blue_middle_early_r<2>(data, n, bhat, tid, nthr); break;
+        default: break;
     }
 }
 template <typename C>

@@ -9,6 +9,9 @@
 // twiddle table of that length live in shared memory.
 #include "ect_internal.h"
 #include "fourier_phases.h"
+#include "fourier_cz.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -24,6 +27,7 @@ struct FtArgs {
     const uint16_t* perm_pool; const double2* tw_pool; const void* cz_pool; const double2* roots;   // cz_pool: double2 (dp) or float2 (sp)
     const int* lat_plan; const i64* latrow0; const int* fft_rec;
     const int* lats;              // latitudes (local index) of this launch
+    const int* lat_aff;           // per local latitude: bit 0: fft_rec[k] = fft_rec[0] + k, bit 1: one destination rank and dst_rec[k] = dst_rec[0] + k
     const int* gpoff; const int* nloen_loc; const double* racthe_loc;
     double* fb; int cp;
     int nfs; int npairs; int nchunks;    // pair chunks per latitude
@@ -377,12 +381,169 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Chirp-z rows, split over a CTA pair (fourier_cz.h).  Cluster of two CTAs = one latitude x a chunk of field pairs;
+// CTA 0 convolves the even bins, CTA 1 the odd bins, each in a work array of H = M/2 elements; the halves are
+// combined in the output phase through distributed shared memory.  No staging area and no chirp copy in shared
+// memory: several CTAs per SM (three for the longest dp rows of TCo1279) hide the global-memory latency instead.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ inline int cz_smem_bytes(int H, int N, int csize) {
+    return (ECT_PADDED_LEN(H) + ECT_TW1_LEN(2 * H) + ECT_TW2_LEN + ECT_ROOTS_OFF(8) + ECT_TW1_LEN(2 * N) + ECT_TW2_LEN) * csize;
+}
+__device__ __forceinline__ void ft_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" :: "l"(p)); }
+#define CZ_MINB(TB, FP32) ((TB) == 128 ? ((FP32) ? 4 : 3) : ((TB) == 192 || (TB) == 256 ? 2 : 1))
+
+template <bool INVERSE, int TB, bool FP32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TB, CZ_MINB(TB, FP32)) k_fourier_cz(FtArgs a) {
+    typedef typename std::conditional<FP32, float2, double2>::type C;
+    typedef typename EctReal<C>::type R_;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ EctFftPlan s_plan;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int half = (int)cluster.block_rank();
+    const int item = blockIdx.x >> 1;
+    const int l = a.lats[item / a.nchunks];
+    const int chunk = item % a.nchunks;
+    const EctLatPlan lp = a.latplans[a.lat_plan[l]];
+    if (threadIdx.x == 0) s_plan = a.plans[lp.plan_h];
+    __syncthreads();
+    const int H = s_plan.n, plan_nst = s_plan.nst;
+    const int N = lp.nlon, km = lp.km;
+    const C* czp = reinterpret_cast<const C*>(a.cz_pool);
+    const C* bhat = czp + (INVERSE ? lp.bhat_inv_eo[half] : lp.bhat_dir_eo[half]);
+    C* data = reinterpret_cast<C*>(smraw);
+    C* t1 = data + ECT_PADDED_LEN(H);
+    C* t2 = t1 + ECT_TW1_LEN(2 * H);
+    C* s_roots = t2 + ECT_TW2_LEN;
+    C* t1c = s_roots + ECT_ROOTS_OFF(8);
+    C* t2c = t1c + ECT_TW1_LEN(2 * N);
+    const int tid = threadIdx.x, nthr = TB;
+    // one two-level table of the M-th roots of unity serves the radix-2 step (w^u) and, with every second entry, the
+    // length-H passes
+    tw_build(t1, t2, a.tw_pool + a.plans[lp.plan].tw_off, 2 * H, tid, nthr);
+    for (int j = tid; j < ECT_ROOTS_OFF(8); j += nthr) s_roots[j] = c_cvt<C>(a.roots[j]);
+    // chirp c[j] = exp(i pi j^2 / N) as entry (j^2 mod 2N) of a two-level table of the 2N-th roots of unity
+    for (int j = tid; j < ECT_TW1_LEN(2 * N) + ECT_TW2_LEN; j += nthr) t1c[j] = czp[lp.ctw_off + j];
+    EctTwT<C> qth; qth.t1 = t1; qth.t2 = t2; qth.sh = 1;
+    CzCtx<C> cx;
+    cx.N = N; cx.km = km; cx.H = H; cx.half = half;
+    cx.twm.t1 = t1; cx.twm.t2 = t2; cx.twm.sh = 0;
+    cx.twc.t1 = t1c; cx.twc.t2 = t2c; cx.twc.sh = 0;
+    cx.n2 = 2u * (unsigned)N; cx.magic = (unsigned)((0x100000000ull + cx.n2 - 1) / cx.n2);
+    const C* other = cluster.map_shared_rank(data, half ^ 1);
+    const int* recs = a.fft_rec + a.latrow0[l];
+    // records of consecutive wavenumbers are consecutive (always on one rank): no index loads in front of the data loads
+    const int aff = a.lat_aff[l];
+    const int rec0 = recs[0];
+    const int cp = a.cp;
+    const int g0 = a.gpoff[l];
+    const bool oneblk = a.nproma >= a.ngptot;
+    const int p0 = chunk * FT_PAIRS_PER_CTA, p1 = min(p0 + FT_PAIRS_PER_CTA, a.npairs);
+    const double racthe = a.racthe_loc[l];
+    const bool warp_local = plan_nst >= 2 && s_plan.radix[0] == 16 && s_plan.radix[1] == 16 && (H & 511) == 0;
+    __syncthreads();
+    for (int p = p0; p < p1; ++p) {
+        const int2 pr = a.pairs[p];
+        const int fa = pr.x, fb2 = pr.y;
+        const bool hasb = fb2 >= 0;
+        if (INVERSE) {
+            const EctFsField sfa = a.fsf[fa];
+            EctFsField sfb; sfb.src_c = -1; sfb.pw = 0; sfb.deriv = 0;
+            if (hasb) sfb = a.fsf[fb2];
+            CzInvScale sc;
+            sc.pwa = sfa.pw; sc.deriva = sfa.deriv; sc.pwb = sfb.pw; sc.derivb = sfb.deriv; sc.hasb = hasb;
+            sc.s1 = racthe; sc.s2 = racthe * racthe;
+            sc.rowscale = a.adj ? a.rw_loc[l] / (double)N : 1.0;       // DIR_TRANSAD: diag(w / N) . INV_TRANS
+            const int ca = sfa.src_c, cb = sfb.src_c;
+            cz_inv_load(data, cx, sc, [&](int k, double2& ra, double2& rb) {
+                const double* src = a.fb + (long long)((aff & 1) ? rec0 + k : recs[k]) * cp;
+                ra = *reinterpret_cast<const double2*>(src + ca);
+                if (hasb) rb = *reinterpret_cast<const double2*>(src + cb);
+            }, tid, nthr);
+            if (p + 1 < p1) {        // the next pair's spectral values on their way into L2 while this pair is transformed
+                const int cn = a.fsf[a.pairs[p + 1].x].src_c;
+                for (int k = 2 * tid + half; k <= km; k += 2 * nthr)
+                    ft_prefetch_l2(a.fb + (long long)((aff & 1) ? rec0 + k : recs[k]) * cp + cn);
+            }
+        } else {
+            const double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
+            const double* bb = hasb ? a.gp_base[fb2] : nullptr; const i64 sb = hasb ? a.gp_blk[fb2] : 0;
+            cz_dir_load(data, cx, [&](int j, R_& va, R_& vb) {
+                const int g = g0 + j;
+                const i64 ia = oneblk ? (i64)g : gp_index(g, a.nproma, sa);
+                va = FP32 ? (R_)reinterpret_cast<const float*>(ba)[ia] : (R_)ba[ia];
+                if (hasb) {
+                    const i64 ib = oneblk ? (i64)g : gp_index(g, a.nproma, sb);
+                    vb = FP32 ? (R_)reinterpret_cast<const float*>(bb)[ib] : (R_)bb[ib];
+                }
+            }, tid, nthr);
+            if (p + 1 < p1) {        // the next pair's rows on their way into L2 (one request per 128 bytes, shared by the two CTAs)
+                const int2 pn = a.pairs[p + 1];
+                const int es = FP32 ? 4 : 8, per = 128 / es;
+                for (int t = 2 * tid + half; t * per < N; t += 2 * nthr) {
+                    const int g = g0 + t * per;
+                    ft_prefetch_l2(reinterpret_cast<const char*>(a.gp_base[pn.x]) + (oneblk ? (i64)g : gp_index(g, a.nproma, a.gp_blk[pn.x])) * es);
+                    if (pn.y >= 0)
+                        ft_prefetch_l2(reinterpret_cast<const char*>(a.gp_base[pn.y]) + (oneblk ? (i64)g : gp_index(g, a.nproma, a.gp_blk[pn.y])) * es);
+                }
+            }
+        }
+        __syncthreads();
+        // Stages 0 and 1 of a 16 x 16 x ... plan work inside aligned blocks of 256 elements, and a warp's 32 consecutive
+        // butterflies cover the same two blocks in either stage: DIF stage 1 -> fused middle -> DIT stage 1 need no
+        // CTA-wide barrier, only the warp's own stores to be visible.  The warps of a CTA then drift apart and their
+        // shared-memory and FP64 phases overlap instead of running in lock step.
+        for (int s = plan_nst - 1; s >= 1; --s) {
+            fft_stage<true, 7, true>(data, H, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qth, (const C*)s_roots, tid, nthr);
+            if (s == 1 && warp_local) __syncwarp(); else __syncthreads();
+        }
+        blue_middle_early(data, H, s_plan.radix[0], bhat, tid, nthr);
+        if (warp_local) __syncwarp(); else __syncthreads();
+        for (int s = 1; s < plan_nst; ++s) {
+            fft_stage<false, 7, true>(data, H, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qth, (const C*)s_roots, tid, nthr);
+            __syncthreads();
+        }
+        cluster.sync();                   // both halves complete and visible to the partner
+        if (INVERSE) {
+            double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
+            double* bb = hasb ? a.gp_base[fb2] : nullptr; const i64 sb = hasb ? a.gp_blk[fb2] : 0;
+            cz_inv_out((const C*)data, other, cx, [&](int j, C y) {
+                const int g = g0 + j;
+                const i64 ia = oneblk ? (i64)g : gp_index(g, a.nproma, sa);
+                if (FP32) reinterpret_cast<float*>(ba)[ia] = (float)y.x; else ba[ia] = (double)y.x;
+                if (hasb) {
+                    const i64 ib = oneblk ? (i64)g : gp_index(g, a.nproma, sb);
+                    if (FP32) reinterpret_cast<float*>(bb)[ib] = (float)y.y; else bb[ib] = (double)y.y;
+                }
+            }, tid, nthr);
+        } else {
+            // 1/N (tpm_fftw.F90:317-321), Gaussian weight (ledir_mod.F90:122) and, for u and v, 1/(a cos theta)
+            // (ldfou2_mod.F90:90-96) in one factor; INV_TRANSAD: neither 1/N nor the weight
+            const double wl = a.adj ? 1.0 : a.rw_loc[l] / (double)N;
+            const R_ sca = (R_)(0.5 * wl * (fa < a.n_uv_fields ? racthe : 1.0));
+            const R_ scb = (R_)(0.5 * wl * (fb2 >= 0 && fb2 < a.n_uv_fields ? racthe : 1.0));
+            const int ca = 2 * fa, cb = hasb ? 2 * fb2 : -1;
+            const int* drank = a.dst_rank + a.latrow0[l];
+            const int* drec = a.dst_rec + a.latrow0[l];
+            double* const peer0 = a.peer[drank[0]];
+            const int drec0 = drec[0];
+            cz_dir_out((const C*)data, other, cx, [&](int k, C Zk, C Zn) {
+                double* rb = (aff & 2) ? peer0 + (long long)(drec0 + k) * cp : a.peer[drank[k]] + (long long)drec[k] * cp;
+                *reinterpret_cast<double2*>(rb + ca) = make_double2((double)((Zk.x + Zn.x) * sca), (double)((Zk.y - Zn.y) * sca));
+                if (cb >= 0) *reinterpret_cast<double2*>(rb + cb) = make_double2((double)((Zk.y + Zn.y) * scb), (double)((Zn.x - Zk.x) * scb));
+            }, tid, nthr);
+        }
+        cluster.sync();                   // the partner has read this CTA's half: the work array may be overwritten
+    }
+}
+
 static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     EctDevice* d = h->d;
     a.latplans = d->latplans; a.plans = d->plans;
     a.perm_pool = d->perm_pool; a.tw_pool = d->tw_pool; a.roots = d->roots;
     a.cz_pool = f.fp32 ? (const void*)d->cz_pool_f : (const void*)d->cz_pool;
-    a.lat_plan = d->lat_plan; a.latrow0 = d->latrow0; a.fft_rec = d->fft_rec;
+    a.lat_plan = d->lat_plan; a.latrow0 = d->latrow0; a.fft_rec = d->fft_rec; a.lat_aff = d->lat_aff;
     a.gpoff = d->gpoff; a.nloen_loc = d->nloen; a.racthe_loc = d->racthe_loc;
     a.fb = d->fbuf_fft; a.cp = f.cp;
     a.peer = d->peer_leg; a.dst_rank = d->fft_dst_rank; a.dst_rec = d->fft_dst_rec;
@@ -424,6 +585,15 @@ static void launch_fourier(EctHandle* h, FtArgs& a) {
         if (fork) { const int k = slot % (EctDevice::kSide + 1); st = k == 0 ? d->stream : d->side[k - 1]; }
         ++slot;
         const int thr = INVERSE ? b.threads_inv : b.threads;
+        if (b.cz) {
+            const unsigned g2 = 2 * grid;          // clusters of two CTAs (__cluster_dims__)
+#define CZ_LAUNCH(TB_) do { if (a.fp32) k_fourier_cz<INVERSE, TB_, true><<<g2, TB_, b.smem, st>>>(a); \
+                            else k_fourier_cz<INVERSE, TB_, false><<<g2, TB_, b.smem, st>>>(a); } while (0)
+            if (b.threads == 128) CZ_LAUNCH(128); else if (b.threads == 192) CZ_LAUNCH(192); else if (b.threads == 256) CZ_LAUNCH(256); else CZ_LAUNCH(384);
+#undef CZ_LAUNCH
+            d->launches++;
+            continue;
+        }
         if (a.fp32) {
             if (b.maxr <= 7 && thr == 512) k_fourier<INVERSE, 7, 512, true><<<grid, thr, b.smem, st>>>(a);
             else if (b.maxr <= 7) k_fourier<INVERSE, 7, 256, true><<<grid, thr, b.smem, st>>>(a);
@@ -464,6 +634,31 @@ static int upload(T*& dptr, const std::vector<T>& v) {
     const size_t n = std::max<size_t>(v.size(), 1);
     ECT_CUDA(cudaMalloc(&dptr, n * sizeof(T)));
     if (!v.empty()) ECT_CUDA(cudaMemcpy(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return ECT_SUCCESS;
+}
+
+
+// Called once the transposition mode (peer memory or NCCL) is known: which latitudes have record tables that are
+// affine in the wavenumber (FtArgs::lat_aff), so that the kernels need no index loads in front of their data accesses
+int ect_fourier_set_affine(EctHandle* h) {
+    EctHostPlan& P = h->hp;
+    EctDevice* d = h->d;
+    int rc;
+    {
+        const bool fused = d->p2p;
+        const std::vector<int>& drk = P.fft_dst_rank; const std::vector<int>& drc = fused ? P.fft_dst_rec : P.fft_rec;
+        std::vector<int> aff(P.nlat, 0);
+        for (int l = 0; l < P.nlat; ++l) {
+            const i64 r0 = P.latrow0[l], n = P.latrow0[l + 1] - r0;
+            bool a0 = true, a1 = true;
+            for (i64 k = 1; k < n; ++k) {
+                if (P.fft_rec[r0 + k] != P.fft_rec[r0] + k) a0 = false;
+                if (drc[r0 + k] != drc[r0] + k || (fused && drk[r0 + k] != drk[r0])) a1 = false;
+            }
+            aff[l] = (a0 ? 1 : 0) | (a1 ? 2 : 0);
+        }
+        if ((rc = upload(d->lat_aff, aff))) return rc;
+    }
     return ECT_SUCCESS;
 }
 
@@ -531,19 +726,48 @@ int ect_fourier_setup(EctHandle* h) {
             b.nostage = i == 6;        // last class: rows too long for a staging area next to the work array
             d->buckets.push_back(b);
         }
+    // chirp-z rows: split over CTA pairs (k_fourier_cz), one class per number of CTAs that fit an SM
+    // ECT_FFT_CZ=1: every chirp-z row; default: only the rows whose undivided work array does not fit one SM (dp rows
+    // longer than ~5400 points, e.g. TCo2559 in double precision) -- on TCo1279 the pair kernel is no faster than the
+    // undivided one (profiles/r02_fourier_cz.md: three CTAs per SM walk through 150 KB of unrolled code in different
+    // phases and saturate the instruction cache, 84 % of the GPC instruction-fetch peak against 27 %)
+    const char* czenv = getenv("ECT_FFT_CZ");          // read at every setup: tests switch it per handle
+    const int cz_mode = czenv ? atoi(czenv) : -1;
+    int smem_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d->dev);
+    const int n_old = (int)d->buckets.size();
+    for (int c = 1; c <= 6; ++c) {
+        EctDevice::Bucket b;
+        b.cz = 1; b.smem = 0; b.maxr = 7; b.nostage = 1;
+        b.threads = c >= 3 ? 128 : (c == 2 ? 192 : 384);
+        static const char* t256 = getenv("ECT_CZ_T256");       // experiment: 2 x 256 threads at 128 registers
+        if (t256 && atoi(t256) && c >= 2) b.threads = 256;
+        b.threads_inv = b.threads;
+        d->buckets.push_back(b);
+    }
     std::vector<int> need_of(P.nlat, 0);
     for (int l = 0; l < P.nlat; ++l) {
         const EctLatPlan& lp = d->fft.latplans[d->h_lat_plan[l]];
-        const EctFftPlan& pl = d->fft.plans[lp.plan];
-        int maxr = 2;
-        for (int s = 0; s < pl.nst; ++s) if (pl.radix[s] & 1) maxr = std::max(maxr, pl.radix[s]);   // 2,4,8,16 are in every variant
-        const int nroots = maxr <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE;
         bool placed = false;
-        int need = 0;
-        for (auto& b : d->buckets) {
-            need = std::max(ft_layout(true, lp.bluestein != 0, pl.n, lp.nlon, lp.km, nroots, csize, iosize, b.nostage).total,
-                            ft_layout(false, lp.bluestein != 0, pl.n, lp.nlon, lp.km, nroots, csize, iosize, b.nostage).total);
-            if (need <= b.smem && maxr <= b.maxr) { b.lats.push_back(l); placed = true; break; }
+        int need = 0, maxr = 2;
+        if (!(lp.bluestein && cz_mode == 1)) {
+            const EctFftPlan& pl = d->fft.plans[lp.plan];
+            for (int s = 0; s < pl.nst; ++s) if (pl.radix[s] & 1) maxr = std::max(maxr, pl.radix[s]);   // 2,4,8,16 are in every variant
+            const int nroots = maxr <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE;
+            for (auto& b : d->buckets) {
+                if (b.cz) continue;
+                need = std::max(ft_layout(true, lp.bluestein != 0, pl.n, lp.nlon, lp.km, nroots, csize, iosize, b.nostage).total,
+                                ft_layout(false, lp.bluestein != 0, pl.n, lp.nlon, lp.km, nroots, csize, iosize, b.nostage).total);
+                if (need <= b.smem && maxr <= b.maxr) { b.lats.push_back(l); placed = true; break; }
+            }
+        }
+        if (!placed && lp.bluestein) {
+            need = cz_smem_bytes(lp.m / 2, lp.nlon, csize);
+            if (need <= maxsm - 1024) {
+                const int c = std::max(1, std::min(6, smem_sm / (need + 1024 + 256)));
+                d->buckets[n_old + c - 1].lats.push_back(l);
+                placed = true;
+            }
         }
         need_of[l] = need;
         if (!placed) {
@@ -573,6 +797,13 @@ int ect_fourier_setup(EctHandle* h) {
     FT_ATTR(true, 7, 512, true); FT_ATTR(false, 7, 512, true);
     FT_ATTR(true, ECT_MAX_RADIX, 256, true); FT_ATTR(false, ECT_MAX_RADIX, 256, true);
 #undef FT_ATTR
+#define CZ_ATTR(...) ECT_CUDA(cudaFuncSetAttribute(k_fourier_cz<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024))
+    CZ_ATTR(true, 128, false); CZ_ATTR(false, 128, false); CZ_ATTR(true, 192, false); CZ_ATTR(false, 192, false);
+    CZ_ATTR(true, 384, false); CZ_ATTR(false, 384, false);
+    CZ_ATTR(true, 128, true); CZ_ATTR(false, 128, true); CZ_ATTR(true, 192, true); CZ_ATTR(false, 192, true);
+    CZ_ATTR(true, 384, true); CZ_ATTR(false, 384, true);
+    CZ_ATTR(true, 256, false); CZ_ATTR(false, 256, false); CZ_ATTR(true, 256, true); CZ_ATTR(false, 256, true);
+#undef CZ_ATTR
     return ECT_SUCCESS;
 }
 

@@ -2,6 +2,7 @@
 // ectrans_b200/csrc single-threaded so that index logic is checked without a GPU.
 // Built by tests/conftest.py into tests/hostemu/_build/; never loaded by the product.
 #include "../../ectrans_b200/csrc/fourier_phases.h"
+#include "../../ectrans_b200/csrc/fourier_cz.h"
 #include <vector>
 #include <cstring>
 extern int g_ect_force_bluestein;
@@ -113,6 +114,112 @@ int emu_ftdir_pair(int nlon, int km, const double* rowa, const double* rowb, dou
     for (int t = 0; t < nthr; ++t) ftdir_store(data.data(), spec, c, 0, 2, t, nthr);
     g_ect_force_bluestein = 0;
     return c.bluestein;
+}
+}
+
+// ---- chirp-z rows split over a CTA pair (fourier_cz.h): both halves run one after the other on the CPU ----
+struct CzEmu {
+    EctFftTables T; EctLatPlan lp; EctFftPlan ph;
+    std::vector<double2> t1, t2, t1c, t2c, dat[2];
+    CzCtx<double2> cx[2]; EctTw qth;
+    int setup(int nlon, int km) {
+        g_ect_force_bluestein = 1;
+        const int id = T.get_latplan(nlon, km);
+        g_ect_force_bluestein = 0;
+        lp = T.latplans[id];
+        if (!lp.bluestein || lp.plan_h < 0) return -1;
+        ph = T.plans[lp.plan_h];
+        const int H = ph.n, M = 2 * H;
+        if (M != lp.m) return -2;
+        t1.assign(ECT_TW1_LEN(M), make_double2(0, 0)); t2.assign(ECT_TW2_LEN, make_double2(0, 0));
+        tw_build(t1.data(), t2.data(), T.tw_pool.data() + T.plans[lp.plan].tw_off, M, 0, 1);
+        qth.t1 = t1.data(); qth.t2 = t2.data(); qth.sh = 1;
+        t1c.assign(T.cz_pool.begin() + lp.ctw_off, T.cz_pool.begin() + lp.ctw_off + ECT_TW1_LEN(2 * nlon));
+        t2c.assign(T.cz_pool.begin() + lp.ctw_off + ECT_TW1_LEN(2 * nlon), T.cz_pool.begin() + lp.ctw_off + ECT_TW1_LEN(2 * nlon) + ECT_TW2_LEN);
+        for (int h = 0; h < 2; ++h) {
+            dat[h].assign(ECT_PADDED_LEN(H), make_double2(1e300, 1e300));      // poison: every element must be written
+            cx[h].N = nlon; cx[h].km = km; cx[h].H = H; cx[h].half = h;
+            cx[h].twm.t1 = t1.data(); cx[h].twm.t2 = t2.data(); cx[h].twm.sh = 0;
+            cx[h].twc.t1 = t1c.data(); cx[h].twc.t2 = t2c.data(); cx[h].twc.sh = 0;
+            cx[h].n2 = 2u * (unsigned)nlon; cx[h].magic = (unsigned)((0x100000000ull + cx[h].n2 - 1) / cx[h].n2);
+        }
+        return 0;
+    }
+    void passes(int h, int dir, int nthr) {
+        double2* data = dat[h].data();
+        const double2* bhat = T.cz_pool.data() + (dir == 0 ? lp.bhat_inv_eo[h] : lp.bhat_dir_eo[h]);
+        const int H = ph.n;
+        for (int s = ph.nst - 1; s >= 1; --s)
+            for (int t = 0; t < nthr; ++t) fft_stage<true, 7, true>(data, H, ph.radix[s], ph.sublen[s], ph.lshift[s], qth, (const double2*)T.roots.data(), t, nthr);
+        for (int t = 0; t < nthr; ++t) blue_middle(data, H, ph.radix[0], bhat, t, nthr);
+        for (int s = 1; s < ph.nst; ++s)
+            for (int t = 0; t < nthr; ++t) fft_stage<false, 7, true>(data, H, ph.radix[s], ph.sublen[s], ph.lshift[s], qth, (const double2*)T.roots.data(), t, nthr);
+    }
+};
+
+extern "C" {
+// radices of the half plan of length n (returns the number of stages)
+int emu_half_plan(int n, int* radices) {
+    std::vector<int> r;
+    if (!ect_fft_factorize_half(n, r)) return -1;
+    for (size_t i = 0; i < r.size(); ++i) radices[i] = r[i];
+    return (int)r.size();
+}
+
+// complex sign-+ FFT of length n on a half plan (composite radices), DIT from the permuted input
+int emu_fft_half(int n, const double* in, double* out) {
+    EctFftTables T;
+    int id = T.get_plan(n, true, true);
+    if (id < 0) return -1;
+    std::vector<double2> d(n);
+    for (int i = 0; i < n; ++i) d[i] = make_double2(in[2 * i], in[2 * i + 1]);
+    ect_fft_host(T, id, d);
+    for (int i = 0; i < n; ++i) { out[2 * i] = d[i].x; out[2 * i + 1] = d[i].y; }
+    return 0;
+}
+
+int emu_cz_inv_pair(int nlon, int km, const double* spec, double* outa, double* outb, int nthr) {
+    CzEmu E;
+    int rc = E.setup(nlon, km);
+    if (rc) return rc;
+    CzInvScale sc; sc.pwa = sc.pwb = 0; sc.deriva = sc.derivb = 0; sc.hasb = 1; sc.s1 = sc.s2 = 1.0; sc.rowscale = 1.0;
+    for (int h = 0; h < 2; ++h) {
+        for (int t = 0; t < nthr; ++t)
+            cz_inv_load(E.dat[h].data(), E.cx[h], sc, [&](int k, double2& ra, double2& rb) {
+                ra = make_double2(spec[4 * k], spec[4 * k + 1]); rb = make_double2(spec[4 * k + 2], spec[4 * k + 3]);
+            }, t, nthr);
+        E.passes(h, 0, nthr);
+    }
+    std::vector<int> cnt(nlon, 0);
+    for (int h = 0; h < 2; ++h)
+        for (int t = 0; t < nthr; ++t)
+            cz_inv_out((const double2*)E.dat[h].data(), (const double2*)E.dat[h ^ 1].data(), E.cx[h],
+                       [&](int j, double2 y) { outa[j] = y.x; outb[j] = y.y; cnt[j]++; }, t, nthr);
+    for (int j = 0; j < nlon; ++j) if (cnt[j] != 1) return -10;      // every longitude written exactly once
+    return E.ph.n;
+}
+
+int emu_cz_dir_pair(int nlon, int km, const double* rowa, const double* rowb, double* spec, int nthr) {
+    CzEmu E;
+    int rc = E.setup(nlon, km);
+    if (rc) return rc;
+    for (int h = 0; h < 2; ++h) {
+        for (int t = 0; t < nthr; ++t)
+            cz_dir_load(E.dat[h].data(), E.cx[h], [&](int j, double& va, double& vb) { va = rowa[j]; vb = rowb[j]; }, t, nthr);
+        E.passes(h, 1, nthr);
+    }
+    const double sc = 0.5 / (double)nlon;
+    std::vector<int> cnt(km + 1, 0);
+    for (int h = 0; h < 2; ++h)
+        for (int t = 0; t < nthr; ++t)
+            cz_dir_out((const double2*)E.dat[h].data(), (const double2*)E.dat[h ^ 1].data(), E.cx[h],
+                       [&](int k, double2 Zk, double2 Zn) {
+                           spec[4 * k] = (Zk.x + Zn.x) * sc; spec[4 * k + 1] = (Zk.y - Zn.y) * sc;
+                           spec[4 * k + 2] = (Zk.y + Zn.y) * sc; spec[4 * k + 3] = (Zn.x - Zk.x) * sc;
+                           cnt[k]++;
+                       }, t, nthr);
+    for (int k = 0; k <= km; ++k) if (cnt[k] != 1) return -10;
+    return E.ph.n;
 }
 }
 

@@ -150,3 +150,77 @@ def test_every_row_of_o1280_and_every_small_length(emu):
     for n in range(3, 601):
         b, e1, e2 = _pair(emu, n, max((n - 1) // 2, 1), 0, 3, rng)
         assert e1 < 1e-14 and e2 < 1e-14, (n, b, e1, e2)
+
+
+# ---- chirp-z rows split over a CTA pair (csrc/fourier_cz.h) ----
+def test_half_plans_use_one_composite_radix(emu):
+    """H = r 2^k half plans: 16s innermost, the odd factor merged with the left-over power of two into one
+    register-resident radix, so the four largest TCo1279 classes are three-stage plans."""
+    import ctypes as C
+    rad = (C.c_int * 16)()
+    for n, want in ((4096, [16, 16, 16]), (3584, [16, 16, 14]), (3072, [16, 16, 12]), (2560, [16, 16, 10]),
+                    (8192, [16, 16, 16, 2]), (7168, [16, 16, 2, 14]), (6144, [16, 16, 2, 12]), (5120, [16, 16, 2, 10]),
+                    (1536, [16, 16, 6]), (768, [16, 16, 3]), (24, [8, 3]), (160, [16, 10]), (448, [16, 2, 14])):
+        k = emu.emu_half_plan(n, rad)
+        assert list(rad[:k]) == want, (n, list(rad[:k]))
+        assert int(np.prod(rad[:k])) == n
+
+
+def test_fft_composite_radices(emu):
+    rng = np.random.default_rng(2)
+    for n in (96, 160, 192, 224, 448, 1536, 2560, 3072, 3584, 5120, 6144, 7168):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        xin = np.ascontiguousarray(np.stack([x.real, x.imag], 1))
+        out = np.zeros((n, 2))
+        assert emu.emu_fft_half(n, P(xin), P(out)) == 0
+        ref = np.fft.ifft(x) * n
+        assert np.abs(out[:, 0] + 1j * out[:, 1] - ref).max() <= 5e-15 * np.abs(ref).max() * np.log2(n)
+
+
+def _cz_pair(emu, nlon, km, nthr, rng):
+    sa = rng.standard_normal(km + 1) + 1j * rng.standard_normal(km + 1)
+    sb = rng.standard_normal(km + 1) + 1j * rng.standard_normal(km + 1)
+    spec = np.ascontiguousarray(np.stack([sa.real, sa.imag, sb.real, sb.imag], 1))
+    oa, ob = np.zeros(nlon), np.zeros(nlon)
+    H = emu.emu_cz_inv_pair(nlon, km, P(spec), P(oa), P(ob), nthr)
+    assert H > 0, H
+
+    def ref(s):
+        h = np.zeros(nlon // 2 + 1, complex)
+        h[:km + 1] = s
+        h[0] = h[0].real
+        return np.fft.irfft(h, n=nlon) * nlon if nlon % 2 == 0 else np.fft.irfft(h, n=nlon) * nlon
+
+    e1 = max(np.abs(oa - ref(sa)).max(), np.abs(ob - ref(sb)).max()) / np.abs(ref(sa)).max()
+    ra, rb = rng.standard_normal(nlon), rng.standard_normal(nlon)
+    sp = np.zeros((km + 1, 4))
+    assert emu.emu_cz_dir_pair(nlon, km, P(ra), P(rb), P(sp), nthr) == H
+    fa, fb = np.fft.rfft(ra)[:km + 1] / nlon, np.fft.rfft(rb)[:km + 1] / nlon
+    e2 = max(np.abs(sp[:, 0] + 1j * sp[:, 1] - fa).max(), np.abs(sp[:, 2] + 1j * sp[:, 3] - fb).max()) / np.abs(fa).max()
+    return H, e1, e2
+
+
+@pytest.mark.parametrize("nlon,km", [(20, 8), (24, 11), (148, 40), (148, 73), (212, 60), (4 * 97, 120), (4 * 1283, 1279),
+                                     (5136, 1279), (20 + 4 * 1000, 1279), (20 + 4 * 700, 1100), (100, 49), (27, 13),
+                                     (75, 37), (1125, 562), (10256, 2559), (3, 1), (5, 2)])
+def test_cz_pair_split(emu, nlon, km):
+    """The split chirp-z (even / odd bins as two half-length convolutions, combined in the output phase) against
+    pocketfft; covers N > H and N < H, odd row lengths, the TCo1279 equator and the TCo2559 equator (H = 8192)."""
+    rng = np.random.default_rng(nlon + km)
+    H, e1, e2 = _cz_pair(emu, nlon, km, 7, rng)
+    assert e1 < 1e-14 and e2 < 1e-14, (H, e1, e2)
+
+
+def test_cz_every_chirpz_row_of_o1280(emu):
+    rng = np.random.default_rng(4)
+    s = eo.setup(1279, 2560, eo.octahedral_nloen(1280), tables=False)
+    worst, n = 0.0, 0
+    for i in range(0, 1280):
+        nlon = 20 + 4 * i
+        if emu.emu_smooth(nlon):
+            continue
+        if i % 3 and i < 1270:
+            continue
+        H, e1, e2 = _cz_pair(emu, nlon, max(int(s.nmen[i]), 1), 5, rng)
+        worst = max(worst, e1, e2); n += 1
+    assert worst < 1e-14 and n > 250

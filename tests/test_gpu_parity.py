@@ -850,3 +850,81 @@ def test_gpnorm_vordiv_single_precision(eb):
     u, v = tr.vordiv_to_uv(T_(vor).astype(np.float32), T_(div).astype(np.float32))
     assert u.dtype == np.float32 and rel(u.T, ur) < 1e-6 and rel(v.T, vr) < 1e-6
     tr.release()
+
+
+# ---- chirp-z rows on CTA pairs (csrc/fourier_cz.h, k_fourier_cz) ----
+@pytest.fixture
+def cz_all(monkeypatch):
+    """Route every chirp-z row through the pair kernel (by default only rows whose undivided work array does not fit)."""
+    monkeypatch.setenv("ECT_FFT_CZ", "1")
+
+
+@pytest.mark.parametrize("T,N,prec,tol", [(159, 160, "dp", 1e-12), (399, 400, "dp", 1e-12), (399, 400, "sp", 5e-6)])
+def test_cz_pair_kernel_against_oracle(eb, cz_all, T, N, prec, tol):
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen, precision=prec)
+    s = eo.setup(T, 2 * N, nloen)
+    nuv, nsc = 3, 4
+    dt = np.float64 if prec == "dp" else np.float32
+    f = (lambda a: a.astype(np.float32).astype(np.float64)) if prec == "sp" else (lambda a: a)
+    vor = f(eo.random_spectral(s, nuv, 1, zero00=True)); div = f(eo.random_spectral(s, nuv, 2, zero00=True))
+    sc = f(eo.random_spectral(s, nsc, 3))
+    opts = dict(scders=True, uvder=True)
+    ref = eo.inv_trans(s, vor, div, sc, **opts)
+    gp = tr.inv_trans(T_(vor).astype(dt), T_(div).astype(dt), T_(sc).astype(dt), nproma=1001, **opts)
+    got = unblock(gp, tr.ngptot).astype(np.float64)
+    for i in range(ref.shape[0]):
+        assert rel(got[i], ref[i]) < tol, i
+    nf = 2 * nuv + nsc
+    gin = f(ref[:nf])
+    rv, rd, rs = eo.dir_trans(s, gin, nuv, nsc)
+    ov, od, os_ = tr.dir_trans(gin[None].astype(dt), nuv, nsc)
+    for a, b in ((ov, rv), (od, rd), (os_, rs)):
+        assert rel(a.T.astype(np.float64), b) < tol
+    tr.release()
+
+
+def test_cz_pair_kernel_odd_rows(eb, cz_all):
+    """Classic reduced grid (odd row lengths 27, 45, 75) through the pair kernel."""
+    nloen = np.asarray(N32_CLASSIC + N32_CLASSIC[::-1], dtype=np.int32)
+    T = 42
+    tr = eb.Transform(T, nloen)
+    s = eo.setup(T, nloen.size, nloen)
+    sc = eo.random_spectral(s, 5, 3)
+    ref = eo.inv_trans(s, None, None, sc)
+    gp = tr.inv_trans(spscalar=T_(sc))
+    assert rel(gp[0], ref) < 1e-12
+    back = tr.dir_trans(gp, 0, 5)[2]
+    rs = eo.dir_trans(s, ref, 0, 5)[2]
+    assert rel(back.T, rs) < 1e-12
+    tr.release()
+
+
+def test_tco2559_rows_dp(eb):
+    """Rows longer than ~5400 points in double precision (TCo2559 / O2560: up to 10256 points, convolution length
+    16384): the undivided chirp-z work array does not fit an SM, the pair kernel's halves (139 KB) do.  Round 1 returned
+    ECT_ERR_NOTIMPL here.  Reduced field count; analytic harmonic, linearity and round trip at the dp tolerance."""
+    T, N = 2559, 2560
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen)
+    nf = 2
+    rng = np.random.default_rng(12)
+    n = np.concatenate([np.repeat(np.arange(m, T + 1), 2) for m in range(T + 1)]).astype(float)
+    a = rng.uniform(-1, 1, (tr.nspec2, nf)) / (1 + n[:, None]) ** 2
+    a[1:2 * (T + 1):2] = 0
+    b = np.zeros_like(a)
+    b[int(tr.nasm0[4]) + 2 * (19 - 4)] = 1.0
+    ga, gb = tr.inv_trans(spscalar=a), tr.inv_trans(spscalar=b)
+    off = np.concatenate([[0], np.cumsum(nloen)])
+    for j in (0, 5, 1000, 2047, 2559, 2560, 4000, 5119):
+        nlon = int(nloen[j])
+        row = gb[0, 0, off[j]:off[j] + nlon]
+        if tr.nmen[j] >= 4:
+            p = eo.supolf(4, 19, tr.rmu[j])[19, 0]
+            assert np.abs(row - 2 * p * np.cos(2 * np.pi * 4 * np.arange(nlon) / nlon)).max() < 1e-12
+    gab = tr.inv_trans(spscalar=a - 2.5 * b)
+    assert rel(gab, ga - 2.5 * gb) < 1e-13
+    back = tr.dir_trans(ga, 0, nf)[2]
+    assert rel(back, a) < 2e-11
+    assert np.abs(tr.specnorm(back) / tr.specnorm(a) - 1).max() < 1e-12
+    tr.release()
