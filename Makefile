@@ -5,7 +5,7 @@ NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Wno-deprecated-gpu
 CSRC := ectrans_b200/csrc
 OBJ := $(CSRC)/_build
 LIB := ectrans_b200/lib/libectrans_b200.so
-SRCS := api.cu legendre.cu fourier.cu fft_plan.cu host_plan.cu gp_partition.cu transi.cu
+SRCS := api.cu legendre.cu legendre_tc.cu fourier.cu fft_plan.cu host_plan.cu gp_partition.cu transi.cu
 OBJS := $(patsubst %.cu,$(OBJ)/%.o,$(SRCS))
 HDRS := $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
 

@@ -241,6 +241,7 @@ void ect_device_free(EctHandle* h) {
     if (!d) return;
     cudaStreamSynchronize(d->stream);
     for (void* m : d->ipc_open) cudaIpcCloseMemHandle(m);
+    ect_tc_free(d);
     if (d->comm) ncclCommDestroy((ncclComm_t)d->comm);
     if (d->comm_world) ncclCommDestroy((ncclComm_t)d->comm_world);
     void* ptrs[] = {d->rw, d->racthe, d->racthe_loc, d->rw_loc, d->nloen, d->gpoff, d->ptab, d->legm, d->leg_rec_n, d->leg_rec_s,
@@ -1335,6 +1336,7 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
         ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
     }
     ECT_CUDA(cudaGetLastError());
+    if (d->launch_error) { d->launch_error = 0; return ECT_ERR_CUDA; }
     if ((rc = release_callbuf(d))) return rc;
     if (host) {
         if (!mode2_gp) ECT_CUDA(cudaMemcpyAsync(a->gp, dgp, (size_t)sz_gp * es, cudaMemcpyDeviceToHost, d->stream));
@@ -1522,6 +1524,7 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     ect_launch_ltdir_epilogue(h, f, d_vor, d_div, d_sc);
     ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
     ECT_CUDA(cudaGetLastError());
+    if (d->launch_error) { d->launch_error = 0; return ECT_ERR_CUDA; }
     if ((rc = release_callbuf(d))) return rc;
     if (host) {
         auto back = [&](double* dst, const double* src, i64 n) -> int {

@@ -103,8 +103,11 @@ struct EctFieldCfg {       // field bookkeeping of one call (INV_TRANS inv_trans
     int adj = 0;           // adjoint call (INV_TRANSAD runs the direct pipeline, DIR_TRANSAD the inverse one, with other scalings)
 };
 
+struct EctTcState;         // tcgen05 contraction of sp handles (legendre_tc.cu)
 struct EctDevice {
     int dev = 0;
+    EctTcState* tc = nullptr;
+    int n_inv_tiles_m0 = 0, n_dir_tiles_m0 = 0;      // leading entries of inv_tiles / dir_tiles that belong to m = 0
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // geometry
@@ -183,6 +186,7 @@ struct EctDevice {
     cudaEvent_t ev[16] = {};
     int last_dir = 0; bool timed = false;
     i64 launches = 0;
+    int launch_error = 0;                 // a stage launcher failed (its ect_last_error text is set); checked after the stages of a call
 };
 
 // V-sets (NPRTRV > 1): tasks form a W x V grid (PE2SET: w = pe / V, v = pe % V).  hp describes the W-group of this task
@@ -219,6 +223,12 @@ void ect_launch_ftdir(EctHandle* h, const EctFieldCfg& f, double* const* d_gp_ba
 void ect_launch_ledir(EctHandle* h, const EctFieldCfg& f);
 void ect_launch_ltdir_epilogue(EctHandle* h, const EctFieldCfg& f, void* d_vor, void* d_div, void* d_sc);
 int ect_legendre_setup(EctHandle* h);
+// sp handles: LEINV / LEDIR of the wavenumbers m > 0 as 3xTF32 on tcgen05 (legendre_tc.cu); m = 0 stays on the FP64 kernels
+bool ect_tc_enabled(EctHandle* h);
+int ect_tc_launch_leinv(EctHandle* h, const EctFieldCfg& f);
+int ect_tc_launch_ledir(EctHandle* h, const EctFieldCfg& f);
+void ect_tc_invalidate(EctHandle* h);
+void ect_tc_free(EctDevice* d);
 int ect_fourier_setup(EctHandle* h);
 int ect_fourier_set_affine(EctHandle* h);       // after the transposition mode is decided
 int ect_legendre_get_table(EctHandle* h, int ml, int par, double* out, long long cap);

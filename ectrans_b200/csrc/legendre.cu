@@ -732,6 +732,16 @@ void ect_launch_leinv(EctHandle* h, const EctFieldCfg& f) {
     a.peer = d->peer_fft; a.dst_rank_n = d->leg_dst_rank_n; a.dst_rank_s = d->leg_dst_rank_s;
     a.dst_rec_n = d->leg_dst_rec_n; a.dst_rec_s = d->leg_dst_rec_s;
     const size_t smem = INV_STAGES * INV_STAGE_DOUBLES * sizeof(double);
+    if (f.fp32 && ect_tc_enabled(h)) {
+        // sp handle: m = 0 in double precision on the DMMA kernel (as the reference keeps it: leinv_mod.F90:264-288),
+        // every other wavenumber as 3xTF32 on tcgen05
+        if (d->n_inv_tiles_m0 > 0) {
+            k_leinv<<<(unsigned)((long long)d->n_inv_tiles_m0 * a.nct), LEG_THREADS, smem, d->stream>>>(a);
+            d->launches++;
+        }
+        if (ect_tc_launch_leinv(h, f) != ECT_SUCCESS) d->launch_error = 1;
+        return;
+    }
     static const char* tma = getenv("ECT_LEINV_TMA");      // bulk-copy loader: measured slower (70.9 vs 48.4 ms at TCo1279), opt-in
     if (tma && atoi(tma)) k_leinv_tma<<<(unsigned)((long long)d->n_inv_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
     else k_leinv<<<(unsigned)((long long)d->n_inv_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
@@ -751,6 +761,14 @@ void ect_launch_ledir(EctHandle* h, const EctFieldCfg& f) {
     a.dbg = dbg ? atoi(dbg) : 0;
     a.peer = nullptr; a.dst_rank_n = a.dst_rank_s = a.dst_rec_n = a.dst_rec_s = nullptr;
     const size_t smem = LEG_STAGES * DIR_STAGE_DOUBLES * sizeof(double);
+    if (f.fp32 && ect_tc_enabled(h)) {         // sp handle: m = 0 in double (ledir_mod.F90:133-171), the rest on tcgen05
+        if (d->n_dir_tiles_m0 > 0) {
+            k_ledir<<<(unsigned)((long long)d->n_dir_tiles_m0 * a.nct), LEG_THREADS, smem, d->stream>>>(a);
+            d->launches++;
+        }
+        if (ect_tc_launch_ledir(h, f) != ECT_SUCCESS) d->launch_error = 1;
+        return;
+    }
     k_ledir<<<(unsigned)((long long)d->n_dir_tiles * a.nct), LEG_THREADS, smem, d->stream>>>(a);
     d->launches++;
 }
@@ -826,6 +844,9 @@ int ect_legendre_setup(EctHandle* h) {
     }
     d->n_inv_tiles = (int)inv.size();
     d->n_dir_tiles = (int)dir.size();
+    d->n_inv_tiles_m0 = d->n_dir_tiles_m0 = 0;
+    for (const int2& t2 : inv) if (d->h_legm[t2.x].m == 0) d->n_inv_tiles_m0++;
+    for (const int2& t2 : dir) if (d->h_legm[t2.x].m == 0) d->n_dir_tiles_m0++;
     ECT_CUDA(cudaMalloc(&d->inv_tiles, std::max<size_t>(inv.size(), 1) * sizeof(int2)));
     ECT_CUDA(cudaMalloc(&d->dir_tiles, std::max<size_t>(dir.size(), 1) * sizeof(int2)));
     ECT_CUDA(cudaMemcpy(d->inv_tiles, inv.data(), inv.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -854,5 +875,6 @@ int ect_legendre_set_table(EctHandle* h, int ml, int par, const double* in) {
     if (k == 0 || lm.ndglu == 0) return ECT_SUCCESS;
     ECT_CUDA(cudaMemcpy2D(d->ptab + (par ? lm.pa_off : lm.ps_off), lm.ldp * sizeof(double), in,
                           lm.ndglu * sizeof(double), lm.ndglu * sizeof(double), k, cudaMemcpyHostToDevice));
+    ect_tc_invalidate(h);          // the hi / lo float tables of the tensor-core path are rebuilt at the next sp transform
     return ECT_SUCCESS;
 }

@@ -928,3 +928,33 @@ def test_tco2559_rows_dp(eb):
     assert rel(back, a) < 2e-11
     assert np.abs(tr.specnorm(back) / tr.specnorm(a) - 1).max() < 1e-12
     tr.release()
+
+
+# ---- sp Legendre contraction on tcgen05 (csrc/legendre_tc.cu) ----
+@pytest.mark.parametrize("T,N,nuv,nsc", [(47, 48, 2, 3), (159, 160, 5, 70), (399, 400, 20, 21)])
+def test_sp_tcgen05_contraction(eb, monkeypatch, T, N, nuv, nsc):
+    """sp handles: m > 0 as 3xTF32 on the tensor cores (TMA-staged MN-major operands, TMEM accumulators), m = 0 on the
+    FP64 kernel.  Against the oracle at the north_star sp tolerance (1e-5), and against the all-FP64 contraction of round 1
+    (ECT_SP_TC=0), which it must stay close to."""
+    nloen = eb.octahedral_nloen(N)
+    s = eo.setup(T, 2 * N, nloen)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    vor, div, sc = f32(eo.random_spectral(s, nuv, 1, zero00=True)), f32(eo.random_spectral(s, nuv, 2, zero00=True)), f32(eo.random_spectral(s, nsc, 3))
+    ref = eo.inv_trans(s, vor, div, sc, scders=True)
+    nf = 2 * nuv + nsc
+    rv, rd, rs = eo.dir_trans(s, f32(ref[:nf]), nuv, nsc)
+    S_ = lambda a: np.ascontiguousarray(a.T).astype(np.float32)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ECT_SP_TC", mode)
+        tr = eb.Transform(T, nloen, precision="sp")
+        gp = tr.inv_trans(S_(vor), S_(div), S_(sc), scders=True)
+        sp3 = tr.dir_trans(f32(ref[:nf])[None].astype(np.float32), nuv, nsc)
+        out[mode] = (gp[0].astype(np.float64), [a.T.astype(np.float64) for a in sp3], tr.timings()["launches"])
+        tr.release()
+    for i in range(ref.shape[0]):
+        assert rel(out["1"][0][i], ref[i]) < 1e-5
+        assert rel(out["1"][0][i], out["0"][0][i]) < 1e-5
+    for a, b in zip(out["1"][1], (rv, rd, rs)):
+        assert rel(a, b) < 1e-5
+    assert out["1"][2] > out["0"][2]          # the tensor-core path really ran (its split / contraction launches)

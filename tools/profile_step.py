@@ -10,15 +10,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="TCo1279_O1280_L137")
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--precision", default="dp", choices=["dp", "sp"])
 a = ap.parse_args()
+tdt = torch.float64 if a.precision == "dp" else torch.float32
 T, N, nlev, nfld = CONFIGS[a.config]
 nuv, nsc = nlev, nlev * nfld + 1
 dev = torch.device("cuda", 0)
-tr = eb.Transform(T, eb.octahedral_nloen(N), stream=torch.cuda.current_stream().cuda_stream)
+tr = eb.Transform(T, eb.octahedral_nloen(N), stream=torch.cuda.current_stream().cuda_stream, precision=a.precision)
 g = torch.Generator(device=dev); g.manual_seed(1)
-mk = lambda n: (torch.rand((tr.nspec2, n), generator=g, device=dev, dtype=torch.float64) - 0.5) * 0.2
+mk = lambda n: (torch.rand((tr.nspec2, n), generator=g, device=dev, dtype=tdt) - 0.5) * 0.2
 v, d, s = mk(nuv), mk(nuv), mk(nsc)
-gp = torch.empty((1, 2 * nuv + nsc, tr.ngptot), dtype=torch.float64, device=dev)
+gp = torch.empty((1, 2 * nuv + nsc, tr.ngptot), dtype=tdt, device=dev)
 out = (torch.empty_like(v), torch.empty_like(d), torch.empty_like(s))
 hist = {"inv": [], "dir": []}
 for i in range(a.warmup + a.steps):
