@@ -31,5 +31,17 @@ probe:
 	@mkdir -p tools/probes/_build
 	$(NVCC) -O2 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -shared -Wno-deprecated-gpu-targets -o tools/probes/_build/libtcprobe.so tools/probes/tcgen05_tf32_probe.cu
 
+# The reference's own transi test program (tests/transi/transi_test_program.c), compiled UNCHANGED from where it lies
+# against include/ectrans/transi.h and linked with the CUDA library.  Only possible where /root/reference exists (the
+# build container); the binary lands in oracle/_ref/ (git-ignored, travels to the GPU box with the snapshot).
+REF ?= /root/reference
+transi_ref:
+	@mkdir -p oracle/_ref
+	@if [ -f $(REF)/tests/transi/transi_test_program.c ]; then \
+	  gcc -O1 -std=gnu99 -Iinclude -I$(REF)/tests/transi -o oracle/_ref/transi_test_program \
+	    $(REF)/tests/transi/transi_test_program.c $(REF)/tests/transi/transi_test.c \
+	    -Lectrans_b200/lib -lectrans_b200 -lm -Wl,-rpath,'$$ORIGIN/../../ectrans_b200/lib' && echo "built oracle/_ref/transi_test_program"; \
+	else echo "reference tree not present: oracle/_ref/transi_test_program not rebuilt"; fi
+
 clean:
 	rm -rf $(OBJ) $(LIB) tests/hostemu/_build

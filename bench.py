@@ -97,7 +97,7 @@ def cpu_sample_step(T, N, nuv, nsc, stride, rng_seed=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ectrans_oracle as eo
     import scipy.fft as sfft
-    cores = os.cpu_count()
+    cores = use_all_host_threads()
     nloen = eo.octahedral_nloen(N)
     ms = list(range(0, T + 1, stride))
     key = (T, N, stride)
@@ -150,30 +150,69 @@ def cpu_sample_step(T, N, nuv, nsc, stride, rng_seed=0):
 
 
 _CPU_SETUP = {}
+CPU_STRIDE = {79: 1, 159: 1, 399: 4, 1279: 16, 2559: 32}     # sampling of the CPU arm: 1 = the whole workload, nothing extrapolated
+
+
+def host_cores():
+    """Cores this process may use (cgroup / affinity aware) -- NOT the OMP_NUM_THREADS a launcher exported:
+    torch.distributed.run sets OMP_NUM_THREADS=1 for its workers, which made the round-1 reference arm 2.5x slower at N > 1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """BLAS (OpenBLAS inside NumPy) and pocketfft on every core, whatever the environment says."""
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["OPENBLAS_NUM_THREADS"] = str(n)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
+def cpu_sample_text(stride, nf):
+    if stride == 1:
+        return (f"the whole workload (every zonal wavenumber and latitude, all {nf} fields), nothing extrapolated; oracle port "
+                "(NumPy + OpenBLAS GEMM, scipy pocketfft), all host threads")
+    return (f"every {stride}th zonal wavenumber (Legendre stage) and every {stride}th latitude (Fourier stage), all {nf} fields, "
+            "EXTRAPOLATED to the whole workload by the sampled share of the Legendre flops / grid points; oracle port "
+            "(NumPy + OpenBLAS GEMM, scipy pocketfft), all host threads")
 
 
 def run_reference(args):
+    """The reference algorithm on the host cores.  ectrans-benchmark-cpu itself cannot be built (no Fortran compiler, fiat,
+    ecbuild, FFTW in this image -- SURVEY 0.2), so this is the oracle port (kind "port"), with every host thread, on the
+    same configuration keys as the GPU arm.  T79 / T159 run the whole workload; larger configurations a stated sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     T, N, nlev, nfld = CONFIGS[args.config]
     nuv, nsc = nlev, nlev * nfld + 1
-    stride = args.cpu_stride or {79: 1, 159: 2, 399: 8, 1279: 32}.get(T, 16)
-    cores = os.cpu_count()
+    nf = 2 * nuv + nsc
+    stride = args.cpu_stride or CPU_STRIDE.get(T, 16)
+    cores = use_all_host_threads()
+    prec = args.precision or PRECISION.get(args.config, "dp")
     vals = []
+    t_run = time.time()
     for i in range(args.warmup + args.steps):
         ms, detail = cpu_sample_step(T, N, nuv, nsc, stride, rng_seed=i)
         if i >= args.warmup:
             vals.append(ms)
     v = float(np.mean(vals))
-    sample = (f"every {stride}th zonal wavenumber (Legendre) and every {stride}th latitude (Fourier), all "
-              f"{2 * nuv + nsc} fields, scaled by sampled flops / grid points; oracle port (NumPy+OpenBLAS GEMM, scipy pocketfft with all cores)")
     line = {"impl": "reference", "metric": "ms per INV_TRANS+DIR_TRANS step", "value": v, "unit": "ms",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.config, "fields": 2 * nuv + nsc},
-            "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample, "detail": detail},
+            "dtype": "f64 (the port computes in double for both precisions)", "data": "synthetic",
+            "config": {"workload": args.config, "truncation": T, "grid": f"O{N}", "levels": nlev, "fields": nf,
+                       "decomposition": f"host, {cores} threads", "l2": "n/a (host)", "precision": prec},
+            "extrapolated": stride != 1, "wall_s": time.time() - t_run,
+            "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": cpu_sample_text(stride, nf),
+                             "detail": detail},
             "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -299,7 +338,7 @@ def run_ours(args):
             tr.dir_trans(h_gp.array, nuv, nsc, out=tuple(x.array for x in h_out))
             return float(h_out[2].array[0, 0])
 
-        ne = max(1, min(args.steps, args.e2e_steps))
+        ne = max(1, args.e2e_steps or args.steps)
         for _ in range(max(1, min(args.warmup, 2))):
             step_host()
         barrier()
@@ -345,7 +384,7 @@ def run_ours(args):
         "metric": "ms per INV_TRANS+DIR_TRANS step", "value": ms_dev, "unit": "ms", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64" if prec == "dp" else "f32 at the boundary and in the Fourier stage, f64 DMMA contraction", "data": "synthetic",
+        "dtype": "f64" if prec == "dp" else "f32 (Fourier stage in float, Legendre contraction 3xTF32 on tcgen05 with fp32 accumulation, m = 0 in f64)", "data": "synthetic",
         "config": {"workload": args.config, "truncation": T, "grid": f"O{N}", "levels": nlev, "fields": nf,
                    "decomposition": f"nprtrw={world},nprtrv=1", "l2": "inputs (GBs) larger than L2, no flush needed"},
         "stages_ms": {"legendre": leg_ms, "fourier": ft_ms, "transpose": tp_ms,
@@ -364,11 +403,10 @@ def run_ours(args):
     if parity is not None:
         line["parity"] = parity
     if world == 1 and not args.no_cpu:
-        stride = args.cpu_stride or {79: 1, 159: 2, 399: 8, 1279: 32}.get(T, 16)
+        stride = args.cpu_stride or CPU_STRIDE.get(T, 16)
         v, detail = cpu_sample_step(T, N, nuv, nsc, stride)
-        line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"every {stride}th zonal wavenumber and latitude, all {nf} fields, scaled; "
-                                          "oracle port (NumPy+OpenBLAS GEMM, scipy pocketfft with all cores)", "detail": detail}
+        line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": host_cores(), "kind": "port", "extrapolated": stride != 1,
+                                "sample": cpu_sample_text(stride, nf), "detail": detail}
     print(json.dumps(line), flush=True)
     tr.release()
 
@@ -384,7 +422,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate that runs before the timed region")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: --steps)")
     ap.add_argument("--cpu-stride", type=int, default=0)
     ap.add_argument("--stage-timings", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -1,6 +1,7 @@
 // transi C face (reference src/transi/transi.h, transi.c, transi_module.F90) over the ect_* C ABI.
 #include "../../include/transi_b200.h"
 #include "../../include/ectrans_b200.h"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -21,13 +22,29 @@ const char* trans_error_msg(int code) {      // transi.c:33-58
 }
 
 static int g_use_mpi = 0;
-int trans_use_mpi(int v) { if (v) return TRANS_NOTIMPL; g_use_mpi = 0; return TRANS_SUCCESS; }
+int trans_use_mpi(_bool v) { if (v) return TRANS_NOTIMPL; g_use_mpi = 0; return TRANS_SUCCESS; }
 int trans_init(void) { return TRANS_SUCCESS; }
 
-int trans_new(struct Trans_t* t) {          // transi.c: defaults
+// src/transi/version.h: this library mirrors ecTrans 1.7.0 (the reference tree's VERSION)
+const char* ectrans_version(void) { return "1.7.0"; }
+unsigned int ectrans_version_int(void) { return 10700u; }
+const char* ectrans_version_str(void) { return "1.7.0 (ectrans_b200: B200-native hot path)"; }
+const char* ectrans_git_sha1(void) { return "not available"; }
+const char* ectrans_git_sha1_abbrev(unsigned int) { return "not available"; }
+
+// transi.h:121-194.  What cannot be honoured is refused, never silently ignored.
+int trans_set_handles_limit(int limit) { return limit > 0 ? TRANS_SUCCESS : TRANS_ERROR; }       // handles are not limited here
+int trans_set_radius(double radius) { return radius == 6371229.0 ? TRANS_SUCCESS : TRANS_NOTIMPL; }
+int trans_set_nprtrv(int nprtrv) { return nprtrv == 1 ? TRANS_SUCCESS : TRANS_NOTIMPL; }
+int trans_set_nprgpew(int nprgpew) { return nprgpew == 1 ? TRANS_SUCCESS : TRANS_NOTIMPL; }
+int trans_set_leq_regions(_bool) { return TRANS_SUCCESS; }
+
+int trans_new(struct Trans_t* t) {          // transi.c:60-82 defaults; every other member cleared
     if (!t) return TRANS_MISSING_ARG;
     memset(t, 0, sizeof(*t));
-    t->nsmax = -1; t->nlon = -1; t->flt = -1; t->lsplit = 1; t->handle = 0;
+    t->handle = 0; t->llatlon = 0; t->lsplit = 1; t->flt = -1; t->fft = TRANS_FFTW;
+    t->nsmax = -1; t->nmsmax = -1; t->ndgl = -1; t->nlon = -1;
+    t->llam = 0; t->ndgux = -1; t->pexwn = 1.; t->peywn = 1.;
     t->myproc = 1; t->nproc = 1; t->nprtrw = 1;
     return TRANS_SUCCESS;
 }
@@ -40,10 +57,41 @@ int trans_set_resol(struct Trans_t* t, int ndgl, const int* nloen) {
     memcpy(t->nloen, nloen, sizeof(int) * ndgl);
     return TRANS_SUCCESS;
 }
+// lon-lat and LAM resolutions are recorded like the reference does (transi.c:93-125) and refused by trans_setup
+int trans_set_resol_lonlat(struct Trans_t* t, int nlon, int nlat) {
+    if (!t) return TRANS_MISSING_ARG;
+    t->ndgl = (nlat % 2 == 0) ? nlat : nlat - 1; t->nlon = nlon; t->llatlon = (nlat % 2 == 0) ? 2 : 1;
+    return TRANS_SUCCESS;
+}
+int trans_set_resol_lam(struct Trans_t* t, int nx, int ny, double dx, double dy) {
+    if (!t) return TRANS_MISSING_ARG;
+    t->ndgl = ny; t->nlon = nx; t->llam = 1;
+    t->pexwn = 2. * 3.14159265358979323846 / ((double)nx * dx); t->peywn = 2. * 3.14159265358979323846 / ((double)ny * dy);
+    return TRANS_SUCCESS;
+}
 
 int trans_set_trunc(struct Trans_t* t, int nsmax) {
     if (!t) return TRANS_MISSING_ARG;
     t->nsmax = nsmax;
+    return TRANS_SUCCESS;
+}
+int trans_set_trunc_lam(struct Trans_t* t, int trunc_x, int trunc_y) {
+    if (!t) return TRANS_MISSING_ARG;
+    t->llam = 1; t->nmsmax = trunc_x; t->nsmax = trunc_y;
+    return TRANS_SUCCESS;
+}
+static int set_path(char*& dst, const char* path) {
+    if (!path) return TRANS_MISSING_ARG;
+    free(dst);
+    dst = (char*)malloc(1024);
+    strncpy(dst, path, 1023); dst[1023] = 0;
+    return TRANS_SUCCESS;
+}
+int trans_set_read(struct Trans_t* t, const char* filepath) { return t ? set_path(t->readfp, filepath) : TRANS_MISSING_ARG; }
+int trans_set_write(struct Trans_t* t, const char* filepath) { return t ? set_path(t->writefp, filepath) : TRANS_MISSING_ARG; }
+int trans_set_cache(struct Trans_t* t, const void* cache, size_t size) {
+    if (!t) return TRANS_MISSING_ARG;
+    t->cache = cache; t->cachesize = size;          // refused by trans_setup (in-memory FLT cache: out of scope)
     return TRANS_SUCCESS;
 }
 
@@ -55,29 +103,40 @@ static int fill_inquire(struct Trans_t* t) {
     if (rc) return rc;
     t->nspec2 = inf.nspec2; t->nspec = inf.nspec2 / 2; t->nspec2g = inf.nspec2g; t->nspec2mx = inf.nspec2;
     t->nump = inf.nump; t->ngptot = inf.ngptot; t->ngptotg = inf.ngptotg; t->ngptotmx = inf.ngptot;
-    t->myproc = inf.rank + 1; t->nproc = inf.nranks; t->nprtrw = inf.nranks;
+    t->myproc = inf.rank + 1; t->nproc = inf.nranks; t->nprtrw = inf.nranks; t->nprtrns = inf.nranks;
+    // grid-point decomposition of this face: the Fourier latitude bands (one task: one region)
+    t->n_regions_NS = inf.nranks; t->n_regions_EW = 1; t->my_region_NS = inf.rank + 1; t->my_region_EW = 1;
+    t->nfrstloff = inf.lat0; t->nptrfloff = inf.lat0;
+    t->nlei3 = inf.ndgnh;
+    int nspolegl = 0;
+    rc = ect_inquire_rpnm(t->handle, nullptr, 0, &nspolegl, nullptr);
+    if (rc) return rc;
+    t->nspolegl = nspolegl;
     return TRANS_SUCCESS;
 }
 
-int trans_setup(struct Trans_t* t) {
+int trans_setup(struct Trans_t* t) {       // transi_module.F90 trans_setup
     if (!t) return TRANS_MISSING_ARG;
     if (t->ndgl <= 0) return TRANS_MISSING_ARG;
-    if (t->llatlon || t->flt > 0) return TRANS_NOTIMPL;
+    if (t->llam || t->llatlon || t->flt > 0 || t->cache) return TRANS_NOTIMPL;        // LAM, lon-lat, FLT, in-memory cache: out of scope
+    if (t->nsmax < 0) return TRANS_NOTIMPL;                                          // grid-only resolutions (LDGRIDONLY)
     std::vector<int> reg;
     const int* nloen = t->nloen;
     if (!nloen) {
-        if (t->nlon <= 0) return TRANS_MISSING_ARG;
+        if (t->nlon <= 0) t->nlon = 2 * t->ndgl;           // transi_module.F90:698-716: regular grid of 2 NDGL points
         reg.assign(t->ndgl, t->nlon);
         nloen = reg.data();
     }
-    if (t->nsmax < 0) t->nsmax = (2 * t->ndgl - 1) / 2;      // linear-grid default as in transi_module.F90
     ect_setup_opts o;
     memset(&o, 0, sizeof(o));
     o.nsmax = t->nsmax; o.ndgl = t->ndgl; o.nloen = nloen; o.nranks = 1; o.rank = 0; o.device = -1; o.precision = ECT_PREC_DP;
+    if (t->readfp) o.flags |= ECT_SETUP_LEGPOL_DEFER;      // CDIO_LEGPOL = 'readf': the table comes from the file
     int h = 0;
     int rc = ect_setup(&o, &h);
     if (rc) return rc;
     t->handle = h;
+    if (t->readfp && (rc = ect_read_legpol(h, t->readfp))) { ect_release(h); t->handle = 0; return rc; }
+    if (t->writefp && (rc = ect_write_legpol(h, t->writefp))) return rc;
     return fill_inquire(t);
 }
 
@@ -97,7 +156,9 @@ int trans_inquire(struct Trans_t* t, const char* varlist) {   // transi_module.F
         pos = e + 1;
         if (v.empty()) continue;
         if (v == "nspec" || v == "nspec2" || v == "nspec2g" || v == "nspec2mx" || v == "nump" || v == "ngptot" ||
-            v == "ngptotg" || v == "ngptotmx" || v == "nprtrw" || v == "myproc" || v == "nproc") {
+            v == "ngptotg" || v == "ngptotmx" || v == "nprtrw" || v == "myproc" || v == "nproc" || v == "nprtrns" ||
+            v == "n_regions_NS" || v == "n_regions_EW" || v == "my_region_NS" || v == "my_region_EW" || v == "nfrstloff" ||
+            v == "nptrfloff" || v == "nlei3" || v == "nspolegl") {
             rc = fill_inquire(t);
         } else if (v == "nmyms") {
             free(t->nmyms); t->nmyms = alloc_int(inf.nump);
@@ -142,6 +203,63 @@ int trans_inquire(struct Trans_t* t, const char* varlist) {   // transi_module.F
             rc = ect_inquire_array(t->handle, ECT_ARR_LATCOUNT, t->nultpp, inf.nranks);
             if (!rc) rc = ect_inquire_array(t->handle, ECT_ARR_LATFIRST, t->nptrls, inf.nranks);
             for (int r = 0; r < inf.nranks; ++r) t->nptrls[r] += 1;
+        } else if (v == "npossp") {                // start of each W-set's coefficients in the global spectral array, 1-based
+            std::vector<int> pm(inf.nsmax + 1);
+            rc = ect_inquire_array(t->handle, ECT_ARR_NPROCM, pm.data(), inf.nsmax + 1);
+            free(t->npossp); t->npossp = alloc_int(inf.nranks + 1);
+            std::vector<long long> cnt(inf.nranks, 0);
+            for (int m = 0; m <= inf.nsmax; ++m) cnt[pm[m]] += 2 * (inf.nsmax - m + 1);
+            t->npossp[0] = 1;
+            for (int r = 0; r < inf.nranks; ++r) t->npossp[r + 1] = t->npossp[r] + (int)cnt[r];
+        } else if (v == "ndim0g") {                // start of wavenumber m in the global array ordered by W-set (suwavedi_mod.F90:150-160)
+            std::vector<int> pm(inf.nsmax + 1);
+            rc = ect_inquire_array(t->handle, ECT_ARR_NPROCM, pm.data(), inf.nsmax + 1);
+            free(t->ndim0g); t->ndim0g = alloc_int(inf.nsmax + 1);
+            int pos = 1;
+            for (int r = 0; r < inf.nranks; ++r)
+                for (int m = 0; m <= inf.nsmax; ++m) if (pm[m] == r) { t->ndim0g[m] = pos; pos += 2 * (inf.nsmax - m + 1); }
+        } else if (v == "n_regions") {
+            free(t->n_regions); t->n_regions = alloc_int(inf.nranks);
+            for (int r = 0; r < inf.nranks; ++r) t->n_regions[r] = 1;
+        } else if (v == "nfrstlat" || v == "nlstlat" || v == "nptrfrstlat" || v == "nptrlstlat") {
+            // latitude bands are never split on this face: the pointers into NSTA / NONL are the latitudes themselves
+            std::vector<int> f(inf.nranks), c(inf.nranks);
+            rc = ect_inquire_array(t->handle, ECT_ARR_LATFIRST, f.data(), inf.nranks);
+            if (!rc) rc = ect_inquire_array(t->handle, ECT_ARR_LATCOUNT, c.data(), inf.nranks);
+            int*& p = v == "nfrstlat" ? t->nfrstlat : v == "nlstlat" ? t->nlstlat : v == "nptrfrstlat" ? t->nptrfrstlat : t->nptrlstlat;
+            free(p); p = alloc_int(inf.nranks);
+            const bool last = (v == "nlstlat" || v == "nptrlstlat");
+            for (int r = 0; r < inf.nranks; ++r) p[r] = last ? f[r] + c[r] : f[r] + 1;
+        } else if (v == "nptrlat") {
+            free(t->nptrlat); t->nptrlat = alloc_int(inf.ndgl);
+            for (int j = 0; j < inf.ndgl; ++j) t->nptrlat[j] = j + 1;
+        } else if (v == "nsta" || v == "nonl") {   // (ndgl + n_regions_NS - 1) x n_regions_EW; whole latitudes: first point 1, NLOEN points
+            std::vector<int> nl(inf.ndgl);
+            rc = ect_inquire_array(t->handle, ECT_ARR_NLOEN, nl.data(), inf.ndgl);
+            int*& p = v == "nsta" ? t->nsta : t->nonl;
+            free(p); p = alloc_int(inf.ndgl + inf.nranks - 1);
+            for (int j = 0; j < inf.ndgl; ++j) p[j] = v == "nsta" ? 1 : nl[j];
+        } else if (v == "ldsplitlat") {
+            free(t->ldsplitlat); t->ldsplitlat = alloc_int(inf.ndgl);
+        } else if (v == "ndglu") {
+            free(t->ndglu); t->ndglu = alloc_int(inf.nsmax + 1);
+            rc = ect_inquire_array(t->handle, ECT_ARR_NDGLU, t->ndglu, inf.nsmax + 1);
+        } else if (v == "npms") {                  // 1-based column of wavenumber m in RPNM (trans_inq.F90), -1: not on this task
+            free(t->npms); t->npms = alloc_int(inf.nsmax + 1);
+            int ns = 0;
+            rc = ect_inquire_rpnm(t->handle, nullptr, 0, &ns, t->npms);
+            for (int m = 0; m <= inf.nsmax; ++m) if (t->npms[m] >= 0) t->npms[m] += 1;
+        } else if (v == "rpnm") {
+            int ns = 0;
+            rc = ect_inquire_rpnm(t->handle, nullptr, 0, &ns, nullptr);
+            if (!rc) {
+                free(t->rpnm); t->rpnm = (double*)calloc((size_t)std::max(1, ns) * inf.ndgnh, sizeof(double));
+                t->nlei3 = inf.ndgnh; t->nspolegl = ns;
+                rc = ect_inquire_rpnm(t->handle, t->rpnm, (long long)ns * inf.ndgnh, &ns, nullptr);
+            }
+        } else if (v == "rlapin") {                // RLAPIN(-1:nsmax+2) = -a^2 / (n (n + 1)), 0 for n <= 0 (suleg_mod.F90)
+            free(t->rlapin); t->rlapin = (double*)calloc(inf.nsmax + 4, sizeof(double));
+            for (int n = 1; n <= inf.nsmax + 2; ++n) t->rlapin[n + 1] = -(6371229.0 * 6371229.0) / ((double)n * (double)(n + 1));
         } else {
             return TRANS_UNRECOGNIZED_ARG;
         }
@@ -325,11 +443,14 @@ int trans_specnorm(struct SpecNorm_t* a) {
 int trans_delete(struct Trans_t* t) {
     if (!t) return TRANS_MISSING_ARG;
     int rc = t->handle ? ect_release(t->handle) : 0;
-    int** ip[] = {&t->nloen, &t->ngptotl, &t->nmyms, &t->nasm0, &t->numpp, &t->nallms, &t->nptrms, &t->nvalue,
-                  &t->nultpp, &t->nptrls, &t->nnmeng};
+    int** ip[] = {&t->nloen, &t->ngptotl, &t->nmyms, &t->nasm0, &t->numpp, &t->npossp, &t->nallms, &t->nptrms, &t->ndim0g,
+                  &t->nvalue, &t->n_regions, &t->nfrstlat, &t->nlstlat, &t->nptrlat, &t->nptrfrstlat, &t->nptrlstlat, &t->nsta,
+                  &t->nonl, &t->ldsplitlat, &t->nultpp, &t->nptrls, &t->nnmeng, &t->npms, &t->ndglu, &t->mvalue};
     for (int** p : ip) { free(*p); *p = nullptr; }
-    free(t->rmu); t->rmu = nullptr;
-    free(t->rgw); t->rgw = nullptr;
+    double** dp[] = {&t->rmu, &t->rgw, &t->rpnm, &t->rlapin, &t->pweight};
+    for (double** p : dp) { free(*p); *p = nullptr; }
+    free(t->readfp); t->readfp = nullptr;
+    free(t->writefp); t->writefp = nullptr;
     t->handle = 0;
     return rc;
 }
