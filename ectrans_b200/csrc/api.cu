@@ -8,6 +8,7 @@
 #include <unistd.h>
 #include "fourier_phases.h"
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges cost nothing unless a profiler injects its library
 #include <dlfcn.h>
 #include <mutex>
 #include <map>
@@ -17,6 +18,13 @@
 #include <cstdlib>
 
 struct EctSpecFieldH { const double* base; long long stride; };
+
+// NVTX ranges with the reference's GSTATS labels (ectrans-benchmark.F90:1681-1697, tpm_stats.F90:33-62 turns the
+// same labels into NVTX ranges on the reference's GPU branch): they bracket where a stage is ENQUEUED on the host.
+struct EctRange {
+    explicit EctRange(const char* name) { nvtxRangePushA(name); }
+    ~EctRange() { nvtxRangePop(); }
+};
 
 static std::mutex g_mu;
 static std::map<int, EctHandle*> g_handles;
@@ -270,6 +278,7 @@ void ect_device_free(EctHandle* h) {
 }
 
 extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
+    EctRange r_setup("SETUP_TRANS    - Setup ecTrans handle");
     if (!o || !handle) { ect_set_error("ect_setup: null argument"); return ECT_ERR_MISSING; }
     EctHandle* h = new EctHandle();
     const int world = o->nranks < 1 ? 1 : o->nranks, V = std::max(1, (o->flags >> 8) & 0xff);
@@ -1081,8 +1090,8 @@ static int vset_guard(int handle, const char* who) {
     if (h && h->vs.V > 1) { ect_set_error("%s: this resolution has NPRTRV = %d; use the *_vset entry points (V-set arrays needed) -- not available for this call", who, h->vs.V); return ECT_ERR_NOTIMPL; }
     return ECT_SUCCESS;
 }
-extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) { int g = vset_guard(handle, "ect_inv_trans"); return g ? g : inv_trans_impl(handle, a, nullptr, 0); }
-extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) { int g = vset_guard(handle, "ect_dir_trans"); return g ? g : dir_trans_impl(handle, a, nullptr, 0); }
+extern "C" int ect_inv_trans(int handle, const ect_inv_args* a) { EctRange r("INV_TRANS      - Inverse transform"); int g = vset_guard(handle, "ect_inv_trans"); return g ? g : inv_trans_impl(handle, a, nullptr, 0); }
+extern "C" int ect_dir_trans(int handle, const ect_dir_args* a) { EctRange r("DIR_TRANS      - Direct transform"); int g = vset_guard(handle, "ect_dir_trans"); return g ? g : dir_trans_impl(handle, a, nullptr, 0); }
 
 // INV_TRANSAD / DIR_TRANSAD (reference cpu/external/inv_transad.F90, dir_transad.F90 and the *ad_mod
 // files of cpu/internal).  With the inner products of the reference's adjoint tests (grid: plain sum; spectral:
@@ -1318,13 +1327,20 @@ static int inv_trans_impl(int handle, const ect_inv_args* a, const SubView* view
     const void* d_fs = db + ((char*)t_fs - hb);
     const void* d_pairs = db + ((char*)t_pairs - hb);
     // ---- stages ----
-    ect_launch_ltinv_prologue(h, f, d_vor, d_div, d_sc);
-    ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
-    if ((rc = ect_transpose_enter(h, 1))) return rc;
-    ect_launch_leinv(h, f);
-    ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
-    if ((rc = ect_transpose(h, f, 1))) return rc;
-    ECT_CUDA(cudaEventRecord(d->ev[4], d->stream));
+    {
+        EctRange r("LTINV_CTL      - Inv. Legendre transform");
+        ect_launch_ltinv_prologue(h, f, d_vor, d_div, d_sc);
+        ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
+        if ((rc = ect_transpose_enter(h, 1))) return rc;
+        ect_launch_leinv(h, f);
+        ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
+    }
+    {
+        EctRange r("LTINV_CTL      - M to L transposition");
+        if ((rc = ect_transpose(h, f, 1))) return rc;
+        ECT_CUDA(cudaEventRecord(d->ev[4], d->stream));
+    }
+    EctRange r_ft("FTINV_CTL      - Inv. Fourier transform");
     if (gpx) {
         double* const* d_bandb = (double* const*)(db + ((char*)t_bandb - hb));
         const i64* d_bands = (const i64*)(db + ((char*)t_bands - hb));
@@ -1506,23 +1522,31 @@ static int dir_trans_impl(int handle, const ect_dir_args* a, const SubView* view
     double* const* d_gpb = (double* const*)(db + ((char*)t_gpb - hb));
     const i64* d_gps = (const i64*)(db + ((char*)t_gps - hb));
     const void* d_pairs = db + ((char*)t_pairs - hb);
+    nvtxRangePushA("FTDIR_CTL      - Dir. Fourier transform");
     if (gpx) {
         double* const* d_bandb = (double* const*)(db + ((char*)t_bandb - hb));
         const i64* d_bands = (const i64*)(db + ((char*)t_bands - hb));
-        if ((rc = gp_exchange(h, f.nfs, f.nfs, std::vector<int>(1, f.nfs), es, 0, d_gpb, d_gps, nproma))) return rc;      // TRGTOL (timed with the Fourier interval)
+        if ((rc = gp_exchange(h, f.nfs, f.nfs, std::vector<int>(1, f.nfs), es, 0, d_gpb, d_gps, nproma))) { nvtxRangePop(); return rc; }      // TRGTOL (timed with the Fourier interval)
         if ((rc = ect_transpose_enter(h, 0))) return rc;
         ect_launch_ftdir(h, f, d_bandb, d_bands, d_pairs, std::max(P.ngpband, 1));
     } else {
         if ((rc = ect_transpose_enter(h, 0))) return rc;
         ect_launch_ftdir(h, f, d_gpb, d_gps, d_pairs, nproma);
     }
+    nvtxRangePop();
     ECT_CUDA(cudaEventRecord(d->ev[2], d->stream));
-    if ((rc = ect_transpose(h, f, 0))) return rc;
-    ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
-    ect_launch_ledir(h, f);
-    ECT_CUDA(cudaEventRecord(d->ev[4], d->stream));
-    ect_launch_ltdir_epilogue(h, f, d_vor, d_div, d_sc);
-    ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
+    {
+        EctRange r("LTDIR_CTL      - L to M transposition");
+        if ((rc = ect_transpose(h, f, 0))) return rc;
+        ECT_CUDA(cudaEventRecord(d->ev[3], d->stream));
+    }
+    {
+        EctRange r("LTDIR_CTL      - Dir. Legendre transform");
+        ect_launch_ledir(h, f);
+        ECT_CUDA(cudaEventRecord(d->ev[4], d->stream));
+        ect_launch_ltdir_epilogue(h, f, d_vor, d_div, d_sc);
+        ECT_CUDA(cudaEventRecord(d->ev[5], d->stream));
+    }
     ECT_CUDA(cudaGetLastError());
     if (d->launch_error) { d->launch_error = 0; return ECT_ERR_CUDA; }
     if ((rc = release_callbuf(d))) return rc;

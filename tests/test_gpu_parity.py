@@ -411,17 +411,23 @@ def test_transi_face(eb):
     import ctypes as C
     L = eb.lib()
 
-    class Trans(C.Structure):
-        _fields_ = [("ndgl", C.c_int), ("nloen", C.POINTER(C.c_int)), ("nlon", C.c_int), ("nsmax", C.c_int),
-                    ("lsplit", C.c_int), ("llatlon", C.c_int), ("flt", C.c_int), ("fft", C.c_int),
-                    ("myproc", C.c_int), ("nproc", C.c_int), ("handle", C.c_int),
-                    ("nspec", C.c_int), ("nspec2", C.c_int), ("nspec2g", C.c_int), ("nspec2mx", C.c_int),
-                    ("nump", C.c_int), ("ngptot", C.c_int), ("ngptotg", C.c_int), ("ngptotmx", C.c_int),
-                    ("ngptotl", C.POINTER(C.c_int)), ("nmyms", C.POINTER(C.c_int)), ("nasm0", C.POINTER(C.c_int)),
-                    ("nprtrw", C.c_int), ("numpp", C.POINTER(C.c_int)), ("nallms", C.POINTER(C.c_int)),
-                    ("nptrms", C.POINTER(C.c_int)), ("nvalue", C.POINTER(C.c_int)), ("nultpp", C.POINTER(C.c_int)),
-                    ("nptrls", C.POINTER(C.c_int)), ("nnmeng", C.POINTER(C.c_int)),
-                    ("rmu", C.POINTER(C.c_double)), ("rgw", C.POINTER(C.c_double))]
+    IP, DP = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+    class Trans(C.Structure):          # include/transi_b200.h struct Trans_t (= the reference's, transi.h:701-850)
+        _fields_ = ([("ndgl", C.c_int), ("nloen", IP), ("nlon", C.c_int), ("nsmax", C.c_int), ("llam", C.c_int),
+                     ("lsplit", C.c_int), ("llatlon", C.c_int), ("flt", C.c_int), ("fft", C.c_int),
+                     ("readfp", C.c_char_p), ("writefp", C.c_char_p), ("cache", C.c_void_p), ("cachesize", C.c_size_t),
+                     ("myproc", C.c_int), ("nproc", C.c_int), ("handle", C.c_int)]
+                    + [(n, C.c_int) for n in ("nspec", "nspec2", "nspec2g", "nspec2mx", "nump", "ngptot", "ngptotg", "ngptotmx")]
+                    + [("ngptotl", IP), ("nmyms", IP), ("nasm0", IP), ("nprtrw", C.c_int)]
+                    + [(n, IP) for n in ("numpp", "npossp", "nptrms", "nallms", "ndim0g", "nvalue")]
+                    + [(n, C.c_int) for n in ("n_regions_NS", "n_regions_EW", "my_region_NS", "my_region_EW")]
+                    + [("n_regions", IP), ("nfrstlat", IP), ("nlstlat", IP), ("nfrstloff", C.c_int), ("nptrlat", IP),
+                       ("nptrfrstlat", IP), ("nptrlstlat", IP), ("nptrfloff", C.c_int), ("nsta", IP), ("nonl", IP),
+                       ("ldsplitlat", IP), ("nprtrns", C.c_int), ("nultpp", IP), ("nptrls", IP), ("nnmeng", IP),
+                       ("rmu", DP), ("rgw", DP), ("rpnm", DP), ("nlei3", C.c_int), ("nspolegl", C.c_int), ("npms", IP),
+                       ("rlapin", DP), ("ndglu", IP), ("pexwn", C.c_double), ("peywn", C.c_double), ("pweight", DP),
+                       ("ndgux", C.c_int), ("nmsmax", C.c_int), ("mvalue", IP)])
 
     class Inv(C.Structure):
         _fields_ = [("rspscalar", C.c_void_p), ("rspvor", C.c_void_p), ("rspdiv", C.c_void_p), ("rmeanu", C.c_void_p),
@@ -450,6 +456,18 @@ def test_transi_face(eb):
     assert L.trans_inquire(C.byref(t), b"nvalue,nmyms,nasm0,rgw") == 0
     assert t.nvalue[0] == 0 and t.nvalue[2] == 1 and t.nasm0[0] == 1
     assert L.trans_inquire(C.byref(t), b"bogus") == -4
+    # every variable list of the reference's transi_test_program.c:51-54
+    for vl in (b"numpp,ngptotl,nmyms,nasm0,npossp,nptrms,nallms,ndim0g,nvalue",
+               b"nfrstlat,nlstlat,nptrlat,nptrfrstlat,nptrlstlat,nsta,nonl,ldsplitlat", b"nultpp,nptrls,nnmeng",
+               b"rmu,rgw,npms,rlapin,ndglu"):
+        assert L.trans_inquire(C.byref(t), vl) == 0, vl
+    assert (t.npossp[0], t.npossp[1]) == (1, t.nspec2 + 1) and t.ndim0g[0] == 1 and t.ndim0g[1] == 2 * 24 + 1
+    assert t.nsta[0] == 1 and t.nonl[0] == int(nl[0]) and t.nonl[47] == int(nl[47]) and t.ldsplitlat[0] == 0
+    assert t.nfrstlat[0] == 1 and t.nlstlat[0] == 48 and t.nptrlat[5] == 6 and t.n_regions_NS == 1 and t.nprtrns == 1
+    assert t.ndglu[0] == 24 and t.npms[0] == 1 and t.npms[1] == 26 and t.nlei3 == 24 and t.nspolegl == sum(25 - m for m in range(24))
+    assert t.rlapin[0] == 0.0 and t.rlapin[1] == 0.0 and abs(t.rlapin[2] + 6371229.0 ** 2 / 2.0) < 1e-3
+    assert L.trans_set_radius(C.c_double(6371229.0)) == 0 and L.trans_set_radius(C.c_double(1.0)) == -2
+    assert L.trans_set_nprtrv(1) == 0 and L.trans_set_nprtrv(2) == -2 and L.trans_set_leq_regions(1) == 0
     nscalar = 2
     rgp = np.zeros((nscalar, t.ngptot))
     rgp[0] = 1.0
