@@ -315,8 +315,16 @@ def run_ours(args):
     clocks = sampler.summary() if rank == 0 else None
     sampler.stop_flag = True
     t = torch.tensor([ms_dev, leg_ms, ft_ms, tp_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
         import torch.distributed as dist
+        # per-rank stage times (the transposition time of a rank is mostly the wait for the slowest producer)
+        mine = torch.tensor([med("inv", "legendre"), med("dir", "legendre"), med("inv", "fourier"), med("dir", "fourier"),
+                             med("inv", "transpose"), med("dir", "transpose")], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {k: [round(float(a[i]), 3) for a in allr] for i, k in enumerate(
+            ("legendre_inv", "legendre_dir", "fourier_inv", "fourier_dir", "transpose_inv", "transpose_dir"))}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, leg_ms, ft_ms, tp_ms = [float(x) for x in t.cpu()]
 
@@ -357,6 +365,7 @@ def run_ours(args):
         e2e = {"value": float(te.cpu()[0]), "unit": "ms", "h2d_bytes_per_step": int(bytes_in),
                "d2h_bytes_per_step": int(bytes_out), "steps": ne}
     if rank != 0:
+        tr.release()
         return
     # ---- roofline of the dominant kernel pair (k_leinv + k_ledir): FP64 tensor (DMMA) ----
     fl = 2.0 * legendre_flops(T, tr.ndglu, nf)       # inverse + direct, whole job
@@ -402,6 +411,8 @@ def run_ours(args):
         line["e2e"] = e2e
     if parity is not None:
         line["parity"] = parity
+    if per_rank is not None:
+        line["stages_ms_per_rank"] = per_rank
     if world == 1 and not args.no_cpu:
         stride = args.cpu_stride or CPU_STRIDE.get(T, 16)
         v, detail = cpu_sample_step(T, N, nuv, nsc, stride)
@@ -409,6 +420,15 @@ def run_ours(args):
                                 "sample": cpu_sample_text(stride, nf), "detail": detail}
     print(json.dumps(line), flush=True)
     tr.release()
+
+
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def main():
@@ -430,7 +450,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        try:
+            run_ours(args)
+        finally:
+            _shutdown()          # no "destroy_process_group() was not called" warning after the JSON line
 
 
 if __name__ == "__main__":

@@ -27,6 +27,7 @@ ECT_SETUP_HOST_ONLY = 1
 ECT_SETUP_STREAM_GIVEN = 2
 ECT_SETUP_LEGPOL_DEFER = 4
 ECT_SETUP_GP_EQ_REGIONS = 8
+ECT_SETUP_BANDS_BY_POINTS = 16
 ECT_NCCL_UID_BYTES = 128
 ECT_PREC_DP, ECT_PREC_SP = 0, 1
 (ARR_NLOEN, ARR_NMEN, ARR_NDGLU, ARR_MYMS, ARR_NASM0, ARR_NPROCM, ARR_RMU, ARR_RGW, ARR_LATFIRST,
@@ -237,12 +238,14 @@ class Transform:
     """
 
     def __init__(self, nsmax, nloen, nranks=1, rank=0, device=-1, stream=None, nccl_uid=None, host_only=False,
-                 precision="dp", legpol_read=None, legpol_write=None, gp_partition="latbands", nprtrv=1):
+                 precision="dp", legpol_read=None, legpol_write=None, gp_partition="latbands", nprtrv=1, bands="cost"):
         """legpol_read / legpol_write: SETUP_TRANS's CDIO_LEGPOL='readf' / 'writef' with CDLEGPOLFNAME (the reference's
         Legendre-polynomial cache file format); with legpol_read the table is not computed.
         gp_partition: "latbands" (native: the caller's grid points are the task's Fourier latitude band, TRLTOG / TRGTOL
         are local) or "eq_regions" (the reference's default LDEQ_REGIONS=T, LDSPLIT=T decomposition; TRLTOG / TRGTOL are
         NCCL all-to-alls).
+        bands: "cost" (default; with more than one rank the Fourier latitude bands are balanced on NLOEN + 0.15 max(NLOEN))
+        or "points" (the reference's SUMPLATB point count).
         nprtrv: NPRTRV; > 1: nranks is NPROC = NPRTRW * NPRTRV, rank pe is W-set pe // nprtrv, V-set pe % nprtrv, the
         grid-point arrays follow eq_regions over all tasks and carry every field (use inv_trans_vset / dir_trans_vset)."""
         self.nprtrv = int(nprtrv)
@@ -257,6 +260,7 @@ class Transform:
                        (ECT_SETUP_HOST_ONLY if host_only else 0) | (ECT_SETUP_STREAM_GIVEN if stream is not None else 0)
                        | (ECT_SETUP_LEGPOL_DEFER if legpol_read else 0)
                        | (ECT_SETUP_GP_EQ_REGIONS if gp_partition == "eq_regions" else 0)
+                       | (ECT_SETUP_BANDS_BY_POINTS if bands == "points" else 0)
                        | ((int(nprtrv) & 0xff) << 8 if int(nprtrv) > 1 else 0),
                        int(device), C.c_void_p(stream) if stream else None,
                        C.cast(self._uid, C.c_void_p) if self._uid else None,

@@ -287,7 +287,7 @@ extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
         // NPRTRV > 1: W = world / V groups of wavenumbers / latitude bands, fields spread over the V tasks of a group
         if (world % V != 0 || o->rank < 0 || o->rank >= world) { delete h; ect_set_error("ect_setup: NPROC = %d inconsistent with NPRTRV = %d", world, V); return ECT_ERR_BADARG; }
         h->vs.V = V; h->vs.world = world; h->vs.wrank = o->rank; h->vs.v = o->rank % V;
-        rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, world / V, o->rank / V, false);
+        rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, world / V, o->rank / V, false, (o->flags & ECT_SETUP_BANDS_BY_POINTS) != 0);
         if (!rc) {
             EctHostPlan& P = h->hp;
             EctGpPartition G;
@@ -313,7 +313,8 @@ extern "C" int ect_setup(const ect_setup_opts* o, int* handle) {
             }
         }
     } else
-        rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, world, o->rank, (o->flags & ECT_SETUP_GP_EQ_REGIONS) != 0);
+        rc = ect_build_host_plan(h->hp, o->nsmax, o->ndgl, o->nloen, world, o->rank, (o->flags & ECT_SETUP_GP_EQ_REGIONS) != 0,
+                                 (o->flags & ECT_SETUP_BANDS_BY_POINTS) != 0);
     if (rc) { delete h; return rc; }
     if (o->precision != ECT_PREC_DP && o->precision != ECT_PREC_SP) { delete h; ect_set_error("ect_setup: unknown precision %d", o->precision); return ECT_ERR_BADARG; }
     h->precision = o->precision;

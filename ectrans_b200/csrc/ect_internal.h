@@ -34,6 +34,7 @@ struct EctHostPlan {
     // Fourier / grid-point space: latitude bands (SUMPLATF)
     std::vector<int> lat_first, lat_count;   // per rank
     int lat0 = 0, nlat = 0;
+    int band_pad = 0;                        // per-latitude weight added to NLOEN when the bands were balanced by cost
     std::vector<int> gpoff;                  // local latitude -> first local grid point
     int ngptot = 0, ngptotg = 0;
     // Fourier-buffer records.  A record = one (latitude, m) pair, m <= NMEN(lat).
@@ -63,7 +64,8 @@ struct EctHostPlan {
     std::string err;
 };
 
-int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank, bool gp_eq = false);
+int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank, bool gp_eq = false,
+                        bool bands_by_points = false);
 
 // Grid-point decomposition LDEQ_REGIONS=T, LDSPLIT=T (gp_partition.cu)
 struct EctGpPartition {

@@ -1,6 +1,8 @@
 // Host plan: Gaussian grid, truncation geometry and the two-phase decomposition.
 // Pure host C++ (no CUDA calls) so that it can be used and tested without a GPU.
 #include "ect_internal.h"
+#include "fft_plan.h"
+#include <cmath>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -151,7 +153,7 @@ static void lat_bands(const std::vector<int>& nloen, int nproca, std::vector<int
     }
 }
 
-int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank, bool gp_eq) {
+int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, int nranks, int rank, bool gp_eq, bool bands_by_points) {
     if (nsmax < 0 || ndgl < 2 || (ndgl & 1) || !nloen || nranks < 1 || rank < 0 || rank >= nranks) {
         ect_set_error("ect_setup: bad arguments (nsmax=%d ndgl=%d nranks=%d rank=%d)", nsmax, ndgl, nranks, rank);
         return ECT_ERR_BADARG;
@@ -212,7 +214,31 @@ int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, i
         P.nspec2 = pos;
     }
     P.nspec2_g = (nsmax + 1) * (nsmax + 2);
-    lat_bands(P.nloen, nranks, P.lat_first, P.lat_count);
+    {
+        // SUMPLATB balances the bands by grid points.  The Fourier kernels cost (i) the FFT work of a row -- N log2 N
+        // for a 31-smooth length, two transforms of the convolution length M for a chirp-z row -- and (ii) a fixed price
+        // per latitude (CTAs set up per row, short rows that do not fill them).  Per-rank stage times on 8 B200s
+        // (profiles/r02_scaling.md: point-balanced TCo1279 bands took 13.4 ms at the poles against 8.5 ms at the
+        // equator) fit  cost = FFT work + 0.16 max(FFT work)  to 7 %.  By default the same SUMPLATB algorithm runs on
+        // that weight; ECT_SETUP_BANDS_BY_POINTS restores the reference's plain point count.
+        std::vector<int> w(P.nloen);
+        P.band_pad = 0;
+        if (!bands_by_points && nranks > 1) {
+            std::vector<double> fw(ndgl);
+            double fmax = 0;
+            for (int j = 0; j < ndgl; ++j) {
+                const int n = P.nloen[j];
+                std::vector<int> rad;
+                double f;
+                if (n % 2 == 0 && ect_fft_factorize(n, rad, false)) f = n * std::log2((double)std::max(n, 2));
+                else { const int M = ect_fft_smooth_size(2 * P.nmen[j] + n); f = 2.0 * M * std::log2((double)M); }
+                fw[j] = f; fmax = std::max(fmax, f);
+            }
+            P.band_pad = (int)(0.16 * fmax / 16.0);
+            for (int j = 0; j < ndgl; ++j) w[j] = (int)(fw[j] / 16.0) + P.band_pad;
+        }
+        lat_bands(w, nranks, P.lat_first, P.lat_count);
+    }
     P.lat0 = P.lat_first[rank];
     P.nlat = P.lat_count[rank];
     P.gpoff.assign(P.nlat + 1, 0);

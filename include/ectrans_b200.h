@@ -59,6 +59,9 @@ extern "C" {
 #define ECT_SETUP_GP_EQ_REGIONS 8 /* grid-point arrays follow the reference's default decomposition (LDEQ_REGIONS=T, LDSPLIT=T:
                                      eq_regions bands x regions, split latitudes) instead of this library's native one (= the
                                      Fourier latitude bands, TRLTOG / TRGTOL local); TRLTOG / TRGTOL then are NCCL all-to-alls */
+#define ECT_SETUP_BANDS_BY_POINTS 16 /* Fourier latitude bands balanced by grid points exactly as SUMPLATB does (sumplatb_mod.F90:171-216);
+                                     default with more than one rank: the same algorithm on NLOEN + 0.15 max(NLOEN), which also
+                                     balances the per-latitude cost of the Fourier kernels */
 #define ECT_SETUP_LEGPOL_DEFER 4 /* do not compute the Legendre table: ect_read_legpol() fills it (CDIO_LEGPOL='readf') */
 
 #define ECT_NCCL_UID_BYTES 128

@@ -82,9 +82,18 @@ def test_golden_grid_inquire(eb, golden):
 def test_decomposition(eb, P):
     T, N = 159, 160
     nloen = eb.octahedral_nloen(N)
-    trs = [eb.Transform(T, nloen, nranks=P, rank=r, host_only=True) for r in range(P)]
+    trs = [eb.Transform(T, nloen, nranks=P, rank=r, host_only=True, bands="points") for r in range(P)]
     nprocm, myms = eo.suwavedi(T, P)
     first, count = eo.sumplatb_fourier(nloen, P)
+    # default: the same SUMPLATB on cost weights (FFT work of a row + a per-latitude constant, host_plan.cu): contiguous
+    # bands covering every latitude, symmetric about the equator, fewer polar latitudes per band than the point count gives
+    tcs = [eb.Transform(T, nloen, nranks=P, rank=r, host_only=True) for r in range(P)]
+    fc, cc = list(tcs[0].lat_first), list(tcs[0].lat_count)
+    assert sum(cc) == 2 * N and fc[0] == 0 and all(fc[i + 1] == fc[i] + cc[i] for i in range(P - 1))
+    assert all(abs(a - b) <= 2 for a, b in zip(cc, cc[::-1])) and cc[0] <= count[0] and all(list(t.lat_count) == cc for t in tcs)
+    assert sum(t.ngptot for t in tcs) == tcs[0].ngptotg
+    for t in tcs:
+        t.release()
     for r, t in enumerate(trs):
         np.testing.assert_array_equal(t.myms, myms[r])
         np.testing.assert_array_equal(t.nprocm, nprocm)
@@ -355,7 +364,7 @@ def test_host_plan_fuzz_against_oracle(eb):
         nloen = np.concatenate([half, half[::-1]]).astype(np.int32)
         T = int(rng.integers(1, 3 * nh))
         W = int(rng.integers(1, min(2 * nh, 12) + 1))
-        trs = [eb.Transform(T, nloen, nranks=W, rank=r, host_only=True) for r in range(W)]
+        trs = [eb.Transform(T, nloen, nranks=W, rank=r, host_only=True, bands="points") for r in range(W)]
         s = eo.setup(T, 2 * nh, nloen, tables=False)
         t = trs[0]
         np.testing.assert_array_equal(t.nmen, s.nmen)
