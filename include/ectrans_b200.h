@@ -60,16 +60,17 @@ extern "C" {
                                      eq_regions bands x regions, split latitudes) instead of this library's native one (= the
                                      Fourier latitude bands, TRLTOG / TRGTOL local); TRLTOG / TRGTOL then are NCCL all-to-alls */
 #define ECT_SETUP_BANDS_BY_POINTS 16 /* Fourier latitude bands balanced by grid points exactly as SUMPLATB does (sumplatb_mod.F90:171-216);
-                                     default with more than one rank: the same algorithm on NLOEN + 0.15 max(NLOEN), which also
-                                     balances the per-latitude cost of the Fourier kernels */
+                                     default with more than one rank: the same algorithm on a cost weight per latitude (FFT work of
+                                     the row + a per-row constant, csrc/host_plan.cu), which balances the Fourier kernels */
 #define ECT_SETUP_LEGPOL_DEFER 4 /* do not compute the Legendre table: ect_read_legpol() fills it (CDIO_LEGPOL='readf') */
 
 #define ECT_NCCL_UID_BYTES 128
 
 /* Precision of the caller's arrays (the reference builds one library per precision, src/trans/CMakeLists.txt:9-39).
    ECT_PREC_SP: every field array in ect_inv_args / ect_dir_args / ect_specnorm is float although the members are
-   typed double*; the contraction and the FFT run in fp64 internally (so the reference's fp64 treatment of m = 0,
-   ledir_mod.F90:133-171, holds for every m), inputs are widened on load and results rounded once on store. */
+   typed double*.  The Fourier stage runs in float; the Legendre contraction runs as 3xTF32 on the tcgen05 tensor
+   cores with fp32 accumulation (csrc/legendre_tc.cu; the reference's GPU sp build: hicblas_cutlass.cuda.h:41-72), m = 0
+   in double precision as in the reference (ledir_mod.F90:133-171); ECT_SP_TC=0 runs every m on the FP64 kernels. */
 #define ECT_PREC_DP 0
 #define ECT_PREC_SP 1
 
