@@ -538,6 +538,203 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TB, CZ_MINB(TB, FP32
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Chirp-z rows, both halves of the split convolution in ONE CTA: two warp groups (E: even bins, O: odd bins), each with
+// its own work array and its own named barrier, meeting only where the staged inputs are consumed and where the
+// outputs are formed.  What this keeps from the undivided kernel: the next pair's inputs are staged by cp.async while the
+// current pair is transformed (no exposed global-memory latency, the inputs are read once), one CTA per SM whose warps
+// walk through the same code (instruction-cache working set = one pass).  What it takes from the pair kernel: two
+// independent half-length transforms -- the groups drift apart, so one group's shared-memory phase overlaps the other's
+// FP64 phase instead of all warps running each pass in lock step -- and two passes less per transform.
+// ---------------------------------------------------------------------------------------
+struct Cz2Layout { int o, t1, roots, tc, stage, rec, total; };
+__host__ __device__ inline Cz2Layout cz2_layout(bool inverse, int H, int N, int km, int csize, int iosize, bool nostage) {
+    Cz2Layout L;
+    L.o = ft_al16(ECT_PADDED_LEN(H) * csize);
+    L.t1 = 2 * L.o;
+    L.roots = L.t1 + ft_al16((ECT_TW1_LEN(2 * H) + ECT_TW2_LEN) * csize);
+    L.tc = L.roots + ft_al16(ECT_ROOTS_OFF(8) * csize);
+    L.stage = L.tc + ft_al16((ECT_TW1_LEN(2 * N) + ECT_TW2_LEN) * csize);      // 16-byte aligned: cp.async destination
+    const int nst = nostage ? 0 : (inverse ? 2 * (km + 1) * (int)sizeof(double2) : 2 * N * iosize);
+    L.rec = L.stage + ft_al16(nst);
+    L.total = L.rec + ft_al16((km + 1) * (int)sizeof(int));
+    return L;
+}
+// named barriers 1 / 2 with constant ids (a register id makes ptxas reserve all 16 hardware barriers: one CTA per SM)
+__device__ __forceinline__ void cz2_group_sync(int g, int n) {
+    if (g == 0) asm volatile("bar.sync 1, %0;\n" :: "r"(n) : "memory");
+    else asm volatile("bar.sync 2, %0;\n" :: "r"(n) : "memory");
+}
+
+template <bool INVERSE, int GS, bool FP32>
+__global__ void __launch_bounds__(2 * GS, 384 / (2 * GS)) k_fourier_cz2(FtArgs a) {
+    typedef typename std::conditional<FP32, float2, double2>::type C;
+    typedef typename EctReal<C>::type R_;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ EctFftPlan s_plan;
+    const int item = blockIdx.x;
+    const int l = a.lats[item / a.nchunks];
+    const int chunk = item % a.nchunks;
+    const EctLatPlan lp = a.latplans[a.lat_plan[l]];
+    if (threadIdx.x == 0) s_plan = a.plans[lp.plan_h];
+    __syncthreads();
+    const int H = s_plan.n, plan_nst = s_plan.nst;
+    const int N = lp.nlon, km = lp.km;
+    const bool staged = !a.nostage;
+    const Cz2Layout lay = cz2_layout(INVERSE, H, N, km, (int)sizeof(C), FP32 ? 4 : 8, !staged);
+    const int tid = threadIdx.x, nthr = 2 * GS;
+    const int g = tid / GS, gt = tid - g * GS;            // warp group (0: even bins, 1: odd bins) and thread in it
+    const C* czp = reinterpret_cast<const C*>(a.cz_pool);
+    const C* bhat = czp + (INVERSE ? lp.bhat_inv_eo[g] : lp.bhat_dir_eo[g]);
+    C* mine = reinterpret_cast<C*>(smraw + (g ? lay.o : 0));
+    const C* other = reinterpret_cast<const C*>(smraw + (g ? 0 : lay.o));
+    C* t1 = reinterpret_cast<C*>(smraw + lay.t1);
+    C* t2 = t1 + ECT_TW1_LEN(2 * H);
+    C* s_roots = reinterpret_cast<C*>(smraw + lay.roots);
+    C* t1c = reinterpret_cast<C*>(smraw + lay.tc);
+    C* t2c = t1c + ECT_TW1_LEN(2 * N);
+    double2* stage = reinterpret_cast<double2*>(smraw + lay.stage);
+    int* s_rec = reinterpret_cast<int*>(smraw + lay.rec);
+    tw_build(t1, t2, a.tw_pool + a.plans[lp.plan].tw_off, 2 * H, tid, nthr);
+    for (int j = tid; j < ECT_ROOTS_OFF(8); j += nthr) s_roots[j] = c_cvt<C>(a.roots[j]);
+    for (int j = tid; j < ECT_TW1_LEN(2 * N) + ECT_TW2_LEN; j += nthr) t1c[j] = czp[lp.ctw_off + j];
+    const int* recs = a.fft_rec + a.latrow0[l];
+    for (int k = tid; k <= km; k += nthr)
+        s_rec[k] = INVERSE ? recs[k] : ((a.dst_rank[a.latrow0[l] + k] << 24) | a.dst_rec[a.latrow0[l] + k]);
+    EctTwT<C> qth; qth.t1 = t1; qth.t2 = t2; qth.sh = 1;
+    CzCtx<C> cx;
+    cx.N = N; cx.km = km; cx.H = H; cx.half = g;
+    cx.twm.t1 = t1; cx.twm.t2 = t2; cx.twm.sh = 0;
+    cx.twc.t1 = t1c; cx.twc.t2 = t2c; cx.twc.sh = 0;
+    cx.n2 = 2u * (unsigned)N; cx.magic = (unsigned)((0x100000000ull + cx.n2 - 1) / cx.n2);
+    const int cp = a.cp;
+    const int g0 = a.gpoff[l];
+    const bool oneblk = a.nproma >= a.ngptot;
+    const int p0 = chunk * FT_PAIRS_PER_CTA, p1 = min(p0 + FT_PAIRS_PER_CTA, a.npairs);
+    const double racthe = a.racthe_loc[l];
+    const bool warp_local = plan_nst >= 2 && s_plan.radix[0] == 16 && s_plan.radix[1] == 16 && (H & 511) == 0;
+
+    auto prefetch = [&](int p) {       // raw inputs of pair p -> stage (asynchronous, all threads)
+        if (!staged) return;
+        const int2 pr = a.pairs[p];
+        const int fa = pr.x, fb2 = pr.y;
+        if (INVERSE) {
+            const int ca = a.fsf[fa].src_c;
+            const int cb = fb2 >= 0 ? a.fsf[fb2].src_c : -1;
+            for (int k = tid; k <= km; k += nthr) {
+                const double* src = a.fb + (long long)s_rec[k] * cp;
+                ft_cp_async16(stage + 2 * k, src + ca);
+                if (cb >= 0) ft_cp_async16(stage + 2 * k + 1, src + cb);
+            }
+        } else {
+            const double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
+            const double* bb = fb2 >= 0 ? a.gp_base[fb2] : nullptr; const i64 sb = fb2 >= 0 ? a.gp_blk[fb2] : 0;
+            if (FP32) {
+                float* st = reinterpret_cast<float*>(stage);
+                const float* fa_ = reinterpret_cast<const float*>(ba); const float* fb_ = reinterpret_cast<const float*>(bb);
+                for (int j = tid; j < N; j += nthr) {
+                    const int gi = g0 + j;
+                    ft_cp_async4(st + j, fa_ + (oneblk ? (i64)gi : gp_index(gi, a.nproma, sa)));
+                    if (bb) ft_cp_async4(st + N + j, fb_ + (oneblk ? (i64)gi : gp_index(gi, a.nproma, sb)));
+                }
+            } else {
+                double* st = reinterpret_cast<double*>(stage);
+                for (int j = tid; j < N; j += nthr) {
+                    const int gi = g0 + j;
+                    ft_cp_async8(st + j, ba + (oneblk ? (i64)gi : gp_index(gi, a.nproma, sa)));
+                    if (bb) ft_cp_async8(st + N + j, bb + (oneblk ? (i64)gi : gp_index(gi, a.nproma, sb)));
+                }
+            }
+        }
+        ft_cp_commit();
+    };
+
+    __syncthreads();                    // tables and s_rec visible
+    if (p0 < p1) prefetch(p0);
+    for (int p = p0; p < p1; ++p) {
+        const int2 pr = a.pairs[p];
+        const int fa = pr.x, fb2 = pr.y;
+        const bool hasb = fb2 >= 0;
+        ft_cp_wait_all();
+        __syncthreads();                 // staged inputs visible; the previous pair's outputs have been read
+        if (INVERSE) {
+            const EctFsField sfa = a.fsf[fa];
+            EctFsField sfb; sfb.src_c = -1; sfb.pw = 0; sfb.deriv = 0;
+            if (hasb) sfb = a.fsf[fb2];
+            CzInvScale sc;
+            sc.pwa = sfa.pw; sc.deriva = sfa.deriv; sc.pwb = sfb.pw; sc.derivb = sfb.deriv; sc.hasb = hasb;
+            sc.s1 = racthe; sc.s2 = racthe * racthe;
+            sc.rowscale = a.adj ? a.rw_loc[l] / (double)N : 1.0;
+            const int ca = sfa.src_c, cb = sfb.src_c;
+            cz_inv_load(mine, cx, sc, [&](int k, double2& ra, double2& rb) {
+                if (staged) { ra = stage[2 * k]; if (hasb) rb = stage[2 * k + 1]; }
+                else {
+                    const double* src = a.fb + (long long)s_rec[k] * cp;
+                    ra = *reinterpret_cast<const double2*>(src + ca);
+                    if (hasb) rb = *reinterpret_cast<const double2*>(src + cb);
+                }
+            }, gt, GS);
+        } else {
+            const double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
+            const double* bb = hasb ? a.gp_base[fb2] : nullptr; const i64 sb = hasb ? a.gp_blk[fb2] : 0;
+            const double* st = reinterpret_cast<const double*>(stage);
+            const float* stf = reinterpret_cast<const float*>(stage);
+            cz_dir_load(mine, cx, [&](int j, R_& va, R_& vb) {
+                if (staged) {
+                    va = FP32 ? (R_)stf[j] : (R_)st[j];
+                    if (hasb) vb = FP32 ? (R_)stf[N + j] : (R_)st[N + j];
+                } else {
+                    const int gi = g0 + j;
+                    const i64 ia = oneblk ? (i64)gi : gp_index(gi, a.nproma, sa);
+                    va = FP32 ? (R_)reinterpret_cast<const float*>(ba)[ia] : (R_)ba[ia];
+                    if (hasb) {
+                        const i64 ib = oneblk ? (i64)gi : gp_index(gi, a.nproma, sb);
+                        vb = FP32 ? (R_)reinterpret_cast<const float*>(bb)[ib] : (R_)bb[ib];
+                    }
+                }
+            }, gt, GS);
+        }
+        __syncthreads();                 // both groups have consumed the stage
+        if (p + 1 < p1) prefetch(p + 1);
+        for (int s = plan_nst - 1; s >= 1; --s) {
+            fft_stage<true, 7, true>(mine, H, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qth, (const C*)s_roots, gt, GS);
+            if (s == 1 && warp_local) __syncwarp(); else cz2_group_sync(g, GS);
+        }
+        blue_middle_early(mine, H, s_plan.radix[0], bhat, gt, GS);
+        if (warp_local) __syncwarp(); else cz2_group_sync(g, GS);
+        for (int s = 1; s < plan_nst; ++s) {
+            fft_stage<false, 7, true>(mine, H, s_plan.radix[s], s_plan.sublen[s], s_plan.lshift[s], qth, (const C*)s_roots, gt, GS);
+            if (s + 1 < plan_nst) cz2_group_sync(g, GS);
+        }
+        __syncthreads();                 // both halves complete
+        if (INVERSE) {
+            double* ba = a.gp_base[fa]; const i64 sa = a.gp_blk[fa];
+            double* bb = hasb ? a.gp_base[fb2] : nullptr; const i64 sb = hasb ? a.gp_blk[fb2] : 0;
+            cz_inv_out((const C*)mine, other, cx, [&](int j, C y) {
+                const int gi = g0 + j;
+                const i64 ia = oneblk ? (i64)gi : gp_index(gi, a.nproma, sa);
+                if (FP32) reinterpret_cast<float*>(ba)[ia] = (float)y.x; else ba[ia] = (double)y.x;
+                if (hasb) {
+                    const i64 ib = oneblk ? (i64)gi : gp_index(gi, a.nproma, sb);
+                    if (FP32) reinterpret_cast<float*>(bb)[ib] = (float)y.y; else bb[ib] = (double)y.y;
+                }
+            }, gt, GS);
+        } else {
+            const double wl = a.adj ? 1.0 : a.rw_loc[l] / (double)N;
+            const R_ sca = (R_)(0.5 * wl * (fa < a.n_uv_fields ? racthe : 1.0));
+            const R_ scb = (R_)(0.5 * wl * (fb2 >= 0 && fb2 < a.n_uv_fields ? racthe : 1.0));
+            const int ca = 2 * fa, cb = hasb ? 2 * fb2 : -1;
+            cz_dir_out((const C*)mine, other, cx, [&](int k, C Zk, C Zn) {
+                const int pk_ = s_rec[k];
+                double* rb = a.peer[pk_ >> 24] + (long long)(pk_ & 0xffffff) * cp;
+                *reinterpret_cast<double2*>(rb + ca) = make_double2((double)((Zk.x + Zn.x) * sca), (double)((Zk.y - Zn.y) * sca));
+                if (cb >= 0) *reinterpret_cast<double2*>(rb + cb) = make_double2((double)((Zk.y + Zn.y) * scb), (double)((Zn.x - Zk.x) * scb));
+            }, gt, GS);
+        }
+    }
+}
+
 static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     EctDevice* d = h->d;
     a.latplans = d->latplans; a.plans = d->plans;
@@ -585,6 +782,14 @@ static void launch_fourier(EctHandle* h, FtArgs& a) {
         if (fork) { const int k = slot % (EctDevice::kSide + 1); st = k == 0 ? d->stream : d->side[k - 1]; }
         ++slot;
         const int thr = INVERSE ? b.threads_inv : b.threads;
+        if (b.cz == 2) {                           // both halves in one CTA, two warp groups
+#define CZ2_LAUNCH(GS_) do { if (a.fp32) k_fourier_cz2<INVERSE, GS_, true><<<grid, 2 * GS_, b.smem, st>>>(a); \
+                             else k_fourier_cz2<INVERSE, GS_, false><<<grid, 2 * GS_, b.smem, st>>>(a); } while (0)
+            if (b.threads == 384) CZ2_LAUNCH(192); else if (b.threads == 192) CZ2_LAUNCH(96); else CZ2_LAUNCH(64);
+#undef CZ2_LAUNCH
+            d->launches++;
+            continue;
+        }
         if (b.cz) {
             const unsigned g2 = 2 * grid;          // clusters of two CTAs (__cluster_dims__)
 #define CZ_LAUNCH(TB_) do { if (a.fp32) k_fourier_cz<INVERSE, TB_, true><<<g2, TB_, b.smem, st>>>(a); \
@@ -727,7 +932,8 @@ int ect_fourier_setup(EctHandle* h) {
             d->buckets.push_back(b);
         }
     // chirp-z rows: split over CTA pairs (k_fourier_cz), one class per number of CTAs that fit an SM
-    // ECT_FFT_CZ=1: every chirp-z row; default: only the rows whose undivided work array does not fit one SM (dp rows
+    // ECT_FFT_CZ=1: every chirp-z row on the CTA-pair kernel; 2: on the two-warp-group kernel (k_fourier_cz2; measured
+    // 112.8 ms against 108.8 ms, profiles/r02_fourier_cz.md); default: only the rows whose undivided work array does not fit one SM (dp rows
     // longer than ~5400 points, e.g. TCo2559 in double precision) -- on TCo1279 the pair kernel is no faster than the
     // undivided one (profiles/r02_fourier_cz.md: three CTAs per SM walk through 150 KB of unrolled code in different
     // phases and saturate the instruction cache, 84 % of the GPC instruction-fetch peak against 27 %)
@@ -745,12 +951,30 @@ int ect_fourier_setup(EctHandle* h) {
         b.threads_inv = b.threads;
         d->buckets.push_back(b);
     }
+    // cz_mode 2: chirp-z rows in k_fourier_cz2 (both halves in one CTA); classes by CTA size (small rows: several
+    // small CTAs per SM) and staged / unstaged inputs
+    const int n_cz1 = (int)d->buckets.size();
+    for (int v = 0; v < 2; ++v)
+        for (int thr : {128, 192, 384}) {
+            EctDevice::Bucket b;
+            b.cz = 2; b.smem = 0; b.maxr = 7; b.nostage = v; b.threads = thr; b.threads_inv = thr;
+            d->buckets.push_back(b);
+        }
     std::vector<int> need_of(P.nlat, 0);
     for (int l = 0; l < P.nlat; ++l) {
         const EctLatPlan& lp = d->fft.latplans[d->h_lat_plan[l]];
         bool placed = false;
         int need = 0, maxr = 2;
-        if (!(lp.bluestein && cz_mode == 1)) {
+        if (lp.bluestein && cz_mode == 2) {
+            const int H = lp.m / 2;
+            const int ti = H >= 2048 ? 2 : (H >= 1024 ? 1 : 0);            // 384 / 192 / 128 threads
+            for (int v = 0; v < 2 && !placed; ++v) {
+                need = std::max(cz2_layout(true, H, lp.nlon, lp.km, csize, iosize, v != 0).total,
+                                cz2_layout(false, H, lp.nlon, lp.km, csize, iosize, v != 0).total);
+                if (need <= maxsm - 1024) { d->buckets[n_cz1 + 3 * v + ti].lats.push_back(l); placed = true; }
+            }
+        }
+        if (!placed && !(lp.bluestein && cz_mode == 1)) {
             const EctFftPlan& pl = d->fft.plans[lp.plan];
             for (int s = 0; s < pl.nst; ++s) if (pl.radix[s] & 1) maxr = std::max(maxr, pl.radix[s]);   // 2,4,8,16 are in every variant
             const int nroots = maxr <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE;
@@ -804,6 +1028,12 @@ int ect_fourier_setup(EctHandle* h) {
     CZ_ATTR(true, 384, true); CZ_ATTR(false, 384, true);
     CZ_ATTR(true, 256, false); CZ_ATTR(false, 256, false); CZ_ATTR(true, 256, true); CZ_ATTR(false, 256, true);
 #undef CZ_ATTR
+#define CZ2_ATTR(...) ECT_CUDA(cudaFuncSetAttribute(k_fourier_cz2<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm - 1024))
+    CZ2_ATTR(true, 192, false); CZ2_ATTR(false, 192, false); CZ2_ATTR(true, 96, false); CZ2_ATTR(false, 96, false);
+    CZ2_ATTR(true, 64, false); CZ2_ATTR(false, 64, false);
+    CZ2_ATTR(true, 192, true); CZ2_ATTR(false, 192, true); CZ2_ATTR(true, 96, true); CZ2_ATTR(false, 96, true);
+    CZ2_ATTR(true, 64, true); CZ2_ATTR(false, 64, true);
+#undef CZ2_ATTR
     return ECT_SUCCESS;
 }
 

@@ -976,3 +976,30 @@ def test_sp_tcgen05_contraction(eb, monkeypatch, T, N, nuv, nsc):
     for a, b in zip(out["1"][1], (rv, rd, rs)):
         assert rel(a, b) < 1e-5
     assert out["1"][2] > out["0"][2]          # the tensor-core path really ran (its split / contraction launches)
+
+
+@pytest.mark.parametrize("T,N,prec,tol", [(159, 160, "dp", 1e-12), (399, 400, "dp", 1e-12), (399, 400, "sp", 5e-6)])
+def test_cz2_two_group_kernel_against_oracle(eb, monkeypatch, T, N, prec, tol):
+    """Chirp-z rows with both halves of the split convolution in one CTA (two warp groups, k_fourier_cz2)."""
+    monkeypatch.setenv("ECT_FFT_CZ", "2")
+    nloen = eb.octahedral_nloen(N)
+    tr = eb.Transform(T, nloen, precision=prec)
+    s = eo.setup(T, 2 * N, nloen)
+    nuv, nsc = 3, 4
+    dt = np.float64 if prec == "dp" else np.float32
+    f = (lambda a: a.astype(np.float32).astype(np.float64)) if prec == "sp" else (lambda a: a)
+    vor = f(eo.random_spectral(s, nuv, 1, zero00=True)); div = f(eo.random_spectral(s, nuv, 2, zero00=True))
+    sc = f(eo.random_spectral(s, nsc, 3))
+    opts = dict(scders=True, uvder=True)
+    ref = eo.inv_trans(s, vor, div, sc, **opts)
+    gp = tr.inv_trans(T_(vor).astype(dt), T_(div).astype(dt), T_(sc).astype(dt), nproma=1001, **opts)
+    got = unblock(gp, tr.ngptot).astype(np.float64)
+    for i in range(ref.shape[0]):
+        assert rel(got[i], ref[i]) < tol, i
+    nf = 2 * nuv + nsc
+    gin = f(ref[:nf])
+    rv, rd, rs = eo.dir_trans(s, gin, nuv, nsc)
+    ov, od, os_ = tr.dir_trans(gin[None].astype(dt), nuv, nsc)
+    for a, b in ((ov, rv), (od, rd), (os_, rs)):
+        assert rel(a.T.astype(np.float64), b) < tol
+    tr.release()
