@@ -372,11 +372,11 @@ def run_ours(args):
     peak_dmma = eb.measure_fp64_peak(0)
     peak_dfma = eb.measure_fp64_peak(1)
     ach = fl / world / (leg_ms * 1e-3) / 1e12          # per GPU
-    hbm_peak = None
+    hbm_peak, hbm_measured = None, True
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
-        hbm_peak = 6650.0
+        hbm_peak, hbm_measured = 6650.0, False
     traffic = None
     try:   # DRAM bytes of one k_leinv launch from the committed ncu --set full capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -384,11 +384,18 @@ def run_ours(args):
             traffic = {"k_leinv_dram_bytes_per_launch": tj["dram_bytes_per_launch"],
                        "k_ledir_dram_bytes_per_launch": tj.get("k_ledir_dram_bytes_per_launch"),
                        "algorithmic_bytes_per_launch": int(tr.info.table_bytes + 8 * (nf * 2) * (sum(T - m + 2 for m in range(T + 1)) + 2 * sum(int(x) for x in tr.ndglu))),
-                       "source": tj["source"]}
+                       "source": tj["source"], "static": True}
     except Exception:
         traffic = None
     fb = 2.0 * fft_bytes(tr.nloen, nf) * esz / 8
     ft_ach = fb / world / (ft_ms * 1e-3) / 1e9
+    ft_traffic = None
+    try:   # static: DRAM bytes of the largest Fourier launch in each direction, from the committed ncu --set full captures
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if tj.get("workload") == args.config and world == 1 and prec == "dp":
+            ft_traffic = dict(tj["fourier"], static=True)
+    except Exception:
+        ft_traffic = None
     line = {
         "metric": "ms per INV_TRANS+DIR_TRANS step", "value": ms_dev, "unit": "ms", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False,
@@ -398,12 +405,18 @@ def run_ours(args):
                    "decomposition": f"nprtrw={world},nprtrv=1", "l2": "inputs (GBs) larger than L2, no flush needed"},
         "stages_ms": {"legendre": leg_ms, "fourier": ft_ms, "transpose": tp_ms,
                       "prologue": med("inv", "prologue"), "epilogue": med("dir", "epilogue")},
-        "roofline": {"bound": "tensor", "kernel": "k_leinv+k_ledir (FP64 DMMA m8n8k4)", "achieved": ach,
-                     "peak": peak_dmma, "unit": "TFLOP/s", "frac": ach / peak_dmma, "traffic": traffic,
-                     "peak_source": "ect_measure_fp64_peak(DMMA) measured live in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                     "dfma_peak": peak_dfma},
-        "roofline_fourier": {"bound": "hbm", "kernel": "k_fourier<inv>+k_fourier<dir>", "achieved": ft_ach,
-                             "peak": hbm_peak, "unit": "GB/s", "frac": ft_ach / hbm_peak},
+        # the dominant kernel of the step is the Fourier stage (half of it): its roofline is the headline one
+        "roofline": {"bound": "hbm", "kernel": "k_fourier<inv>+k_fourier<dir> (all launches of the Fourier stage)", "achieved": ft_ach,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": ft_ach / hbm_peak, "traffic": ft_traffic,
+                     "algorithmic_bytes_per_step": fb, "share_of_step": ft_ms / max(ms_dev, 1e-9),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_measured else "fallback 6650 GB/s (of fallback)",
+                     "note": "arithmetic (FP64) bound, not HBM bound: see DESIGN.md section 4 and profiles/r02_fourier_cz.md"},
+        "roofline_legendre": {"bound": "tensor", "kernel": ("k_leinv+k_ledir (FP64 DMMA m8n8k4)" if prec == "dp" else
+                                                            "k_leg_tc (tcgen05 kind::tf32, 3xTF32) + m = 0 on DMMA + operand split kernels"),
+                              "achieved": ach, "peak": peak_dmma if prec == "dp" else None, "unit": "TFLOP/s",
+                              "frac": ach / peak_dmma if prec == "dp" else None, "traffic": traffic,
+                              "peak_source": "ect_measure_fp64_peak(DMMA) measured live in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                              "dfma_peak": peak_dfma, "share_of_step": leg_ms / max(ms_dev, 1e-9)},
         "gpu_launches": launches * args.steps,
         "clocks": clocks, "setup_s": setup_s,
     }

@@ -400,6 +400,12 @@ def test_ectrans4py_face(eb, golden):
     assert np.abs(gp - gpdata).max() < 1e-10
     sp = ectrans4py.gp2sp_gauss4py(11175 * 2, 150, 148, 10, len(nl), nl, len(gpdata), False, gpdata)
     assert np.abs(sp - golden["sp"]).max() < 1e-10
+    # LREORDER=True: the same golden field given / returned in the 'model' coefficient order (sp2gp_gauss4py.F90:82-108)
+    model = ectrans4py._to_model_order(148, golden["sp"], len(golden["sp"]))
+    gp_m = ectrans4py.sp2gp_gauss4py(150, 148, 10, int(sum(nl)), len(nl), nl, len(model), False, True, model)[0]
+    assert np.array_equal(gp_m, gp)
+    sp_m = ectrans4py.gp2sp_gauss4py(11175 * 2, 150, 148, 10, len(nl), nl, len(gpdata), True, gpdata)
+    assert np.array_equal(ectrans4py._from_model_order(148, sp_m), np.where(np.arange(sp.size) < 2 * 149, np.where(np.arange(sp.size) % 2 == 1, 0.0, sp), sp))
     nspec = sum(148 + 2 - im for im in range(149))
     knmeng, weights, polys = ectrans4py.get_legendre_assets(150, 148, len(nl), nspec, nl, 10)
     assert abs(sum(weights) - 1.0) < 1e-10

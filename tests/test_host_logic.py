@@ -377,3 +377,29 @@ def test_host_plan_fuzz_against_oracle(eb):
         assert sum(x.nspec2 for x in trs) == (T + 1) * (T + 2) and sum(x.ngptot for x in trs) == int(nloen.sum())
         for x in trs:
             x.release()
+
+
+def test_ectrans4py_model_order_permutation():
+    """LREORDER=True of the reference's ectrans4py (sp2gp_gauss4py.F90:82-108): the 'model' order <-> ecTrans order maps,
+    restated literally from the Fortran loops and compared with the vectorised helpers."""
+    from ectrans_b200 import ectrans4py as e4
+    T = 7
+    size = (T + 1) * (T + 2)
+    rng = np.random.default_rng(0)
+    pspec = rng.standard_normal(size)
+    nasm0, ji = {}, 1
+    for n in range(T + 1):
+        nasm0[n] = ji
+        ji = ji + 1 + n + (n + 1)
+    buf, ji = np.zeros(size), 0
+    for m in range(T + 1):
+        for n in range(m, T + 1):
+            buf[ji] = pspec[nasm0[n] + m - 1]; ji += 1
+            buf[ji] = 0.0 if m == 0 else pspec[nasm0[n] - m - 1]; ji += 1
+    got = e4._from_model_order(T, pspec)
+    assert np.array_equal(got, buf)
+    back = e4._to_model_order(T, got, size)
+    used = np.zeros(size, bool)
+    re, im = e4._model_order(T)
+    used[re] = True; used[im[im >= 0]] = True
+    assert used.sum() == (T + 1) ** 2 and np.array_equal(back[used], pspec[used]) and np.all(back[~used] == 0)
