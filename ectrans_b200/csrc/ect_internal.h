@@ -228,6 +228,7 @@ int ect_legendre_setup(EctHandle* h);
 // sp handles: LEINV / LEDIR of the wavenumbers m > 0 as 3xTF32 on tcgen05 (legendre_tc.cu); m = 0 stays on the FP64 kernels
 bool ect_tc_enabled(EctHandle* h);
 int ect_tc_launch_leinv(EctHandle* h, const EctFieldCfg& f);
+int ect_tc_operands(EctHandle* h, int cp, float** xh, float** xl);     // inverse operand rows for the prologue to fill
 int ect_tc_launch_ledir(EctHandle* h, const EctFieldCfg& f);
 void ect_tc_invalidate(EctHandle* h);
 void ect_tc_free(EctDevice* d);

@@ -80,6 +80,9 @@ struct ProArgs {
     double* x; int cp; int nsmax;
     int kf_uv, kf_sc, scders, vorgp, divgp, fp32;
     int adj;      // DIR_TRANSAD: UVTVD^T = VDTUV . diag(n (n + 1) / a^2), the inputs are scaled on load
+    // sp handles on the tensor-core contraction (legendre_tc.cu): rows of m > 0 are written as hi = tf32(x) and
+    // lo = x - hi float rows in parity-split order (m, parity, k) instead of the double rows (m = 0 stays double)
+    float* xh; float* xl;
 };
 
 __device__ __forceinline__ double d_eps(int m, int n) {     // pre_suleg_mod.F90:46-65
@@ -124,6 +127,16 @@ __global__ void k_ltinv_prologue(ProArgs a) {
     const bool m0 = (m == 0);
     const bool v0 = (n <= T), vm = (n - 1 >= m), vp = (n + 1 <= T);
     double* row = a.x + (lm.xrow0 + r) * (long long)a.cp;
+    const bool tc = a.xh != nullptr && m > 0;
+    const long long frow = (lm.xrow0 + ((r & 1) ? lm.ils : 0) + (r >> 1)) * (long long)a.cp;
+    auto put = [&](int c, double2 v) {
+        if (tc) {
+            const float f0 = (float)v.x, f1 = (float)v.y;
+            const float h0 = __uint_as_float(__float_as_uint(f0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(f1) & 0xffffe000u);
+            *reinterpret_cast<float2*>(a.xh + frow + c) = make_float2(h0, h1);
+            *reinterpret_cast<float2*>(a.xl + frow + c) = make_float2(f0 - h0, f1 - h1);
+        } else *reinterpret_cast<double2*>(row + c) = v;
+    };
     const int o_vor = 0, o_div = a.vorgp ? a.kf_uv : 0;
     const int o_u = o_div + (a.divgp ? a.kf_uv : 0), o_v = o_u + a.kf_uv;
     const int o_sc = o_v + a.kf_uv, o_nsd = o_sc + a.kf_sc;
@@ -144,19 +157,18 @@ __global__ void k_ltinv_prologue(ProArgs a) {
             v.x = -zl * z0.y - c1 * dm.x + c2 * dp.x;
             v.y = zl * z0.x - c1 * dm.y + c2 * dp.y;
             if (m0) { u.y = 0.0; v.y = 0.0; }
-            if (a.vorgp) *reinterpret_cast<double2*>(row + 2 * (o_vor + j)) = z0;
-            if (a.divgp) *reinterpret_cast<double2*>(row + 2 * (o_div + j)) = d0;
-            *reinterpret_cast<double2*>(row + 2 * (o_u + j)) = u;
-            *reinterpret_cast<double2*>(row + 2 * (o_v + j)) = v;
+            if (a.vorgp) put(2 * (o_vor + j), z0);
+            if (a.divgp) put(2 * (o_div + j), d0);
+            put(2 * (o_u + j), u);
+            put(2 * (o_v + j), v);
         } else {
             const int s = j - a.kf_uv;
             const EctSpecField f = a.sc[s];
             const double2 f0 = ld_spec<FP32>(f, idx, v0, m0);
-            *reinterpret_cast<double2*>(row + 2 * (o_sc + s)) = f0;
+            put(2 * (o_sc + s), f0);
             if (a.scders) {
                 const double2 fm = ld_spec<FP32>(f, idx - 2, vm, m0), fp = ld_spec<FP32>(f, idx + 2, vp, m0);
-                *reinterpret_cast<double2*>(row + 2 * (o_nsd + s)) =
-                    make_double2(-e1 * fm.x + e2 * fp.x, -e1 * fm.y + e2 * fp.y);
+                put(2 * (o_nsd + s), make_double2(-e1 * fm.x + e2 * fp.x, -e1 * fm.y + e2 * fp.y));
             }
         }
     }
@@ -172,7 +184,9 @@ void ect_launch_ltinv_prologue(EctHandle* h, const EctFieldCfg& f, const void* d
     a.x = d->xwork; a.cp = f.cp; a.nsmax = h->hp.nsmax;
     a.kf_uv = f.kf_uv; a.kf_sc = f.kf_sc; a.scders = f.scders; a.vorgp = f.vorgp; a.divgp = f.divgp;
     a.adj = f.adj;
+    a.xh = a.xl = nullptr;
     if (h->hp.nump == 0) return;
+    if (f.fp32 && ect_tc_enabled(h) && ect_tc_operands(h, f.cp, &a.xh, &a.xl) != ECT_SUCCESS) { d->launch_error = 1; return; }
     dim3 grid((h->hp.nsmax + 2 + PRO_ROWS - 1) / PRO_ROWS, h->hp.nump);
     int items = f.kf_uv + f.kf_sc;
     int threads = items >= 192 ? 256 : (items >= 96 ? 128 : 64);

@@ -46,6 +46,7 @@ struct EctTcState {
     int n_inv_tiles = 0, n_dir_tiles = 0;
     CUtensorMap map_ainv[2], map_adir[2];
     bool tables_ready = false;
+    bool x_split_by_prologue = false;           // the prologue of the current call wrote b[0] / b[1] itself
     int enabled = -1;
 };
 
@@ -541,6 +542,16 @@ static void tc_fill_args(EctHandle* h, const EctFieldCfg& f, TcArgs& a) {
     a.dst_rec_n = d->leg_dst_rec_n; a.dst_rec_s = d->leg_dst_rec_s;
 }
 
+// Operand rows of the inverse contraction (hi / lo float rows, parity-split order): written by k_ltinv_prologue itself
+int ect_tc_operands(EctHandle* h, int cp, float** xh, float** xl) {
+    int rc = tc_ensure_operands(h, cp);
+    if (rc) return rc;
+    EctTcState* t = h->d->tc;
+    *xh = t->b[0]; *xl = t->b[1];
+    t->x_split_by_prologue = true;
+    return ECT_SUCCESS;
+}
+
 // LEINV for the wavenumbers m > 0 of an sp handle (m = 0: k_leinv on its own tiles, see ect_launch_leinv)
 int ect_tc_launch_leinv(EctHandle* h, const EctFieldCfg& f) {
     EctDevice* d = h->d;
@@ -549,8 +560,12 @@ int ect_tc_launch_leinv(EctHandle* h, const EctFieldCfg& f) {
     if (!t->tables_ready && (rc = tc_build_tables(h))) return rc;
     if ((rc = tc_ensure_operands(h, f.cp))) return rc;
     if (t->n_inv_tiles == 0) return ECT_SUCCESS;
-    dim3 g((h->hp.nsmax + 2 + 3) / 4, h->hp.nump);
-    k_tc_split_x<<<g, 128, 0, d->stream>>>(d->legm, d->xwork, f.cp, h->hp.nsmax, t->b[0], t->b[1]);
+    if (!t->x_split_by_prologue) {      // (callers that fill the double rows themselves)
+        dim3 g((h->hp.nsmax + 2 + 3) / 4, h->hp.nump);
+        k_tc_split_x<<<g, 128, 0, d->stream>>>(d->legm, d->xwork, f.cp, h->hp.nsmax, t->b[0], t->b[1]);
+        d->launches++;
+    }
+    t->x_split_by_prologue = false;
     TcMaps maps;
     maps.a[0] = t->map_ainv[0]; maps.a[1] = t->map_ainv[1];
     for (int hl = 0; hl < 2; ++hl) {
@@ -561,7 +576,7 @@ int ect_tc_launch_leinv(EctHandle* h, const EctFieldCfg& f) {
     tc_fill_args(h, f, a);
     a.tiles = t->inv_tiles;
     k_leg_tc<false><<<(unsigned)((long long)t->n_inv_tiles * a.nct), TC_THREADS, TC_SMEM_BYTES, d->stream>>>(maps, a);
-    d->launches += 2;
+    d->launches += 1;
     ECT_CUDA(cudaGetLastError());
     return ECT_SUCCESS;
 }
