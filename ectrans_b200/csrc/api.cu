@@ -256,7 +256,7 @@ void ect_device_free(EctHandle* h) {
                     d->nasm0, d->inv_tiles, d->dir_tiles, d->plans, d->latplans, d->perm_pool, d->tw_pool,
                     d->cz_pool, d->cz_pool_f, d->roots, d->lat_plan, d->latrow0, d->fft_rec, d->lat_aff, d->xwork, d->fbuf_leg,
                     d->stage_sp, d->stage_gp, d->normbuf, d->leg_dst_rank_n, d->leg_dst_rank_s, d->leg_dst_rec_n,
-                    d->leg_dst_rec_s, d->fft_dst_rank, d->fft_dst_rec, d->peer_fft, d->peer_leg, d->barrier_buf,
+                    d->leg_dst_rec_s, d->fft_dst_rank, d->fft_dst_rec, d->peer_fft, d->peer_leg, d->barrier_buf, d->push_scr, d->push_mask,
                     d->gpband, d->gpsend, d->gprecv, d->xb_idx, d->xb_off, d->xg_off};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < EctDevice::kSlots; ++i) {

@@ -141,7 +141,8 @@ struct EctDevice {
     std::vector<int> h_lat_plan;
     // per smem-class work lists (latitudes sorted by cost)
     struct Bucket { int smem; int threads; int threads_inv = 0; int maxr; int nostage = 0; int cz = 0;   // cz: chirp-z rows on CTA pairs (k_fourier_cz)
-                    std::vector<int> lats; int* d_lats = nullptr; };
+                    std::vector<int> lats; int* d_lats = nullptr;
+                    int push_sps = 0; i64 push_slot = 0; };   // direct stage, push mode: scratch slots per SM, double2 per slot
     std::vector<Bucket> buckets;
     // workspaces (grow only)
     double* xwork = nullptr; i64 xwork_elems = 0;       // X (inverse input) / POA (direct output)
@@ -180,6 +181,9 @@ struct EctDevice {
     int* barrier_buf = nullptr;
     int p2p_last = -1;                    // pipeline of the previous peer-mode transform (1: inverse / TRMTOL, 0: direct / TRLTOM)
     i64 entry_barriers = 0;               // consumer-done barriers issued (ect_transpose_enter)
+    // direct Fourier stage in peer mode: a CTA collects the records of its field-pair chunk in a local (L2 resident)
+    // slot and pushes them to the consumer rank as 256-byte runs instead of 16-byte pieces (fourier.cu, FtArgs::push_scr)
+    void* push_scr = nullptr; unsigned* push_mask = nullptr; size_t push_bytes = 0; int push_nsm = 0;
     // side streams: the shared-memory classes of the Fourier stage run concurrently so that small classes fill the
     // tails of large ones
     static const int kSide = 3;

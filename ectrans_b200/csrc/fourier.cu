@@ -43,7 +43,32 @@ struct FtArgs {
     int adj;                      // adjoint call: direct pipeline without 1/N and Gaussian weight (INV_TRANSAD), inverse with them (DIR_TRANSAD)
     int nostage;                  // this launch's rows do not fit with a staging area: inputs are read straight from HBM
     int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum
+    // direct, peer mode: records of one CTA's field chunk are collected in a local slot ([m][FT_PUSH_W] double2) and leave
+    // the GPU as runs of up to 256 bytes per (lat, m) record.  Slots: push_sps per SM, claimed through a bit mask per SM
+    double2* push_scr; unsigned* push_mask; int push_sps; i64 push_slot;     // push_slot: double2 per slot
 };
+#define FT_PUSH_W (2 * FT_PAIRS_PER_CTA)
+
+// Claim / release one of the push_sps scratch slots of the SM this CTA runs on (thread 0 of the CTA).  At most push_sps - 1
+// CTAs of a launch are resident per SM (host: launch_fourier), so a free bit always exists; the loop only rides out the
+// window between a neighbour's release and our read.
+__device__ __forceinline__ int ft_slot_acquire(unsigned* masks, int sps) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned* m = masks + smid;
+    const unsigned all = sps >= 32 ? 0xffffffffu : ((1u << sps) - 1u);
+    for (;;) {
+        const unsigned cur = *reinterpret_cast<volatile unsigned*>(m);
+        const unsigned fr = ~cur & all;
+        if (!fr) { __nanosleep(200); continue; }
+        const int b = __ffs(fr) - 1;
+        if (!(atomicOr(m, 1u << b) & (1u << b))) return (int)smid * 32 + b;
+    }
+}
+__device__ __forceinline__ void ft_slot_release(unsigned* masks, int id) {
+    __threadfence();
+    atomicAnd(masks + (id >> 5), ~(1u << (id & 31)));
+}
 
 __device__ __forceinline__ i64 gp_index(int g, int nproma, i64 blkstride) {
     const int blk = g / nproma;
@@ -94,12 +119,17 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
     typedef typename EctReal<C>::type R_;
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ EctFftPlan s_plan;        // stage list indexed at run time: keep it out of local memory
+    __shared__ int s_slot;
     constexpr int NROOTS = MAXR <= 7 ? ECT_ROOTS_OFF(8) : ECT_ROOTS_SIZE;
     const int item = blockIdx.x;
     const int l = a.lats[item / a.nchunks];
     const int chunk = item % a.nchunks;
     const EctLatPlan lp = a.latplans[a.lat_plan[l]];
-    if (threadIdx.x == 0) s_plan = a.plans[lp.plan];
+    const bool push = !INVERSE && a.push_scr != nullptr;
+    if (threadIdx.x == 0) {
+        s_plan = a.plans[lp.plan];
+        if (push) s_slot = ft_slot_acquire(a.push_mask, a.push_sps);
+    }
     __syncthreads();
     const int plan_n = s_plan.n, plan_nst = s_plan.nst;
     const uint16_t* perm = a.perm_pool + s_plan.perm_off;
@@ -137,6 +167,13 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
     constexpr int NB = 4;      // global loads issued per thread before the first use (latency batching)
     const double racthe = a.racthe_loc[l];
     const R_ s1 = (R_)racthe, s2 = (R_)(racthe * racthe);
+    // push mode: slot of this CTA, first field of its chunk (fields of a chunk are consecutive, api.cu make_pairs)
+    double2* scr = nullptr;
+    int pf0 = 0;
+    if (push) {
+        scr = a.push_scr + (i64)((s_slot >> 5) * a.push_sps + (s_slot & 31)) * a.push_slot;
+        pf0 = p0 < p1 ? a.pairs[p0].x : 0;
+    }
 
     auto prefetch = [&](int p) {       // raw inputs of pair p -> stage (asynchronous)
         if (!staged) return;
@@ -371,13 +408,50 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
                     if (blue) { a_ = c_mul(ch[i], a_); b_ = c_mul(ch[i], b_); }
                     // stored values are swapped (sign - transform on the sign + core): Z = (y, x)
                     const C Zk = c_make<C>(a_.y, a_.x), Zn = c_make<C>(b_.y, b_.x);
-                    *reinterpret_cast<double2*>(rb[i] + ca) = make_double2((double)((Zk.x + Zn.x) * sca), (double)((Zk.y - Zn.y) * sca));
-                    if (cb >= 0) *reinterpret_cast<double2*>(rb[i] + cb) = make_double2((double)((Zk.y + Zn.y) * scb), (double)((Zn.x - Zk.x) * scb));
+                    const double2 ra_ = make_double2((double)((Zk.x + Zn.x) * sca), (double)((Zk.y - Zn.y) * sca));
+                    const double2 rb_ = make_double2((double)((Zk.y + Zn.y) * scb), (double)((Zn.x - Zk.x) * scb));
+                    if (push) {
+                        double2* q = scr + (i64)k * FT_PUSH_W + (fa - pf0);
+                        q[0] = ra_;
+                        if (cb >= 0) q[fb2 - fa] = rb_;
+                    } else {
+                        *reinterpret_cast<double2*>(rb[i] + ca) = ra_;
+                        if (cb >= 0) *reinterpret_cast<double2*>(rb[i] + cb) = rb_;
+                    }
                 }
             }
         }
         __syncthreads();
         FT_PROBE(20);
+    }
+    if (push) {
+        // the chunk's records, [m][field] in the slot (written by this CTA: L2 hits), go to their consumer as one run of
+        // nfc * 16 bytes per (lat, m): 16 lanes per record
+        if (p0 < p1) {
+            const int2 pl = a.pairs[p1 - 1];
+            const int nfc = (pl.y >= 0 ? pl.y : pl.x) - pf0 + 1;
+            const int j = tid & (FT_PUSH_W - 1), kstep = nthr / FT_PUSH_W;
+            constexpr int NP = 8;              // loads in flight per thread: the slot is read once, at L2 latency
+            if (j < nfc)
+                for (int k0 = tid / FT_PUSH_W; k0 <= km; k0 += NP * kstep) {
+                    double2 v[NP];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        const int k = k0 + i * kstep;
+                        if (k <= km) v[i] = __ldcg(scr + (i64)k * FT_PUSH_W + j);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        const int k = k0 + i * kstep;
+                        if (k > km) continue;
+                        const int pk_ = s_rec[k];
+                        double* dst = a.peer[pk_ >> 24] + (long long)(pk_ & 0xffffff) * cp + 2 * (pf0 + j);
+                        *reinterpret_cast<double2*>(dst) = v[i];
+                    }
+                }
+        }
+        __syncthreads();
+        if (tid == 0) ft_slot_release(a.push_mask, s_slot);
     }
 }
 
@@ -751,6 +825,7 @@ static void fill_args(EctHandle* h, const EctFieldCfg& f, FtArgs& a) {
     a.rw_loc = d->rw_loc; a.n_uv_fields = 2 * f.kf_uv;
     static const char* dbg = getenv("ECT_FFT_DBG");
     a.dbg = dbg ? atoi(dbg) : 0;
+    a.push_scr = nullptr; a.push_mask = nullptr; a.push_sps = 0; a.push_slot = 0;
 }
 
 template <bool INVERSE>
@@ -777,6 +852,9 @@ static void launch_fourier(EctHandle* h, FtArgs& a) {
         if (only && atoi(only) != bi) continue;
         a.lats = b.d_lats;
         a.nostage = b.nostage;
+        const bool pushb = !INVERSE && b.push_sps > 0 && d->push_scr != nullptr;
+        a.push_scr = pushb ? (double2*)d->push_scr : nullptr;
+        a.push_mask = d->push_mask; a.push_sps = b.push_sps; a.push_slot = b.push_slot;
         const unsigned grid = (unsigned)(b.lats.size() * (size_t)a.nchunks);
         cudaStream_t st = d->stream;
         if (fork) { const int k = slot % (EctDevice::kSide + 1); st = k == 0 ? d->stream : d->side[k - 1]; }
@@ -863,6 +941,46 @@ int ect_fourier_set_affine(EctHandle* h) {
             aff[l] = (a0 ? 1 : 0) | (a1 ? 2 : 0);
         }
         if ((rc = upload(d->lat_aff, aff))) return rc;
+    }
+    // Peer mode: scratch slots of the direct stage's record push (k_fourier, FtArgs::push_scr).  ECT_FFT_PUSH=0 keeps
+    // the direct 16-byte remote stores, 2 forces the slots on one rank too (tests).
+    {
+        const char* pe = getenv("ECT_FFT_PUSH");
+        const int mode = pe ? atoi(pe) : 1;
+        const bool on = mode == 2 || (mode != 0 && d->p2p && P.nranks > 1);
+        int smem_sm = 0, nsm = 0, thr_sm = 2048;
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d->dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->dev);
+        cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, d->dev);
+        size_t need = 0;
+        for (auto& b : d->buckets) {
+            b.push_sps = 0; b.push_slot = 0;
+            if (!on || b.cz || b.lats.empty()) continue;
+            int kmmax = 0;
+            for (int l : b.lats) kmmax = std::max(kmmax, d->fft.latplans[d->h_lat_plan[l]].km);
+            // resident CTAs per SM are bounded by shared memory and threads; one spare slot
+            const int res = std::max(1, std::min(smem_sm / (b.smem + 1024), thr_sm / std::max(b.threads, 32)));
+            b.push_sps = std::min(32, res + 1);
+            b.push_slot = (i64)(kmmax + 1) * FT_PUSH_W;
+            need = std::max(need, (size_t)nsm * b.push_sps * (size_t)b.push_slot * sizeof(double2));
+        }
+        if (need > 0) {
+            if (need > d->push_bytes) {
+                if (d->push_scr) cudaFree(d->push_scr);
+                d->push_scr = nullptr; d->push_bytes = 0;
+                if (cudaMalloc(&d->push_scr, need) != cudaSuccess) {
+                    // no room: the direct stage keeps storing straight into the consumer's buffer
+                    cudaGetLastError();
+                    for (auto& b : d->buckets) b.push_sps = 0;
+                    need = 0;
+                } else d->push_bytes = need;
+            }
+            if (need > 0 && !d->push_mask) {
+                ECT_CUDA(cudaMalloc(&d->push_mask, (size_t)nsm * sizeof(unsigned)));
+                ECT_CUDA(cudaMemset(d->push_mask, 0, (size_t)nsm * sizeof(unsigned)));
+                d->push_nsm = nsm;
+            }
+        }
     }
     return ECT_SUCCESS;
 }

@@ -3,7 +3,7 @@
 #include "ect_internal.h"
 #include "fft_plan.h"
 #include <cmath>
-#include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
@@ -234,7 +234,9 @@ int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, i
                 else { const int M = ect_fft_smooth_size(2 * P.nmen[j] + n); f = 2.0 * M * std::log2((double)M); }
                 fw[j] = f; fmax = std::max(fmax, f);
             }
-            P.band_pad = (int)(0.16 * fmax / 16.0);
+            const char* pe = getenv("ECT_BAND_PAD");        // experiments: the per-latitude constant as a fraction of max(FFT work)
+            const double padf = pe ? atof(pe) : 0.16;
+            P.band_pad = (int)(padf * fmax / 16.0);
             for (int j = 0; j < ndgl; ++j) w[j] = (int)(fw[j] / 16.0) + P.band_pad;
         }
         lat_bands(w, nranks, P.lat_first, P.lat_count);

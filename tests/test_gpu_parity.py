@@ -1009,3 +1009,34 @@ def test_cz2_two_group_kernel_against_oracle(eb, monkeypatch, T, N, prec, tol):
     for a, b in ((ov, rv), (od, rd), (os_, rs)):
         assert rel(a.T.astype(np.float64), b) < tol
     tr.release()
+
+
+# ---- direct Fourier stage: records collected in a local slot and pushed as long runs (peer mode; forced here) ----
+@pytest.mark.parametrize("T,N,prec,nuv,nsc", [(159, 160, "dp", 3, 4), (399, 400, "dp", 9, 23), (399, 400, "sp", 5, 14),
+                                              (95, 96, "dp", 0, 1)])
+def test_direct_push_slots_bit_identical(eb, monkeypatch, T, N, prec, nuv, nsc):
+    """ECT_FFT_PUSH=2 runs the slot + push store path of k_fourier<direct> on one rank (the consumer's buffer is then the
+    local one): same arithmetic, so the spectra must equal the direct-store path bit for bit -- whole chunks of 16
+    fields, a ragged last chunk, single-field pairs at group ends -- and match the oracle."""
+    nloen = eb.octahedral_nloen(N)
+    s = eo.setup(T, 2 * N, nloen)
+    dt = np.float64 if prec == "dp" else np.float32
+    rng = np.random.default_rng(7)
+    nf = 2 * nuv + nsc
+    gin = rng.standard_normal((nf, s.ngptot)).astype(dt)
+    out = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("ECT_FFT_PUSH", mode)
+        tr = eb.Transform(T, nloen, precision=prec)
+        for rep in range(2):                       # twice: slots are released and claimed again
+            res = tr.dir_trans(gin[None], nuv, nsc)
+        out[mode] = [np.array(x) for x in res if x is not None]
+        tr.release()
+    for a, b in zip(out["0"], out["2"]):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    if T <= 159:
+        ref = eo.dir_trans(s, gin.astype(np.float64), nuv, nsc)
+        got = out["2"]
+        refs = [r for r in ref if r is not None and r.size]
+        for a, b in zip(got, refs):
+            assert rel(a.T.astype(np.float64), b) < (1e-12 if prec == "dp" else 5e-6)
