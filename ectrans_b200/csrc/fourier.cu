@@ -943,11 +943,14 @@ int ect_fourier_set_affine(EctHandle* h) {
         if ((rc = upload(d->lat_aff, aff))) return rc;
     }
     // Peer mode: scratch slots of the direct stage's record push (k_fourier, FtArgs::push_scr).  ECT_FFT_PUSH=0 keeps
-    // the direct 16-byte remote stores, 2 forces the slots on one rank too (tests).
+    // the direct 16-byte remote stores, 2 forces the slots whatever the rank count (tests), 1 turns them on for any peer-mode
+    // run.  Default: three ranks or more -- NVLink takes about 8 G of the 16-byte packets per second from one GPU, which two
+    // ranks stay under (3.2 GB per rank in 28 ms of FFT work: 110.5 ms per step against 112.0 with the push, whose extra pass
+    // through L2 costs 2.5 ms there), four and eight do not (61.3 -> 57.2 ms, 33.1 -> 30.0 ms; profiles/r02_scaling.md)
     {
         const char* pe = getenv("ECT_FFT_PUSH");
-        const int mode = pe ? atoi(pe) : 1;
-        const bool on = mode == 2 || (mode != 0 && d->p2p && P.nranks > 1);
+        const int mode = pe ? atoi(pe) : -1;
+        const bool on = mode == 2 || (d->p2p && P.nranks > 1 && (mode == 1 || (mode < 0 && P.nranks >= 3)));
         int smem_sm = 0, nsm = 0, thr_sm = 2048;
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d->dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->dev);
