@@ -36,6 +36,16 @@ static EctHandle* get_handle(int id) {
     return it == g_handles.end() ? nullptr : it->second;
 }
 
+// debug / tests: state of the direct stage's record push {enabled, SM id range, scratch bytes, largest slots per SM}
+extern "C" int ect_debug_push_info(int handle, long long* out4) {
+    EctHandle* h = get_handle(handle);
+    if (!h || !h->d || !out4) return ECT_ERR_BADARG;
+    int sps = 0;
+    for (auto& b : h->d->buckets) sps = std::max(sps, b.push_sps);
+    out4[0] = h->d->push_scr != nullptr && sps > 0; out4[1] = h->d->push_nsm; out4[2] = (long long)h->d->push_bytes; out4[3] = sps;
+    return ECT_SUCCESS;
+}
+
 extern "C" const char* ect_strerror(int code) {
     switch (code) {
         case ECT_SUCCESS: return "success";

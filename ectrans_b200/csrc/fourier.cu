@@ -65,6 +65,12 @@ __device__ __forceinline__ int ft_slot_acquire(unsigned* masks, int sps) {
         if (!(atomicOr(m, 1u << b) & (1u << b))) return (int)smid * 32 + b;
     }
 }
+// %smid is not guaranteed to be contiguous: the tables are sized by %nsmid, read once on the device
+__global__ void k_ft_nsmid(unsigned* out) {
+    unsigned n;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n));
+    *out = n;
+}
 __device__ __forceinline__ void ft_slot_release(unsigned* masks, int id) {
     __threadfence();
     atomicAnd(masks + (id >> 5), ~(1u << (id & 31)));
@@ -852,7 +858,8 @@ static void launch_fourier(EctHandle* h, FtArgs& a) {
         if (only && atoi(only) != bi) continue;
         a.lats = b.d_lats;
         a.nostage = b.nostage;
-        const bool pushb = !INVERSE && b.push_sps > 0 && d->push_scr != nullptr;
+        // buckets on concurrent streams would share the slots with different slot sizes: direct stores then
+        const bool pushb = !INVERSE && !fork && b.push_sps > 0 && d->push_scr != nullptr;
         a.push_scr = pushb ? (double2*)d->push_scr : nullptr;
         a.push_mask = d->push_mask; a.push_sps = b.push_sps; a.push_slot = b.push_slot;
         const unsigned grid = (unsigned)(b.lats.size() * (size_t)a.nchunks);
@@ -955,6 +962,16 @@ int ect_fourier_set_affine(EctHandle* h) {
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d->dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->dev);
         cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, d->dev);
+        if (on && d->push_nsm == 0) {
+            unsigned* dn = nullptr; unsigned hn = 0;
+            ECT_CUDA(cudaMalloc(&dn, sizeof(unsigned)));
+            k_ft_nsmid<<<1, 1, 0, d->stream>>>(dn);
+            ECT_CUDA(cudaMemcpyAsync(&hn, dn, sizeof(unsigned), cudaMemcpyDeviceToHost, d->stream));
+            ECT_CUDA(cudaStreamSynchronize(d->stream));
+            cudaFree(dn);
+            d->push_nsm = std::max(nsm, (int)hn);
+        }
+        nsm = std::max(nsm, d->push_nsm);
         size_t need = 0;
         for (auto& b : d->buckets) {
             b.push_sps = 0; b.push_slot = 0;
@@ -981,7 +998,6 @@ int ect_fourier_set_affine(EctHandle* h) {
             if (need > 0 && !d->push_mask) {
                 ECT_CUDA(cudaMalloc(&d->push_mask, (size_t)nsm * sizeof(unsigned)));
                 ECT_CUDA(cudaMemset(d->push_mask, 0, (size_t)nsm * sizeof(unsigned)));
-                d->push_nsm = nsm;
             }
         }
     }

@@ -1030,6 +1030,14 @@ def test_direct_push_slots_bit_identical(eb, monkeypatch, T, N, prec, nuv, nsc):
         tr = eb.Transform(T, nloen, precision=prec)
         for rep in range(2):                       # twice: slots are released and claimed again
             res = tr.dir_trans(gin[None], nuv, nsc)
+        import ctypes, torch
+        info = (ctypes.c_longlong * 4)()
+        assert eb.lib().ect_debug_push_info(ctypes.c_int(tr.handle), info) == 0
+        assert bool(info[0]) == (mode == "2")
+        if mode == "2":
+            nsm = torch.cuda.get_device_properties(0).multi_processor_count
+            assert info[1] >= nsm and info[2] > 0 and 2 <= info[3] <= 32, list(info)
+            print("push info (enabled, sm id range, scratch bytes, slots per SM):", list(info))
         out[mode] = [np.array(x) for x in res if x is not None]
         tr.release()
     for a, b in zip(out["0"], out["2"]):
