@@ -42,7 +42,7 @@ struct FtArgs {
     int fp32;                     // sp handle: grid-point arrays are float and the FFT arithmetic is float
     int adj;                      // adjoint call: direct pipeline without 1/N and Gaussian weight (INV_TRANSAD), inverse with them (DIR_TRANSAD)
     int nostage;                  // this launch's rows do not fit with a staging area: inputs are read straight from HBM
-    int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum
+    int dbg;                      // debug switches (ECT_FFT_DBG): 1 no output chirp, 2 no stores, 4 no middle kernel spectrum, 8 direct: no chirp loads, 16 direct: no record stores (timing experiments, wrong results)
     // direct, peer mode: records of one CTA's field chunk are collected in a local slot ([m][FT_PUSH_W] double2) and leave
     // the GPU as runs of up to 256 bytes per (lat, m) record.  Slots: push_sps per SM, claimed through a bit mask per SM
     double2* push_scr; unsigned* push_mask; int push_sps; i64 push_slot;     // push_slot: double2 per slot
@@ -293,8 +293,8 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
                     const int j = j0 + i * nthr;
                     ch[i] = c_make<C>(1, 0); pj[i] = 0; xa[i] = xb[i] = 0;
                     if (j < N) {
-                        if (blue) { ch[i] = g_chirp[j > N / 2 ? N - j : j]; if (oddrefl && j > N / 2) ch[i] = c_make<C>(-ch[i].x, -ch[i].y); }
-                        else pj[i] = perm[j];
+                        if (blue && !(a.dbg & 8)) { ch[i] = g_chirp[j > N / 2 ? N - j : j]; if (oddrefl && j > N / 2) ch[i] = c_make<C>(-ch[i].x, -ch[i].y); }
+                        else if (!blue) pj[i] = perm[j];
                         if (!staged) {
                             const int g = g0 + j;
                             const i64 ia = oneblk ? (i64)g : gp_index(g, a.nproma, sa);
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
                         const int pk_ = s_rec[k];
                         rb[i] = a.peer[pk_ >> 24] + (long long)(pk_ & 0xffffff) * cp;
                         if (!blue) { zk[i] = data[ECT_PAD(k)]; zn[i] = data[ECT_PAD(k == 0 ? 0 : N - k)]; }
-                        else { zk[i] = data[ECT_PAD(km + k)]; zn[i] = data[ECT_PAD(km - k)]; ch[i] = g_chirp[k]; }
+                        else { zk[i] = data[ECT_PAD(km + k)]; zn[i] = data[ECT_PAD(km - k)]; ch[i] = (a.dbg & 8) ? c_make<C>(1, 0) : g_chirp[k]; }
                     }
                 }
 #pragma unroll
@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(TB) k_fourier(FtArgs a) {
                     const C Zk = c_make<C>(a_.y, a_.x), Zn = c_make<C>(b_.y, b_.x);
                     const double2 ra_ = make_double2((double)((Zk.x + Zn.x) * sca), (double)((Zk.y - Zn.y) * sca));
                     const double2 rb_ = make_double2((double)((Zk.y + Zn.y) * scb), (double)((Zn.x - Zk.x) * scb));
+                    if ((a.dbg & 16) && ra_.x != 12345.678) continue;      // timing experiment: no record stores
                     if (push) {
                         double2* q = scr + (i64)k * FT_PUSH_W + (fa - pf0);
                         q[0] = ra_;
