@@ -34,7 +34,7 @@ struct EctHostPlan {
     // Fourier / grid-point space: latitude bands (SUMPLATF)
     std::vector<int> lat_first, lat_count;   // per rank
     int lat0 = 0, nlat = 0;
-    int band_pad = 0;                        // per-latitude weight added to NLOEN when the bands were balanced by cost
+    int band_pad = 0;                        // per-latitude constant of the band cost model (host_plan.cu), 0 when balanced by points
     std::vector<int> gpoff;                  // local latitude -> first local grid point
     int ngptot = 0, ngptotg = 0;
     // Fourier-buffer records.  A record = one (latitude, m) pair, m <= NMEN(lat).

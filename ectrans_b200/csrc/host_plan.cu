@@ -215,29 +215,39 @@ int ect_build_host_plan(EctHostPlan& P, int nsmax, int ndgl, const int* nloen, i
     }
     P.nspec2_g = (nsmax + 1) * (nsmax + 2);
     {
-        // SUMPLATB balances the bands by grid points.  The Fourier kernels cost (i) the FFT work of a row -- N log2 N
-        // for a 31-smooth length, two transforms of the convolution length M for a chirp-z row -- and (ii) a fixed price
-        // per latitude (CTAs set up per row, short rows that do not fill them).  Per-rank stage times on 8 B200s
-        // (profiles/r02_scaling.md: point-balanced TCo1279 bands took 13.4 ms at the poles against 8.5 ms at the
-        // equator) fit  cost = FFT work + 0.16 max(FFT work)  to 7 %.  By default the same SUMPLATB algorithm runs on
-        // that weight; ECT_SETUP_BANDS_BY_POINTS restores the reference's plain point count.
+        // SUMPLATB balances the bands by grid points.  The Fourier kernels cost, per latitude: (i) the FFT work -- N log2 N
+        // for a 31-smooth length, two transforms of the convolution length M for a chirp-z row --, (ii) the gather /
+        // scatter of its NMEN + 1 records and (iii) a fixed price (CTAs set up per row, short rows that do not fill them).
+        // A least-squares fit of the per-rank Fourier times (inverse + direct) of 8 B200s under three different
+        // partitions (profiles/r02b_push_bench_n8.log, 24 band times) gives, in ms,
+        //     3.98e-7 N log2 N  |  2.58e-7 * 2 M log2 M   +   1.78e-5 (NMEN + 1)   +   5.67e-3
+        // to 1.2 %, and predicts the four band times of the 4-GPU run (not in the fit) to 0.5 % of each other, as
+        // measured.  By default the same SUMPLATB algorithm runs on that weight (in ns); ECT_SETUP_BANDS_BY_POINTS
+        // restores the reference's plain point count, ECT_BAND_PAD=x the one-constant model of the first half of round 2
+        // (FFT work + x max(FFT work), x = 0.16: polar bands 5 % over-, the next ones 5 % under-estimated).
         std::vector<int> w(P.nloen);
         P.band_pad = 0;
         if (!bands_by_points && nranks > 1) {
+            const char* pe = getenv("ECT_BAND_PAD");
             std::vector<double> fw(ndgl);
+            std::vector<char> cz(ndgl, 0);
             double fmax = 0;
             for (int j = 0; j < ndgl; ++j) {
                 const int n = P.nloen[j];
                 std::vector<int> rad;
                 double f;
                 if (n % 2 == 0 && ect_fft_factorize(n, rad, false)) f = n * std::log2((double)std::max(n, 2));
-                else { const int M = ect_fft_smooth_size(2 * P.nmen[j] + n); f = 2.0 * M * std::log2((double)M); }
+                else { const int M = ect_fft_smooth_size(2 * P.nmen[j] + n); f = 2.0 * M * std::log2((double)M); cz[j] = 1; }
                 fw[j] = f; fmax = std::max(fmax, f);
             }
-            const char* pe = getenv("ECT_BAND_PAD");        // experiments: the per-latitude constant as a fraction of max(FFT work)
-            const double padf = pe ? atof(pe) : 0.16;
-            P.band_pad = (int)(padf * fmax / 16.0);
-            for (int j = 0; j < ndgl; ++j) w[j] = (int)(fw[j] / 16.0) + P.band_pad;
+            if (pe) {
+                P.band_pad = (int)(atof(pe) * fmax / 16.0);
+                for (int j = 0; j < ndgl; ++j) w[j] = (int)(fw[j] / 16.0) + P.band_pad;
+            } else {
+                P.band_pad = 5672;
+                for (int j = 0; j < ndgl; ++j)
+                    w[j] = (int)((cz[j] ? 0.2583 : 0.3975) * fw[j] + 17.80 * (P.nmen[j] + 1)) + P.band_pad;
+            }
         }
         lat_bands(w, nranks, P.lat_first, P.lat_count);
     }

@@ -78,6 +78,28 @@ def test_golden_grid_inquire(eb, golden):
     t.release()
 
 
+def test_cost_balanced_bands_tco1279(eb, monkeypatch):
+    """The band cost model (host_plan.cu: FFT work + records + a constant per latitude, fitted to per-rank stage times on 8
+    B200s) at the headline resolution: the partition the fit asks for, every rank agreeing on it, and the one-constant model
+    of ECT_BAND_PAD for comparison."""
+    T, N = 1279, 1280
+    nloen = eb.octahedral_nloen(N)
+    monkeypatch.delenv("ECT_BAND_PAD", raising=False)
+    cnt = {}
+    for P in (4, 8):
+        trs = [eb.Transform(T, nloen, nranks=P, rank=r, host_only=True) for r in range(P)]
+        cnt[P] = [int(c) for c in trs[0].lat_count]
+        assert all([int(c) for c in t.lat_count] == cnt[P] for t in trs) and sum(cnt[P]) == 2 * N
+        for t in trs:
+            t.release()
+    assert cnt[8] == [580, 275, 222, 203, 203, 222, 275, 580]
+    assert cnt[4] == [855, 425, 425, 855]
+    monkeypatch.setenv("ECT_BAND_PAD", "0.16")
+    t = eb.Transform(T, nloen, nranks=8, rank=0, host_only=True)
+    assert [int(c) for c in t.lat_count] == [565, 289, 227, 198, 200, 227, 289, 565]
+    t.release()
+
+
 @pytest.mark.parametrize("P", [2, 3, 4, 8])
 def test_decomposition(eb, P):
     T, N = 159, 160
