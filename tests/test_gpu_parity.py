@@ -1048,3 +1048,40 @@ def test_direct_push_slots_bit_identical(eb, monkeypatch, T, N, prec, nuv, nsc):
         refs = [r for r in ref if r is not None and r.size]
         for a, b in zip(got, refs):
             assert rel(a.T.astype(np.float64), b) < (1e-12 if prec == "dp" else 5e-6)
+
+
+def test_winds_and_derivatives_known_answers_gpu(eb):
+    """The CUDA path against the closed forms of tests/test_oracle_golden.py::test_winds_and_derivatives_known_answers
+    (solid-body rotation, purely divergent flow, N-S / E-W derivatives of Pbar_1^0 and Pbar_1^1): pins the wind and
+    derivative conventions independently of the oracle."""
+    T, N = 79, 80
+    nloen = eb.octahedral_nloen(N)
+    s = eo.setup(T, 2 * N, nloen, tables=False)
+    tr = eb.Transform(T, nloen)
+    ra, c = 6371229.0, 3.0e-5
+
+    def one(m, n):
+        sp = np.zeros((1, s.nspec2))
+        sp[0, int(s.nasm0[m]) + 2 * (n - m)] = c
+        return T_(sp)
+
+    zero = T_(np.zeros((1, s.nspec2)))
+    lat_of = np.repeat(np.arange(s.ndgl), s.nloen)
+    cost = np.sqrt(1.0 - s.rmu ** 2)[lat_of]
+    mu = s.rmu[lat_of]
+    lam = np.concatenate([2 * np.pi * np.arange(n) / n for n in s.nloen])
+    omega = c * np.sqrt(3.0) / 2
+    tol = 1e-11
+    u, v = unblock(tr.inv_trans(one(0, 1), zero), tr.ngptot)[:2]
+    assert np.abs(u - omega * ra * cost).max() < tol * omega * ra and np.abs(v).max() < tol * omega * ra
+    u, v = unblock(tr.inv_trans(zero, one(0, 1)), tr.ngptot)[:2]
+    assert np.abs(v + 0.5 * ra * c * np.sqrt(3.0) * cost).max() < tol * omega * ra and np.abs(u).max() < tol * omega * ra
+    f, ns, ew = unblock(tr.inv_trans(None, None, one(0, 1), scders=True), tr.ngptot)
+    assert np.abs(f - c * np.sqrt(3.0) * mu).max() < tol * c
+    assert np.abs(ns - c * np.sqrt(3.0) * cost / ra).max() < tol * c / ra and np.abs(ew).max() < tol * c / ra
+    f, ns, ew = unblock(tr.inv_trans(None, None, one(1, 1), scders=True), tr.ngptot)
+    k = 2 * c * np.sqrt(1.5)
+    assert np.abs(f - k * cost * np.cos(lam)).max() < tol * k
+    assert np.abs(ns + k * mu * np.cos(lam) / ra).max() < tol * k / ra
+    assert np.abs(ew + k * np.sin(lam) / ra).max() < tol * k / ra
+    tr.release()

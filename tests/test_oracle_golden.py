@@ -173,3 +173,40 @@ def test_oracle_gpnorm_vordiv_rpnm_known_answers():
     assert r.shape == (N, sum(T + 2 - m for m in range(T + 1)))
     assert np.allclose(r[:, T + 1], 1.0, rtol=1e-13)                  # m = 0, p = T + 2: n = 0
     assert np.allclose(r[:, T], np.sqrt(3.0) * s.rmu[:N], rtol=1e-13)  # n = 1: sqrt(3) mu
+
+
+def _one_coef(s, m, n, val):
+    sp = np.zeros((1, s.nspec2))
+    sp[0, int(s.nasm0[m]) + 2 * (n - m)] = val
+    return sp
+
+
+def test_winds_and_derivatives_known_answers(s79):
+    """Closed-form answers that pin the conventions no golden array of the reference covers (vor/div -> u, v and
+    the derivatives): with Pbar_1^0 = sqrt(3) mu and Pbar_1^1 = sqrt(3/2) cos(theta) (supolf_mod.F90 normalisation),
+      vorticity   c Pbar_1^0 = 2 Omega mu   ->  solid-body rotation u = Omega a cos(theta), v = 0   (vdtuv_mod.F90:121-139,
+                                                 fsc_mod.F90:138-160);
+      divergence  c Pbar_1^0                ->  chi = -a^2 D / 2, v = (1/a) d chi / d theta = -(a/2) c sqrt(3) cos(theta), u = 0;
+      scalar      c Pbar_1^0                ->  N-S derivative (1/a) d f / d theta = c sqrt(3) cos(theta) / a  (spnsde_mod.F90:95-114);
+      scalar      c Pbar_1^1 e^{i lambda}   ->  f = 2 c sqrt(3/2) cos(theta) cos(lambda), N-S derivative -2 c sqrt(3/2) mu cos(lambda) / a,
+                                                 E-W derivative (1/(a cos theta)) d f / d lambda = -2 c sqrt(3/2) sin(lambda) / a."""
+    s = s79
+    ra, c = 6371229.0, 3.0e-5
+    zero = np.zeros((1, s.nspec2))
+    lat_of = np.repeat(np.arange(s.ndgl), s.nloen)
+    cost = np.sqrt(1.0 - s.rmu ** 2)[lat_of]
+    mu = s.rmu[lat_of]
+    lam = np.concatenate([2 * np.pi * np.arange(n) / n for n in s.nloen])
+    omega = c * np.sqrt(3.0) / 2
+    u, v = eo.inv_trans(s, _one_coef(s, 0, 1, c), zero)[:2]
+    assert np.abs(u - omega * ra * cost).max() < 1e-11 * omega * ra and np.abs(v).max() < 1e-11 * omega * ra
+    u, v = eo.inv_trans(s, zero, _one_coef(s, 0, 1, c))[:2]
+    assert np.abs(v + 0.5 * ra * c * np.sqrt(3.0) * cost).max() < 1e-11 * omega * ra and np.abs(u).max() < 1e-11 * omega * ra
+    f, ns, ew = eo.inv_trans(s, spscalar=_one_coef(s, 0, 1, c), scders=True)
+    assert np.abs(f - c * np.sqrt(3.0) * mu).max() < 1e-11 * c
+    assert np.abs(ns - c * np.sqrt(3.0) * cost / ra).max() < 1e-11 * c / ra and np.abs(ew).max() < 1e-11 * c / ra
+    f, ns, ew = eo.inv_trans(s, spscalar=_one_coef(s, 1, 1, c), scders=True)
+    k = 2 * c * np.sqrt(1.5)
+    assert np.abs(f - k * cost * np.cos(lam)).max() < 1e-11 * k
+    assert np.abs(ns + k * mu * np.cos(lam) / ra).max() < 1e-11 * k / ra
+    assert np.abs(ew + k * np.sin(lam) / ra).max() < 1e-11 * k / ra
